@@ -1,0 +1,389 @@
+// tcgen05 TF32 GEMM for sm_100a:  D = epilogue(alpha * A . B^T), fp32 in HBM, fp32 accumulate in TMEM.
+//
+//   * operands stay fp32 in HBM; TMA (cp.async.bulk.tensor, SWIZZLE_128B) stages [rows x 32 floats]
+//     boxes into shared memory, tcgen05.mma.kind::tf32 reads them as TF32 (top 19 bits);
+//   * one 128 x BN output tile per CTA, accumulator = BN TMEM columns x 128 lanes;
+//   * warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
+//     (one elected lane), warps 2..5 = epilogue (tcgen05.ld 32x32b, one TMEM lane quadrant each);
+//   * smem ring of STAGES {A,B} slots guarded by full/empty mbarriers; tcgen05.commit releases a
+//     slot when the MMAs that read it retire and signals the epilogue after the last k-block;
+//   * both operands may be K-major (row . row) or MN-major (transposed in memory): MN-major tiles
+//     are staged as [k][32 floats] boxes and described to the tensor core with a_major/b_major = 1,
+//     so weight gradients (dY^T . X) and P^T/V^T products need no transposition pass;
+//   * smem per CTA is kept under half an SM so two CTAs are co-resident and one tile's epilogue
+//     overlaps the other's main loop.
+//
+// Descriptor encodings follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor"
+// tables (cross-checked against cute/arch/mma_sm100_desc.hpp).
+#include <cuda.h>
+#include <mutex>
+#include "gemm.cuh"
+
+namespace corrif {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // fp32 elements per k-block = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;              // tf32: 32 bytes of K per instruction
+constexpr int ROW_BYTES = BK * 4;      // 128
+constexpr int A_BYTES = BM * ROW_BYTES;
+constexpr int NUM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (SWIZZLE_128B, sm_100 "version 1").
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
+//   bits [46,48) = 1, bits [61,64) layout type (2 = SWIZZLE_128B).
+//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: [k][32 floats] boxes; 8-k groups 1024 B apart (SBO); next 32 MN elements LBO apart.
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  constexpr uint64_t lbo = MN_MAJOR ? (uint64_t)(BK * ROW_BYTES) >> 4 : 1;
+  constexpr uint64_t sbo = 1024 >> 4;
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// Instruction descriptor, kind::tf32, fp32 accumulate:
+//   [4,6) c_format = 1 (F32), [7,10) a_format = 2 (TF32), [10,13) b_format = 2, bit 15 a_major,
+//   bit 16 b_major (1 = MN-major), [17,23) N >> 3, [24,29) M >> 4.
+template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct KernelArgs {
+  EpiArgs epi;
+  int K;
+  int batch_inner, split_k;
+  // TMA start coordinates per batch index: c0 is the contiguous dim of the operand in memory
+  int64_t a_bo, a_bi, b_bo, b_bi, d_bo, d_bi;
+  int64_t lda, ldb;
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const KernelArgs args) {
+  constexpr int B_BYTES = BN * ROW_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;   // BN in {64,128,256}: already a power of two
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_holder;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B: 1024-B aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- which problem / tile / k-range -------------------------------------------------------
+  const int z = blockIdx.z;
+  const int split = z % args.split_k, batch = z / args.split_k;
+  const int bi = batch % args.batch_inner, bo = batch / args.batch_inner;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int total_kb = (args.K + BK - 1) / BK;
+  const int kb_per_split = (total_kb + args.split_k - 1) / args.split_k;
+  const int kb_begin = split * kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + kb_per_split);
+  const int num_kb = kb_end - kb_begin;           // may be <= 0 for a trailing split: nothing to add
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(&tmem_base_holder)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (num_kb > 0) {
+    if (warp == 0 && lane == 0) {
+      // ================= TMA producer =================
+      const int64_t a_off = bo * args.a_bo + bi * args.a_bi;
+      const int64_t b_off = bo * args.b_bo + bi * args.b_bi;
+      const int a_c0 = (int)(a_off % args.lda), a_c1 = (int)(a_off / args.lda);
+      const int b_c0 = (int)(b_off % args.ldb), b_c1 = (int)(b_off / args.ldb);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        const int k0 = (kb_begin + i) * BK;
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+        if (!A_MN) {
+          tma_load_2d(sa, &tmA, &full_bar[s], a_c0 + k0, a_c1 + m0);          // box {32 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j)                                    // box {32 rows, 32 k}
+            tma_load_2d(sa + j * (BK * ROW_BYTES), &tmA, &full_bar[s], a_c0 + m0 + 32 * j, a_c1 + k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &tmB, &full_bar[s], b_c0 + k0, b_c1 + n0);          // box {32 k, BN rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_2d(sb + j * (BK * ROW_BYTES), &tmB, &full_bar[s], b_c0 + n0 + 32 * j, b_c1 + k0);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major: step 32 B inside the 128-B swizzle row; MN-major: step one 8-k group (1024 B)
+          const uint64_t ad = make_smem_desc<A_MN>(sa + k * (A_MN ? 1024 : UMMA_K * 4));
+          const uint64_t bd = make_smem_desc<B_MN>(sb + k * (B_MN ? 1024 : UMMA_K * 4));
+          tcgen05_mma_tf32(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        tcgen05_commit(&empty_bar[s]);          // frees the slot when these MMAs have read it
+      }
+      tcgen05_commit(&tmem_full_bar);           // accumulator complete
+    } else if (warp >= 2) {
+      // ================= epilogue: TMEM -> registers -> global =================
+      mbar_wait(&tmem_full_bar, 0);
+      tcgen05_fence_after();
+      EpiArgs e = args.epi;
+      const int64_t doff = bo * args.d_bo + bi * args.d_bi;
+      e.D += doff;
+      if (e.residual) e.residual += doff;
+      if (e.aux) e.aux += doff;
+      const int quad = warp & 3;                // TMEM lanes [32*quad, 32*quad+32)
+      const int m = m0 + quad * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+        if (m < e.M) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = n0 + c * 32 + j * 4;
+            if (n < e.N)
+              epilogue_store4(e, m, n, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// 2-D fp32 tensor map over memory [dim1][ld] of which dim0 columns are addressable.
+static int encode_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, int64_t ld,
+                      uint32_t box0, uint32_t box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not found"); return CORRIF_EDRIVER; }
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): base %p dims %llu x %llu ld %lld box %u x %u",
+                   (int)r, (const void*)base, (unsigned long long)dim0, (unsigned long long)dim1,
+                   (long long)ld, box0, box1);
+    return CORRIF_EDRIVER;
+  }
+  return 0;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch_variant(const corrif_gemm_desc& g, const CUtensorMap& ta, const CUtensorMap& tb,
+                          cudaStream_t stream) {
+  constexpr int smem = STAGES * (A_BYTES + BN * ROW_BYTES) + 1024;
+  auto kern = gemm_tf32_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool configured = false;   // per template instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_last_error("gemm_tf32: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  KernelArgs a;
+  a.epi = EpiArgs{g.D, g.bias, g.residual, g.aux, g.ldd, g.ldr, g.ldaux, g.M, g.N, g.epilogue, g.alpha};
+  a.K = g.K; a.batch_inner = g.batch_inner; a.split_k = g.split_k;
+  a.a_bo = g.a_bo; a.a_bi = g.a_bi; a.b_bo = g.b_bo; a.b_bi = g.b_bi; a.d_bo = g.d_bo; a.d_bi = g.d_bi;
+  a.lda = g.lda; a.ldb = g.ldb;
+  dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, g.batch_outer * g.batch_inner * g.split_k);
+  kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, a);
+  return launch_status("gemm_tf32");
+}
+
+template <int BN, int STAGES>
+static int launch_bn(const corrif_gemm_desc& g, const CUtensorMap& ta, const CUtensorMap& tb,
+                     cudaStream_t stream) {
+  if (!g.a_mn_major && !g.b_mn_major) return launch_variant<BN, STAGES, false, false>(g, ta, tb, stream);
+  if (!g.a_mn_major && g.b_mn_major) return launch_variant<BN, STAGES, false, true>(g, ta, tb, stream);
+  if (g.a_mn_major && !g.b_mn_major) return launch_variant<BN, STAGES, true, false>(g, ta, tb, stream);
+  return launch_variant<BN, STAGES, true, true>(g, ta, tb, stream);
+}
+
+}  // namespace tc
+
+int gemm_tf32_launch(const corrif_gemm_desc& g, cudaStream_t stream) {
+  using namespace tc;
+  const int BN = g.N <= 64 ? 64 : 128;
+  const bool batched = g.batch_outer * g.batch_inner > 1;
+  // Extent of the memory an operand's tensor map must cover.  Un-batched: exact logical extent, so
+  // TMA zero-fills ragged M/N/K edges.  Batched: the whole buffer reachable through the offsets;
+  // the contraction dim then has no zero fill, hence K % 32 == 0 is required (checked by caller).
+  auto span = [&](int64_t bo_stride, int64_t bi_stride) {
+    return (int64_t)(g.batch_outer - 1) * bo_stride + (int64_t)(g.batch_inner - 1) * bi_stride;
+  };
+  CUtensorMap ta, tb;
+  int st;
+  {
+    const int64_t extra = span(g.a_bo, g.a_bi);
+    const int64_t rows = g.a_mn_major ? g.K : g.M, cols = g.a_mn_major ? g.M : g.K;
+    const uint64_t dim0 = batched ? (uint64_t)g.lda : (uint64_t)cols;
+    const uint64_t dim1 = (uint64_t)(rows + (batched ? (extra + g.lda - 1) / g.lda : 0));
+    st = encode_map(&ta, g.A, dim0, dim1, g.lda, 32, g.a_mn_major ? BK : BM);
+    if (st) return st;
+  }
+  {
+    const int64_t extra = span(g.b_bo, g.b_bi);
+    const int64_t rows = g.b_mn_major ? g.K : g.N, cols = g.b_mn_major ? g.N : g.K;
+    const uint64_t dim0 = batched ? (uint64_t)g.ldb : (uint64_t)cols;
+    const uint64_t dim1 = (uint64_t)(rows + (batched ? (extra + g.ldb - 1) / g.ldb : 0));
+    st = encode_map(&tb, g.B, dim0, dim1, g.ldb, 32, g.b_mn_major ? BK : BN);
+    if (st) return st;
+  }
+  if (BN == 64) return launch_bn<64, 4>(g, ta, tb, stream);
+  return launch_bn<128, 3>(g, ta, tb, stream);
+}
+
+}  // namespace corrif
+
+using namespace corrif;
+
+extern "C" int corrif_gemm(const corrif_gemm_desc* d, void* stream) {
+  CORRIF_REQUIRE(d != nullptr, "gemm: null descriptor");
+  const corrif_gemm_desc& g = *d;
+  CORRIF_REQUIRE(g.A && g.B && g.D, "gemm: null operand");
+  CORRIF_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: M,N,K must be positive (%d,%d,%d)", g.M, g.N, g.K);
+  CORRIF_REQUIRE(g.batch_outer >= 1 && g.batch_inner >= 1 && g.split_k >= 1, "gemm: batch/split >= 1");
+  CORRIF_REQUIRE((int64_t)g.batch_outer * g.batch_inner * g.split_k <= 65535, "gemm: grid.z too large");
+  CORRIF_REQUIRE(g.N % 4 == 0 && g.ldd % 4 == 0 && g.lda % 4 == 0 && g.ldb % 4 == 0,
+                 "gemm: N and leading dims must be multiples of 4");
+  CORRIF_REQUIRE(((uintptr_t)g.A % 16 == 0) && ((uintptr_t)g.B % 16 == 0) && ((uintptr_t)g.D % 16 == 0),
+                 "gemm: operands must be 16-byte aligned");
+  CORRIF_REQUIRE(g.a_bo % 4 == 0 && g.a_bi % 4 == 0 && g.b_bo % 4 == 0 && g.b_bi % 4 == 0 &&
+                 g.d_bo % 4 == 0 && g.d_bi % 4 == 0, "gemm: batch offsets must be multiples of 4");
+  CORRIF_REQUIRE(g.epilogue >= CORRIF_EPI_STORE && g.epilogue <= CORRIF_EPI_ATOMIC_ADD, "gemm: epilogue");
+  CORRIF_REQUIRE(g.split_k == 1 || g.epilogue == CORRIF_EPI_ATOMIC_ADD,
+                 "gemm: split_k > 1 requires CORRIF_EPI_ATOMIC_ADD");
+  if (g.epilogue == CORRIF_EPI_BIAS || g.epilogue == CORRIF_EPI_BIAS_GELU ||
+      g.epilogue == CORRIF_EPI_BIAS_RESIDUAL)
+    CORRIF_REQUIRE(g.bias != nullptr && (uintptr_t)g.bias % 16 == 0, "gemm: bias missing/unaligned");
+  if (g.epilogue == CORRIF_EPI_BIAS_RESIDUAL)
+    CORRIF_REQUIRE(g.residual != nullptr && g.ldr % 4 == 0 && (uintptr_t)g.residual % 16 == 0,
+                   "gemm: residual missing/unaligned");
+  if (g.epilogue == CORRIF_EPI_BIAS_GELU || g.epilogue == CORRIF_EPI_MUL_DGELU)
+    CORRIF_REQUIRE(g.aux != nullptr && g.ldaux % 4 == 0 && (uintptr_t)g.aux % 16 == 0,
+                   "gemm: aux missing/unaligned");
+  if (g.precision == CORRIF_GEMM_FP32) return gemm_fp32_launch(g, (cudaStream_t)stream);
+  CORRIF_REQUIRE(g.precision == CORRIF_GEMM_TF32, "gemm: unknown precision %d", g.precision);
+  if (g.batch_outer * g.batch_inner > 1)
+    CORRIF_REQUIRE(g.K % 32 == 0, "gemm(tf32): batched problems need K %% 32 == 0 (K=%d)", g.K);
+  if (g.split_k > 1)
+    CORRIF_REQUIRE(g.K % 32 == 0, "gemm(tf32): split_k needs K %% 32 == 0 (K=%d)", g.K);
+  return gemm_tf32_launch(g, (cudaStream_t)stream);
+}

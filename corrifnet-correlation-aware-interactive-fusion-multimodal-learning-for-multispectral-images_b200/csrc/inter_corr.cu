@@ -1,0 +1,181 @@
+// Inter-modal correlation (InterFormer) forward/backward, mmvit4.py:481-507, M = 3 modalities.
+//
+// Reference semantics: scores of query modality X are flattened to
+// [3, B*C*S], soft-maxed over the 3 key modalities and re-viewed as [B, 3C, S].  The view keeps the
+// element position (s,c) but re-interprets the (key modality m, batch b) pair: with
+// j = 3*b' + i = m*B + b, output sample b' multiplies v_i[b'] by A_X[m,b].
+//
+// HBM-bound, no contraction: 128-bit coalesced accesses along the channel dim, everything else in
+// registers.  The forward gathers (thread = output element), the backward is organised per SCORE
+// sample (thread = (b,s,c)) because j is a bijection: every dv_i[b'] has exactly one producer, so
+// no atomics are needed.
+#include "common.cuh"
+
+namespace corrif {
+
+constexpr int IC_M = 3;
+constexpr float IC_RSQRT_M = 0.57735026918962576451f;  // 1/sqrt(3), mmvit4.py:484
+
+struct f4 { float v[4]; };
+__device__ __forceinline__ f4 ldf4(const float* p) {
+  const float4 t = ld4(p);
+  return f4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ void stf4(float* p, const f4& a) { st4(p, make_float4(a.v[0], a.v[1], a.v[2], a.v[3])); }
+
+// qkv [M][B][S][3C]; skip [M][B][S][C]; tokens [B][(M+1)S][C]
+__global__ void __launch_bounds__(128)
+inter_corr_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ skip,
+                      float* __restrict__ tokens, int B, int S, int C) {
+  const int cq = C / 4;
+  const int64_t total = (int64_t)B * S * cq;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cq) * 4;
+  const int s = (int)((idx / cq) % S);
+  const int bp = (int)(idx / ((int64_t)cq * S));
+  const int64_t C3 = 3 * (int64_t)C;
+  const int64_t mod_stride = (int64_t)B * S * C3;
+
+  f4 acc[IC_M];
+#pragma unroll
+  for (int X = 0; X < IC_M; ++X) acc[X] = ldf4(skip + (((int64_t)X * B + bp) * S + s) * C + c);
+
+#pragma unroll
+  for (int i = 0; i < IC_M; ++i) {
+    const int j = IC_M * bp + i;
+    const int m = j / B, b = j % B;
+    const int64_t row_b = ((int64_t)b * S + s) * C3 + c;     // offset inside one modality
+    const int64_t row_bp = ((int64_t)bp * S + s) * C3 + c;
+    f4 k[IC_M];
+#pragma unroll
+    for (int mm = 0; mm < IC_M; ++mm) k[mm] = ldf4(qkv + mm * mod_stride + row_b + C);
+    const f4 v = ldf4(qkv + i * mod_stride + row_bp + 2 * C);
+#pragma unroll
+    for (int X = 0; X < IC_M; ++X) {
+      const f4 q = ldf4(qkv + X * mod_stride + row_b);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float s0 = q.v[e] * k[0].v[e] * IC_RSQRT_M;
+        const float s1 = q.v[e] * k[1].v[e] * IC_RSQRT_M;
+        const float s2 = q.v[e] * k[2].v[e] * IC_RSQRT_M;
+        const float mx = fmaxf(s0, fmaxf(s1, s2));
+        const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
+        const float em = m == 0 ? e0 : (m == 1 ? e1 : e2);
+        acc[X].v[e] += em / (e0 + e1 + e2) * v.v[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int X = 0; X < IC_M; ++X)
+    stf4(tokens + ((int64_t)bp * (IC_M + 1) * S + (int64_t)X * S + s) * C + c, acc[X]);
+}
+
+// g = dL/dtokens [B][(M+1)S][C]; dqkv [M][B][S][3C]
+__global__ void __launch_bounds__(128)
+inter_corr_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g,
+                      float* __restrict__ dqkv, int B, int S, int C) {
+  const int cq = C / 4;
+  const int64_t total = (int64_t)B * S * cq;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % cq) * 4;
+  const int s = (int)((idx / cq) % S);
+  const int b = (int)(idx / ((int64_t)cq * S));
+  const int64_t C3 = 3 * (int64_t)C;
+  const int64_t mod_stride = (int64_t)B * S * C3;
+  const int64_t row_b = ((int64_t)b * S + s) * C3 + c;
+
+  f4 q[IC_M], k[IC_M];
+#pragma unroll
+  for (int X = 0; X < IC_M; ++X) {
+    q[X] = ldf4(qkv + X * mod_stride + row_b);
+    k[X] = ldf4(qkv + X * mod_stride + row_b + C);
+  }
+  // A[X][m] = softmax over m of q_X * k_m / sqrt(3)
+  f4 A[IC_M][IC_M];
+#pragma unroll
+  for (int X = 0; X < IC_M; ++X)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float s0 = q[X].v[e] * k[0].v[e] * IC_RSQRT_M;
+      const float s1 = q[X].v[e] * k[1].v[e] * IC_RSQRT_M;
+      const float s2 = q[X].v[e] * k[2].v[e] * IC_RSQRT_M;
+      const float mx = fmaxf(s0, fmaxf(s1, s2));
+      const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
+      const float inv = 1.0f / (e0 + e1 + e2);
+      A[X][0].v[e] = e0 * inv; A[X][1].v[e] = e1 * inv; A[X][2].v[e] = e2 * inv;
+    }
+  // dA[X][m] = g_X[b'] * v_i[b'] with (b', i) = divmod(m*B + b, 3); dv_i[b'] = sum_X A[X][m]*g_X[b']
+  f4 dA[IC_M][IC_M];
+#pragma unroll
+  for (int m = 0; m < IC_M; ++m) {
+    const int j = m * B + b;
+    const int bp = j / IC_M, i = j % IC_M;
+    const int64_t row_bp = ((int64_t)bp * S + s) * C3 + c;
+    const f4 v = ldf4(qkv + i * mod_stride + row_bp + 2 * C);
+    f4 dv = {{0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int X = 0; X < IC_M; ++X) {
+      const f4 gx = ldf4(g + ((int64_t)bp * (IC_M + 1) * S + (int64_t)X * S + s) * C + c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        dA[X][m].v[e] = gx.v[e] * v.v[e];
+        dv.v[e] += A[X][m].v[e] * gx.v[e];
+      }
+    }
+    stf4(dqkv + i * mod_stride + row_bp + 2 * C, dv);
+  }
+  // ds[X][m] = A*(dA - sum_m' A*dA)/sqrt(3);  dq_X = sum_m ds*k_m;  dk_m = sum_X ds*q_X
+  f4 dk[IC_M];
+#pragma unroll
+  for (int m = 0; m < IC_M; ++m) dk[m] = f4{{0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+  for (int X = 0; X < IC_M; ++X) {
+    f4 dq = {{0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float dot = A[X][0].v[e] * dA[X][0].v[e] + A[X][1].v[e] * dA[X][1].v[e] +
+                        A[X][2].v[e] * dA[X][2].v[e];
+#pragma unroll
+      for (int m = 0; m < IC_M; ++m) {
+        const float ds = A[X][m].v[e] * (dA[X][m].v[e] - dot) * IC_RSQRT_M;
+        dq.v[e] += ds * k[m].v[e];
+        dk[m].v[e] += ds * q[X].v[e];
+      }
+    }
+    stf4(dqkv + X * mod_stride + row_b, dq);
+  }
+#pragma unroll
+  for (int m = 0; m < IC_M; ++m) stf4(dqkv + m * mod_stride + row_b + C, dk[m]);
+}
+
+}  // namespace corrif
+
+using namespace corrif;
+
+extern "C" {
+
+int corrif_inter_corr_fwd(const float* qkv, const float* skip, float* tokens, int32_t M, int32_t B,
+                          int32_t S, int32_t C, void* stream) {
+  CORRIF_REQUIRE(M == IC_M, "inter_corr: M must be 3 (got %d)", M);
+  CORRIF_REQUIRE(qkv && skip && tokens && B > 0 && S > 0 && C > 0 && C % 4 == 0,
+                 "inter_corr_fwd: bad arguments");
+  const int64_t total = (int64_t)B * S * (C / 4);
+  inter_corr_fwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      qkv, skip, tokens, B, S, C);
+  return launch_status("inter_corr_fwd");
+}
+
+int corrif_inter_corr_bwd(const float* qkv, const float* g_tokens, float* dqkv, int32_t M,
+                          int32_t B, int32_t S, int32_t C, void* stream) {
+  CORRIF_REQUIRE(M == IC_M, "inter_corr: M must be 3 (got %d)", M);
+  CORRIF_REQUIRE(qkv && g_tokens && dqkv && B > 0 && S > 0 && C > 0 && C % 4 == 0,
+                 "inter_corr_bwd: bad arguments");
+  const int64_t total = (int64_t)B * S * (C / 4);
+  inter_corr_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      qkv, g_tokens, dqkv, B, S, C);
+  return launch_status("inter_corr_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+"""The CorrIFNet fusion hot path (reference mmvit4.py:456-529) as a sequence of libcorrif_b200
+kernels, forward and hand-written backward.
+
+Data layout in HBM (all fp32, row-major "tokens": row = b*N + s, s = d*64 + h*8 + w, C = 512 cols):
+  x6tok[X]   [B*S, 64]      NCDHW -> token-major copy of the encoder bottleneck (transpose kernel)
+  skip       [3, B*S, 512]  encode-conv output = pre-transformer token (mmvit4.py:462)
+  per transformer: x1 (=x+pos), h (LN1), qkv [R,1536], P [B*8,N,N], O, x2, h2 (LN2), u (pre-GELU),
+                   f1 (GELU out), x3 (output)               R = B*N, N = 512 (intra) / 2048 (multi)
+  qkvi       [3, B*S, 1536] qkv_* conv outputs, consumed element-wise by inter_corr
+  tokens     [B, 2048, 512] multimodal input: rows X*512+s written by inter_corr (skip add fused),
+                            rows 1536+s by the fused6 encode GEMM -> the reference's cats vanish
+  ytok       [B*S, 192]     decode-conv output, transposed back to NCDHW [B,192,8,8,8]
+
+The token re-grouping before multimodal_decode_conv (mmvit4.py:525-529) is a pure re-view:
+[B,2048,512] == [B*512, 2048] row-major, so the decode conv is one GEMM with K = 2048.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .ops import (EPI_ATOMIC_ADD, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_MUL_DGELU,
+                  EPI_STORE, GEMM_FP32, GEMM_TF32, NO_SITE)
+
+MODALITIES = ("RGB", "NIR", "SWIR")
+C = 512
+HEADS = 8
+HD = 64
+S = 512          # tokens per modality (8^3)
+ENC = 64
+NM = 3
+SITE_ATTN, SITE_PROJ, SITE_PRENORM, SITE_FFN1, SITE_FFN2 = range(5)
+
+
+def transformer_keys(prefix: str) -> Dict[str, str]:
+    a = f"{prefix}.cross_attention_list.0.fn"
+    f = f"{prefix}.cross_ffn_list.0.fn"
+    return {
+        "ln1_w": f"{a}.norm.weight", "ln1_b": f"{a}.norm.bias", "qkv_w": f"{a}.fn.qkv.weight",
+        "proj_w": f"{a}.fn.proj.weight", "proj_b": f"{a}.fn.proj.bias",
+        "ln2_w": f"{f}.norm.weight", "ln2_b": f"{f}.norm.bias",
+        "fc1_w": f"{f}.fn.net.0.weight", "fc1_b": f"{f}.fn.net.0.bias",
+        "fc2_w": f"{f}.fn.net.3.weight", "fc2_b": f"{f}.fn.net.3.bias",
+    }
+
+
+def param_names() -> List[str]:
+    names = []
+    for m in MODALITIES:
+        names += [f"{m}_encode_conv.weight", f"{m}_encode_conv.bias"]
+    names += ["fused6_encode_conv.weight", "fused6_encode_conv.bias"]
+    names += [f"{m}_pos" for m in MODALITIES] + ["fused6_pos"]
+    for m in MODALITIES:
+        names += list(transformer_keys(f"{m}_transformer").values())
+    for m in MODALITIES:
+        names += [f"qkv_{m}.weight", f"qkv_{m}.bias"]
+    names += list(transformer_keys("multimodal_transformer").values())
+    names += ["multimodal_decode_conv.weight", "multimodal_decode_conv.bias"]
+    return names
+
+
+def _split_for(out_tiles: int, kblocks: int, sms: int = 148) -> int:
+    """split-K factor for weight gradients: enough CTAs for ~2 waves, at least 4 k-blocks each."""
+    want = max(1, (2 * sms + out_tiles - 1) // out_tiles)
+    return max(1, min(want, max(1, kblocks // 4), 64))
+
+
+class _TBuf:
+    """Saved activations + gradient scratch of one Transformer at a given (B, N)."""
+
+    def __init__(self, B: int, N: int, dev, attn_scratch: bool):
+        R = B * N
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        self.B, self.N, self.R = B, N, R
+        self.x1, self.h, self.qkv = f(R, C), f(R, C), f(R, 3 * C)
+        self.mean1, self.rstd1, self.mean2, self.rstd2 = f(R), f(R), f(R), f(R)
+        self.P = f(B * HEADS, N, N)
+        self.O, self.x2, self.h2, self.u, self.f1, self.x3 = (f(R, C) for _ in range(6))
+        # backward scratch
+        self.t0, self.t1, self.t2, self.din = f(R, C), f(R, C), f(R, C), f(R, C)
+        self.dqkv = f(R, 3 * C)
+        self.dP = f(B * HEADS, N, N) if attn_scratch else None
+
+
+class FusionBlockEngine:
+    """Runs the block for a fixed parameter set.  ``params`` maps the reference's state_dict keys to
+    CUDA fp32 tensors (conv weights may keep their [out,in,1,1,1] shape)."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], dropout_p: float = 0.0,
+                 precision: str = "tf32"):
+        ops.check_device()
+        self.p = params
+        for k in param_names():
+            t = params[k]
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError(f"parameter {k} must be a contiguous CUDA fp32 tensor")
+        self.dev = params["RGB_pos"].device
+        self.dropout_p = float(dropout_p)
+        self.prec = {"tf32": GEMM_TF32, "fp32": GEMM_FP32}[precision]
+        self.tk = [transformer_keys(f"{m}_transformer") for m in MODALITIES]
+        self.tk.append(transformer_keys("multimodal_transformer"))
+        self._ws: Dict[int, dict] = {}
+        self.seed = 0
+        self.seed_dev: Optional[torch.Tensor] = None   # int64[1] device step counter (graph replay)
+        self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+
+    # ------------------------------------------------------------------------------------------
+    def workspace(self, B: int) -> dict:
+        ws = self._ws.get(B)
+        if ws is not None:
+            return ws
+        dev = self.dev
+        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        ws = {
+            "x6tok": f(NM, B * S, ENC), "skip": f(NM, B * S, C), "qkvi": f(NM, B * S, 3 * C),
+            "fx6tok": f(B * S, ENC * NM), "tokens": f(B, (NM + 1) * S, C), "posmm": f((NM + 1) * S, C),
+            "ytok": f(B * S, ENC * NM), "out": f(B, ENC * NM, S),
+            "tb": [_TBuf(B, S, dev, True) for _ in range(NM)] + [_TBuf(B, (NM + 1) * S, dev, True)],
+            # backward
+            "dytok": f(B * S, ENC * NM), "dtokc": f(NM + 1, B * S, C), "dqkvi": f(NM, B * S, 3 * C),
+            "dtok": f(B * S, C), "dx6tok": f(B * S, ENC), "dfx6tok": f(B * S, ENC * NM),
+            "dx6": f(NM, B, ENC, S), "dfused": f(B, ENC * NM, S), "dposmm": f((NM + 1) * S, C),
+            "scratch": f(max(ops.layernorm_bwd_scratch_floats(B * 4 * S),
+                             ops.colsum_scratch_floats(B * 4 * S, 3 * C))),
+        }
+        self._ws[B] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------
+    def _gemm(self, *a, **k):
+        ops.gemm(*a, precision=self.prec, **k)
+
+    def _linear(self, x, w, out, M, N, K, bias=None, epilogue=EPI_STORE, **k):
+        """out[M,N] = x[M,K] . w[N,K]^T (+ epilogue)."""
+        self._gemm(x, w, out, M=M, N=N, K=K, lda=K, ldb=K, ldd=N, bias=bias, epilogue=epilogue, **k)
+
+    def _dgrad(self, dy, w, dx, M, N_out, K_in, **k):
+        """dx[M,K_in] = dy[M,N_out] . w[N_out,K_in]: w is read MN-major (no transposed copy)."""
+        self._gemm(dy, w, dx, M=M, N=K_in, K=N_out, lda=N_out, ldb=K_in, ldd=K_in, b_mn=True, **k)
+
+    def _wgrad(self, dy, x, dw, R, N_out, K_in, ldy=None, ldx=None):
+        """dw[N_out,K_in] += dy[R,N_out]^T . x[R,K_in]: both operands MN-major, split-K + atomics."""
+        tiles = ((N_out + 127) // 128) * ((K_in + (63 if K_in <= 64 else 127)) // (64 if K_in <= 64 else 128))
+        split = _split_for(tiles, R // 32, self.sms)
+        self._gemm(dy, x, dw, M=N_out, N=K_in, K=R, lda=ldy or N_out, ldb=ldx or K_in, ldd=K_in,
+                   a_mn=True, b_mn=True, split_k=split, epilogue=EPI_ATOMIC_ADD)
+
+    def _site(self, t: int, kind: int) -> int:
+        return t * 8 + kind
+
+    # ------------------------------------------------------------------------------------------
+    def _attention_fwd(self, t: int, tb: _TBuf):
+        B, N = tb.B, tb.N
+        p = self.dropout_p
+        # S = 0.125 * Q K^T per (batch, head): strided views into qkv, no reshape/permute copies
+        self._gemm(tb.qkv, (tb.qkv, C), tb.P, M=N, N=N, K=HD, lda=3 * C, ldb=3 * C, ldd=N,
+                   batch=(B, HEADS), a_step=(N * 3 * C, HD), b_step=(N * 3 * C, HD),
+                   d_step=(HEADS * N * N, N * N), alpha=HD ** -0.5)
+        pd = tb.dP if p > 0 else None
+        ops.softmax_fwd(tb.P, pd, B * HEADS * N, N, p, self.seed, self.seed_dev, self._site(t, SITE_ATTN))
+        # O[b, n, h*64+d] = P V : V is read MN-major straight out of qkv
+        self._gemm(pd if p > 0 else tb.P, (tb.qkv, 2 * C), tb.O, M=N, N=HD, K=N, lda=N, ldb=3 * C,
+                   ldd=C, b_mn=True, batch=(B, HEADS), a_step=(HEADS * N * N, N * N),
+                   b_step=(N * 3 * C, HD), d_step=(N * C, HD))
+
+    def _attention_bwd(self, t: int, tb: _TBuf, dO: torch.Tensor):
+        B, N = tb.B, tb.N
+        p = self.dropout_p
+        bat = dict(batch=(B, HEADS))
+        pstep, qstep, ostep = (HEADS * N * N, N * N), (N * 3 * C, HD), (N * C, HD)
+        pd = tb.P
+        if p > 0:   # regenerate the dropped probabilities (same Philox counters as the forward)
+            ops.dropout(tb.P, tb.dP, tb.P.numel(), p, self.seed, self._site(t, SITE_ATTN), self.seed_dev)
+            pd = tb.dP
+        # dV = Pd^T dO
+        self._gemm(pd, dO, (tb.dqkv, 2 * C), M=N, N=HD, K=N, lda=N, ldb=C, ldd=3 * C, a_mn=True,
+                   b_mn=True, a_step=pstep, b_step=ostep, d_step=qstep, **bat)
+        # dP = dO V^T
+        self._gemm(dO, (tb.qkv, 2 * C), tb.dP, M=N, N=N, K=HD, lda=C, ldb=3 * C, ldd=N,
+                   a_step=ostep, b_step=qstep, d_step=pstep, **bat)
+        # dS = P * (dP*keep - rowsum(dP*keep*P)) * scale, in place
+        ops.softmax_bwd(tb.P, tb.dP, B * HEADS * N, N, HD ** -0.5, p, self.seed, self.seed_dev,
+                        self._site(t, SITE_ATTN))
+        # dQ = dS K ; dK = dS^T Q
+        self._gemm(tb.dP, (tb.qkv, C), tb.dqkv, M=N, N=HD, K=N, lda=N, ldb=3 * C, ldd=3 * C,
+                   b_mn=True, a_step=pstep, b_step=qstep, d_step=qstep, **bat)
+        self._gemm(tb.dP, tb.qkv, (tb.dqkv, C), M=N, N=HD, K=N, lda=N, ldb=3 * C, ldd=3 * C,
+                   a_mn=True, b_mn=True, a_step=pstep, b_step=qstep, d_step=qstep, **bat)
+
+    # ------------------------------------------------------------------------------------------
+    def _transformer_fwd(self, t: int, x_in, pos, pos_rows: int, tb: _TBuf):
+        """Transformer.forward, mmvit4.py:383-388 (depth 1)."""
+        k, P_, R, p = self.tk[t], self.p, tb.R, self.dropout_p
+        ops.layernorm_fwd(x_in, pos, pos_rows, P_[k["ln1_w"]], P_[k["ln1_b"]], tb.x1, tb.h,
+                          tb.mean1, tb.rstd1, R)
+        self._linear(tb.h, P_[k["qkv_w"]], tb.qkv, R, 3 * C, C)
+        self._attention_fwd(t, tb)
+        if p == 0:
+            self._linear(tb.O, P_[k["proj_w"]], tb.x2, R, C, C, bias=P_[k["proj_b"]],
+                         epilogue=EPI_BIAS_RESIDUAL, residual=tb.x1, ldr=C)
+        else:
+            self._linear(tb.O, P_[k["proj_w"]], tb.t0, R, C, C, bias=P_[k["proj_b"]], epilogue=EPI_BIAS)
+            ops.dropout_add(tb.t0, tb.x1, tb.x2, R * C, p, self.seed, self._site(t, SITE_PROJ),
+                            self._site(t, SITE_PRENORM), self.seed_dev)
+        ops.layernorm_fwd(tb.x2, None, 1, P_[k["ln2_w"]], P_[k["ln2_b"]], None, tb.h2, tb.mean2,
+                          tb.rstd2, R)
+        self._linear(tb.h2, P_[k["fc1_w"]], tb.f1, R, C, C, bias=P_[k["fc1_b"]],
+                     epilogue=EPI_BIAS_GELU, aux=tb.u, ldaux=C)
+        if p > 0:
+            ops.dropout(tb.f1, tb.f1, R * C, p, self.seed, self._site(t, SITE_FFN1), self.seed_dev)
+        if p == 0:
+            self._linear(tb.f1, P_[k["fc2_w"]], tb.x3, R, C, C, bias=P_[k["fc2_b"]],
+                         epilogue=EPI_BIAS_RESIDUAL, residual=tb.x2, ldr=C)
+        else:
+            self._linear(tb.f1, P_[k["fc2_w"]], tb.t0, R, C, C, bias=P_[k["fc2_b"]], epilogue=EPI_BIAS)
+            ops.dropout_add(tb.t0, tb.x2, tb.x3, R * C, p, self.seed, self._site(t, SITE_FFN2),
+                            NO_SITE, self.seed_dev)
+        return tb.x3
+
+    def _transformer_bwd(self, t: int, dx3, tb: _TBuf, g: Dict[str, torch.Tensor], scratch):
+        """Backward of _transformer_fwd.  ``dx3`` must not alias tb.t0/t1/t2 (callers pass tb.din).
+        Returns d(x_in) == d(x1) in tb.t0 (also the pos gradient before the batch reduction).
+        Matrix-weight grads are ACCUMULATED into ``g`` (atomics); LayerNorm and bias grads are
+        OVERWRITTEN."""
+        k, P_, R, p = self.tk[t], self.p, tb.R, self.dropout_p
+        # ---- FeedForward branch: x3 = x2 + drop(fc2(drop(gelu(fc1(LN2(x2))))))
+        df2 = dx3
+        if p > 0:
+            ops.dropout(dx3, tb.t0, R * C, p, self.seed, self._site(t, SITE_FFN2), self.seed_dev)
+            df2 = tb.t0
+        self._wgrad(df2, tb.f1, g[k["fc2_w"]], R, C, C)
+        ops.colsum(df2, C, R, C, g[k["fc2_b"]], scratch)
+        self._dgrad(df2, P_[k["fc2_w"]], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C)
+        if p > 0:
+            ops.dropout(tb.t1, tb.t1, R * C, p, self.seed, self._site(t, SITE_FFN1), self.seed_dev)
+        self._wgrad(tb.t1, tb.h2, g[k["fc1_w"]], R, C, C)
+        ops.colsum(tb.t1, C, R, C, g[k["fc1_b"]], scratch)
+        self._dgrad(tb.t1, P_[k["fc1_w"]], tb.t2, R, C, C)                    # d(h2)
+        ops.layernorm_bwd(tb.t2, tb.x2, P_[k["ln2_w"]], tb.mean2, tb.rstd2, dx3, tb.t1,
+                          g[k["ln2_w"]], g[k["ln2_b"]], scratch, R)           # t1 = d(x2)
+        dx2 = tb.t1
+        # ---- attention branch: x2 = x1 + drop(drop(proj(attn(LN1(x1)))))
+        dy = dx2
+        if p > 0:
+            ops.dropout_add(dx2, None, tb.t0, R * C, p, self.seed, self._site(t, SITE_PROJ),
+                            self._site(t, SITE_PRENORM), self.seed_dev)
+            dy = tb.t0
+        self._wgrad(dy, tb.O, g[k["proj_w"]], R, C, C)
+        ops.colsum(dy, C, R, C, g[k["proj_b"]], scratch)
+        self._dgrad(dy, P_[k["proj_w"]], tb.t2, R, C, C)                      # d(O)
+        self._attention_bwd(t, tb, tb.t2)
+        self._wgrad(tb.dqkv, tb.h, g[k["qkv_w"]], R, 3 * C, C)
+        self._dgrad(tb.dqkv, P_[k["qkv_w"]], tb.t2, R, 3 * C, C)              # d(h)
+        ops.layernorm_bwd(tb.t2, tb.x1, P_[k["ln1_w"]], tb.mean1, tb.rstd1, dx2, tb.t0,
+                          g[k["ln1_w"]], g[k["ln1_b"]], scratch, R)           # t0 = d(x1)
+        return tb.t0
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x6: List[torch.Tensor], fused_x6: torch.Tensor) -> torch.Tensor:
+        """x6: three [B,64,8,8,8]; fused_x6 [B,192,8,8,8] -> x6_inter [B,192,8,8,8] (workspace-owned;
+        clone it if it must survive the next forward)."""
+        B = fused_x6.shape[0]
+        ws, P_ = self.workspace(B), self.p
+        self._B = B
+        for X, m in enumerate(MODALITIES):
+            ops.transpose(x6[X], ws["x6tok"][X], B, ENC, S)                                # :459
+            self._linear(ws["x6tok"][X], P_[f"{m}_encode_conv.weight"], ws["skip"][X], B * S, C, ENC,
+                         bias=P_[f"{m}_encode_conv.bias"], epilogue=EPI_BIAS)              # :458
+            x3 = self._transformer_fwd(X, ws["skip"][X], P_[f"{m}_pos"], S, ws["tb"][X])   # :462
+            self._linear(x3, P_[f"qkv_{m}.weight"], ws["qkvi"][X], B * S, 3 * C, C,
+                         bias=P_[f"qkv_{m}.bias"], epilogue=EPI_BIAS)                      # :477-479
+        ops.inter_corr_fwd(ws["qkvi"], ws["skip"], ws["tokens"], NM, B, S, C)              # :481-507
+        ops.transpose(fused_x6, ws["fx6tok"], B, ENC * NM, S)
+        self._gemm(ws["fx6tok"], P_["fused6_encode_conv.weight"], (ws["tokens"], NM * S * C),
+                   M=S, N=C, K=ENC * NM, lda=ENC * NM, ldb=ENC * NM, ldd=C,
+                   bias=P_["fused6_encode_conv.bias"], epilogue=EPI_BIAS, batch=(B, 1),
+                   a_step=(S * ENC * NM, 0), d_step=((NM + 1) * S * C, 0))                 # :510-513
+        for X, m in enumerate(MODALITIES + ("fused6",)):
+            ws["posmm"][X * S:(X + 1) * S].copy_(P_[f"{m}_pos"][0])                        # :516,521
+        tbm = ws["tb"][NM]
+        x3 = self._transformer_fwd(NM, ws["tokens"], ws["posmm"], (NM + 1) * S, tbm)       # :519-522
+        self._linear(x3, P_["multimodal_decode_conv.weight"], ws["ytok"], B * S, ENC * NM,
+                     (NM + 1) * C, bias=P_["multimodal_decode_conv.bias"], epilogue=EPI_BIAS)  # :525
+        ops.transpose(ws["ytok"], ws["out"], B, S, ENC * NM)                               # :527-528
+        return ws["out"].view(B, ENC * NM, 8, 8, 8)
+
+    def backward(self, gout: torch.Tensor, grads: Optional[Dict[str, torch.Tensor]] = None):
+        """gout [B,192,8,8,8] -> (dx6 [3,B,64,8,8,8], dfused_x6 [B,192,8,8,8], {param: grad}).
+        If ``grads`` is given the parameter gradients are accumulated into it."""
+        B = self._B
+        ws, P_ = self.workspace(B), self.p
+        if grads is None:
+            grads = {k: torch.zeros_like(P_[k]) for k in param_names()}
+        g, sc = grads, ws["scratch"]
+        R = B * S
+        # ---- decode conv
+        ops.transpose(gout, ws["dytok"], B, ENC * NM, S)
+        tbm = ws["tb"][NM]
+        self._wgrad(ws["dytok"], tbm.x3, g["multimodal_decode_conv.weight"], R, ENC * NM, (NM + 1) * C)
+        ops.colsum(ws["dytok"], ENC * NM, R, ENC * NM, g["multimodal_decode_conv.bias"], sc, accumulate=True)
+        self._dgrad(ws["dytok"], P_["multimodal_decode_conv.weight"], tbm.din, R, ENC * NM, (NM + 1) * C)
+        # ---- multimodal transformer
+        gm = {k: torch.zeros_like(P_[k]) for k in self.tk[NM].values() if "norm" in k or k.endswith(".bias")}
+        gt = dict(g)
+        gt.update(gm)
+        dtokens = self._transformer_bwd(NM, tbm.din, tbm, gt, sc)                 # [B,2048,512]
+        for k_, v in gm.items():
+            g[k_] += v
+        ops.batchsum(dtokens, B, (NM + 1) * S * C, (NM + 1) * S * C, ws["dposmm"])
+        # contiguous per-group copies of the token gradient: [4][B*S][512]
+        ws["dtokc"].view(NM + 1, B, S, C).copy_(dtokens.view(B, NM + 1, S, C).transpose(0, 1))
+        # ---- fused6 encode conv
+        df6 = ws["dtokc"][NM]
+        self._wgrad(df6, ws["fx6tok"], g["fused6_encode_conv.weight"], R, C, ENC * NM)
+        ops.colsum(df6, C, R, C, g["fused6_encode_conv.bias"], sc, accumulate=True)
+        self._dgrad(df6, P_["fused6_encode_conv.weight"], ws["dfx6tok"], R, C, ENC * NM)
+        ops.transpose(ws["dfx6tok"], ws["dfused"], B, S, ENC * NM)
+        g["fused6_pos"] += ws["dposmm"][NM * S:].view(1, S, C)
+        # ---- inter-modal correlation
+        ops.inter_corr_bwd(ws["qkvi"], dtokens, ws["dqkvi"], NM, B, S, C)
+        for X, m in enumerate(MODALITIES):
+            tb = ws["tb"][X]
+            dq = ws["dqkvi"][X]
+            self._wgrad(dq, tb.x3, g[f"qkv_{m}.weight"], R, 3 * C, C)
+            ops.colsum(dq, 3 * C, R, 3 * C, g[f"qkv_{m}.bias"], sc, accumulate=True)
+            self._dgrad(dq, P_[f"qkv_{m}.weight"], tb.din, R, 3 * C, C)         # d(trans_X)
+            gx = {k: torch.zeros_like(P_[k]) for k in self.tk[X].values() if "norm" in k or k.endswith(".bias")}
+            gt = dict(g)
+            gt.update(gx)
+            dx1 = self._transformer_bwd(X, tb.din, tb, gt, sc)
+            for k_, v in gx.items():
+                g[k_] += v
+            ops.batchsum(dx1, B, S * C, S * C, ws["dposmm"][X * S:(X + 1) * S], accumulate=True)
+            g[f"{m}_pos"] += ws["dposmm"][X * S:(X + 1) * S].view(1, S, C)
+            ops.add_rows(dx1, C, ws["dtokc"][X], C, ws["dtok"], C, R, C)        # + skip path (:505)
+            self._wgrad(ws["dtok"], ws["x6tok"][X], g[f"{m}_encode_conv.weight"], R, C, ENC)
+            ops.colsum(ws["dtok"], C, R, C, g[f"{m}_encode_conv.bias"], sc, accumulate=True)
+            self._dgrad(ws["dtok"], P_[f"{m}_encode_conv.weight"], ws["dx6tok"], R, C, ENC)
+            ops.transpose(ws["dx6tok"], ws["dx6"][X], B, S, ENC)
+        return (ws["dx6"].view(NM, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * NM, 8, 8, 8), grads)

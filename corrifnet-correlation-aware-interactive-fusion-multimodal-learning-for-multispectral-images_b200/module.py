@@ -1,0 +1,145 @@
+"""torch-facing layer: the fusion block as a registered custom op with autograd, and an nn.Module
+whose parameters carry the reference's state_dict keys (mmvit4.py:398-426)."""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import fusion
+from .fusion import FusionBlockEngine, param_names
+
+_ENGINES: Dict[Tuple, FusionBlockEngine] = {}
+
+
+def _engine_for(params: Sequence[Tensor], dropout_p: float, precision: str) -> FusionBlockEngine:
+    """One engine (workspace + saved activations) per parameter set; keyed by storage addresses so
+    in-place optimizer updates keep hitting the same engine."""
+    key = (tuple(p.data_ptr() for p in params), float(dropout_p), precision)
+    eng = _ENGINES.get(key)
+    if eng is None:
+        if len(_ENGINES) > 8:
+            _ENGINES.clear()
+        named = {n: p.detach() for n, p in zip(param_names(), params)}
+        eng = FusionBlockEngine(named, dropout_p=dropout_p, precision=precision)
+        _ENGINES[key] = eng
+    return eng
+
+
+@torch.library.custom_op("corrif::fusion_block", mutates_args=(), device_types="cuda")
+def fusion_block_op(x6_rgb: Tensor, x6_nir: Tensor, x6_swir: Tensor, fused_x6: Tensor,
+                    params: Sequence[Tensor], dropout_p: float, seed: int, precision: str) -> Tensor:
+    """x6_inter = CorrIFNet fusion block (mmvit4.py:456-529).  ``params`` in ``param_names()`` order."""
+    eng = _engine_for(params, dropout_p, precision)
+    eng.seed = int(seed)
+    out = eng.forward([x6_rgb.contiguous(), x6_nir.contiguous(), x6_swir.contiguous()],
+                      fused_x6.contiguous())
+    return out.clone()
+
+
+@fusion_block_op.register_fake
+def _(x6_rgb, x6_nir, x6_swir, fused_x6, params, dropout_p, seed, precision):
+    return torch.empty_like(fused_x6)
+
+
+@torch.library.custom_op("corrif::fusion_block_backward", mutates_args=(), device_types="cuda")
+def fusion_block_backward_op(gout: Tensor, params: Sequence[Tensor], dropout_p: float, seed: int,
+                             precision: str) -> List[Tensor]:
+    """Backward of the most recent corrif::fusion_block call on the same parameter set.  Returns
+    [d x6_rgb, d x6_nir, d x6_swir, d fused_x6, *d params]."""
+    eng = _engine_for(params, dropout_p, precision)
+    eng.seed = int(seed)
+    dx6, dfused, grads = eng.backward(gout.contiguous())
+    return [dx6[0].clone(), dx6[1].clone(), dx6[2].clone(), dfused.clone()] + \
+        [grads[n] for n in param_names()]
+
+
+@fusion_block_backward_op.register_fake
+def _(gout, params, dropout_p, seed, precision):
+    b = gout.shape[0]
+    x = gout.new_empty(b, 64, 8, 8, 8)
+    return [x, x.clone(), x.clone(), torch.empty_like(gout)] + [torch.empty_like(p) for p in params]
+
+
+def _setup_ctx(ctx, inputs, output):
+    _, _, _, _, params, dropout_p, seed, precision = inputs
+    ctx.params = list(params)
+    ctx.dropout_p, ctx.seed, ctx.precision = dropout_p, seed, precision
+
+
+def _backward(ctx, gout):
+    res = torch.ops.corrif.fusion_block_backward(gout, ctx.params, ctx.dropout_p, ctx.seed, ctx.precision)
+    return res[0], res[1], res[2], res[3], list(res[4:]), None, None, None
+
+
+fusion_block_op.register_autograd(_backward, setup_context=_setup_ctx)
+
+
+# --------------------------------------------------------------------------------------------------
+def _attach(root: nn.Module, dotted: str, param: nn.Parameter):
+    """Register ``param`` under a dotted state_dict key, creating plain container modules."""
+    parts = dotted.split(".")
+    mod = root
+    for part in parts[:-1]:
+        child = mod._modules.get(part)
+        if child is None:
+            child = nn.Module()
+            mod.add_module(part, child)
+        mod = child
+    mod.register_parameter(parts[-1], param)
+
+
+def fusion_param_shapes() -> Dict[str, Tuple[int, ...]]:
+    C, E, S = fusion.C, fusion.ENC, fusion.S
+    shapes: Dict[str, Tuple[int, ...]] = {}
+    for n in param_names():
+        if n.endswith("_pos"):
+            shapes[n] = (1, S, C)
+        elif n.startswith("fused6_encode_conv"):
+            shapes[n] = (C, 3 * E, 1, 1, 1) if n.endswith("weight") else (C,)
+        elif "_encode_conv" in n:
+            shapes[n] = (C, E, 1, 1, 1) if n.endswith("weight") else (C,)
+        elif n.startswith("qkv_"):
+            shapes[n] = (3 * C, C, 1, 1, 1) if n.endswith("weight") else (3 * C,)
+        elif n.startswith("multimodal_decode_conv"):
+            shapes[n] = (3 * E, 4 * C, 1, 1, 1) if n.endswith("weight") else (3 * E,)
+        elif n.endswith("qkv.weight"):
+            shapes[n] = (3 * C, C)
+        elif n.endswith(".weight") and "norm" not in n:
+            shapes[n] = (C, C)
+        else:
+            shapes[n] = (C,)
+    return shapes
+
+
+class CorrIFusionBlock(nn.Module):
+    """Stand-alone fusion block.  ``state_dict()`` keys and shapes equal the corresponding entries
+    of the reference ``MMVit4`` (strict loading both ways for this subset).  forward(x6 list,
+    fused_x6) -> x6_inter; ``self.training`` selects dropout p=0.1 as in the reference
+    (mmvit4.py:361)."""
+
+    def __init__(self, dropout_rate: float = 0.1, precision: str = "tf32"):
+        super().__init__()
+        self.dropout_rate = dropout_rate
+        self.precision = precision
+        self._step = 0
+        self.base_seed = 0x5EED
+        for name, shape in fusion_param_shapes().items():
+            p = nn.Parameter(torch.zeros(shape))
+            if name.endswith("norm.weight"):
+                nn.init.ones_(p)
+            elif name.endswith(".weight"):
+                nn.init.kaiming_normal_(p) if p.dim() == 5 else nn.init.kaiming_uniform_(p, a=5 ** 0.5)
+            _attach(self, name, p)
+
+    def ordered_params(self) -> List[nn.Parameter]:
+        named = dict(self.named_parameters())
+        return [named[n] for n in param_names()]
+
+    def forward(self, x6: Sequence[Tensor], fused_x6: Tensor) -> Tensor:
+        p = self.dropout_rate if self.training else 0.0
+        self._step += 1
+        return torch.ops.corrif.fusion_block(x6[0], x6[1], x6[2], fused_x6, self.ordered_params(), p,
+                                             self.base_seed + self._step, self.precision)

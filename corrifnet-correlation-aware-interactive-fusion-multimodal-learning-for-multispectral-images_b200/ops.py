@@ -1,0 +1,200 @@
+"""Tensor-level wrappers over the C ABI (include/corrif.h): torch owns memory and streams, the
+library does the work.  Every function launches on ``torch.cuda.current_stream()`` and never syncs.
+
+No CPU path: tensors must be CUDA fp32 contiguous, otherwise ``CorrifError``/``ValueError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple, Union
+
+import torch
+
+from . import _lib as L
+from ._lib import (EPI_ATOMIC_ADD, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_MUL_DGELU,  # noqa: F401
+                   EPI_STORE, GEMM_FP32, GEMM_TF32, NO_SITE, CorrifError, GemmDesc)
+
+TensorOrView = Union[torch.Tensor, Tuple[torch.Tensor, int]]  # (tensor, element offset)
+
+_launches = 0          # number of library kernels enqueued (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n: int = 1):
+    global _launches
+    _launches += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[TensorOrView], dtype=torch.float32) -> Optional[int]:
+    if t is None:
+        return None
+    off = 0
+    if isinstance(t, tuple):
+        t, off = t
+    if not t.is_cuda:
+        raise ValueError("corrif ops need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError("expected %s, got %s" % (dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("corrif ops need contiguous tensors")
+    return t.data_ptr() + off * t.element_size()
+
+
+def lib():
+    return L.load()
+
+
+def check_device():
+    L.check(lib().corrif_check_device(), "corrif_check_device")
+
+
+# ------------------------------------------------------------------------------------------------
+def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K: int, lda: int,
+         ldb: int, ldd: int, a_mn: bool = False, b_mn: bool = False, bias=None, residual=None,
+         ldr: int = 0, aux=None, ldaux: int = 0, batch=(1, 1), a_step=(0, 0), b_step=(0, 0),
+         d_step=(0, 0), split_k: int = 1, epilogue: int = EPI_STORE, precision: int = GEMM_TF32,
+         alpha: float = 1.0):
+    """D = epilogue(alpha * A . B^T); see corrif_gemm in include/corrif.h for the layout rules."""
+    g = GemmDesc()
+    g.A, g.B, g.D = _ptr(A), _ptr(B), _ptr(D)
+    g.bias, g.residual, g.aux = _ptr(bias), _ptr(residual), _ptr(aux)
+    g.lda, g.ldb, g.ldd, g.ldr, g.ldaux = lda, ldb, ldd, ldr, ldaux
+    g.M, g.N, g.K = M, N, K
+    g.a_mn_major, g.b_mn_major = int(a_mn), int(b_mn)
+    g.batch_outer, g.batch_inner = batch
+    g.a_bo, g.a_bi = a_step
+    g.b_bo, g.b_bi = b_step
+    g.d_bo, g.d_bi = d_step
+    g.split_k, g.epilogue, g.precision, g.alpha = split_k, epilogue, precision, alpha
+    L.check(lib().corrif_gemm(C.byref(g), _stream()), "corrif_gemm")
+    _count()
+
+
+def transpose(x: TensorOrView, out: TensorOrView, batch: int, rows: int, cols: int):
+    L.check(lib().corrif_transpose(_ptr(x), _ptr(out), batch, rows, cols, _stream()), "corrif_transpose")
+    _count()
+
+
+def layernorm_fwd(x, pos, pos_rows, gamma, beta, x1_out, y, mean, rstd, rows, C_=512):
+    L.check(lib().corrif_layernorm_fwd(_ptr(x), _ptr(pos), pos_rows, _ptr(gamma), _ptr(beta),
+                                       _ptr(x1_out), _ptr(y), _ptr(mean), _ptr(rstd), rows, C_,
+                                       _stream()), "corrif_layernorm_fwd")
+    _count()
+
+
+def layernorm_bwd_scratch_floats(rows, C_=512) -> int:
+    return int(lib().corrif_layernorm_bwd_scratch_floats(rows, C_))
+
+
+def layernorm_bwd(dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, scratch, rows, C_=512):
+    L.check(lib().corrif_layernorm_bwd(_ptr(dy), _ptr(x1), _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                       _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                                       _ptr(scratch), rows, C_, _stream()), "corrif_layernorm_bwd")
+    _count(2)
+
+
+def _seed_dev(seed_dev):
+    return None if seed_dev is None else _ptr(seed_dev, torch.int64)
+
+
+def softmax_fwd(S, Pdrop, rows, cols, p=0.0, seed=0, seed_dev=None, site=0):
+    L.check(lib().corrif_softmax_fwd(_ptr(S), _ptr(Pdrop), rows, cols, p, seed, _seed_dev(seed_dev),
+                                     site, _stream()), "corrif_softmax_fwd")
+    _count()
+
+
+def softmax_bwd(P, dP, rows, cols, scale, p=0.0, seed=0, seed_dev=None, site=0):
+    L.check(lib().corrif_softmax_bwd(_ptr(P), _ptr(dP), rows, cols, scale, p, seed,
+                                     _seed_dev(seed_dev), site, _stream()), "corrif_softmax_bwd")
+    _count()
+
+
+def dropout(x, out, n, p, seed, site, seed_dev=None):
+    L.check(lib().corrif_dropout(_ptr(x), _ptr(out), n, p, seed, _seed_dev(seed_dev), site, _stream()),
+            "corrif_dropout")
+    _count()
+
+
+def dropout_mask(mask, n, p, seed, site, seed_dev=None):
+    L.check(lib().corrif_dropout_mask(_ptr(mask), n, p, seed, _seed_dev(seed_dev), site, _stream()),
+            "corrif_dropout_mask")
+    _count()
+
+
+def dropout_add(x, res, out, n, p, seed, site_a, site_b=NO_SITE, seed_dev=None):
+    L.check(lib().corrif_dropout_add(_ptr(x), _ptr(res), _ptr(out), n, p, seed, _seed_dev(seed_dev),
+                                     site_a, site_b, _stream()), "corrif_dropout_add")
+    _count()
+
+
+def colsum_scratch_floats(rows, cols) -> int:
+    return int(lib().corrif_colsum_scratch_floats(rows, cols))
+
+
+def colsum(x, ld, rows, cols, out, scratch, accumulate=False):
+    L.check(lib().corrif_colsum(_ptr(x), ld, rows, cols, _ptr(out), int(accumulate), _ptr(scratch),
+                                _stream()), "corrif_colsum")
+    _count(2)
+
+
+def batchsum(x, batch, stride, n, out, accumulate=False):
+    L.check(lib().corrif_batchsum(_ptr(x), batch, stride, n, _ptr(out), int(accumulate), _stream()),
+            "corrif_batchsum")
+    _count()
+
+
+def add_rows(a, lda, b, ldb, out, ldo, rows, cols):
+    L.check(lib().corrif_add_rows(_ptr(a), lda, _ptr(b), ldb, _ptr(out), ldo, rows, cols, _stream()),
+            "corrif_add_rows")
+    _count()
+
+
+def inter_corr_fwd(qkv, skip, tokens, M, B, S, C_):
+    L.check(lib().corrif_inter_corr_fwd(_ptr(qkv), _ptr(skip), _ptr(tokens), M, B, S, C_, _stream()),
+            "corrif_inter_corr_fwd")
+    _count()
+
+
+def inter_corr_bwd(qkv, g_tokens, dqkv, M, B, S, C_):
+    L.check(lib().corrif_inter_corr_bwd(_ptr(qkv), _ptr(g_tokens), _ptr(dqkv), M, B, S, C_, _stream()),
+            "corrif_inter_corr_bwd")
+    _count()
+
+
+def jaccard_sums(y, y_pred, P, sums):
+    L.check(lib().corrif_jaccard_sums(_ptr(y), _ptr(y_pred), P, _ptr(sums, torch.float64), _stream()),
+            "corrif_jaccard_sums")
+    _count()
+
+
+def jaccard_finish(sums, epsilon, out3):
+    L.check(lib().corrif_jaccard_finish(_ptr(sums, torch.float64), epsilon, _ptr(out3), _stream()),
+            "corrif_jaccard_finish")
+    _count()
+
+
+def confusion_counts(label, pred, P, num_classes, counts):
+    L.check(lib().corrif_confusion_counts(_ptr(label, torch.uint8), _ptr(pred, torch.uint8), P,
+                                          num_classes, _ptr(counts, torch.int64), _stream()),
+            "corrif_confusion_counts")
+    _count()
+
+
+def bce_probs_fwd_bwd(x, y, n, grad_scale, loss_sum, dx):
+    L.check(lib().corrif_bce_probs_fwd_bwd(_ptr(x), _ptr(y), n, grad_scale,
+                                           _ptr(loss_sum, torch.float64), _ptr(dx), _stream()),
+            "corrif_bce_probs_fwd_bwd")
+    _count()
+
+
+def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, grad_scale, step):
+    L.check(lib().corrif_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), n, lr, beta1, beta2, eps,
+                                   grad_scale, step, _stream()), "corrif_adam_step")
+    _count()

@@ -1,0 +1,204 @@
+/*
+ * corrif.h - C ABI of libcorrif_b200.so: the sm_100a kernels of CorrIFNet's fusion hot path.
+ *
+ * The reference (iremulku/CorrIFNet) has no FFI or operator-plugin interface: its seam is
+ * Python.  Each entry point below therefore names the reference lines it
+ * replaces; the Python host layer (corrif_b200.ops / dropin/) binds them with ctypes and
+ * registers them as torch custom ops, which is what a maintainer of the reference would call
+ * (INTEGRATION.md).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless stated otherwise; the caller owns all
+ *     memory (no allocation, no global state besides a per-thread last-error string);
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream ordered, no host sync;
+ *   - return 0 on success, a negative CORRIF_E* for argument errors, or a positive cudaError_t;
+ *   - "tokens" are row-major [rows, C] fp32 with token s = d*64 + h*8 + w (mmvit4.py:458-461).
+ */
+#ifndef CORRIF_H_
+#define CORRIF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CORRIF_ABI_VERSION 1
+
+#define CORRIF_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
+#define CORRIF_EARCH  (-2)  /* device is not sm_100 */
+#define CORRIF_EDRIVER (-3) /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+
+int corrif_abi_version(void);
+/* Last error message of the calling thread ("" if none). */
+const char* corrif_last_error(void);
+/* 0 if the current device can run the kernels (compute capability 10.x). */
+int corrif_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * GEMM  D = epilogue(alpha * A . B^T)   A: logical [M,K], B: logical [N,K], D: [M,N] row-major.
+ * Replaces every nn.Linear / 1x1x1 Conv3d / bmm on the path: mmvit4.py:307,309,312,313 (attention),
+ * :351,354 (FeedForward), :398-402 (encode convs), :417-419 (qkv convs), :426 (decode conv) and
+ * their autograd backward (dgrad, wgrad).
+ *
+ * Operand storage:  *_mn_major == 0 : element (r,k) at ptr[r*ld + k]   (K-major, "row . row")
+ *                   *_mn_major == 1 : element (r,k) at ptr[k*ld + r]   (MN-major, transposed)
+ * Batching: grid of batch_outer x batch_inner problems; problem (bo,bi) uses
+ *   A + bo*a_bo + bi*a_bi (element offsets), likewise B and D, aux, residual.
+ * split_k > 1 splits the contraction across CTAs and REQUIRES epilogue CORRIF_EPI_ATOMIC_ADD
+ *   (D += alpha*A.B^T with red.global.add; used for weight gradients, which also gives gradient
+ *   accumulation across micro-batches).
+ * precision: CORRIF_GEMM_TF32 = tcgen05.mma kind::tf32 (fp32 operands read as TF32, fp32
+ *   accumulate in TMEM); CORRIF_GEMM_FP32 = CUDA-core FFMA (exact-fp32 checking mode).
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  CORRIF_EPI_STORE = 0,       /* D = v                                     */
+  CORRIF_EPI_BIAS = 1,        /* D = v + bias[n]                            */
+  CORRIF_EPI_BIAS_GELU = 2,   /* aux = v + bias[n]; D = gelu_erf(aux)   (mmvit4.py:345,351-352) */
+  CORRIF_EPI_BIAS_RESIDUAL = 3, /* D = v + bias[n] + residual[m,n]       (mmvit4.py:322)        */
+  CORRIF_EPI_MUL_DGELU = 4,   /* D = v * gelu_erf'(aux[m,n])            (backward of :345)     */
+  CORRIF_EPI_ATOMIC_ADD = 5   /* D += v  (atomic)                                            */
+};
+enum { CORRIF_GEMM_TF32 = 0, CORRIF_GEMM_FP32 = 1 };
+
+typedef struct corrif_gemm_desc {
+  const float* A; const float* B; float* D;
+  const float* bias;       /* [N] or NULL                                      */
+  const float* residual;   /* [M,N] with ldr, or NULL                          */
+  float* aux;              /* [M,N] with ldaux: written by BIAS_GELU, read by MUL_DGELU */
+  int64_t lda, ldb, ldd, ldr, ldaux;
+  int32_t M, N, K;
+  int32_t a_mn_major, b_mn_major;
+  int32_t batch_outer, batch_inner;         /* >= 1 */
+  int64_t a_bo, a_bi, b_bo, b_bi, d_bo, d_bi; /* element offsets per batch index (D offsets also
+                                                 apply to residual and aux)   */
+  int32_t split_k;                          /* >= 1 */
+  int32_t epilogue;
+  int32_t precision;
+  float alpha;
+} corrif_gemm_desc;
+
+int corrif_gemm(const corrif_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout: batched 2-D transpose  in [batch, rows, cols] -> out [batch, cols, rows].
+ * Replaces .permute(0,2,3,4,1).contiguous() / .permute(0,4,1,2,3).contiguous()
+ * (mmvit4.py:459-461, 474-475, 499-501, 511-513, 526-528).
+ * ------------------------------------------------------------------------------------------ */
+int corrif_transpose(const float* in, float* out, int64_t batch, int32_t rows, int32_t cols,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (C == 512, eps 1e-5, affine) with the positional add fused:
+ *   x1 = x + pos[row % pos_rows]      (mmvit4.py:385; pos == NULL: x1 = x, x1_out may be NULL)
+ *   y  = LN(x1) * gamma + beta         (mmvit4.py:327-339)
+ * mean / rstd [rows] are saved for the backward.
+ * ------------------------------------------------------------------------------------------ */
+int corrif_layernorm_fwd(const float* x, const float* pos, int64_t pos_rows, const float* gamma,
+                         const float* beta, float* x1_out, float* y, float* mean, float* rstd,
+                         int64_t rows, int32_t C, void* stream);
+/* dx = LN'(dy) (+ dres if not NULL).  dgamma/dbeta [C] are OVERWRITTEN.  `scratch` must hold
+ * corrif_layernorm_bwd_scratch_floats(rows, C) floats. */
+int64_t corrif_layernorm_bwd_scratch_floats(int64_t rows, int32_t C);
+int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, const float* mean,
+                         const float* rstd, const float* dres, float* dx, float* dgamma,
+                         float* dbeta, float* scratch, int64_t rows, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row softmax in place, for the materialised attention path: P = softmax(S) over `cols`
+ * (mmvit4.py:310; the 0.125 scale of :309 is folded into the producing GEMM's alpha), with the
+ * optional attention dropout of :311: when p_drop > 0 the dropped-and-rescaled probabilities
+ * (Philox keyed by seed/site/element index, scaled 1/(1-p)) are written to Pdrop, while S keeps
+ * the un-dropped P that the backward needs.
+ * Backward in place on dP:  dS = P * (dP*keep/(1-p) - sum_j(dP*keep/(1-p)*P)) * scale.
+ * ------------------------------------------------------------------------------------------ */
+int corrif_softmax_fwd(float* S, float* Pdrop, int64_t rows, int32_t cols, float p_drop,
+                       uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream);
+int corrif_softmax_bwd(const float* P, float* dP, int64_t rows, int32_t cols, float scale,
+                       float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dropout  out = x * keep(seed, site, index) / (1-p)   (nn.Dropout sites mmvit4.py:311,314,339,
+ * 353,355).  Counter based (Philox4x32-10): the same call on a gradient is the backward.
+ * In place allowed.  corrif_dropout_mask writes the 0/1 keep mask itself (for tests).
+ * corrif_dropout_add: out = x * keep_a * keep_b / (1-p)^2 + res  - the two stacked dropouts of the
+ *   attention branch (proj_drop :314 then PreNormDrop.dropout :339) and the residual add (:322) in
+ *   one pass; site_b == CORRIF_NO_SITE applies one mask only (FeedForward output, :355 + :322).
+ * Effective seed = seed + (seed_dev ? *seed_dev : 0): a device-resident step counter lets a
+ *   captured CUDA graph draw fresh masks on every replay.
+ * ------------------------------------------------------------------------------------------ */
+#define CORRIF_NO_SITE 0xFFFFFFFFu
+int corrif_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed,
+                   const uint64_t* seed_dev, uint32_t site, void* stream);
+int corrif_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev,
+                        uint32_t site, void* stream);
+int corrif_dropout_add(const float* x, const float* res, float* out, int64_t n, float p,
+                       uint64_t seed, const uint64_t* seed_dev, uint32_t site_a, uint32_t site_b,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Reductions used by the backward:
+ *   colsum:   out[c] (+)= sum_r x[r*ld + c]          bias gradients
+ *   batchsum: out[i] (+)= sum_b x[b*stride + i]      positional-embedding gradients
+ *   add:      out[i] = a[i] + b[i]
+ * `scratch` for colsum must hold corrif_colsum_scratch_floats(rows, cols) floats.
+ * ------------------------------------------------------------------------------------------ */
+int64_t corrif_colsum_scratch_floats(int64_t rows, int32_t cols);
+int corrif_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out,
+                  int accumulate, float* scratch, void* stream);
+int corrif_batchsum(const float* x, int64_t batch, int64_t stride, int64_t n, float* out,
+                    int accumulate, void* stream);
+/* out[r*ldo + c] = a[r*lda + c] + b[r*ldb + c]   (rows x cols, cols % 4 == 0) */
+int corrif_add_rows(const float* a, int64_t lda, const float* b, int64_t ldb, float* out,
+                    int64_t ldo, int64_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Inter-modal correlation (InterFormer), mmvit4.py:481-507, including the batch-mixing .view of
+ * :485 and the skip add of :505-507, written straight into the
+ * multimodal token buffer (which removes the cats of :515-521):
+ *   qkv   [M, B, S, 3C]  q = cols [0,C), k = [C,2C), v = [2C,3C)   (outputs of the qkv_* convs)
+ *   skip  [M, B, S, C]   pre-transformer tokens (mmvit4.py:462)
+ *   tokens[B, (M+1)*S, C] rows X*S+s receive skip_X + sum_i A_X[m,b] * v_i[b'],
+ *                          (m,b) = divmod(M*b'+i, B), A_X[:,b] = softmax_m(q_X[b]*k_m[b]/sqrt(M)).
+ * Backward: g = dL/dtokens (same layout) -> dqkv [M,B,S,3C] (overwritten).  dskip_X = g_X.
+ * M must be 3.
+ * ------------------------------------------------------------------------------------------ */
+int corrif_inter_corr_fwd(const float* qkv, const float* skip, float* tokens, int32_t M,
+                          int32_t B, int32_t S, int32_t C, void* stream);
+int corrif_inter_corr_bwd(const float* qkv, const float* g_tokens, float* dqkv, int32_t M,
+                          int32_t B, int32_t S, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Jaccard family, F5_JACCARD2.py:4-36 / F5_JACCARD.py:4-9.
+ * corrif_jaccard_sums: one pass over y, y_pred [P] fp32 producing, in double, sums[0..3] =
+ *   sum(y), sum(y_pred), sum(y*y_pred), P.  From these (all exact integers for {0,1} inputs)
+ *   TP = s2, "FP" = s0 - s2, "FN" = s1 - s2, and for the empty-mask inversion of :12-14
+ *   TP' = P - s1, "FP'" = s1, "FN'" = 0 - resolved on device by corrif_jaccard_finish, which
+ *   writes out[0] = Jaccard, out[1] = Jaccard2, out[2] = JaccardAndF1 (fp32 arithmetic as :19,
+ *   :33-35) without a host sync.  sums must be zeroed by the caller (or accumulate over calls).
+ * corrif_confusion_counts: K x K integer confusion matrix (rows label, cols pred) of uint8 class
+ *   maps, shared-memory privatised; counts [K*K] uint64 accumulate (caller zeroes).
+ * ------------------------------------------------------------------------------------------ */
+int corrif_jaccard_sums(const float* y, const float* y_pred, int64_t P, double* sums,
+                        void* stream);
+int corrif_jaccard_finish(const double* sums, float epsilon, float* out3, void* stream);
+int corrif_confusion_counts(const uint8_t* label, const uint8_t* pred, int64_t P,
+                            int32_t num_classes, unsigned long long* counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Train-step tail, F4_TRAIN.py:58-62: BCEWithLogitsLoss applied to the sigmoid output, and Adam.
+ *   bce_probs_fwd_bwd: loss_sum (double, accumulates; caller zeroes) += sum softplus(x) - x*y;
+ *                      dx = (sigmoid(x) - y) * grad_scale      (grad_scale = 1/numel)
+ *   adam_step: torch.optim.Adam defaults (F2_MAIN.py:168-169), in place on p, m, v.
+ * ------------------------------------------------------------------------------------------ */
+int corrif_bce_probs_fwd_bwd(const float* x, const float* y, int64_t n, float grad_scale,
+                             double* loss_sum, float* dx, void* stream);
+int corrif_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float grad_scale, int32_t step,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORRIF_H_ */
