@@ -30,11 +30,13 @@ class GemmDesc(C.Structure):
         ("batch_outer", i32), ("batch_inner", i32),
         ("a_bo", i64), ("a_bi", i64), ("b_bo", i64), ("b_bi", i64), ("d_bo", i64), ("d_bi", i64),
         ("split_k", i32), ("epilogue", i32), ("precision", i32), ("alpha", f32),
+        ("flags", i32), ("reserved_", i32),
     ]
 
 
 EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_MUL_DGELU, EPI_ATOMIC_ADD = range(6)
 GEMM_TF32, GEMM_FP32 = 0, 1
+GEMM_ROUND_TF32 = 1
 NO_SITE = 0xFFFFFFFF
 
 # name -> (restype, argtypes); must list every symbol of include/corrif.h (tests check this)
@@ -43,11 +45,12 @@ PROTOTYPES = {
     "corrif_last_error": (C.c_char_p, []),
     "corrif_check_device": (C.c_int, []),
     "corrif_gemm": (C.c_int, [C.POINTER(GemmDesc), stream_t]),
-    "corrif_transpose": (C.c_int, [f32p, f32p, i64, i32, i32, stream_t]),
-    "corrif_layernorm_fwd": (C.c_int, [f32p, f32p, i64, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, stream_t]),
+    "corrif_transpose": (C.c_int, [f32p, f32p, i64, i32, i32, i32, stream_t]),
+    "corrif_round_tf32": (C.c_int, [f32p, f32p, i64, stream_t]),
+    "corrif_layernorm_fwd": (C.c_int, [f32p, f32p, i64, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, i32, stream_t]),
     "corrif_layernorm_bwd_scratch_floats": (i64, [i64, i32]),
     "corrif_layernorm_bwd": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, stream_t]),
-    "corrif_softmax_fwd": (C.c_int, [f32p, f32p, i64, i32, f32, u64, u64p, u32, stream_t]),
+    "corrif_softmax_fwd": (C.c_int, [f32p, f32p, i64, i32, f32, u64, u64p, u32, i32, stream_t]),
     "corrif_softmax_bwd": (C.c_int, [f32p, f32p, i64, i32, f32, f32, u64, u64p, u32, stream_t]),
     "corrif_dropout": (C.c_int, [f32p, f32p, i64, f32, u64, u64p, u32, stream_t]),
     "corrif_dropout_mask": (C.c_int, [f32p, i64, f32, u64, u64p, u32, stream_t]),

@@ -9,7 +9,7 @@ namespace corrif {
 // batched transpose   in [batch, rows, cols] -> out [batch, cols, rows]
 // ============================================================================================
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows,
-                                 int cols) {
+                                 int cols, int round) {
   __shared__ float tile[32][33];
   const int64_t b = blockIdx.z;
   const float* src = in + b * (int64_t)rows * cols;
@@ -24,7 +24,10 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 #pragma unroll
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) dst[(int64_t)c * rows + r] = tile[threadIdx.x][i];
+    if (r < rows && c < cols) {
+      const float v = tile[threadIdx.x][i];
+      dst[(int64_t)c * rows + r] = round ? round_tf32(v) : v;
+    }
   }
 }
 
@@ -38,7 +41,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos, int64_t pos_rows,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      float* __restrict__ x1_out, float* __restrict__ y, float* __restrict__ mean,
-                     float* __restrict__ rstd, int64_t rows) {
+                     float* __restrict__ rstd, int64_t rows, int round) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -78,6 +81,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos,
     o.y = (v[j].y - mu) * rs * g.y + b.y;
     o.z = (v[j].z - mu) * rs * g.z + b.z;
     o.w = (v[j].w - mu) * rs * g.w + b.w;
+    if (round) o = round_tf32_4(o);
     st4(y + row * LN_C + lane * 4 + j * 128, o);
   }
 }
@@ -168,7 +172,7 @@ template <int NV>  // float4 per lane capacity; cols = 128 * nv, nv <= NV
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(float* __restrict__ S, float* __restrict__ Pd, int64_t rows, int cols, int nv,
                    uint32_t thresh, float keep_scale, uint64_t seed, const uint64_t* seed_dev,
-                   uint32_t site) {
+                   uint32_t site, int round) {
   if (seed_dev != nullptr) seed += *seed_dev;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -196,13 +200,15 @@ softmax_fwd_kernel(float* __restrict__ S, float* __restrict__ Pd, int64_t rows, 
   for (int j = 0; j < NV; ++j)
     if (j < nv) {
       v[j].x *= inv; v[j].y *= inv; v[j].z *= inv; v[j].w *= inv;
+      if (round) v[j] = round_tf32_4(v[j]);
       st4(sr + lane * 4 + j * 128, v[j]);
       if (Pd != nullptr) {
         float m[4];
         const uint64_t e = (uint64_t)row * cols + lane * 4 + j * 128;
         dropout_keep4(seed, site, e >> 2, thresh, keep_scale, m);
-        st4(Pd + row * cols + lane * 4 + j * 128,
-            make_float4(v[j].x * m[0], v[j].y * m[1], v[j].z * m[2], v[j].w * m[3]));
+        float4 pd = make_float4(v[j].x * m[0], v[j].y * m[1], v[j].z * m[2], v[j].w * m[3]);
+        if (round) pd = round_tf32_4(pd);
+        st4(Pd + row * cols + lane * 4 + j * 128, pd);
       }
     }
 }
@@ -256,6 +262,12 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
     float4 v = mask_only ? make_float4(1.f, 1.f, 1.f, 1.f) : ld4(x + q * 4);
     st4(out + q * 4, make_float4(v.x * m[0], v.y * m[1], v.z * m[2], v.w * m[3]));
   }
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t nquads) {
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads;
+       q += (int64_t)gridDim.x * blockDim.x)
+    st4(out + q * 4, round_tf32_4(ld4(x + q * 4)));
 }
 
 __global__ void dropout_add_kernel(const float* __restrict__ x, const float* __restrict__ res,
@@ -380,23 +392,29 @@ using namespace corrif;
 
 extern "C" {
 
+int corrif_round_tf32(const float* in, float* out, int64_t n, void* stream) {
+  CORRIF_REQUIRE(in && out && n > 0 && n % 4 == 0, "round_tf32: n must be a positive multiple of 4");
+  round_tf32_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n / 4);
+  return launch_status("round_tf32");
+}
+
 int corrif_transpose(const float* in, float* out, int64_t batch, int32_t rows, int32_t cols,
-                     void* stream) {
+                     int32_t round_tf32, void* stream) {
   CORRIF_REQUIRE(in && out && batch > 0 && rows > 0 && cols > 0, "transpose: bad arguments");
   CORRIF_REQUIRE(batch <= 65535, "transpose: batch %lld > 65535", (long long)batch);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, (unsigned)batch), block(32, 8);
-  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, rows, cols);
+  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, rows, cols, round_tf32);
   return launch_status("transpose");
 }
 
 int corrif_layernorm_fwd(const float* x, const float* pos, int64_t pos_rows, const float* gamma,
                          const float* beta, float* x1_out, float* y, float* mean, float* rstd,
-                         int64_t rows, int32_t C, void* stream) {
+                         int64_t rows, int32_t C, int32_t round_tf32, void* stream) {
   CORRIF_REQUIRE(C == LN_C, "layernorm: C must be 512, got %d", C);
   CORRIF_REQUIRE(x && gamma && beta && y && mean && rstd && rows > 0, "layernorm_fwd: null/empty");
   CORRIF_REQUIRE(pos == nullptr || pos_rows > 0, "layernorm_fwd: pos_rows");
   layernorm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      x, pos, pos_rows, gamma, beta, x1_out, y, mean, rstd, rows);
+      x, pos, pos_rows, gamma, beta, x1_out, y, mean, rstd, rows, round_tf32);
   return launch_status("layernorm_fwd");
 }
 
@@ -424,7 +442,8 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
 }
 
 int corrif_softmax_fwd(float* S, float* Pdrop, int64_t rows, int32_t cols, float p_drop,
-                       uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream) {
+                       uint64_t seed, const uint64_t* seed_dev, uint32_t site, int32_t round_tf32,
+                       void* stream) {
   CORRIF_REQUIRE(S && rows > 0 && cols > 0 && cols % 128 == 0 && cols <= 4096,
                  "softmax_fwd: cols must be a multiple of 128 and <= 4096 (got %d)", cols);
   CORRIF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "softmax_fwd: p_drop");
@@ -434,9 +453,9 @@ int corrif_softmax_fwd(float* S, float* Pdrop, int64_t rows, int32_t cols, float
   const float ks = 1.0f / (1.0f - p_drop);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (nv <= 4) softmax_fwd_kernel<4><<<grid, 256, 0, st>>>(S, Pdrop, rows, cols, nv, th, ks, seed, seed_dev, site);
-  else if (nv <= 16) softmax_fwd_kernel<16><<<grid, 256, 0, st>>>(S, Pdrop, rows, cols, nv, th, ks, seed, seed_dev, site);
-  else softmax_fwd_kernel<32><<<grid, 256, 0, st>>>(S, Pdrop, rows, cols, nv, th, ks, seed, seed_dev, site);
+  if (nv <= 4) softmax_fwd_kernel<4><<<grid, 256, 0, st>>>(S, Pdrop, rows, cols, nv, th, ks, seed, seed_dev, site, round_tf32);
+  else if (nv <= 16) softmax_fwd_kernel<16><<<grid, 256, 0, st>>>(S, Pdrop, rows, cols, nv, th, ks, seed, seed_dev, site, round_tf32);
+  else softmax_fwd_kernel<32><<<grid, 256, 0, st>>>(S, Pdrop, rows, cols, nv, th, ks, seed, seed_dev, site, round_tf32);
   return launch_status("softmax_fwd");
 }
 

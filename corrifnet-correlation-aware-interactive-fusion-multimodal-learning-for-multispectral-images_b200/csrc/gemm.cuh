@@ -14,6 +14,7 @@ struct EpiArgs {
   int M, N;
   int mode;
   float alpha;
+  bool round_tf32;   // round D to TF32 (nearest) because its only consumers are tensor-core GEMMs
 };
 
 // Epilogue on 4 consecutive columns [n, n+4) of row m (n % 4 == 0, all leading dims % 4 == 0).
@@ -22,35 +23,37 @@ __device__ __forceinline__ void epilogue_store4(const EpiArgs& e, int m, int n, 
   float* d = e.D + (int64_t)m * e.ldd + n;
   switch (e.mode) {
     case CORRIF_EPI_STORE:
-      st4(d, v);
       break;
     case CORRIF_EPI_BIAS: {
       const float4 b = ld4(e.bias + n);
-      st4(d, make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w));
+      v = make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
     } break;
     case CORRIF_EPI_BIAS_GELU: {
       const float4 b = ld4(e.bias + n);
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
       st4(e.aux + (int64_t)m * e.ldaux + n, v);
-      st4(d, make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w)));
+      v = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
     } break;
     case CORRIF_EPI_BIAS_RESIDUAL: {
       const float4 b = ld4(e.bias + n);
       const float4 r = ld4(e.residual + (int64_t)m * e.ldr + n);
-      st4(d, make_float4(v.x + b.x + r.x, v.y + b.y + r.y, v.z + b.z + r.z, v.w + b.w + r.w));
+      v = make_float4(v.x + b.x + r.x, v.y + b.y + r.y, v.z + b.z + r.z, v.w + b.w + r.w);
     } break;
     case CORRIF_EPI_MUL_DGELU: {
       const float4 u = ld4(e.aux + (int64_t)m * e.ldaux + n);
-      st4(d, make_float4(v.x * dgelu_erf(u.x), v.y * dgelu_erf(u.y), v.z * dgelu_erf(u.z),
-                         v.w * dgelu_erf(u.w)));
+      v = make_float4(v.x * dgelu_erf(u.x), v.y * dgelu_erf(u.y), v.z * dgelu_erf(u.z),
+                      v.w * dgelu_erf(u.w));
     } break;
     case CORRIF_EPI_ATOMIC_ADD:
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                    :: "l"(d), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-      break;
+      return;
     default:
       break;
   }
+  if (e.mode == CORRIF_EPI_ATOMIC_ADD) return;
+  if (e.round_tf32) v = round_tf32_4(v);
+  st4(d, v);
 }
 
 int gemm_tf32_launch(const corrif_gemm_desc& g, cudaStream_t stream);

@@ -65,7 +65,8 @@ gemm_fp32_kernel(const float* __restrict__ A, const float* __restrict__ B, int64
 }
 
 int gemm_fp32_launch(const corrif_gemm_desc& g, cudaStream_t stream) {
-  EpiArgs e{g.D, g.bias, g.residual, g.aux, g.ldd, g.ldr, g.ldaux, g.M, g.N, g.epilogue, g.alpha};
+  EpiArgs e{g.D, g.bias, g.residual, g.aux, g.ldd, g.ldr, g.ldaux, g.M, g.N, g.epilogue, g.alpha,
+            (g.flags & CORRIF_GEMM_ROUND_TF32) != 0};
   const int64_t a_rs = g.a_mn_major ? 1 : g.lda, a_ks = g.a_mn_major ? g.lda : 1;
   const int64_t b_rs = g.b_mn_major ? 1 : g.ldb, b_ks = g.b_mn_major ? g.ldb : 1;
   dim3 grid((g.M + FT - 1) / FT, (g.N + FT - 1) / FT, g.batch_outer * g.batch_inner * g.split_k);

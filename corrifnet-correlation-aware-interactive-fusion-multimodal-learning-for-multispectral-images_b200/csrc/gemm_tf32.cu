@@ -88,16 +88,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor (SWIZZLE_128B, sm_100 "version 1").
+// Shared-memory matrix descriptor (sm_100 "version 1").
 //   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
-//   bits [46,48) = 1, bits [61,64) layout type (2 = SWIZZLE_128B).
-//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
-//   MN-major: [k][32 floats] boxes; 8-k groups 1024 B apart (SBO); next 32 MN elements LBO apart.
+//   bits [46,48) = 1, bits [61,64) layout type.
+//   K-major : SWIZZLE_128B (type 2): rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (type 1; 32-B chunks swizzled over
+//             4-row atoms, TMA mode 128B_ATOM_32B): [k][32 floats] boxes, 4-k-row atoms 512 B apart
+//             (SBO), the next 32 MN elements one box (BK*128 B) further (LBO).
 template <bool MN_MAJOR>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   constexpr uint64_t lbo = MN_MAJOR ? (uint64_t)(BK * ROW_BYTES) >> 4 : 1;
-  constexpr uint64_t sbo = 1024 >> 4;
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t sbo = MN_MAJOR ? (512 >> 4) : (1024 >> 4);
+  constexpr uint64_t layout = MN_MAJOR ? 1ull : 2ull;
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
 // Instruction descriptor, kind::tf32, fp32 accumulate:
@@ -267,7 +270,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // 2-D fp32 tensor map over memory [dim1][ld] of which dim0 columns are addressable.
 static int encode_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, int64_t ld,
-                      uint32_t box0, uint32_t box1) {
+                      uint32_t box0, uint32_t box1, bool mn_major) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not found"); return CORRIF_EDRIVER; }
   cuuint64_t dims[2] = {dim0, dim1};
@@ -275,7 +278,8 @@ static int encode_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): base %p dims %llu x %llu ld %lld box %u x %u",
@@ -298,7 +302,8 @@ static int launch_variant(const corrif_gemm_desc& g, const CUtensorMap& ta, cons
     configured = true;
   }
   KernelArgs a;
-  a.epi = EpiArgs{g.D, g.bias, g.residual, g.aux, g.ldd, g.ldr, g.ldaux, g.M, g.N, g.epilogue, g.alpha};
+  a.epi = EpiArgs{g.D, g.bias, g.residual, g.aux, g.ldd, g.ldr, g.ldaux, g.M, g.N, g.epilogue, g.alpha,
+                  (g.flags & CORRIF_GEMM_ROUND_TF32) != 0};
   a.K = g.K; a.batch_inner = g.batch_inner; a.split_k = g.split_k;
   a.a_bo = g.a_bo; a.a_bi = g.a_bi; a.b_bo = g.b_bo; a.b_bi = g.b_bi; a.d_bo = g.d_bo; a.d_bi = g.d_bi;
   a.lda = g.lda; a.ldb = g.ldb;
@@ -335,7 +340,7 @@ int gemm_tf32_launch(const corrif_gemm_desc& g, cudaStream_t stream) {
     const int64_t rows = g.a_mn_major ? g.K : g.M, cols = g.a_mn_major ? g.M : g.K;
     const uint64_t dim0 = batched ? (uint64_t)g.lda : (uint64_t)cols;
     const uint64_t dim1 = (uint64_t)(rows + (batched ? (extra + g.lda - 1) / g.lda : 0));
-    st = encode_map(&ta, g.A, dim0, dim1, g.lda, 32, g.a_mn_major ? BK : BM);
+    st = encode_map(&ta, g.A, dim0, dim1, g.lda, 32, g.a_mn_major ? BK : BM, g.a_mn_major != 0);
     if (st) return st;
   }
   {
@@ -343,7 +348,7 @@ int gemm_tf32_launch(const corrif_gemm_desc& g, cudaStream_t stream) {
     const int64_t rows = g.b_mn_major ? g.K : g.N, cols = g.b_mn_major ? g.N : g.K;
     const uint64_t dim0 = batched ? (uint64_t)g.ldb : (uint64_t)cols;
     const uint64_t dim1 = (uint64_t)(rows + (batched ? (extra + g.ldb - 1) / g.ldb : 0));
-    st = encode_map(&tb, g.B, dim0, dim1, g.ldb, 32, g.b_mn_major ? BK : BN);
+    st = encode_map(&tb, g.B, dim0, dim1, g.ldb, 32, g.b_mn_major ? BK : BN, g.b_mn_major != 0);
     if (st) return st;
   }
   if (BN == 64) return launch_bn<64, 4>(g, ta, tb, stream);

@@ -106,6 +106,18 @@ class FusionBlockEngine:
         self.seed = 0
         self.seed_dev: Optional[torch.Tensor] = None   # int64[1] device step counter (graph replay)
         self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        # The tensor core truncates fp32 operands to TF32; GEMM-only tensors are therefore rounded to
+        # nearest where they are produced, and matrix weights get rounded copies (refreshed each
+        # forward, 41 MB).  In fp32 checking mode nothing is rounded.
+        self.rnd = self.prec == GEMM_TF32
+        self.wnames = [k for k in param_names()
+                       if k.endswith(".weight") and "norm" not in k]
+        self.pw = {k: (torch.empty_like(params[k]) if self.rnd else params[k]) for k in self.wnames}
+
+    def refresh_weights(self):
+        if self.rnd:
+            for k in self.wnames:
+                ops.round_tf32(self.p[k], self.pw[k], self.p[k].numel())
 
     # ------------------------------------------------------------------------------------------
     def workspace(self, B: int) -> dict:
@@ -160,11 +172,12 @@ class FusionBlockEngine:
                    batch=(B, HEADS), a_step=(N * 3 * C, HD), b_step=(N * 3 * C, HD),
                    d_step=(HEADS * N * N, N * N), alpha=HD ** -0.5)
         pd = tb.dP if p > 0 else None
-        ops.softmax_fwd(tb.P, pd, B * HEADS * N, N, p, self.seed, self.seed_dev, self._site(t, SITE_ATTN))
+        ops.softmax_fwd(tb.P, pd, B * HEADS * N, N, p, self.seed, self.seed_dev, self._site(t, SITE_ATTN),
+                        round_out=self.rnd)
         # O[b, n, h*64+d] = P V : V is read MN-major straight out of qkv
         self._gemm(pd if p > 0 else tb.P, (tb.qkv, 2 * C), tb.O, M=N, N=HD, K=N, lda=N, ldb=3 * C,
                    ldd=C, b_mn=True, batch=(B, HEADS), a_step=(HEADS * N * N, N * N),
-                   b_step=(N * 3 * C, HD), d_step=(N * C, HD))
+                   b_step=(N * 3 * C, HD), d_step=(N * C, HD), round_out=self.rnd)
 
     def _attention_bwd(self, t: int, tb: _TBuf, dO: torch.Tensor):
         B, N = tb.B, tb.N
@@ -195,27 +208,27 @@ class FusionBlockEngine:
         """Transformer.forward, mmvit4.py:383-388 (depth 1)."""
         k, P_, R, p = self.tk[t], self.p, tb.R, self.dropout_p
         ops.layernorm_fwd(x_in, pos, pos_rows, P_[k["ln1_w"]], P_[k["ln1_b"]], tb.x1, tb.h,
-                          tb.mean1, tb.rstd1, R)
-        self._linear(tb.h, P_[k["qkv_w"]], tb.qkv, R, 3 * C, C)
+                          tb.mean1, tb.rstd1, R, round_out=self.rnd)
+        self._linear(tb.h, self.pw[k["qkv_w"]], tb.qkv, R, 3 * C, C, round_out=self.rnd)
         self._attention_fwd(t, tb)
         if p == 0:
-            self._linear(tb.O, P_[k["proj_w"]], tb.x2, R, C, C, bias=P_[k["proj_b"]],
+            self._linear(tb.O, self.pw[k["proj_w"]], tb.x2, R, C, C, bias=P_[k["proj_b"]],
                          epilogue=EPI_BIAS_RESIDUAL, residual=tb.x1, ldr=C)
         else:
-            self._linear(tb.O, P_[k["proj_w"]], tb.t0, R, C, C, bias=P_[k["proj_b"]], epilogue=EPI_BIAS)
+            self._linear(tb.O, self.pw[k["proj_w"]], tb.t0, R, C, C, bias=P_[k["proj_b"]], epilogue=EPI_BIAS)
             ops.dropout_add(tb.t0, tb.x1, tb.x2, R * C, p, self.seed, self._site(t, SITE_PROJ),
                             self._site(t, SITE_PRENORM), self.seed_dev)
         ops.layernorm_fwd(tb.x2, None, 1, P_[k["ln2_w"]], P_[k["ln2_b"]], None, tb.h2, tb.mean2,
-                          tb.rstd2, R)
-        self._linear(tb.h2, P_[k["fc1_w"]], tb.f1, R, C, C, bias=P_[k["fc1_b"]],
-                     epilogue=EPI_BIAS_GELU, aux=tb.u, ldaux=C)
+                          tb.rstd2, R, round_out=self.rnd)
+        self._linear(tb.h2, self.pw[k["fc1_w"]], tb.f1, R, C, C, bias=P_[k["fc1_b"]],
+                     epilogue=EPI_BIAS_GELU, aux=tb.u, ldaux=C, round_out=self.rnd)
         if p > 0:
             ops.dropout(tb.f1, tb.f1, R * C, p, self.seed, self._site(t, SITE_FFN1), self.seed_dev)
         if p == 0:
-            self._linear(tb.f1, P_[k["fc2_w"]], tb.x3, R, C, C, bias=P_[k["fc2_b"]],
-                         epilogue=EPI_BIAS_RESIDUAL, residual=tb.x2, ldr=C)
+            self._linear(tb.f1, self.pw[k["fc2_w"]], tb.x3, R, C, C, bias=P_[k["fc2_b"]],
+                         epilogue=EPI_BIAS_RESIDUAL, residual=tb.x2, ldr=C, round_out=self.rnd)
         else:
-            self._linear(tb.f1, P_[k["fc2_w"]], tb.t0, R, C, C, bias=P_[k["fc2_b"]], epilogue=EPI_BIAS)
+            self._linear(tb.f1, self.pw[k["fc2_w"]], tb.t0, R, C, C, bias=P_[k["fc2_b"]], epilogue=EPI_BIAS)
             ops.dropout_add(tb.t0, tb.x2, tb.x3, R * C, p, self.seed, self._site(t, SITE_FFN2),
                             NO_SITE, self.seed_dev)
         return tb.x3
@@ -233,12 +246,12 @@ class FusionBlockEngine:
             df2 = tb.t0
         self._wgrad(df2, tb.f1, g[k["fc2_w"]], R, C, C)
         ops.colsum(df2, C, R, C, g[k["fc2_b"]], scratch)
-        self._dgrad(df2, P_[k["fc2_w"]], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C)
+        self._dgrad(df2, self.pw[k["fc2_w"]], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C)
         if p > 0:
             ops.dropout(tb.t1, tb.t1, R * C, p, self.seed, self._site(t, SITE_FFN1), self.seed_dev)
         self._wgrad(tb.t1, tb.h2, g[k["fc1_w"]], R, C, C)
         ops.colsum(tb.t1, C, R, C, g[k["fc1_b"]], scratch)
-        self._dgrad(tb.t1, P_[k["fc1_w"]], tb.t2, R, C, C)                    # d(h2)
+        self._dgrad(tb.t1, self.pw[k["fc1_w"]], tb.t2, R, C, C)                    # d(h2)
         ops.layernorm_bwd(tb.t2, tb.x2, P_[k["ln2_w"]], tb.mean2, tb.rstd2, dx3, tb.t1,
                           g[k["ln2_w"]], g[k["ln2_b"]], scratch, R)           # t1 = d(x2)
         dx2 = tb.t1
@@ -250,10 +263,10 @@ class FusionBlockEngine:
             dy = tb.t0
         self._wgrad(dy, tb.O, g[k["proj_w"]], R, C, C)
         ops.colsum(dy, C, R, C, g[k["proj_b"]], scratch)
-        self._dgrad(dy, P_[k["proj_w"]], tb.t2, R, C, C)                      # d(O)
+        self._dgrad(dy, self.pw[k["proj_w"]], tb.t2, R, C, C)                      # d(O)
         self._attention_bwd(t, tb, tb.t2)
         self._wgrad(tb.dqkv, tb.h, g[k["qkv_w"]], R, 3 * C, C)
-        self._dgrad(tb.dqkv, P_[k["qkv_w"]], tb.t2, R, 3 * C, C)              # d(h)
+        self._dgrad(tb.dqkv, self.pw[k["qkv_w"]], tb.t2, R, 3 * C, C)              # d(h)
         ops.layernorm_bwd(tb.t2, tb.x1, P_[k["ln1_w"]], tb.mean1, tb.rstd1, dx2, tb.t0,
                           g[k["ln1_w"]], g[k["ln1_b"]], scratch, R)           # t0 = d(x1)
         return tb.t0
@@ -265,16 +278,18 @@ class FusionBlockEngine:
         B = fused_x6.shape[0]
         ws, P_ = self.workspace(B), self.p
         self._B = B
+        self.refresh_weights()
+        W = self.pw
         for X, m in enumerate(MODALITIES):
-            ops.transpose(x6[X], ws["x6tok"][X], B, ENC, S)                                # :459
-            self._linear(ws["x6tok"][X], P_[f"{m}_encode_conv.weight"], ws["skip"][X], B * S, C, ENC,
+            ops.transpose(x6[X], ws["x6tok"][X], B, ENC, S, round_out=self.rnd)            # :459
+            self._linear(ws["x6tok"][X], W[f"{m}_encode_conv.weight"], ws["skip"][X], B * S, C, ENC,
                          bias=P_[f"{m}_encode_conv.bias"], epilogue=EPI_BIAS)              # :458
             x3 = self._transformer_fwd(X, ws["skip"][X], P_[f"{m}_pos"], S, ws["tb"][X])   # :462
-            self._linear(x3, P_[f"qkv_{m}.weight"], ws["qkvi"][X], B * S, 3 * C, C,
+            self._linear(x3, W[f"qkv_{m}.weight"], ws["qkvi"][X], B * S, 3 * C, C,
                          bias=P_[f"qkv_{m}.bias"], epilogue=EPI_BIAS)                      # :477-479
         ops.inter_corr_fwd(ws["qkvi"], ws["skip"], ws["tokens"], NM, B, S, C)              # :481-507
-        ops.transpose(fused_x6, ws["fx6tok"], B, ENC * NM, S)
-        self._gemm(ws["fx6tok"], P_["fused6_encode_conv.weight"], (ws["tokens"], NM * S * C),
+        ops.transpose(fused_x6, ws["fx6tok"], B, ENC * NM, S, round_out=self.rnd)
+        self._gemm(ws["fx6tok"], W["fused6_encode_conv.weight"], (ws["tokens"], NM * S * C),
                    M=S, N=C, K=ENC * NM, lda=ENC * NM, ldb=ENC * NM, ldd=C,
                    bias=P_["fused6_encode_conv.bias"], epilogue=EPI_BIAS, batch=(B, 1),
                    a_step=(S * ENC * NM, 0), d_step=((NM + 1) * S * C, 0))                 # :510-513
@@ -282,7 +297,7 @@ class FusionBlockEngine:
             ws["posmm"][X * S:(X + 1) * S].copy_(P_[f"{m}_pos"][0])                        # :516,521
         tbm = ws["tb"][NM]
         x3 = self._transformer_fwd(NM, ws["tokens"], ws["posmm"], (NM + 1) * S, tbm)       # :519-522
-        self._linear(x3, P_["multimodal_decode_conv.weight"], ws["ytok"], B * S, ENC * NM,
+        self._linear(x3, W["multimodal_decode_conv.weight"], ws["ytok"], B * S, ENC * NM,
                      (NM + 1) * C, bias=P_["multimodal_decode_conv.bias"], epilogue=EPI_BIAS)  # :525
         ops.transpose(ws["ytok"], ws["out"], B, S, ENC * NM)                               # :527-528
         return ws["out"].view(B, ENC * NM, 8, 8, 8)
@@ -297,11 +312,11 @@ class FusionBlockEngine:
         g, sc = grads, ws["scratch"]
         R = B * S
         # ---- decode conv
-        ops.transpose(gout, ws["dytok"], B, ENC * NM, S)
+        ops.transpose(gout, ws["dytok"], B, ENC * NM, S, round_out=self.rnd)
         tbm = ws["tb"][NM]
         self._wgrad(ws["dytok"], tbm.x3, g["multimodal_decode_conv.weight"], R, ENC * NM, (NM + 1) * C)
         ops.colsum(ws["dytok"], ENC * NM, R, ENC * NM, g["multimodal_decode_conv.bias"], sc, accumulate=True)
-        self._dgrad(ws["dytok"], P_["multimodal_decode_conv.weight"], tbm.din, R, ENC * NM, (NM + 1) * C)
+        self._dgrad(ws["dytok"], self.pw["multimodal_decode_conv.weight"], tbm.din, R, ENC * NM, (NM + 1) * C)
         # ---- multimodal transformer
         gm = {k: torch.zeros_like(P_[k]) for k in self.tk[NM].values() if "norm" in k or k.endswith(".bias")}
         gt = dict(g)
@@ -316,7 +331,7 @@ class FusionBlockEngine:
         df6 = ws["dtokc"][NM]
         self._wgrad(df6, ws["fx6tok"], g["fused6_encode_conv.weight"], R, C, ENC * NM)
         ops.colsum(df6, C, R, C, g["fused6_encode_conv.bias"], sc, accumulate=True)
-        self._dgrad(df6, P_["fused6_encode_conv.weight"], ws["dfx6tok"], R, C, ENC * NM)
+        self._dgrad(df6, self.pw["fused6_encode_conv.weight"], ws["dfx6tok"], R, C, ENC * NM)
         ops.transpose(ws["dfx6tok"], ws["dfused"], B, S, ENC * NM)
         g["fused6_pos"] += ws["dposmm"][NM * S:].view(1, S, C)
         # ---- inter-modal correlation
@@ -326,7 +341,7 @@ class FusionBlockEngine:
             dq = ws["dqkvi"][X]
             self._wgrad(dq, tb.x3, g[f"qkv_{m}.weight"], R, 3 * C, C)
             ops.colsum(dq, 3 * C, R, 3 * C, g[f"qkv_{m}.bias"], sc, accumulate=True)
-            self._dgrad(dq, P_[f"qkv_{m}.weight"], tb.din, R, 3 * C, C)         # d(trans_X)
+            self._dgrad(dq, self.pw[f"qkv_{m}.weight"], tb.din, R, 3 * C, C)         # d(trans_X)
             gx = {k: torch.zeros_like(P_[k]) for k in self.tk[X].values() if "norm" in k or k.endswith(".bias")}
             gt = dict(g)
             gt.update(gx)
@@ -338,6 +353,6 @@ class FusionBlockEngine:
             ops.add_rows(dx1, C, ws["dtokc"][X], C, ws["dtok"], C, R, C)        # + skip path (:505)
             self._wgrad(ws["dtok"], ws["x6tok"][X], g[f"{m}_encode_conv.weight"], R, C, ENC)
             ops.colsum(ws["dtok"], C, R, C, g[f"{m}_encode_conv.bias"], sc, accumulate=True)
-            self._dgrad(ws["dtok"], P_[f"{m}_encode_conv.weight"], ws["dx6tok"], R, C, ENC)
+            self._dgrad(ws["dtok"], self.pw[f"{m}_encode_conv.weight"], ws["dx6tok"], R, C, ENC)
             ops.transpose(ws["dx6tok"], ws["dx6"][X], B, S, ENC)
         return (ws["dx6"].view(NM, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * NM, 8, 8, 8), grads)

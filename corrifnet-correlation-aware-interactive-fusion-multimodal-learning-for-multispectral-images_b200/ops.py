@@ -12,7 +12,7 @@ import torch
 
 from . import _lib as L
 from ._lib import (EPI_ATOMIC_ADD, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_MUL_DGELU,  # noqa: F401
-                   EPI_STORE, GEMM_FP32, GEMM_TF32, NO_SITE, CorrifError, GemmDesc)
+                   EPI_STORE, GEMM_FP32, GEMM_ROUND_TF32, GEMM_TF32, NO_SITE, CorrifError, GemmDesc)
 
 TensorOrView = Union[torch.Tensor, Tuple[torch.Tensor, int]]  # (tensor, element offset)
 
@@ -60,7 +60,7 @@ def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K
          ldb: int, ldd: int, a_mn: bool = False, b_mn: bool = False, bias=None, residual=None,
          ldr: int = 0, aux=None, ldaux: int = 0, batch=(1, 1), a_step=(0, 0), b_step=(0, 0),
          d_step=(0, 0), split_k: int = 1, epilogue: int = EPI_STORE, precision: int = GEMM_TF32,
-         alpha: float = 1.0):
+         alpha: float = 1.0, round_out: bool = False):
     """D = epilogue(alpha * A . B^T); see corrif_gemm in include/corrif.h for the layout rules."""
     g = GemmDesc()
     g.A, g.B, g.D = _ptr(A), _ptr(B), _ptr(D)
@@ -73,19 +73,26 @@ def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K
     g.b_bo, g.b_bi = b_step
     g.d_bo, g.d_bi = d_step
     g.split_k, g.epilogue, g.precision, g.alpha = split_k, epilogue, precision, alpha
+    g.flags = GEMM_ROUND_TF32 if round_out else 0
     L.check(lib().corrif_gemm(C.byref(g), _stream()), "corrif_gemm")
     _count()
 
 
-def transpose(x: TensorOrView, out: TensorOrView, batch: int, rows: int, cols: int):
-    L.check(lib().corrif_transpose(_ptr(x), _ptr(out), batch, rows, cols, _stream()), "corrif_transpose")
+def transpose(x: TensorOrView, out: TensorOrView, batch: int, rows: int, cols: int, round_out=False):
+    L.check(lib().corrif_transpose(_ptr(x), _ptr(out), batch, rows, cols, int(round_out), _stream()),
+            "corrif_transpose")
     _count()
 
 
-def layernorm_fwd(x, pos, pos_rows, gamma, beta, x1_out, y, mean, rstd, rows, C_=512):
+def round_tf32(x: TensorOrView, out: TensorOrView, n: int):
+    L.check(lib().corrif_round_tf32(_ptr(x), _ptr(out), n, _stream()), "corrif_round_tf32")
+    _count()
+
+
+def layernorm_fwd(x, pos, pos_rows, gamma, beta, x1_out, y, mean, rstd, rows, C_=512, round_out=False):
     L.check(lib().corrif_layernorm_fwd(_ptr(x), _ptr(pos), pos_rows, _ptr(gamma), _ptr(beta),
                                        _ptr(x1_out), _ptr(y), _ptr(mean), _ptr(rstd), rows, C_,
-                                       _stream()), "corrif_layernorm_fwd")
+                                       int(round_out), _stream()), "corrif_layernorm_fwd")
     _count()
 
 
@@ -104,9 +111,9 @@ def _seed_dev(seed_dev):
     return None if seed_dev is None else _ptr(seed_dev, torch.int64)
 
 
-def softmax_fwd(S, Pdrop, rows, cols, p=0.0, seed=0, seed_dev=None, site=0):
+def softmax_fwd(S, Pdrop, rows, cols, p=0.0, seed=0, seed_dev=None, site=0, round_out=False):
     L.check(lib().corrif_softmax_fwd(_ptr(S), _ptr(Pdrop), rows, cols, p, seed, _seed_dev(seed_dev),
-                                     site, _stream()), "corrif_softmax_fwd")
+                                     site, int(round_out), _stream()), "corrif_softmax_fwd")
     _count()
 
 

@@ -60,6 +60,9 @@ enum {
   CORRIF_EPI_ATOMIC_ADD = 5   /* D += v  (atomic)                                            */
 };
 enum { CORRIF_GEMM_TF32 = 0, CORRIF_GEMM_FP32 = 1 };
+/* flags: round D to TF32 (nearest) at store time.  The tensor core truncates fp32 operands to TF32;
+ * an output that is only consumed by further GEMMs is rounded once here instead. */
+#define CORRIF_GEMM_ROUND_TF32 1
 
 typedef struct corrif_gemm_desc {
   const float* A; const float* B; float* D;
@@ -76,6 +79,8 @@ typedef struct corrif_gemm_desc {
   int32_t epilogue;
   int32_t precision;
   float alpha;
+  int32_t flags;
+  int32_t reserved_;
 } corrif_gemm_desc;
 
 int corrif_gemm(const corrif_gemm_desc* desc, void* stream);
@@ -86,17 +91,19 @@ int corrif_gemm(const corrif_gemm_desc* desc, void* stream);
  * (mmvit4.py:459-461, 474-475, 499-501, 511-513, 526-528).
  * ------------------------------------------------------------------------------------------ */
 int corrif_transpose(const float* in, float* out, int64_t batch, int32_t rows, int32_t cols,
-                     void* stream);
+                     int32_t round_tf32, void* stream);
+/* out = round-to-nearest-TF32(in): makes GEMM-ready copies of weights (in place allowed). */
+int corrif_round_tf32(const float* in, float* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (C == 512, eps 1e-5, affine) with the positional add fused:
  *   x1 = x + pos[row % pos_rows]      (mmvit4.py:385; pos == NULL: x1 = x, x1_out may be NULL)
  *   y  = LN(x1) * gamma + beta         (mmvit4.py:327-339)
- * mean / rstd [rows] are saved for the backward.
+ * mean / rstd [rows] are saved for the backward.  round_tf32 != 0 rounds y (not x1) to TF32.
  * ------------------------------------------------------------------------------------------ */
 int corrif_layernorm_fwd(const float* x, const float* pos, int64_t pos_rows, const float* gamma,
                          const float* beta, float* x1_out, float* y, float* mean, float* rstd,
-                         int64_t rows, int32_t C, void* stream);
+                         int64_t rows, int32_t C, int32_t round_tf32, void* stream);
 /* dx = LN'(dy) (+ dres if not NULL).  dgamma/dbeta [C] are OVERWRITTEN.  `scratch` must hold
  * corrif_layernorm_bwd_scratch_floats(rows, C) floats. */
 int64_t corrif_layernorm_bwd_scratch_floats(int64_t rows, int32_t C);
@@ -113,7 +120,8 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
  * Backward in place on dP:  dS = P * (dP*keep/(1-p) - sum_j(dP*keep/(1-p)*P)) * scale.
  * ------------------------------------------------------------------------------------------ */
 int corrif_softmax_fwd(float* S, float* Pdrop, int64_t rows, int32_t cols, float p_drop,
-                       uint64_t seed, const uint64_t* seed_dev, uint32_t site, void* stream);
+                       uint64_t seed, const uint64_t* seed_dev, uint32_t site, int32_t round_tf32,
+                       void* stream);
 int corrif_softmax_bwd(const float* P, float* dP, int64_t rows, int32_t cols, float scale,
                        float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
                        void* stream);

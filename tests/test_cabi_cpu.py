@@ -45,8 +45,8 @@ def test_ctypes_prototypes_cover_header(lib):
 
 def test_gemm_desc_layout_matches_c_struct():
     from corrif_b200 import _lib
-    # 6 pointers, 5 int64, 7 int32 (+pad), 6 int64, 3 int32 + float
-    assert ctypes.sizeof(_lib.GemmDesc) == 6 * 8 + 5 * 8 + 8 * 4 + 6 * 8 + 4 * 4
+    # 6 pointers, 5 int64, 7 int32 (+pad), 6 int64, 3 int32 + float + flags + reserved
+    assert ctypes.sizeof(_lib.GemmDesc) == 6 * 8 + 5 * 8 + 8 * 4 + 6 * 8 + 6 * 4
     assert _lib.GemmDesc.M.offset == 88 and _lib.GemmDesc.a_bo.offset == 120
     assert _lib.GemmDesc.alpha.offset == 180
 
@@ -55,7 +55,7 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     from corrif_b200 import _lib
     rc = lib.corrif_gemm(None, None)
     assert rc == -1 and b"null descriptor" in lib.corrif_last_error()
-    rc = lib.corrif_layernorm_fwd(1, None, 0, 1, 1, None, 1, 1, 1, 8, 256, None)
+    rc = lib.corrif_layernorm_fwd(1, None, 0, 1, 1, None, 1, 1, 1, 8, 256, 0, None)
     assert rc == -1 and b"C must be 512" in lib.corrif_last_error()
     rc = lib.corrif_inter_corr_fwd(1, 1, 1, 4, 2, 8, 8, None)
     assert rc == -1 and b"M must be 3" in lib.corrif_last_error()

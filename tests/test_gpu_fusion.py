@@ -2,10 +2,13 @@
 reference (tests/golden/make_golden.py) and against the CPU oracle.
 
 Tolerances (relative L2 per tensor, stated per the north-star):
-  precision="fp32" (CUDA-core checking mode): out 2e-5, input grads 5e-5, parameter grads 2e-4
-  precision="tf32" (tcgen05 hot path):        out 3e-3, input grads 1e-2, parameter grads 5e-2
-The TF32 numbers follow SURVEY.md section 7 ("hard parts"): operand rounding to 10 mantissa bits
-gives ~6e-4 on the output and 1e-3..2e-2 on gradients for this block.
+  precision="fp32" (CUDA-core checking mode): out 1e-5, input grads 1e-5, parameter grads 2e-5
+  precision="tf32" (tcgen05 hot path):        out 1e-3, input grads 3e-3, parameter grads 6e-3
+Measured on B200 (round 1): fp32 mode 9.6e-7 / 8.8e-7 / 1.5e-6; tf32 mode 5.5e-4 / 1.2e-3 / 2.4e-3
+(worst tensor: LayerNorm-1 weight and qkv weight gradients of the intra transformers).  The TF32
+numbers agree with SURVEY.md section 7: rounding operands to 10 mantissa bits gives ~6e-4 on the
+output and ~1e-3 on gradients; the north-star's 1e-3 holds for the output, gradients carry the
+per-tensor tolerance stated here.
 """
 import os
 
@@ -21,7 +24,7 @@ if torch.cuda.is_available():
     from corrif_b200 import fusion, module
     from oracle import corrif_oracle as O
 
-TOL = {"fp32": dict(out=2e-5, xgrad=5e-5, pgrad=2e-4), "tf32": dict(out=3e-3, xgrad=1e-2, pgrad=5e-2)}
+TOL = {"fp32": dict(out=1e-5, xgrad=1e-5, pgrad=2e-5), "tf32": dict(out=1e-3, xgrad=3e-3, pgrad=6e-3)}
 
 
 def _sample_idx(n, k=2048):
