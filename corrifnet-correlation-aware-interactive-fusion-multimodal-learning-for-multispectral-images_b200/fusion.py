@@ -147,18 +147,20 @@ class FusionBlockEngine:
 
     def _linear(self, x, w, out, M, N, K, bias=None, epilogue=EPI_STORE, **k):
         """out[M,N] = x[M,K] . w[N,K]^T (+ epilogue)."""
-        self._gemm(x, w, out, M=M, N=N, K=K, lda=K, ldb=K, ldd=N, bias=bias, epilogue=epilogue, **k)
+        self._gemm(x, w, out, M=M, N=N, K=K, lda=K, ldb=K, ldd=N, bias=bias, epilogue=epilogue,
+                   tag="linear", **k)
 
     def _dgrad(self, dy, w, dx, M, N_out, K_in, **k):
         """dx[M,K_in] = dy[M,N_out] . w[N_out,K_in]: w is read MN-major (no transposed copy)."""
-        self._gemm(dy, w, dx, M=M, N=K_in, K=N_out, lda=N_out, ldb=K_in, ldd=K_in, b_mn=True, **k)
+        self._gemm(dy, w, dx, M=M, N=K_in, K=N_out, lda=N_out, ldb=K_in, ldd=K_in, b_mn=True,
+                   tag="dgrad", **k)
 
     def _wgrad(self, dy, x, dw, R, N_out, K_in, ldy=None, ldx=None):
         """dw[N_out,K_in] += dy[R,N_out]^T . x[R,K_in]: both operands MN-major, split-K + atomics."""
         tiles = ((N_out + 127) // 128) * ((K_in + (63 if K_in <= 64 else 127)) // (64 if K_in <= 64 else 128))
         split = _split_for(tiles, R // 32, self.sms)
         self._gemm(dy, x, dw, M=N_out, N=K_in, K=R, lda=ldy or N_out, ldb=ldx or K_in, ldd=K_in,
-                   a_mn=True, b_mn=True, split_k=split, epilogue=EPI_ATOMIC_ADD)
+                   a_mn=True, b_mn=True, split_k=split, epilogue=EPI_ATOMIC_ADD, tag="wgrad")
 
     def _site(self, t: int, kind: int) -> int:
         return t * 8 + kind
@@ -170,19 +172,19 @@ class FusionBlockEngine:
         # S = 0.125 * Q K^T per (batch, head): strided views into qkv, no reshape/permute copies
         self._gemm(tb.qkv, (tb.qkv, C), tb.P, M=N, N=N, K=HD, lda=3 * C, ldb=3 * C, ldd=N,
                    batch=(B, HEADS), a_step=(N * 3 * C, HD), b_step=(N * 3 * C, HD),
-                   d_step=(HEADS * N * N, N * N), alpha=HD ** -0.5)
+                   d_step=(HEADS * N * N, N * N), alpha=HD ** -0.5, tag="attn_qk")
         pd = tb.dP if p > 0 else None
         ops.softmax_fwd(tb.P, pd, B * HEADS * N, N, p, self.seed, self.seed_dev, self._site(t, SITE_ATTN),
                         round_out=self.rnd)
         # O[b, n, h*64+d] = P V : V is read MN-major straight out of qkv
         self._gemm(pd if p > 0 else tb.P, (tb.qkv, 2 * C), tb.O, M=N, N=HD, K=N, lda=N, ldb=3 * C,
                    ldd=C, b_mn=True, batch=(B, HEADS), a_step=(HEADS * N * N, N * N),
-                   b_step=(N * 3 * C, HD), d_step=(N * C, HD), round_out=self.rnd)
+                   b_step=(N * 3 * C, HD), d_step=(N * C, HD), round_out=self.rnd, tag="attn_pv")
 
     def _attention_bwd(self, t: int, tb: _TBuf, dO: torch.Tensor):
         B, N = tb.B, tb.N
         p = self.dropout_p
-        bat = dict(batch=(B, HEADS))
+        bat = dict(batch=(B, HEADS), tag="attn_bwd")
         pstep, qstep, ostep = (HEADS * N * N, N * N), (N * 3 * C, HD), (N * C, HD)
         pd = tb.P
         if p > 0:   # regenerate the dropped probabilities (same Philox counters as the forward)
@@ -291,7 +293,7 @@ class FusionBlockEngine:
         ops.transpose(fused_x6, ws["fx6tok"], B, ENC * NM, S, round_out=self.rnd)
         self._gemm(ws["fx6tok"], W["fused6_encode_conv.weight"], (ws["tokens"], NM * S * C),
                    M=S, N=C, K=ENC * NM, lda=ENC * NM, ldb=ENC * NM, ldd=C,
-                   bias=P_["fused6_encode_conv.bias"], epilogue=EPI_BIAS, batch=(B, 1),
+                   bias=P_["fused6_encode_conv.bias"], epilogue=EPI_BIAS, batch=(B, 1), tag="linear",
                    a_step=(S * ENC * NM, 0), d_step=((NM + 1) * S * C, 0))                 # :510-513
         for X, m in enumerate(MODALITIES + ("fused6",)):
             ws["posmm"][X * S:(X + 1) * S].copy_(P_[f"{m}_pos"][0])                        # :516,521

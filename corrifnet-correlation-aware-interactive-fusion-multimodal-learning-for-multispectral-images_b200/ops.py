@@ -28,6 +28,66 @@ def _count(n: int = 1):
     _launches += n
 
 
+# ---- optional per-launch device timing (bench.py's roofline leg) ---------------------------------
+_prof = None     # list of (kernel class, algorithmic work, start event, end event) while profiling
+
+
+class profile:
+    """``with ops.profile() as rec:`` brackets every library launch with CUDA events on the launching
+    stream.  ``rec.summary()`` (after a sync) returns {class: (launches, ms, work)} where work is
+    algorithmic FLOPs for GEMMs and algorithmic bytes for the HBM-bound kernels."""
+
+    def __enter__(self):
+        global _prof
+        _prof = []
+        self.records = _prof
+        return self
+
+    def __exit__(self, *exc):
+        global _prof
+        _prof = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for cls, work, e0, e1 in self.records:
+            n, ms, w = out.get(cls, (0, 0.0, 0.0))
+            out[cls] = (n + 1, ms + e0.elapsed_time(e1), w + work)
+        return out
+
+
+class _Rec:
+    __slots__ = ("cls", "work", "e0")
+
+    def __init__(self, cls, work):
+        self.cls, self.work = cls, work
+
+    def __enter__(self):
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e0.record()
+
+    def __exit__(self, *exc):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        if _prof is not None:
+            _prof.append((self.cls, self.work, self.e0, e1))
+
+
+class _NoRec:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOREC = _NoRec()
+
+
+def _rec(cls: str, work: float):
+    return _NOREC if _prof is None else _Rec(cls, work)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -60,7 +120,7 @@ def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K
          ldb: int, ldd: int, a_mn: bool = False, b_mn: bool = False, bias=None, residual=None,
          ldr: int = 0, aux=None, ldaux: int = 0, batch=(1, 1), a_step=(0, 0), b_step=(0, 0),
          d_step=(0, 0), split_k: int = 1, epilogue: int = EPI_STORE, precision: int = GEMM_TF32,
-         alpha: float = 1.0, round_out: bool = False):
+         alpha: float = 1.0, round_out: bool = False, tag: str = ""):
     """D = epilogue(alpha * A . B^T); see corrif_gemm in include/corrif.h for the layout rules."""
     g = GemmDesc()
     g.A, g.B, g.D = _ptr(A), _ptr(B), _ptr(D)
@@ -74,25 +134,30 @@ def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K
     g.d_bo, g.d_bi = d_step
     g.split_k, g.epilogue, g.precision, g.alpha = split_k, epilogue, precision, alpha
     g.flags = GEMM_ROUND_TF32 if round_out else 0
-    L.check(lib().corrif_gemm(C.byref(g), _stream()), "corrif_gemm")
+    cls = ("gemm_tf32" if precision == GEMM_TF32 else "gemm_fp32") + ("/" + tag if tag else "")
+    with _rec(cls, 2.0 * M * N * K * batch[0] * batch[1]):
+        L.check(lib().corrif_gemm(C.byref(g), _stream()), "corrif_gemm")
     _count()
 
 
 def transpose(x: TensorOrView, out: TensorOrView, batch: int, rows: int, cols: int, round_out=False):
-    L.check(lib().corrif_transpose(_ptr(x), _ptr(out), batch, rows, cols, int(round_out), _stream()),
-            "corrif_transpose")
+    with _rec('transpose', 8.0 * batch * rows * cols):
+        L.check(lib().corrif_transpose(_ptr(x), _ptr(out), batch, rows, cols, int(round_out), _stream()),
+                "corrif_transpose")
     _count()
 
 
 def round_tf32(x: TensorOrView, out: TensorOrView, n: int):
-    L.check(lib().corrif_round_tf32(_ptr(x), _ptr(out), n, _stream()), "corrif_round_tf32")
+    with _rec('round_tf32', 8.0 * n):
+        L.check(lib().corrif_round_tf32(_ptr(x), _ptr(out), n, _stream()), "corrif_round_tf32")
     _count()
 
 
 def layernorm_fwd(x, pos, pos_rows, gamma, beta, x1_out, y, mean, rstd, rows, C_=512, round_out=False):
-    L.check(lib().corrif_layernorm_fwd(_ptr(x), _ptr(pos), pos_rows, _ptr(gamma), _ptr(beta),
-                                       _ptr(x1_out), _ptr(y), _ptr(mean), _ptr(rstd), rows, C_,
-                                       int(round_out), _stream()), "corrif_layernorm_fwd")
+    with _rec('layernorm_fwd', (12.0 if pos is not None else 8.0) * rows * C_):
+        L.check(lib().corrif_layernorm_fwd(_ptr(x), _ptr(pos), pos_rows, _ptr(gamma), _ptr(beta),
+                                           _ptr(x1_out), _ptr(y), _ptr(mean), _ptr(rstd), rows, C_,
+                                           int(round_out), _stream()), "corrif_layernorm_fwd")
     _count()
 
 
@@ -101,9 +166,10 @@ def layernorm_bwd_scratch_floats(rows, C_=512) -> int:
 
 
 def layernorm_bwd(dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, scratch, rows, C_=512):
-    L.check(lib().corrif_layernorm_bwd(_ptr(dy), _ptr(x1), _ptr(gamma), _ptr(mean), _ptr(rstd),
-                                       _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                                       _ptr(scratch), rows, C_, _stream()), "corrif_layernorm_bwd")
+    with _rec('layernorm_bwd', (16.0 if dres is not None else 12.0) * rows * C_):
+        L.check(lib().corrif_layernorm_bwd(_ptr(dy), _ptr(x1), _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                           _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                                           _ptr(scratch), rows, C_, _stream()), "corrif_layernorm_bwd")
     _count(2)
 
 
@@ -112,32 +178,37 @@ def _seed_dev(seed_dev):
 
 
 def softmax_fwd(S, Pdrop, rows, cols, p=0.0, seed=0, seed_dev=None, site=0, round_out=False):
-    L.check(lib().corrif_softmax_fwd(_ptr(S), _ptr(Pdrop), rows, cols, p, seed, _seed_dev(seed_dev),
-                                     site, int(round_out), _stream()), "corrif_softmax_fwd")
+    with _rec('softmax_fwd', (8.0 if Pdrop is None else 12.0) * rows * cols):
+        L.check(lib().corrif_softmax_fwd(_ptr(S), _ptr(Pdrop), rows, cols, p, seed, _seed_dev(seed_dev),
+                                         site, int(round_out), _stream()), "corrif_softmax_fwd")
     _count()
 
 
 def softmax_bwd(P, dP, rows, cols, scale, p=0.0, seed=0, seed_dev=None, site=0):
-    L.check(lib().corrif_softmax_bwd(_ptr(P), _ptr(dP), rows, cols, scale, p, seed,
-                                     _seed_dev(seed_dev), site, _stream()), "corrif_softmax_bwd")
+    with _rec('softmax_bwd', 12.0 * rows * cols):
+        L.check(lib().corrif_softmax_bwd(_ptr(P), _ptr(dP), rows, cols, scale, p, seed,
+                                         _seed_dev(seed_dev), site, _stream()), "corrif_softmax_bwd")
     _count()
 
 
 def dropout(x, out, n, p, seed, site, seed_dev=None):
-    L.check(lib().corrif_dropout(_ptr(x), _ptr(out), n, p, seed, _seed_dev(seed_dev), site, _stream()),
-            "corrif_dropout")
+    with _rec('dropout', 8.0 * n):
+        L.check(lib().corrif_dropout(_ptr(x), _ptr(out), n, p, seed, _seed_dev(seed_dev), site, _stream()),
+                "corrif_dropout")
     _count()
 
 
 def dropout_mask(mask, n, p, seed, site, seed_dev=None):
-    L.check(lib().corrif_dropout_mask(_ptr(mask), n, p, seed, _seed_dev(seed_dev), site, _stream()),
-            "corrif_dropout_mask")
+    with _rec('dropout', 4.0 * n):
+        L.check(lib().corrif_dropout_mask(_ptr(mask), n, p, seed, _seed_dev(seed_dev), site, _stream()),
+                "corrif_dropout_mask")
     _count()
 
 
 def dropout_add(x, res, out, n, p, seed, site_a, site_b=NO_SITE, seed_dev=None):
-    L.check(lib().corrif_dropout_add(_ptr(x), _ptr(res), _ptr(out), n, p, seed, _seed_dev(seed_dev),
-                                     site_a, site_b, _stream()), "corrif_dropout_add")
+    with _rec('dropout', (8.0 if res is None else 12.0) * n):
+        L.check(lib().corrif_dropout_add(_ptr(x), _ptr(res), _ptr(out), n, p, seed, _seed_dev(seed_dev),
+                                         site_a, site_b, _stream()), "corrif_dropout_add")
     _count()
 
 
@@ -146,38 +217,44 @@ def colsum_scratch_floats(rows, cols) -> int:
 
 
 def colsum(x, ld, rows, cols, out, scratch, accumulate=False):
-    L.check(lib().corrif_colsum(_ptr(x), ld, rows, cols, _ptr(out), int(accumulate), _ptr(scratch),
-                                _stream()), "corrif_colsum")
+    with _rec('colsum', 4.0 * rows * cols):
+        L.check(lib().corrif_colsum(_ptr(x), ld, rows, cols, _ptr(out), int(accumulate), _ptr(scratch),
+                                    _stream()), "corrif_colsum")
     _count(2)
 
 
 def batchsum(x, batch, stride, n, out, accumulate=False):
-    L.check(lib().corrif_batchsum(_ptr(x), batch, stride, n, _ptr(out), int(accumulate), _stream()),
-            "corrif_batchsum")
+    with _rec('batchsum', 4.0 * (batch + 1) * n):
+        L.check(lib().corrif_batchsum(_ptr(x), batch, stride, n, _ptr(out), int(accumulate), _stream()),
+                "corrif_batchsum")
     _count()
 
 
 def add_rows(a, lda, b, ldb, out, ldo, rows, cols):
-    L.check(lib().corrif_add_rows(_ptr(a), lda, _ptr(b), ldb, _ptr(out), ldo, rows, cols, _stream()),
-            "corrif_add_rows")
+    with _rec('add_rows', 12.0 * rows * cols):
+        L.check(lib().corrif_add_rows(_ptr(a), lda, _ptr(b), ldb, _ptr(out), ldo, rows, cols, _stream()),
+                "corrif_add_rows")
     _count()
 
 
 def inter_corr_fwd(qkv, skip, tokens, M, B, S, C_):
-    L.check(lib().corrif_inter_corr_fwd(_ptr(qkv), _ptr(skip), _ptr(tokens), M, B, S, C_, _stream()),
-            "corrif_inter_corr_fwd")
+    with _rec('inter_corr_fwd', 4.0 * (3 * M + 2 * M) * B * S * C_):
+        L.check(lib().corrif_inter_corr_fwd(_ptr(qkv), _ptr(skip), _ptr(tokens), M, B, S, C_, _stream()),
+                "corrif_inter_corr_fwd")
     _count()
 
 
 def inter_corr_bwd(qkv, g_tokens, dqkv, M, B, S, C_):
-    L.check(lib().corrif_inter_corr_bwd(_ptr(qkv), _ptr(g_tokens), _ptr(dqkv), M, B, S, C_, _stream()),
-            "corrif_inter_corr_bwd")
+    with _rec('inter_corr_bwd', 4.0 * (3 * M + M + 3 * M) * B * S * C_):
+        L.check(lib().corrif_inter_corr_bwd(_ptr(qkv), _ptr(g_tokens), _ptr(dqkv), M, B, S, C_, _stream()),
+                "corrif_inter_corr_bwd")
     _count()
 
 
 def jaccard_sums(y, y_pred, P, sums):
-    L.check(lib().corrif_jaccard_sums(_ptr(y), _ptr(y_pred), P, _ptr(sums, torch.float64), _stream()),
-            "corrif_jaccard_sums")
+    with _rec('jaccard', 8.0 * P):
+        L.check(lib().corrif_jaccard_sums(_ptr(y), _ptr(y_pred), P, _ptr(sums, torch.float64), _stream()),
+                "corrif_jaccard_sums")
     _count()
 
 
@@ -188,9 +265,10 @@ def jaccard_finish(sums, epsilon, out3):
 
 
 def confusion_counts(label, pred, P, num_classes, counts):
-    L.check(lib().corrif_confusion_counts(_ptr(label, torch.uint8), _ptr(pred, torch.uint8), P,
-                                          num_classes, _ptr(counts, torch.int64), _stream()),
-            "corrif_confusion_counts")
+    with _rec('confusion', 2.0 * P):
+        L.check(lib().corrif_confusion_counts(_ptr(label, torch.uint8), _ptr(pred, torch.uint8), P,
+                                              num_classes, _ptr(counts, torch.int64), _stream()),
+                "corrif_confusion_counts")
     _count()
 
 

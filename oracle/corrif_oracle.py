@@ -209,6 +209,22 @@ def fusion_block(params, x6, fused_x6, masks=None, modalities=MODALITIES):
     return y.reshape(B, S, -1).transpose(1, 2).reshape(B, -1, PATCH, PATCH, PATCH)  # :527-529
 
 
+def random_masks(batch: int, p: float, dtype=torch.float32, modalities=MODALITIES):
+    """Fresh pre-scaled Bernoulli keep masks for all 20 dropout sites (what the 20 nn.Dropout modules
+    of the reference draw in train mode, mmvit4.py:311,314,339,353,355); used by the CPU timing legs so
+    the baseline pays the same RNG cost as the reference does."""
+    masks = {}
+    names = [f"{m}_transformer" for m in modalities] + ["multimodal_transformer"]
+    for t, name in enumerate(names):
+        N = TOKENS if t < len(modalities) else TOKENS * (len(modalities) + 1)
+        a, f = f"{name}.cross_attention_list.0.fn", f"{name}.cross_ffn_list.0.fn"
+        for key, shape in ((f"{a}.fn.attn_drop", (batch, HEADS, N, N)), (f"{a}.fn.proj_drop", (batch, N, DIM)),
+                           (f"{a}.dropout", (batch, N, DIM)), (f"{f}.fn.net.2", (batch, N, MLP)),
+                           (f"{f}.fn.net.4", (batch, N, DIM))):
+            masks[key] = torch.empty(shape, dtype=dtype).bernoulli_(1 - p).div_(1 - p)
+    return masks
+
+
 def fusion_block_fwd_bwd(params, x6, fused_x6, gout, masks=None, dtype=torch.float64):
     """Forward + autograd backward in ``dtype``.  Returns (out, {name: grad}) where the grad
     dict holds every parameter plus ``x6.<i>`` and ``fused_x6``."""
