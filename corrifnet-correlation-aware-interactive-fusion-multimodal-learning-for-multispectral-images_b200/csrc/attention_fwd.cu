@@ -1,0 +1,267 @@
+// Fused multi-head self-attention forward for sm_100a (SelfAttention.forward, mmvit4.py:307-312):
+//   O[b, q, h*64 + :] = dropout(softmax(Q K^T * scale)) V      per (batch b, head h), head_dim 64
+// Q, K, V are strided views of the qkv GEMM output [B*N, 3*C] (no reshape/permute copies); the
+// N x N score matrix never touches HBM (the reference materialises [B,8,N,N]: 134 MB per sample at
+// N = 2048).
+//
+// One CTA = one 128-row query tile of one (b, h); it walks the keys in tiles of 64:
+//   warp 0      TMA producer: Q once, then K_j / V_j tiles (SWIZZLE_128B K-major for Q and K;
+//               V is the B operand of P.V with the contraction (key) index slow in memory, i.e.
+//               MN-major -> 128B_ATOM_32B boxes)
+//   warp 1      tcgen05 issuer: S = Q K_j^T (TF32, fp32 accumulate, 64 TMEM columns), and, once the
+//               softmax warps have published P_j in shared memory, O_j = P_j V_j (64 more columns)
+//   warps 2..5  online softmax: thread = query row = TMEM lane.  tcgen05.ld S, running max / sum in
+//               the log2 domain (ex2.approx), Philox dropout, P_j written to shared memory in the
+//               SWIZZLE_128B K-major layout the tensor core expects, then O_j is pulled from TMEM
+//               and folded into a register accumulator with the usual rescale.
+// Shared memory is ~97 KB and TMEM 128 columns per CTA, so two CTAs share an SM and one's softmax
+// overlaps the other's MMAs.  lse (log2-domain log-sum-exp) is saved for the backward.
+#include "tc05.cuh"
+
+namespace corrif {
+namespace attn {
+using namespace tc05;
+
+constexpr int TQ = 128, TK = 64, HD = 64;
+constexpr int Q_BYTES = TQ * HD * 4, K_BYTES = TK * HD * 4, V_BYTES = TK * HD * 4, P_BYTES = TQ * TK * 4;
+constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + K_BYTES, OFF_P = OFF_V + V_BYTES;
+constexpr int SMEM_BYTES = OFF_P + P_BYTES + 1024;
+constexpr uint32_t TMEM_COLS = 128;   // S: [0,64)  O_j: [64,128)
+
+struct FwdArgs {
+  float* O;
+  float* lse;
+  uint32_t* maskbits;   // [B*H, N, N/32] keep bits (written when dropout is on), or nullptr
+  int N, H;
+  int64_t ldo;
+  float scale_log2e;
+  uint32_t thresh;
+  float keep_scale;
+  uint64_t seed;
+  const uint64_t* seed_dev;
+  uint32_t site;
+  int round_out;
+};
+
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const FwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t q_full, k_full, k_free, v_full, v_free, s_full, s_free, p_full, o_full;
+  __shared__ uint32_t tmem_holder;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = sbase + OFF_Q, sK = sbase + OFF_K, sV = sbase + OFF_V, sP = sbase + OFF_P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, bh = blockIdx.y;
+  const int b = bh / a.H, h = bh % a.H;
+  const int C = a.H * HD;
+  const int q_row0 = b * a.N + qt * TQ;     // row in the [B*N, 3C] qkv matrix
+  const int kv_row0 = b * a.N;
+  const int ntiles = a.N / TK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmV) : "memory");
+    mbar_init(&q_full, 1); mbar_init(&k_full, 1); mbar_init(&k_free, 1);
+    mbar_init(&v_full, 1); mbar_init(&v_free, 1); mbar_init(&s_full, 1);
+    mbar_init(&s_free, 128); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_holder, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_holder;
+  const uint32_t tS = tmem, tO = tmem + 64;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(&q_full, Q_BYTES);
+    tma_load_2d(sQ, &tmQ, &q_full, h * HD, q_row0);
+    tma_load_2d(sQ + TQ * 128, &tmQ, &q_full, h * HD + 32, q_row0);
+    for (int j = 0; j < ntiles; ++j) {
+      const uint32_t ph = (uint32_t)j & 1u;
+      mbar_wait(&k_free, ph ^ 1u);
+      mbar_expect_tx(&k_full, K_BYTES);
+      tma_load_2d(sK, &tmK, &k_full, C + h * HD, kv_row0 + j * TK);
+      tma_load_2d(sK + TK * 128, &tmK, &k_full, C + h * HD + 32, kv_row0 + j * TK);
+      mbar_wait(&v_free, ph ^ 1u);
+      mbar_expect_tx(&v_full, V_BYTES);
+      tma_load_2d(sV, &tmV, &v_full, 2 * C + h * HD, kv_row0 + j * TK);
+      tma_load_2d(sV + TK * 128, &tmV, &v_full, 2 * C + h * HD + 32, kv_row0 + j * TK);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== tcgen05 issuer =====================
+    constexpr uint32_t idesc_s = idesc_tf32(TK, false, false);   // S[128 x 64] = Q . K^T
+    constexpr uint32_t idesc_o = idesc_tf32(HD, false, true);    // O[128 x 64] = P . V (V MN-major)
+    mbar_wait(&q_full, 0);
+    for (int j = 0; j < ntiles; ++j) {
+      const uint32_t ph = (uint32_t)j & 1u;
+      mbar_wait(&k_full, ph);
+      mbar_wait(&s_free, ph ^ 1u);                 // softmax finished reading S_{j-1}
+      tcgen05_fence_after();
+#pragma unroll
+      for (int t = 0; t < HD / 8; ++t) {
+        const uint64_t ad = smem_desc_kmajor(sQ + (t >> 2) * (TQ * 128) + (t & 3) * 32);
+        const uint64_t bd = smem_desc_kmajor(sK + (t >> 2) * (TK * 128) + (t & 3) * 32);
+        tcgen05_mma_tf32(tS, ad, bd, idesc_s, t > 0 ? 1u : 0u);
+      }
+      tcgen05_commit(&k_free);
+      tcgen05_commit(&s_full);
+      mbar_wait(&p_full, ph);                      // P_j in smem, O_{j-1} already consumed
+      mbar_wait(&v_full, ph);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int t = 0; t < TK / 8; ++t) {
+        const uint64_t ad = smem_desc_kmajor(sP + (t >> 2) * (TQ * 128) + (t & 3) * 32);
+        const uint64_t bd = smem_desc_mnmajor(sV + t * 1024, TK * 128);
+        tcgen05_mma_tf32(tO, ad, bd, idesc_o, t > 0 ? 1u : 0u);
+      }
+      tcgen05_commit(&v_free);
+      tcgen05_commit(&o_full);
+    }
+  } else if (warp >= 2) {
+    // ===================== online softmax =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                       // query row in the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int q_in_head = qt * TQ + row;
+    uint64_t seed = a.seed;
+    if (a.thresh != 0u && a.seed_dev != nullptr) seed += *a.seed_dev;
+    const uint64_t drop_row = ((uint64_t)bh * a.N + q_in_head) * (uint64_t)a.N;
+    float m = -INFINITY, l = 0.f;
+    float acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+    uint32_t r[32];
+    for (int j = 0; j < ntiles; ++j) {
+      const uint32_t ph = (uint32_t)j & 1u;
+      mbar_wait(&s_full, ph);
+      tcgen05_fence_after();
+      // pass 1: row max of the raw scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld32(tS + lane_addr + half * 32, r);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+      }
+      const float m_new = fmaxf(m, mx * a.scale_log2e);
+      const float alpha = ex2_approx(m - m_new);
+      m = m_new;
+      // fold in O_{j-1} (its P.V has finished: this also means the P buffer is free again)
+      if (j > 0) {
+        mbar_wait(&o_full, ph ^ 1u);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tmem_ld32(tO + lane_addr + half * 32, r);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[half * 32 + c] += __uint_as_float(r[c]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] *= alpha;
+      // pass 2: p = 2^(s*scale*log2e - m), row sum, dropout, publish P_j (swizzled K-major)
+      float rs = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t keepbits = 0u;
+        tmem_ld32(tS + lane_addr + half * 32, r);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 p;
+          p.x = ex2_approx(__uint_as_float(r[4 * g + 0]) * a.scale_log2e - m);
+          p.y = ex2_approx(__uint_as_float(r[4 * g + 1]) * a.scale_log2e - m);
+          p.z = ex2_approx(__uint_as_float(r[4 * g + 2]) * a.scale_log2e - m);
+          p.w = ex2_approx(__uint_as_float(r[4 * g + 3]) * a.scale_log2e - m);
+          rs += (p.x + p.y) + (p.z + p.w);
+          if (a.thresh != 0u) {
+            float km[4];
+            const uint64_t e = drop_row + (uint64_t)(j * TK + half * 32 + 4 * g);
+            dropout_keep4(seed, a.site, e >> 2, a.thresh, a.keep_scale, km);
+            p.x *= km[0]; p.y *= km[1]; p.z *= km[2]; p.w *= km[3];
+            keepbits |= ((km[0] != 0.f ? 1u : 0u) | (km[1] != 0.f ? 2u : 0u) | (km[2] != 0.f ? 4u : 0u) |
+                         (km[3] != 0.f ? 8u : 0u)) << (4 * g);
+          }
+          p = round_tf32_4(p);                      // P is only ever a tensor-core operand
+          const uint32_t addr = sP + half * (TQ * 128) + row * 128 + ((uint32_t)(g ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                       :: "r"(addr), "f"(p.x), "f"(p.y), "f"(p.z), "f"(p.w) : "memory");
+        }
+        if (a.thresh != 0u && a.maskbits != nullptr)
+          a.maskbits[((int64_t)bh * a.N + q_in_head) * (a.N / 32) + j * (TK / 32) + half] = keepbits;
+      }
+      l = l * alpha + rs;
+      tcgen05_fence_before();
+      mbar_arrive(&s_free);                         // S may be overwritten by Q K_{j+1}^T
+      fence_proxy_async();                          // make the P stores visible to the tensor core
+      mbar_arrive(&p_full);
+    }
+    // last tile's O
+    mbar_wait(&o_full, (uint32_t)(ntiles - 1) & 1u);
+    tcgen05_fence_after();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      tmem_ld32(tO + lane_addr + half * 32, r);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[half * 32 + c] += __uint_as_float(r[c]);
+    }
+    const float inv = 1.0f / l;
+    float* orow = a.O + (int64_t)(q_row0 + row) * a.ldo + h * HD;
+#pragma unroll
+    for (int g = 0; g < HD / 4; ++g) {
+      float4 o = make_float4(acc[4 * g] * inv, acc[4 * g + 1] * inv, acc[4 * g + 2] * inv, acc[4 * g + 3] * inv);
+      if (a.round_out) o = round_tf32_4(o);
+      st4(orow + 4 * g, o);
+    }
+    a.lse[(int64_t)bh * a.N + q_in_head] = m + log2f(l);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace attn
+}  // namespace corrif
+
+using namespace corrif;
+
+extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint32_t* maskbits,
+                                    int32_t B, int32_t N, int32_t H, int32_t D, float scale,
+                                    float p_drop, uint64_t seed,
+                                    const uint64_t* seed_dev, uint32_t site, int32_t round_tf32,
+                                    void* stream) {
+  using namespace corrif::attn;
+  CORRIF_REQUIRE(qkv && O && lse && B > 0, "attention_fwd: null/empty");
+  CORRIF_REQUIRE(D == HD, "attention_fwd: head_dim must be 64 (got %d)", D);
+  CORRIF_REQUIRE(H > 0 && N > 0 && N % TQ == 0, "attention_fwd: N must be a multiple of 128 (got %d)", N);
+  CORRIF_REQUIRE((int64_t)B * H <= 65535, "attention_fwd: B*H too large");
+  CORRIF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "attention_fwd: p_drop");
+  CORRIF_REQUIRE(p_drop == 0.f || maskbits != nullptr, "attention_fwd: dropout needs a maskbits buffer");
+  CORRIF_REQUIRE(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)O % 16 == 0), "attention_fwd: alignment");
+  const int C = H * D;
+  CUtensorMap tq, tk, tv;
+  int st = tc05::encode_map(&tq, qkv, 3 * C, (uint64_t)B * N, 3 * C, 32, TQ, false);
+  if (st) return st;
+  st = tc05::encode_map(&tk, qkv, 3 * C, (uint64_t)B * N, 3 * C, 32, TK, false);
+  if (st) return st;
+  st = tc05::encode_map(&tv, qkv, 3 * C, (uint64_t)B * N, 3 * C, 32, TK, true);
+  if (st) return st;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { set_last_error("attention_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  FwdArgs a;
+  a.O = O; a.lse = lse; a.maskbits = maskbits; a.N = N; a.H = H; a.ldo = C;
+  a.scale_log2e = scale * 1.4426950408889634f;
+  a.thresh = p_drop > 0.f ? dropout_threshold(p_drop) : 0u;
+  a.keep_scale = 1.0f / (1.0f - p_drop);
+  a.seed = seed; a.seed_dev = seed_dev; a.site = site; a.round_out = round_tf32;
+  dim3 grid(N / TQ, B * H);
+  attn_fwd_kernel<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  return launch_status("attention_fwd");
+}

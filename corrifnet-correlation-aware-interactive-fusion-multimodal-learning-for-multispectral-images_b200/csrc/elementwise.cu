@@ -153,16 +153,25 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
   }
 }
 
-__global__ void fold_partials_kernel(const float* __restrict__ partial, int nparts, int width,
-                                     float* __restrict__ out0, float* __restrict__ out1, int split,
-                                     int accumulate) {
-  // partial [nparts][width]; columns [0,split) go to out0, [split,width) to out1
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= width) return;
+// partial [nparts][width] -> out: columns [0,split) go to out0, [split,width) to out1.  16 threads
+// share one column (strided over the partials, coalesced across columns), combined through smem.
+__global__ void __launch_bounds__(512)
+fold_partials_kernel(const float* __restrict__ partial, int nparts, int width,
+                     float* __restrict__ out0, float* __restrict__ out1, int split, int accumulate) {
+  __shared__ float red[16][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * width + c];
-  float* dst = c < split ? out0 + c : out1 + (c - split);
-  *dst = accumulate ? *dst + s : s;
+  if (c < width)
+    for (int p = threadIdx.y; p < nparts; p += 16) s += partial[(int64_t)p * width + c];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 16; ++y) t += red[y][threadIdx.x];
+    float* dst = c < split ? out0 + c : out1 + (c - split);
+    *dst = accumulate ? *dst + t : t;
+  }
 }
 
 // ============================================================================================
@@ -425,7 +434,8 @@ int64_t corrif_layernorm_bwd_scratch_floats(int64_t rows, int32_t C) {
 
 int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, const float* mean,
                          const float* rstd, const float* dres, float* dx, float* dgamma,
-                         float* dbeta, float* scratch, int64_t rows, int32_t C, void* stream) {
+                         float* dbeta, float* scratch, int64_t rows, int32_t C, int32_t accumulate,
+                         void* stream) {
   CORRIF_REQUIRE(C == LN_C, "layernorm: C must be 512, got %d", C);
   CORRIF_REQUIRE(dy && x1 && gamma && mean && rstd && dx && dgamma && dbeta && scratch && rows > 0,
                  "layernorm_bwd: null/empty");
@@ -436,8 +446,8 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
                                                                  dx, scratch, rows);
   int st = launch_status("layernorm_bwd");
   if (st) return st;
-  fold_partials_kernel<<<(2 * LN_C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      scratch, blocks, 2 * LN_C, dgamma, dbeta, LN_C, 0);
+  fold_partials_kernel<<<(2 * LN_C + 31) / 32, dim3(32, 16), 0, (cudaStream_t)stream>>>(
+      scratch, blocks, 2 * LN_C, dgamma, dbeta, LN_C, accumulate);
   return launch_status("layernorm_bwd_fold");
 }
 
@@ -510,13 +520,13 @@ static int colsum_chunks(int64_t rows, int32_t cols) {
   int64_t want = ((int64_t)num_sms() * 4 + bx - 1) / bx;
   if (want > (rows + 15) / 16) want = (rows + 15) / 16;
   if (want < 1) want = 1;
-  if (want > 1024) want = 1024;
+  if (want > 256) want = 256;
   return (int)want;
 }
 
 int64_t corrif_colsum_scratch_floats(int64_t rows, int32_t cols) {
   (void)rows;
-  return (int64_t)1024 * cols;
+  return (int64_t)256 * cols;
 }
 
 int corrif_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out,
@@ -528,9 +538,8 @@ int corrif_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float*
   colsum_partial_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, scratch);
   int st = launch_status("colsum");
   if (st) return st;
-  fold_partials_kernel<<<(cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, chunks, cols,
-                                                                             out, out, cols,
-                                                                             accumulate);
+  fold_partials_kernel<<<(cols + 31) / 32, dim3(32, 16), 0, (cudaStream_t)stream>>>(
+      scratch, chunks, cols, out, out, cols, accumulate);
   return launch_status("colsum_fold");
 }
 

@@ -71,18 +71,24 @@ def _split_for(out_tiles: int, kblocks: int, sms: int = 148) -> int:
 class _TBuf:
     """Saved activations + gradient scratch of one Transformer at a given (B, N)."""
 
-    def __init__(self, B: int, N: int, dev, attn_scratch: bool):
+    def __init__(self, B: int, N: int, dev, fused_attn: bool, dropout: bool):
         R = B * N
         f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         self.B, self.N, self.R = B, N, R
         self.x1, self.h, self.qkv = f(R, C), f(R, C), f(R, 3 * C)
         self.mean1, self.rstd1, self.mean2, self.rstd2 = f(R), f(R), f(R), f(R)
-        self.P = f(B * HEADS, N, N)
+        self.fused = fused_attn
+        if fused_attn:    # fused tcgen05 attention: no N x N tensor in HBM, only lse (+ keep bits)
+            self.P = self.dP = None
+            self.lse, self.delta = f(B * HEADS, N), f(B * HEADS, N)
+            self.maskbits = (torch.empty(B * HEADS, N, N // 32, device=dev, dtype=torch.int32)
+                             if dropout else None)
+        else:             # materialised path (fp32 checking mode)
+            self.P, self.dP = f(B * HEADS, N, N), f(B * HEADS, N, N)
         self.O, self.x2, self.h2, self.u, self.f1, self.x3 = (f(R, C) for _ in range(6))
         # backward scratch
         self.t0, self.t1, self.t2, self.din = f(R, C), f(R, C), f(R, C), f(R, C)
         self.dqkv = f(R, 3 * C)
-        self.dP = f(B * HEADS, N, N) if attn_scratch else None
 
 
 class FusionBlockEngine:
@@ -110,9 +116,22 @@ class FusionBlockEngine:
         # nearest where they are produced, and matrix weights get rounded copies (refreshed each
         # forward, 41 MB).  In fp32 checking mode nothing is rounded.
         self.rnd = self.prec == GEMM_TF32
+        self.fused_attn = self.prec == GEMM_TF32     # fused flash-style attention on the tcgen05 path
         self.wnames = [k for k in param_names()
                        if k.endswith(".weight") and "norm" not in k]
         self.pw = {k: (torch.empty_like(params[k]) if self.rnd else params[k]) for k in self.wnames}
+
+    def new_grad_buffers(self):
+        """(flat, {name: view}): one zero-filled flat fp32 buffer holding every parameter gradient in
+        ``param_names()`` order - one memset per step, one all-reduce under data parallelism."""
+        names = param_names()
+        flat = torch.zeros(sum(self.p[n].numel() for n in names), device=self.dev)
+        views, off = {}, 0
+        for n in names:
+            k = self.p[n].numel()
+            views[n] = flat[off:off + k].view_as(self.p[n])
+            off += k
+        return flat, views
 
     def refresh_weights(self):
         if self.rnd:
@@ -130,7 +149,8 @@ class FusionBlockEngine:
             "x6tok": f(NM, B * S, ENC), "skip": f(NM, B * S, C), "qkvi": f(NM, B * S, 3 * C),
             "fx6tok": f(B * S, ENC * NM), "tokens": f(B, (NM + 1) * S, C), "posmm": f((NM + 1) * S, C),
             "ytok": f(B * S, ENC * NM), "out": f(B, ENC * NM, S),
-            "tb": [_TBuf(B, S, dev, True) for _ in range(NM)] + [_TBuf(B, (NM + 1) * S, dev, True)],
+            "tb": [_TBuf(B, S, dev, self.fused_attn, self.dropout_p > 0) for _ in range(NM)]
+                  + [_TBuf(B, (NM + 1) * S, dev, self.fused_attn, self.dropout_p > 0)],
             # backward
             "dytok": f(B * S, ENC * NM), "dtokc": f(NM + 1, B * S, C), "dqkvi": f(NM, B * S, 3 * C),
             "dtok": f(B * S, C), "dx6tok": f(B * S, ENC), "dfx6tok": f(B * S, ENC * NM),
@@ -169,6 +189,10 @@ class FusionBlockEngine:
     def _attention_fwd(self, t: int, tb: _TBuf):
         B, N = tb.B, tb.N
         p = self.dropout_p
+        if tb.fused:
+            ops.attention_fwd(tb.qkv, tb.O, tb.lse, tb.maskbits, B, N, HEADS, HD, HD ** -0.5, p, self.seed,
+                              self.seed_dev, self._site(t, SITE_ATTN), round_out=self.rnd)
+            return
         # S = 0.125 * Q K^T per (batch, head): strided views into qkv, no reshape/permute copies
         self._gemm(tb.qkv, (tb.qkv, C), tb.P, M=N, N=N, K=HD, lda=3 * C, ldb=3 * C, ldd=N,
                    batch=(B, HEADS), a_step=(N * 3 * C, HD), b_step=(N * 3 * C, HD),
@@ -184,6 +208,10 @@ class FusionBlockEngine:
     def _attention_bwd(self, t: int, tb: _TBuf, dO: torch.Tensor):
         B, N = tb.B, tb.N
         p = self.dropout_p
+        if tb.fused:
+            ops.attention_bwd(tb.qkv, tb.O, dO, tb.lse, tb.maskbits, tb.delta, tb.dqkv, B, N, HEADS, HD,
+                              HD ** -0.5, p)
+            return
         bat = dict(batch=(B, HEADS), tag="attn_bwd")
         pstep, qstep, ostep = (HEADS * N * N, N * N), (N * 3 * C, HD), (N * C, HD)
         pd = tb.P
@@ -238,8 +266,7 @@ class FusionBlockEngine:
     def _transformer_bwd(self, t: int, dx3, tb: _TBuf, g: Dict[str, torch.Tensor], scratch):
         """Backward of _transformer_fwd.  ``dx3`` must not alias tb.t0/t1/t2 (callers pass tb.din).
         Returns d(x_in) == d(x1) in tb.t0 (also the pos gradient before the batch reduction).
-        Matrix-weight grads are ACCUMULATED into ``g`` (atomics); LayerNorm and bias grads are
-        OVERWRITTEN."""
+        All parameter gradients are ACCUMULATED into ``g`` (which the caller zero-initialises)."""
         k, P_, R, p = self.tk[t], self.p, tb.R, self.dropout_p
         # ---- FeedForward branch: x3 = x2 + drop(fc2(drop(gelu(fc1(LN2(x2))))))
         df2 = dx3
@@ -247,15 +274,15 @@ class FusionBlockEngine:
             ops.dropout(dx3, tb.t0, R * C, p, self.seed, self._site(t, SITE_FFN2), self.seed_dev)
             df2 = tb.t0
         self._wgrad(df2, tb.f1, g[k["fc2_w"]], R, C, C)
-        ops.colsum(df2, C, R, C, g[k["fc2_b"]], scratch)
+        ops.colsum(df2, C, R, C, g[k["fc2_b"]], scratch, accumulate=True)
         self._dgrad(df2, self.pw[k["fc2_w"]], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C)
         if p > 0:
             ops.dropout(tb.t1, tb.t1, R * C, p, self.seed, self._site(t, SITE_FFN1), self.seed_dev)
         self._wgrad(tb.t1, tb.h2, g[k["fc1_w"]], R, C, C)
-        ops.colsum(tb.t1, C, R, C, g[k["fc1_b"]], scratch)
+        ops.colsum(tb.t1, C, R, C, g[k["fc1_b"]], scratch, accumulate=True)
         self._dgrad(tb.t1, self.pw[k["fc1_w"]], tb.t2, R, C, C)                    # d(h2)
         ops.layernorm_bwd(tb.t2, tb.x2, P_[k["ln2_w"]], tb.mean2, tb.rstd2, dx3, tb.t1,
-                          g[k["ln2_w"]], g[k["ln2_b"]], scratch, R)           # t1 = d(x2)
+                          g[k["ln2_w"]], g[k["ln2_b"]], scratch, R, accumulate=True)   # t1 = d(x2)
         dx2 = tb.t1
         # ---- attention branch: x2 = x1 + drop(drop(proj(attn(LN1(x1)))))
         dy = dx2
@@ -264,13 +291,13 @@ class FusionBlockEngine:
                             self._site(t, SITE_PRENORM), self.seed_dev)
             dy = tb.t0
         self._wgrad(dy, tb.O, g[k["proj_w"]], R, C, C)
-        ops.colsum(dy, C, R, C, g[k["proj_b"]], scratch)
+        ops.colsum(dy, C, R, C, g[k["proj_b"]], scratch, accumulate=True)
         self._dgrad(dy, self.pw[k["proj_w"]], tb.t2, R, C, C)                      # d(O)
         self._attention_bwd(t, tb, tb.t2)
         self._wgrad(tb.dqkv, tb.h, g[k["qkv_w"]], R, 3 * C, C)
         self._dgrad(tb.dqkv, self.pw[k["qkv_w"]], tb.t2, R, 3 * C, C)              # d(h)
         ops.layernorm_bwd(tb.t2, tb.x1, P_[k["ln1_w"]], tb.mean1, tb.rstd1, dx2, tb.t0,
-                          g[k["ln1_w"]], g[k["ln1_b"]], scratch, R)           # t0 = d(x1)
+                          g[k["ln1_w"]], g[k["ln1_b"]], scratch, R, accumulate=True)   # t0 = d(x1)
         return tb.t0
 
     # ------------------------------------------------------------------------------------------
@@ -310,7 +337,7 @@ class FusionBlockEngine:
         B = self._B
         ws, P_ = self.workspace(B), self.p
         if grads is None:
-            grads = {k: torch.zeros_like(P_[k]) for k in param_names()}
+            grads = self.new_grad_buffers()[1]
         g, sc = grads, ws["scratch"]
         R = B * S
         # ---- decode conv
@@ -320,13 +347,9 @@ class FusionBlockEngine:
         ops.colsum(ws["dytok"], ENC * NM, R, ENC * NM, g["multimodal_decode_conv.bias"], sc, accumulate=True)
         self._dgrad(ws["dytok"], self.pw["multimodal_decode_conv.weight"], tbm.din, R, ENC * NM, (NM + 1) * C)
         # ---- multimodal transformer
-        gm = {k: torch.zeros_like(P_[k]) for k in self.tk[NM].values() if "norm" in k or k.endswith(".bias")}
-        gt = dict(g)
-        gt.update(gm)
-        dtokens = self._transformer_bwd(NM, tbm.din, tbm, gt, sc)                 # [B,2048,512]
-        for k_, v in gm.items():
-            g[k_] += v
-        ops.batchsum(dtokens, B, (NM + 1) * S * C, (NM + 1) * S * C, ws["dposmm"])
+        dtokens = self._transformer_bwd(NM, tbm.din, tbm, g, sc)                  # [B,2048,512]
+        for X, m in enumerate(MODALITIES + ("fused6",)):      # pos grads of the concatenated [2048,512]
+            ops.batchsum((dtokens, X * S * C), B, (NM + 1) * S * C, S * C, g[f"{m}_pos"], accumulate=True)
         # contiguous per-group copies of the token gradient: [4][B*S][512]
         ws["dtokc"].view(NM + 1, B, S, C).copy_(dtokens.view(B, NM + 1, S, C).transpose(0, 1))
         # ---- fused6 encode conv
@@ -335,7 +358,6 @@ class FusionBlockEngine:
         ops.colsum(df6, C, R, C, g["fused6_encode_conv.bias"], sc, accumulate=True)
         self._dgrad(df6, self.pw["fused6_encode_conv.weight"], ws["dfx6tok"], R, C, ENC * NM)
         ops.transpose(ws["dfx6tok"], ws["dfused"], B, S, ENC * NM)
-        g["fused6_pos"] += ws["dposmm"][NM * S:].view(1, S, C)
         # ---- inter-modal correlation
         ops.inter_corr_bwd(ws["qkvi"], dtokens, ws["dqkvi"], NM, B, S, C)
         for X, m in enumerate(MODALITIES):
@@ -344,14 +366,8 @@ class FusionBlockEngine:
             self._wgrad(dq, tb.x3, g[f"qkv_{m}.weight"], R, 3 * C, C)
             ops.colsum(dq, 3 * C, R, 3 * C, g[f"qkv_{m}.bias"], sc, accumulate=True)
             self._dgrad(dq, self.pw[f"qkv_{m}.weight"], tb.din, R, 3 * C, C)         # d(trans_X)
-            gx = {k: torch.zeros_like(P_[k]) for k in self.tk[X].values() if "norm" in k or k.endswith(".bias")}
-            gt = dict(g)
-            gt.update(gx)
-            dx1 = self._transformer_bwd(X, tb.din, tb, gt, sc)
-            for k_, v in gx.items():
-                g[k_] += v
-            ops.batchsum(dx1, B, S * C, S * C, ws["dposmm"][X * S:(X + 1) * S], accumulate=True)
-            g[f"{m}_pos"] += ws["dposmm"][X * S:(X + 1) * S].view(1, S, C)
+            dx1 = self._transformer_bwd(X, tb.din, tb, g, sc)
+            ops.batchsum(dx1, B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
             ops.add_rows(dx1, C, ws["dtokc"][X], C, ws["dtok"], C, R, C)        # + skip path (:505)
             self._wgrad(ws["dtok"], ws["x6tok"][X], g[f"{m}_encode_conv.weight"], R, C, ENC)
             ops.colsum(ws["dtok"], C, R, C, g[f"{m}_encode_conv.bias"], sc, accumulate=True)

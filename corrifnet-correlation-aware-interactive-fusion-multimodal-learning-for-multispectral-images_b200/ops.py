@@ -165,11 +165,13 @@ def layernorm_bwd_scratch_floats(rows, C_=512) -> int:
     return int(lib().corrif_layernorm_bwd_scratch_floats(rows, C_))
 
 
-def layernorm_bwd(dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, scratch, rows, C_=512):
+def layernorm_bwd(dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, scratch, rows, C_=512,
+                  accumulate=False):
     with _rec('layernorm_bwd', (16.0 if dres is not None else 12.0) * rows * C_):
         L.check(lib().corrif_layernorm_bwd(_ptr(dy), _ptr(x1), _ptr(gamma), _ptr(mean), _ptr(rstd),
                                            _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                                           _ptr(scratch), rows, C_, _stream()), "corrif_layernorm_bwd")
+                                           _ptr(scratch), rows, C_, int(accumulate), _stream()),
+                    "corrif_layernorm_bwd")
     _count(2)
 
 
@@ -189,6 +191,24 @@ def softmax_bwd(P, dP, rows, cols, scale, p=0.0, seed=0, seed_dev=None, site=0):
         L.check(lib().corrif_softmax_bwd(_ptr(P), _ptr(dP), rows, cols, scale, p, seed,
                                          _seed_dev(seed_dev), site, _stream()), "corrif_softmax_bwd")
     _count()
+
+
+def attention_fwd(qkv, O, lse, maskbits, B, N, H=8, D=64, scale=0.125, p=0.0, seed=0, seed_dev=None,
+                  site=0, round_out=False):
+    with _rec("attn_fwd", 4.0 * B * H * N * N * D):
+        L.check(lib().corrif_attention_fwd(_ptr(qkv), _ptr(O), _ptr(lse), _ptr(maskbits, torch.int32), B, N,
+                                           H, D, scale, p, seed, _seed_dev(seed_dev), site,
+                                           int(round_out), _stream()), "corrif_attention_fwd")
+    _count()
+
+
+def attention_bwd(qkv, O, dO, lse, maskbits, delta, dqkv, B, N, H=8, D=64, scale=0.125, p=0.0):
+    # algorithmic FLOPs of the backward: dV, dP, dQ, dK = 4 products (recomputing S is not counted)
+    with _rec("attn_bwd", 8.0 * B * H * N * N * D):
+        L.check(lib().corrif_attention_bwd(_ptr(qkv), _ptr(O), _ptr(dO), _ptr(lse),
+                                           _ptr(maskbits, torch.int32), _ptr(delta), _ptr(dqkv), B, N, H,
+                                           D, scale, p, _stream()), "corrif_attention_bwd")
+    _count(3)
 
 
 def dropout(x, out, n, p, seed, site, seed_dev=None):

@@ -104,12 +104,13 @@ int corrif_round_tf32(const float* in, float* out, int64_t n, void* stream);
 int corrif_layernorm_fwd(const float* x, const float* pos, int64_t pos_rows, const float* gamma,
                          const float* beta, float* x1_out, float* y, float* mean, float* rstd,
                          int64_t rows, int32_t C, int32_t round_tf32, void* stream);
-/* dx = LN'(dy) (+ dres if not NULL).  dgamma/dbeta [C] are OVERWRITTEN.  `scratch` must hold
- * corrif_layernorm_bwd_scratch_floats(rows, C) floats. */
+/* dx = LN'(dy) (+ dres if not NULL).  dgamma/dbeta [C] are overwritten, or added to when
+ * accumulate != 0.  `scratch` must hold corrif_layernorm_bwd_scratch_floats(rows, C) floats. */
 int64_t corrif_layernorm_bwd_scratch_floats(int64_t rows, int32_t C);
 int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, const float* mean,
                          const float* rstd, const float* dres, float* dx, float* dgamma,
-                         float* dbeta, float* scratch, int64_t rows, int32_t C, void* stream);
+                         float* dbeta, float* scratch, int64_t rows, int32_t C, int32_t accumulate,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row softmax in place, for the materialised attention path: P = softmax(S) over `cols`
@@ -125,6 +126,25 @@ int corrif_softmax_fwd(float* S, float* Pdrop, int64_t rows, int32_t cols, float
 int corrif_softmax_bwd(const float* P, float* dP, int64_t rows, int32_t cols, float scale,
                        float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t site,
                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention (SelfAttention.forward, mmvit4.py:307-312, and its autograd
+ * backward): per (batch, head)  O = dropout(softmax(Q K^T * scale)) V  with Q, K, V the strided
+ * column blocks [0,C), [C,2C), [2C,3C) of qkv [B*N, 3C] (head h = columns h*D..h*D+D of a block),
+ * O / dO [B*N, C], dqkv [B*N, 3C].  tcgen05 (TF32 operands, fp32 accumulate in TMEM); the N x N
+ * probabilities never reach HBM.  D must be 64, N a multiple of 128.
+ *   lse      [B*H, N]        log2-domain log-sum-exp, written by fwd, read by bwd
+ *   maskbits [B*H, N, N/32]  dropout keep bits (bit kv%32 of word kv/32), written by fwd when
+ *                            p_drop > 0 (Philox keyed by seed/site/element index as corrif_dropout),
+ *                            read by bwd; may be NULL when p_drop == 0
+ *   delta    [B*H, N]        scratch of bwd (rowsum(dO*O))
+ * ------------------------------------------------------------------------------------------ */
+int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint32_t* maskbits, int32_t B,
+                         int32_t N, int32_t H, int32_t D, float scale, float p_drop, uint64_t seed,
+                         const uint64_t* seed_dev, uint32_t site, int32_t round_tf32, void* stream);
+int corrif_attention_bwd(const float* qkv, const float* O, const float* dO, const float* lse,
+                         const uint32_t* maskbits, float* delta, float* dqkv, int32_t B, int32_t N,
+                         int32_t H, int32_t D, float scale, float p_drop, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dropout  out = x * keep(seed, site, index) / (1-p)   (nn.Dropout sites mmvit4.py:311,314,339,

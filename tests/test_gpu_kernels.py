@@ -360,3 +360,43 @@ def test_bce_and_adam():
         opt.step()
         ops.adam_step(p, gr, m, v, p.numel(), 1e-3, 0.9, 0.999, 1e-8, 1.0, step)
     assert torch.allclose(p, pr.detach(), rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused attention (tcgen05): forward and backward against torch fp64, with and without dropout
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,p", [(1, 128, 0.0), (2, 512, 0.0), (1, 2048, 0.0), (2, 256, 0.1), (1, 512, 0.1)])
+def test_fused_attention_fwd_bwd(B, N, p):
+    H, d, Cc = 8, 64, 512
+    qkv = _rand(B * N, 3 * Cc, seed=N + 1)
+    dO = _rand(B * N, Cc, seed=N + 2)
+    O = torch.full((B * N, Cc), float("nan"), device=dev())
+    lse = torch.empty(B * H, N, device=dev())
+    delta = torch.empty(B * H, N, device=dev())
+    bits = torch.zeros(B * H, N, N // 32, dtype=torch.int32, device=dev()) if p > 0 else None
+    dqkv = torch.full((B * N, 3 * Cc), float("nan"), device=dev())
+    ops.attention_fwd(qkv, O, lse, bits, B, N, H, d, 0.125, p, seed=31, site=8)
+    ops.attention_bwd(qkv, O, dO, lse, bits, delta, dqkv, B, N, H, d, 0.125, p)
+    torch.cuda.synchronize()
+    x = qkv.double().requires_grad_(True)
+    q, k, v = (x.view(B, N, 3, H, d).permute(2, 0, 3, 1, 4)[i] for i in range(3))
+    P = torch.softmax(0.125 * q @ k.transpose(-1, -2), -1)
+    if p > 0:
+        m = torch.empty(B * H * N * N, device=dev())
+        ops.dropout_mask(m, m.numel(), p, 31, 8)
+        m = m.view(B, H, N, N)
+        # the keep bits saved by the forward are the same Philox decisions
+        w = bits.view(B, H, N, N // 32).long() & 0xFFFFFFFF
+        unpacked = ((w.unsqueeze(-1) >> torch.arange(32, device=dev())) & 1).reshape(B, H, N, N)
+        assert torch.equal(unpacked.float(), m)
+        P = P * m.double() / (1 - p)
+    ref = (P @ v).transpose(1, 2).reshape(B * N, Cc)
+    ref.backward(dO.double())
+    assert rel_l2(O.cpu().numpy(), ref.detach().cpu().numpy()) < 1.5e-3
+    lse_ref = torch.logsumexp(0.125 * q @ k.transpose(-1, -2), -1) / math.log(2.0)
+    assert rel_l2(lse.view(B, H, N).cpu().numpy(), lse_ref.detach().cpu().numpy()) < 5e-4
+    g = x.grad.view(B * N, 3, Cc)
+    got = dqkv.view(B * N, 3, Cc)
+    for i, nm in enumerate("qkv"):
+        e = rel_l2(got[:, i].cpu().numpy(), g[:, i].cpu().numpy())
+        assert e < 3e-3, f"d{nm}: {e:.3e}"
