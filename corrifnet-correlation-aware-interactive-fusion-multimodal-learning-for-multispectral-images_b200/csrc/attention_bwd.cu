@@ -93,23 +93,44 @@ attn_delta_kernel(const float* __restrict__ O, const float* __restrict__ dO, flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// dQ kernel
+// Both backward kernels: warp 0 = TMA producer, warp 1 = tcgen05 issuer, warps 2..9 = element-wise
+// (thread = (accumulator row = TMEM lane, column half g)); no cross-thread reduction is needed in the
+// backward because lse and delta are given.
+// ------------------------------------------------------------------------------------------------
+constexpr int BWD_THREADS = 320;
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// dQ kernel: S/dP double-buffered in TMEM, K/V tiles double-buffered in smem
 // ------------------------------------------------------------------------------------------------
 namespace dq {
 constexpr int OFF_Q = 0, OFF_DO = OFF_Q + TB * 256, OFF_DS = OFF_DO + TB * 256;
 constexpr int OFF_STAGE = OFF_DS + TB * TL * 4;
 constexpr int STAGE_BYTES = 3 * TL * 256;   // K (K-major), K (MN-major), V (K-major)
 constexpr int SMEM_BYTES = OFF_STAGE + 2 * STAGE_BYTES + 1024;
-constexpr uint32_t TMEM_COLS = 256;         // S [0,64) dP [64,128) dQ [128,192)
+constexpr uint32_t TMEM_COLS = 512;         // buffer u: S [128u, 128u+64) dP [128u+64, 128u+128); dQ [256,320)
 }  // namespace dq
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmKmn,
                    const BwdArgs a) {
   using namespace dq;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t own_full, kv_full[2], kv_free[2], sdp_full, sdp_free, ds_full, ds_free, fin;
+  __shared__ __align__(8) uint64_t own_full, kv_full[2], kv_free[2], sdp_full[2], sdp_free[2], ds_full, ds_free, fin;
   __shared__ uint32_t tmem_holder;
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = sb + OFF_Q, sDO = sb + OFF_DO, sDS = sb + OFF_DS;
@@ -121,9 +142,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     mbar_init(&own_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1); }
-    mbar_init(&sdp_full, 1); mbar_init(&sdp_free, 128); mbar_init(&ds_full, 128); mbar_init(&ds_free, 1);
-    mbar_init(&fin, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1);
+      mbar_init(&sdp_full[s], 1); mbar_init(&sdp_free[s], 256);
+    }
+    mbar_init(&ds_full, 256); mbar_init(&ds_free, 1); mbar_init(&fin, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_holder, TMEM_COLS);
@@ -131,7 +154,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_holder;
-  const uint32_t tS = tmem, tDP = tmem + 64, tDQ = tmem + 128;
+  const uint32_t tDQ = tmem + 256;
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(&own_full, 2 * TB * 256);
@@ -151,69 +174,69 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t id_s = idesc_tf32(TL, false, false);   // [128 x 64] = own . loop^T over d
     constexpr uint32_t id_q = idesc_tf32(HD, false, true);    // [128 x 64] = dS . K (K MN-major)
     mbar_wait(&own_full, 0);
+    auto issue_sdp = [&](int j) {
+      const int u = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      const uint32_t st = sb + OFF_STAGE + u * STAGE_BYTES;
+      mbar_wait(&kv_full[u], ph);
+      mbar_wait(&sdp_free[u], ph ^ 1u);                        // element-wise done with buffer u (tile j-2)
+      tcgen05_fence_after();
+      mma_headdim(tmem + 128 * u, sQ, TB, st, TL, id_s);                       // S  = Q  K_j^T
+      mma_headdim(tmem + 128 * u + 64, sDO, TB, st + 2 * TL * 256, TL, id_s);  // dP = dO V_j^T
+      tcgen05_commit(&sdp_full[u]);
+    };
+    issue_sdp(0);
     for (int j = 0; j < ntiles; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (uint32_t)j & 1u;
-      const uint32_t st = sb + OFF_STAGE + s * STAGE_BYTES;
-      mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1u);
-      mbar_wait(&sdp_free, ph ^ 1u);
+      if (j + 1 < ntiles) issue_sdp(j + 1);                    // overlaps the element-wise work of tile j
+      const int u = j & 1;
+      mbar_wait(&ds_full, (uint32_t)j & 1u);
       tcgen05_fence_after();
-      mma_headdim(tS, sQ, TB, st, TL, id_s);                   // S  = Q  K_j^T
-      mma_headdim(tDP, sDO, TB, st + 2 * TL * 256, TL, id_s);  // dP = dO V_j^T
-      tcgen05_commit(&sdp_full);
-      mbar_wait(&ds_full, ph);
-      tcgen05_fence_after();
-      mma_tile64(tDQ, sDS, st + TL * 256, id_q, j > 0);        // dQ += dS K_j
+      mma_tile64(tDQ, sDS, sb + OFF_STAGE + u * STAGE_BYTES + TL * 256, id_q, j > 0);   // dQ += dS K_j
       tcgen05_commit(&ds_free);
-      tcgen05_commit(&kv_free[s]);
+      tcgen05_commit(&kv_free[u]);
     }
     tcgen05_commit(&fin);
   } else if (warp >= 2) {
-    const int quad = warp & 3, row = quad * 32 + lane;
+    const int quad = warp & 3, g = (warp - 2) >> 2, row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int q = qt * TB + row;
     const float lse = a.lse[(int64_t)bh * a.N + q], dl = a.delta[(int64_t)bh * a.N + q];
     const uint32_t* mrow = a.maskbits ? a.maskbits + ((int64_t)bh * a.N + q) * (a.N / 32) : nullptr;
     uint32_t rs[32], rp[32];
     for (int j = 0; j < ntiles; ++j) {
-      const uint32_t ph = (uint32_t)j & 1u;
-      mbar_wait(&sdp_full, ph);
+      const int u = j & 1;
+      const uint32_t bits = mrow ? mrow[j * 2 + g] : 0xffffffffu;
+      mbar_wait(&sdp_full[u], (uint32_t)(j >> 1) & 1u);
       tcgen05_fence_after();
-      mbar_wait(&ds_free, ph ^ 1u);                            // dQ MMA of tile j-1 has read sDS
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld32(tS + lane_addr + half * 32, rs);
-        tmem_ld32(tDP + lane_addr + half * 32, rp);
-        const uint32_t bits = mrow ? mrow[j * 2 + half] : 0xffffffffu;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = 4 * g + e;
-            const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - lse);
-            const float keep = ((bits >> c) & 1u) ? a.keep_scale : 0.f;
-            v[e] = round_tf32(p * (__uint_as_float(rp[c]) * keep - dl) * a.scale);
-          }
-          st_swz(sDS, row, half * 8 + g, make_float4(v[0], v[1], v[2], v[3]));
-        }
-      }
+      tmem_ld32_nowait(tmem + 128 * u + lane_addr + g * 32, rs);
+      tmem_ld32_nowait(tmem + 128 * u + 64 + lane_addr + g * 32, rp);
+      tmem_wait_ld();
       tcgen05_fence_before();
-      mbar_arrive(&sdp_free);
+      mbar_arrive(&sdp_free[u]);                               // S/dP buffer u may be refilled
+      mbar_wait(&ds_free, ((uint32_t)j & 1u) ^ 1u);            // dQ MMA of tile j-1 has read sDS
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 4 * q4 + e;
+          const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - lse);
+          const float keep = ((bits >> c) & 1u) ? a.keep_scale : 0.f;
+          v[e] = round_tf32(p * (__uint_as_float(rp[c]) * keep - dl) * a.scale);
+        }
+        st_swz(sDS, row, g * 8 + q4, make_float4(v[0], v[1], v[2], v[3]));
+      }
       fence_proxy_async();
       mbar_arrive(&ds_full);
     }
     mbar_wait(&fin, 0);
     tcgen05_fence_after();
-    float* orow = a.dqkv + (int64_t)(q_row0 + row) * (3 * C) + h * HD;
+    float* orow = a.dqkv + (int64_t)(q_row0 + row) * (3 * C) + h * HD + g * 32;
+    tmem_ld32(tDQ + lane_addr + g * 32, rs);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      tmem_ld32(tDQ + lane_addr + half * 32, rs);
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        st4(orow + half * 32 + 4 * g, make_float4(__uint_as_float(rs[4 * g]), __uint_as_float(rs[4 * g + 1]),
-                                                  __uint_as_float(rs[4 * g + 2]), __uint_as_float(rs[4 * g + 3])));
-    }
+    for (int q4 = 0; q4 < 8; ++q4)
+      st4(orow + 4 * q4, make_float4(__uint_as_float(rs[4 * q4]), __uint_as_float(rs[4 * q4 + 1]),
+                                     __uint_as_float(rs[4 * q4 + 2]), __uint_as_float(rs[4 * q4 + 3])));
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -233,7 +256,7 @@ constexpr int SMEM_BYTES = OFF_DOMN + TL * 256 + 1024;
 constexpr uint32_t TMEM_COLS = 256;                 // S^T [0,64) dP^T [64,128) dV [128,192) dK [192,256)
 }  // namespace dkv
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {32,128} K-major (K_j, V_j)
                     const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {32, 64} K-major (Q_i)
                     const __grid_constant__ CUtensorMap tmQmn,   // qkv,  box {32, 64} MN-major (Q_i)
@@ -245,6 +268,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
   __shared__ __align__(8) uint64_t own_full, km_full, km_free, mn_full, mn_free, st_full, st_free, pds_full, pds_free, fin;
   __shared__ uint32_t tmem_holder;
   __shared__ float s_lse[2][TL], s_delta[2][TL];
+  __shared__ uint32_t s_bits[2][TL][4];              // keep bits of (query c, key word w) for this tile
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = sb + OFF_K, sV = sb + OFF_V, sPT = sb + OFF_PT, sDST = sb + OFF_DST;
   const uint32_t sQK = sb + OFF_QK, sDOK = sb + OFF_DOK, sQMN = sb + OFF_QMN, sDOMN = sb + OFF_DOMN;
@@ -256,7 +280,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
 
   if (warp == 0 && lane == 0) {
     mbar_init(&own_full, 1); mbar_init(&km_full, 1); mbar_init(&km_free, 1); mbar_init(&mn_full, 1);
-    mbar_init(&mn_free, 1); mbar_init(&st_full, 1); mbar_init(&st_free, 128); mbar_init(&pds_full, 128);
+    mbar_init(&mn_free, 1); mbar_init(&st_full, 1); mbar_init(&st_free, 256); mbar_init(&pds_full, 256);
     mbar_init(&pds_free, 1); mbar_init(&fin, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -305,64 +329,60 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
     }
     tcgen05_commit(&fin);
   } else if (warp >= 2) {
-    const int quad = warp & 3, row = quad * 32 + lane;          // kv row in the tile == TMEM lane
+    const int quad = warp & 3, g = (warp - 2) >> 2, row = quad * 32 + lane;   // kv row == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const int t128 = threadIdx.x - 64;                           // 0..127 among the 4 warps
-    const int kv = kt * TB + row;
+    const int t256 = threadIdx.x - 64;                           // 0..255 among the 8 warps
     const int words = a.N / 32;
     uint32_t rs[32], rp[32];
     for (int i = 0; i < ntiles; ++i) {
       const uint32_t ph = (uint32_t)i & 1u;
-      // per-column statistics of this query tile
-      if (t128 < TL) s_lse[i & 1][t128] = a.lse[(int64_t)bh * a.N + i * TL + t128];
-      else s_delta[i & 1][t128 - TL] = a.delta[(int64_t)bh * a.N + i * TL + (t128 - TL)];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int bf = i & 1;
+      // per-column statistics and keep bits of this query tile -> smem (double-buffered by tile parity)
+      if (t256 < TL) s_lse[bf][t256] = a.lse[(int64_t)bh * a.N + i * TL + t256];
+      else if (t256 < 2 * TL) s_delta[bf][t256 - TL] = a.delta[(int64_t)bh * a.N + i * TL + (t256 - TL)];
+      if (a.maskbits)
+        s_bits[bf][t256 >> 2][t256 & 3] =
+            a.maskbits[((int64_t)bh * a.N + i * TL + (t256 >> 2)) * words + kt * 4 + (t256 & 3)];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&st_full, ph);
       tcgen05_fence_after();
-      mbar_wait(&pds_free, ph ^ 1u);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld32(tST + lane_addr + half * 32, rs);
-        tmem_ld32(tDPT + lane_addr + half * 32, rp);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float pv[4], dv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = half * 32 + 4 * g + e;                 // query column inside the tile
-            const float p = ex2_approx(__uint_as_float(rs[4 * g + e]) * a.scale_log2e - s_lse[i & 1][c]);
-            float keep = 1.0f;
-            if (a.maskbits) {
-              const uint32_t w = a.maskbits[((int64_t)bh * a.N + i * TL + c) * words + (kv >> 5)];
-              keep = ((w >> (kv & 31)) & 1u) ? a.keep_scale : 0.f;
-            }
-            pv[e] = round_tf32(p * keep);
-            dv[e] = round_tf32(p * (__uint_as_float(rp[4 * g + e]) * keep - s_delta[i & 1][c]) * a.scale);
-          }
-          st_swz(sPT, row, half * 8 + g, make_float4(pv[0], pv[1], pv[2], pv[3]));
-          st_swz(sDST, row, half * 8 + g, make_float4(dv[0], dv[1], dv[2], dv[3]));
-        }
-      }
+      tmem_ld32_nowait(tST + lane_addr + g * 32, rs);
+      tmem_ld32_nowait(tDPT + lane_addr + g * 32, rp);
+      tmem_wait_ld();
       tcgen05_fence_before();
       mbar_arrive(&st_free);
+      mbar_wait(&pds_free, ph ^ 1u);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        float pv[4], dv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = g * 32 + 4 * q4 + e;                     // query column inside the tile
+          const float p = ex2_approx(__uint_as_float(rs[4 * q4 + e]) * a.scale_log2e - s_lse[bf][c]);
+          float keep = 1.0f;
+          if (a.maskbits) keep = ((s_bits[bf][c][quad] >> lane) & 1u) ? a.keep_scale : 0.f;
+          pv[e] = round_tf32(p * keep);
+          dv[e] = round_tf32(p * (__uint_as_float(rp[4 * q4 + e]) * keep - s_delta[bf][c]) * a.scale);
+        }
+        st_swz(sPT, row, g * 8 + q4, make_float4(pv[0], pv[1], pv[2], pv[3]));
+        st_swz(sDST, row, g * 8 + q4, make_float4(dv[0], dv[1], dv[2], dv[3]));
+      }
       fence_proxy_async();
       mbar_arrive(&pds_full);
     }
     mbar_wait(&fin, 0);
     tcgen05_fence_after();
-    float* krow = a.dqkv + (int64_t)(kv_row0 + row) * (3 * C) + C + h * HD;
+    float* krow = a.dqkv + (int64_t)(kv_row0 + row) * (3 * C) + C + h * HD + g * 32;
     float* vrow = krow + C;
+    tmem_ld32_nowait(tDV + lane_addr + g * 32, rs);
+    tmem_ld32_nowait(tDK + lane_addr + g * 32, rp);
+    tmem_wait_ld();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      tmem_ld32(tDV + lane_addr + half * 32, rs);
-      tmem_ld32(tDK + lane_addr + half * 32, rp);
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        st4(vrow + half * 32 + 4 * g, make_float4(__uint_as_float(rs[4 * g]), __uint_as_float(rs[4 * g + 1]),
-                                                  __uint_as_float(rs[4 * g + 2]), __uint_as_float(rs[4 * g + 3])));
-        st4(krow + half * 32 + 4 * g, make_float4(__uint_as_float(rp[4 * g]), __uint_as_float(rp[4 * g + 1]),
-                                                  __uint_as_float(rp[4 * g + 2]), __uint_as_float(rp[4 * g + 3])));
-      }
+    for (int q4 = 0; q4 < 8; ++q4) {
+      st4(vrow + 4 * q4, make_float4(__uint_as_float(rs[4 * q4]), __uint_as_float(rs[4 * q4 + 1]),
+                                     __uint_as_float(rs[4 * q4 + 2]), __uint_as_float(rs[4 * q4 + 3])));
+      st4(krow + 4 * q4, make_float4(__uint_as_float(rp[4 * q4]), __uint_as_float(rp[4 * q4 + 1]),
+                                     __uint_as_float(rp[4 * q4 + 2]), __uint_as_float(rp[4 * q4 + 3])));
     }
   }
   tcgen05_fence_before();
@@ -414,8 +434,8 @@ extern "C" int corrif_attention_bwd(const float* qkv, const float* O, const floa
   a.N = N; a.H = H; a.scale = scale; a.scale_log2e = scale * 1.4426950408889634f;
   a.keep_scale = 1.0f / (1.0f - p_drop);
   dim3 grid(N / TB, B * H);
-  attn_bwd_dq_kernel<<<grid, 192, dq::SMEM_BYTES, st>>>(q128, do128, k64, k64mn, a);
+  attn_bwd_dq_kernel<<<grid, BWD_THREADS, dq::SMEM_BYTES, st>>>(q128, do128, k64, k64mn, a);
   if ((rc = launch_status("attention_bwd_dq"))) return rc;
-  attn_bwd_dkv_kernel<<<grid, 192, dkv::SMEM_BYTES, st>>>(kv128, q64, q64mn, do64, do64mn, a);
+  attn_bwd_dkv_kernel<<<grid, BWD_THREADS, dkv::SMEM_BYTES, st>>>(kv128, q64, q64mn, do64, do64mn, a);
   return launch_status("attention_bwd_dkv");
 }

@@ -10,10 +10,13 @@
 //               MN-major -> 128B_ATOM_32B boxes)
 //   warp 1      tcgen05 issuer: S = Q K_j^T (TF32, fp32 accumulate, 64 TMEM columns), and, once the
 //               softmax warps have published P_j in shared memory, O_j = P_j V_j (64 more columns)
-//   warps 2..5  online softmax: thread = query row = TMEM lane.  tcgen05.ld S, running max / sum in
-//               the log2 domain (ex2.approx), Philox dropout, P_j written to shared memory in the
-//               SWIZZLE_128B K-major layout the tensor core expects, then O_j is pulled from TMEM
-//               and folded into a register accumulator with the usual rescale.
+//   warps 2..9  online softmax, two warpgroups: thread = (query row = TMEM lane, column half g).
+//               Group g owns score columns [32g, 32g+32) of the tile and output columns [32g, 32g+32):
+//               one tcgen05.ld of S, row max exchanged between the halves through shared memory, running
+//               max / sum in the log2 domain (ex2.approx), counter-RNG dropout (keep bits saved for the
+//               backward), P_j written to shared memory in the SWIZZLE_128B K-major layout the tensor
+//               core expects, then O_j is pulled from TMEM and folded into a register accumulator with
+//               the usual rescale.
 // Shared memory is ~97 KB and TMEM 128 columns per CTA, so two CTAs share an SM and one's softmax
 // overlaps the other's MMAs.  lse (log2-domain log-sum-exp) is saved for the backward.
 #include "tc05.cuh"
@@ -43,12 +46,16 @@ struct FwdArgs {
   int round_out;
 };
 
-__global__ void __launch_bounds__(192, 2)
+constexpr int NUM_THREADS = 320;     // producer warp, MMA warp, 8 softmax warps
+
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, k_full, k_free, v_full, v_free, s_full, s_free, p_full, o_full;
   __shared__ uint32_t tmem_holder;
+  __shared__ float s_max[2][2][TQ];    // [tile parity][column half][row]
+  __shared__ float s_sum[2][TQ];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = sbase + OFF_Q, sK = sbase + OFF_K, sV = sbase + OFF_V, sP = sbase + OFF_P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,7 +72,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmV) : "memory");
     mbar_init(&q_full, 1); mbar_init(&k_full, 1); mbar_init(&k_free, 1);
     mbar_init(&v_full, 1); mbar_init(&v_free, 1); mbar_init(&s_full, 1);
-    mbar_init(&s_free, 128); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
+    mbar_init(&s_free, 256); mbar_init(&p_full, 256); mbar_init(&o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_holder, TMEM_COLS);
@@ -122,101 +129,96 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tcgen05_commit(&o_full);
     }
   } else if (warp >= 2) {
-    // ===================== online softmax =====================
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;                       // query row in the tile == TMEM lane
+    // ===================== online softmax (8 warps) =====================
+    const int quad = warp & 3;                               // TMEM lane quadrant this warp may access
+    const int g = (warp - 2) >> 2;                           // column half
+    const int row = quad * 32 + lane;                        // query row in the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int q_in_head = qt * TQ + row;
-    uint64_t seed = a.seed;
-    if (a.thresh != 0u && a.seed_dev != nullptr) seed += *a.seed_dev;
+    uint64_t key = 0;
+    if (a.thresh != 0u) key = dropout_key(a.seed + (a.seed_dev ? *a.seed_dev : 0ull), a.site);
     const uint64_t drop_row = ((uint64_t)bh * a.N + q_in_head) * (uint64_t)a.N;
     float m = -INFINITY, l = 0.f;
-    float acc[HD];
+    float acc[32];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
     uint32_t r[32];
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
-      mbar_wait(&s_full, ph);
-      tcgen05_fence_after();
-      // pass 1: row max of the raw scores
-      float mx = -INFINITY;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tmem_ld32(tS + lane_addr + half * 32, r);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
-      }
-      const float m_new = fmaxf(m, mx * a.scale_log2e);
-      const float alpha = ex2_approx(m - m_new);
-      m = m_new;
-      // fold in O_{j-1} (its P.V has finished: this also means the P buffer is free again)
+      // add my half of O_{j-1} (its P.V has finished: the P buffer is free again too); the rescale
+      // by this tile's alpha follows once the new row max is known
       if (j > 0) {
         mbar_wait(&o_full, ph ^ 1u);
         tcgen05_fence_after();
+        tmem_ld32(tO + lane_addr + g * 32, r);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          tmem_ld32(tO + lane_addr + half * 32, r);
-#pragma unroll
-          for (int c = 0; c < 32; ++c) acc[half * 32 + c] += __uint_as_float(r[c]);
-        }
+        for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(r[c]);
       }
+      mbar_wait(&s_full, ph);
+      tcgen05_fence_after();
+      tmem_ld32(tS + lane_addr + g * 32, r);                 // my 32 score columns (kept in registers)
+      float mx = -INFINITY;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] *= alpha;
-      // pass 2: p = 2^(s*scale*log2e - m), row sum, dropout, publish P_j (swizzled K-major)
+      for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+      s_max[ph][g][row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, s_max[ph][g ^ 1][row]);
+      const float m_new = fmaxf(m, mx * a.scale_log2e);
+      const float alpha = ex2_approx(m - m_new);
+      m = m_new;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] *= alpha;
+      // p = 2^(s*scale*log2e - m), partial row sum, dropout, publish my k-block of P_j
       float rs = 0.f;
+      uint32_t keepbits = 0u;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t keepbits = 0u;
-        tmem_ld32(tS + lane_addr + half * 32, r);
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float4 p;
-          p.x = ex2_approx(__uint_as_float(r[4 * g + 0]) * a.scale_log2e - m);
-          p.y = ex2_approx(__uint_as_float(r[4 * g + 1]) * a.scale_log2e - m);
-          p.z = ex2_approx(__uint_as_float(r[4 * g + 2]) * a.scale_log2e - m);
-          p.w = ex2_approx(__uint_as_float(r[4 * g + 3]) * a.scale_log2e - m);
-          rs += (p.x + p.y) + (p.z + p.w);
-          if (a.thresh != 0u) {
-            float km[4];
-            const uint64_t e = drop_row + (uint64_t)(j * TK + half * 32 + 4 * g);
-            dropout_keep4(seed, a.site, e >> 2, a.thresh, a.keep_scale, km);
-            p.x *= km[0]; p.y *= km[1]; p.z *= km[2]; p.w *= km[3];
-            keepbits |= ((km[0] != 0.f ? 1u : 0u) | (km[1] != 0.f ? 2u : 0u) | (km[2] != 0.f ? 4u : 0u) |
-                         (km[3] != 0.f ? 8u : 0u)) << (4 * g);
-          }
-          p = round_tf32_4(p);                      // P is only ever a tensor-core operand
-          const uint32_t addr = sP + half * (TQ * 128) + row * 128 + ((uint32_t)(g ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                       :: "r"(addr), "f"(p.x), "f"(p.y), "f"(p.z), "f"(p.w) : "memory");
+      for (int q4 = 0; q4 < 8; ++q4) {
+        float4 p;
+        p.x = ex2_approx(__uint_as_float(r[4 * q4 + 0]) * a.scale_log2e - m);
+        p.y = ex2_approx(__uint_as_float(r[4 * q4 + 1]) * a.scale_log2e - m);
+        p.z = ex2_approx(__uint_as_float(r[4 * q4 + 2]) * a.scale_log2e - m);
+        p.w = ex2_approx(__uint_as_float(r[4 * q4 + 3]) * a.scale_log2e - m);
+        rs += (p.x + p.y) + (p.z + p.w);
+        if (a.thresh != 0u) {
+          float km[4];
+          const uint64_t e = drop_row + (uint64_t)(j * TK + g * 32 + 4 * q4);
+          dropout_keep4(key, e >> 2, a.thresh, a.keep_scale, km);
+          p.x *= km[0]; p.y *= km[1]; p.z *= km[2]; p.w *= km[3];
+          keepbits |= ((km[0] != 0.f ? 1u : 0u) | (km[1] != 0.f ? 2u : 0u) | (km[2] != 0.f ? 4u : 0u) |
+                       (km[3] != 0.f ? 8u : 0u)) << (4 * q4);
         }
-        if (a.thresh != 0u && a.maskbits != nullptr)
-          a.maskbits[((int64_t)bh * a.N + q_in_head) * (a.N / 32) + j * (TK / 32) + half] = keepbits;
+        p = round_tf32_4(p);                        // P is only ever a tensor-core operand
+        const uint32_t addr = sP + g * (TQ * 128) + row * 128 + ((uint32_t)(q4 ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                     :: "r"(addr), "f"(p.x), "f"(p.y), "f"(p.z), "f"(p.w) : "memory");
       }
+      if (a.thresh != 0u && a.maskbits != nullptr)
+        a.maskbits[((int64_t)bh * a.N + q_in_head) * (a.N / 32) + j * (TK / 32) + g] = keepbits;
       l = l * alpha + rs;
       tcgen05_fence_before();
       mbar_arrive(&s_free);                         // S may be overwritten by Q K_{j+1}^T
       fence_proxy_async();                          // make the P stores visible to the tensor core
       mbar_arrive(&p_full);
     }
-    // last tile's O
+    // last tile's O, then combine the two halves' partial row sums
     mbar_wait(&o_full, (uint32_t)(ntiles - 1) & 1u);
     tcgen05_fence_after();
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      tmem_ld32(tO + lane_addr + half * 32, r);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) acc[half * 32 + c] += __uint_as_float(r[c]);
-    }
+    tmem_ld32(tO + lane_addr + g * 32, r);
+    s_sum[g][row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += s_sum[g ^ 1][row];
     const float inv = 1.0f / l;
-    float* orow = a.O + (int64_t)(q_row0 + row) * a.ldo + h * HD;
+    float* orow = a.O + (int64_t)(q_row0 + row) * a.ldo + h * HD + g * 32;
 #pragma unroll
-    for (int g = 0; g < HD / 4; ++g) {
-      float4 o = make_float4(acc[4 * g] * inv, acc[4 * g + 1] * inv, acc[4 * g + 2] * inv, acc[4 * g + 3] * inv);
-      if (a.round_out) o = round_tf32_4(o);
-      st4(orow + 4 * g, o);
+    for (int q4 = 0; q4 < 8; ++q4) {
+      float4 v = make_float4((acc[4 * q4] + __uint_as_float(r[4 * q4])) * inv,
+                             (acc[4 * q4 + 1] + __uint_as_float(r[4 * q4 + 1])) * inv,
+                             (acc[4 * q4 + 2] + __uint_as_float(r[4 * q4 + 2])) * inv,
+                             (acc[4 * q4 + 3] + __uint_as_float(r[4 * q4 + 3])) * inv);
+      if (a.round_out) v = round_tf32_4(v);
+      st4(orow + 4 * q4, v);
     }
-    a.lse[(int64_t)bh * a.N + q_in_head] = m + log2f(l);
+    if (g == 0) a.lse[(int64_t)bh * a.N + q_in_head] = m + log2f(l);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -262,6 +264,6 @@ extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint
   a.keep_scale = 1.0f / (1.0f - p_drop);
   a.seed = seed; a.seed_dev = seed_dev; a.site = site; a.round_out = round_tf32;
   dim3 grid(N / TQ, B * H);
-  attn_fwd_kernel<<<grid, 192, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
   return launch_status("attention_fwd");
 }

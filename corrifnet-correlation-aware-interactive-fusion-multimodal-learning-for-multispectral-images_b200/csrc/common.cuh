@@ -81,35 +81,37 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return cdf + x * pdf;
 }
 
-// ---- Philox4x32-10 counter RNG: keep(seed, site, element) is a pure function -------------------
-struct Philox4 { uint32_t x, y, z, w; };
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                  uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return Philox4{c0, c1, c2, c3};
+// ---- counter-based dropout RNG -------------------------------------------------------------------
+// keep(seed, site, element) is a pure function, so the backward regenerates (or the attention forward
+// saves as bits) exactly the forward's decisions.  One SplitMix64 finaliser (Steele/Lea/Flood, the
+// java.util.SplittableRandom mixer) of (key + quad * golden) yields 64 bits = four 16-bit draws for
+// the 4 consecutive elements [4*quad, 4*quad+4): ~5 instructions per element, against ~18 for
+// Philox4x32-10, which matters inside the fused attention kernels where the softmax warps are the
+// critical resource.  Element e is kept iff its 16-bit draw >= round(p * 65536).
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
 }
-// Keep flags of the 4 consecutive elements [4*quad, 4*quad+4).  Element e is kept iff its 32-bit
-// draw >= p * 2^32.
-__device__ __forceinline__ void dropout_keep4(uint64_t seed, uint32_t site, uint64_t quad,
-                                              uint32_t thresh, float scale, float (&m)[4]) {
-  Philox4 r = philox4x32_10((uint32_t)quad, (uint32_t)(quad >> 32), site, 0x5EEDu,
-                            (uint32_t)seed, (uint32_t)(seed >> 32));
-  m[0] = r.x >= thresh ? scale : 0.f;
-  m[1] = r.y >= thresh ? scale : 0.f;
-  m[2] = r.z >= thresh ? scale : 0.f;
-  m[3] = r.w >= thresh ? scale : 0.f;
+__device__ __forceinline__ uint64_t dropout_key(uint64_t seed, uint32_t site) {
+  return splitmix64(seed ^ ((uint64_t)(site + 1u) * 0xD6E8FEB86659FD93ull));
+}
+__device__ __forceinline__ uint64_t dropout_bits(uint64_t key, uint64_t quad) {
+  return splitmix64(key + quad * 0x9E3779B97F4A7C15ull);
+}
+__device__ __forceinline__ void dropout_keep4(uint64_t key, uint64_t quad, uint32_t thresh, float scale,
+                                              float (&m)[4]) {
+  const uint64_t r = dropout_bits(key, quad);
+  const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+  m[0] = (lo & 0xFFFFu) >= thresh ? scale : 0.f;
+  m[1] = (lo >> 16) >= thresh ? scale : 0.f;
+  m[2] = (hi & 0xFFFFu) >= thresh ? scale : 0.f;
+  m[3] = (hi >> 16) >= thresh ? scale : 0.f;
 }
 static inline uint32_t dropout_threshold(float p) {
-  double t = (double)p * 4294967296.0;
+  double t = (double)p * 65536.0 + 0.5;
   if (t < 0) t = 0;
-  if (t > 4294967295.0) t = 4294967295.0;
+  if (t > 65535.0) t = 65535.0;
   return (uint32_t)t;
 }
 

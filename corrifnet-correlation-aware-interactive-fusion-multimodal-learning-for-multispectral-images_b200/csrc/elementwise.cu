@@ -183,6 +183,7 @@ softmax_fwd_kernel(float* __restrict__ S, float* __restrict__ Pd, int64_t rows, 
                    uint32_t thresh, float keep_scale, uint64_t seed, const uint64_t* seed_dev,
                    uint32_t site, int round) {
   if (seed_dev != nullptr) seed += *seed_dev;
+  const uint64_t key = dropout_key(seed, site);
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -214,7 +215,7 @@ softmax_fwd_kernel(float* __restrict__ S, float* __restrict__ Pd, int64_t rows, 
       if (Pd != nullptr) {
         float m[4];
         const uint64_t e = (uint64_t)row * cols + lane * 4 + j * 128;
-        dropout_keep4(seed, site, e >> 2, thresh, keep_scale, m);
+        dropout_keep4(key, e >> 2, thresh, keep_scale, m);
         float4 pd = make_float4(v[j].x * m[0], v[j].y * m[1], v[j].z * m[2], v[j].w * m[3]);
         if (round) pd = round_tf32_4(pd);
         st4(Pd + row * cols + lane * 4 + j * 128, pd);
@@ -228,6 +229,7 @@ softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ dP, int64_t 
                    int nv, float scale, uint32_t thresh, float keep_scale, uint64_t seed,
                    const uint64_t* seed_dev, uint32_t site, int use_drop) {
   if (seed_dev != nullptr) seed += *seed_dev;
+  const uint64_t key = dropout_key(seed, site);
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -241,7 +243,7 @@ softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ dP, int64_t 
       if (use_drop) {
         float m[4];
         const uint64_t e = (uint64_t)row * cols + lane * 4 + j * 128;
-        dropout_keep4(seed, site, e >> 2, thresh, keep_scale, m);
+        dropout_keep4(key, e >> 2, thresh, keep_scale, m);
         d[j].x *= m[0]; d[j].y *= m[1]; d[j].z *= m[2]; d[j].w *= m[3];
       }
       dot += (p[j].x * d[j].x + p[j].y * d[j].y) + (p[j].z * d[j].z + p[j].w * d[j].w);
@@ -264,10 +266,11 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
                                uint32_t thresh, float keep_scale, uint64_t seed,
                                const uint64_t* seed_dev, uint32_t site, int mask_only) {
   if (seed_dev != nullptr) seed += *seed_dev;
+  const uint64_t key = dropout_key(seed, site);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads;
        q += (int64_t)gridDim.x * blockDim.x) {
     float m[4];
-    dropout_keep4(seed, site, (uint64_t)q, thresh, mask_only ? 1.0f : keep_scale, m);
+    dropout_keep4(key, (uint64_t)q, thresh, mask_only ? 1.0f : keep_scale, m);
     float4 v = mask_only ? make_float4(1.f, 1.f, 1.f, 1.f) : ld4(x + q * 4);
     st4(out + q * 4, make_float4(v.x * m[0], v.y * m[1], v.z * m[2], v.w * m[3]));
   }
@@ -284,11 +287,12 @@ __global__ void dropout_add_kernel(const float* __restrict__ x, const float* __r
                                    float keep_scale, uint64_t seed, const uint64_t* seed_dev,
                                    uint32_t site_a, uint32_t site_b) {
   if (seed_dev != nullptr) seed += *seed_dev;
+  const uint64_t key_a = dropout_key(seed, site_a), key_b = dropout_key(seed, site_b);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads;
        q += (int64_t)gridDim.x * blockDim.x) {
     float m[4], m2[4] = {1.f, 1.f, 1.f, 1.f};
-    dropout_keep4(seed, site_a, (uint64_t)q, thresh, keep_scale, m);
-    if (site_b != CORRIF_NO_SITE) dropout_keep4(seed, site_b, (uint64_t)q, thresh, keep_scale, m2);
+    dropout_keep4(key_a, (uint64_t)q, thresh, keep_scale, m);
+    if (site_b != CORRIF_NO_SITE) dropout_keep4(key_b, (uint64_t)q, thresh, keep_scale, m2);
     const float4 v = ld4(x + q * 4);
     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
     if (res != nullptr) r = ld4(res + q * 4);

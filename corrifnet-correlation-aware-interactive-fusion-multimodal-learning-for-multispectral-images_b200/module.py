@@ -48,19 +48,20 @@ def _(x6_rgb, x6_nir, x6_swir, fused_x6, params, dropout_p, seed, precision):
 def fusion_block_backward_op(gout: Tensor, params: Sequence[Tensor], dropout_p: float, seed: int,
                              precision: str) -> List[Tensor]:
     """Backward of the most recent corrif::fusion_block call on the same parameter set.  Returns
-    [d x6_rgb, d x6_nir, d x6_swir, d fused_x6, *d params]."""
+    [d x6_rgb, d x6_nir, d x6_swir, d fused_x6, flat parameter gradients (param_names() order)]."""
     eng = _engine_for(params, dropout_p, precision)
     eng.seed = int(seed)
-    dx6, dfused, grads = eng.backward(gout.contiguous())
-    return [dx6[0].clone(), dx6[1].clone(), dx6[2].clone(), dfused.clone()] + \
-        [grads[n] for n in param_names()]
+    flat, views = eng.new_grad_buffers()
+    dx6, dfused, _ = eng.backward(gout.contiguous(), views)
+    return [dx6[0].clone(), dx6[1].clone(), dx6[2].clone(), dfused.clone(), flat]
 
 
 @fusion_block_backward_op.register_fake
 def _(gout, params, dropout_p, seed, precision):
     b = gout.shape[0]
     x = gout.new_empty(b, 64, 8, 8, 8)
-    return [x, x.clone(), x.clone(), torch.empty_like(gout)] + [torch.empty_like(p) for p in params]
+    return [x, x.clone(), x.clone(), torch.empty_like(gout),
+            gout.new_empty(sum(p.numel() for p in params))]
 
 
 def _setup_ctx(ctx, inputs, output):
@@ -71,7 +72,11 @@ def _setup_ctx(ctx, inputs, output):
 
 def _backward(ctx, gout):
     res = torch.ops.corrif.fusion_block_backward(gout, ctx.params, ctx.dropout_p, ctx.seed, ctx.precision)
-    return res[0], res[1], res[2], res[3], list(res[4:]), None, None, None
+    pgrads, off = [], 0
+    for p in ctx.params:          # slice the flat buffer: one memset + one kernel set wrote all of it
+        pgrads.append(res[4][off:off + p.numel()].view_as(p))
+        off += p.numel()
+    return res[0], res[1], res[2], res[3], pgrads, None, None, None
 
 
 fusion_block_op.register_autograd(_backward, setup_context=_setup_ctx)

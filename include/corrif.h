@@ -116,7 +116,7 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
  * Row softmax in place, for the materialised attention path: P = softmax(S) over `cols`
  * (mmvit4.py:310; the 0.125 scale of :309 is folded into the producing GEMM's alpha), with the
  * optional attention dropout of :311: when p_drop > 0 the dropped-and-rescaled probabilities
- * (Philox keyed by seed/site/element index, scaled 1/(1-p)) are written to Pdrop, while S keeps
+ * (counter RNG keyed by seed/site/element index, scaled 1/(1-p)) are written to Pdrop, while S keeps
  * the un-dropped P that the backward needs.
  * Backward in place on dP:  dS = P * (dP*keep/(1-p) - sum_j(dP*keep/(1-p)*P)) * scale.
  * ------------------------------------------------------------------------------------------ */
@@ -135,7 +135,7 @@ int corrif_softmax_bwd(const float* P, float* dP, int64_t rows, int32_t cols, fl
  * probabilities never reach HBM.  D must be 64, N a multiple of 128.
  *   lse      [B*H, N]        log2-domain log-sum-exp, written by fwd, read by bwd
  *   maskbits [B*H, N, N/32]  dropout keep bits (bit kv%32 of word kv/32), written by fwd when
- *                            p_drop > 0 (Philox keyed by seed/site/element index as corrif_dropout),
+ *                            p_drop > 0 (counter RNG keyed by seed/site/element index as corrif_dropout),
  *                            read by bwd; may be NULL when p_drop == 0
  *   delta    [B*H, N]        scratch of bwd (rowsum(dO*O))
  * ------------------------------------------------------------------------------------------ */
@@ -148,7 +148,8 @@ int corrif_attention_bwd(const float* qkv, const float* O, const float* dO, cons
 
 /* ------------------------------------------------------------------------------------------
  * Dropout  out = x * keep(seed, site, index) / (1-p)   (nn.Dropout sites mmvit4.py:311,314,339,
- * 353,355).  Counter based (Philox4x32-10): the same call on a gradient is the backward.
+ * 353,355).  Counter based (SplitMix64 hash of seed, site and element index, 16-bit draws; p is realised as
+ * round(p*65536)/65536): the same call on a gradient is the backward.
  * In place allowed.  corrif_dropout_mask writes the 0/1 keep mask itself (for tests).
  * corrif_dropout_add: out = x * keep_a * keep_b / (1-p)^2 + res  - the two stacked dropouts of the
  *   attention branch (proj_drop :314 then PreNormDrop.dropout :339) and the residual add (:322) in

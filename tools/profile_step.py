@@ -14,6 +14,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--dropout", type=float, default=0.1)
 ap.add_argument("--gemm", type=int, nargs="*", default=None)
+ap.add_argument("--attn", type=int, nargs=2, default=None, help="B N: fused attention fwd+bwd only")
+ap.add_argument("--pdrop", type=float, default=0.1)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 
@@ -30,6 +32,26 @@ if args.gemm:
     torch.cuda.profiler.start()
     for _ in range(3):
         ops.gemm(A, B, D, **kw)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
+
+if args.attn:
+    B, N = args.attn
+    p = args.pdrop
+    qkv = torch.randn(B * N, 1536, device=dev)
+    dO = torch.randn(B * N, 512, device=dev)
+    O = torch.empty(B * N, 512, device=dev)
+    lse = torch.empty(B * 8, N, device=dev)
+    delta = torch.empty(B * 8, N, device=dev)
+    bits = torch.zeros(B * 8, N, N // 32, dtype=torch.int32, device=dev) if p > 0 else None
+    dqkv = torch.empty(B * N, 1536, device=dev)
+    for it in range(2):
+        if it == 1:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+        ops.attention_fwd(qkv, O, lse, bits, B, N, 8, 64, 0.125, p, seed=1, site=0)
+        ops.attention_bwd(qkv, O, dO, lse, bits, delta, dqkv, B, N, 8, 64, 0.125, p)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     sys.exit(0)
