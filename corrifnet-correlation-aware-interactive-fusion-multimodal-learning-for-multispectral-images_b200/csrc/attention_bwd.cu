@@ -221,8 +221,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int e = 0; e < 4; ++e) {
           const int c = 4 * q4 + e;
           const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - lse);
-          const float keep = ((bits >> c) & 1u) ? a.keep_scale : 0.f;
-          v[e] = round_tf32(p * (__uint_as_float(rp[c]) * keep - dl) * a.scale);
+          const float dp = ((bits >> c) & 1u) ? __uint_as_float(rp[c]) * a.keep_scale : 0.f;
+          v[e] = round_tf32(p * (dp - dl) * a.scale);
         }
         st_swz(sDS, row, g * 8 + q4, make_float4(v[0], v[1], v[2], v[3]));
       }

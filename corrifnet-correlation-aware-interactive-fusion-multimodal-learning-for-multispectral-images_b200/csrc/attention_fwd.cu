@@ -179,13 +179,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         p.z = ex2_approx(__uint_as_float(r[4 * q4 + 2]) * a.scale_log2e - m);
         p.w = ex2_approx(__uint_as_float(r[4 * q4 + 3]) * a.scale_log2e - m);
         rs += (p.x + p.y) + (p.z + p.w);
-        if (a.thresh != 0u) {
-          float km[4];
+        if (a.thresh != 0u) {     // 1/(1-p) is applied once to the output, not per element
           const uint64_t e = drop_row + (uint64_t)(j * TK + g * 32 + 4 * q4);
-          dropout_keep4(key, e >> 2, a.thresh, a.keep_scale, km);
-          p.x *= km[0]; p.y *= km[1]; p.z *= km[2]; p.w *= km[3];
-          keepbits |= ((km[0] != 0.f ? 1u : 0u) | (km[1] != 0.f ? 2u : 0u) | (km[2] != 0.f ? 4u : 0u) |
-                       (km[3] != 0.f ? 8u : 0u)) << (4 * q4);
+          const uint32_t km = dropout_keepmask4(key, e >> 2, a.thresh);
+          p.x = (km & 1u) ? p.x : 0.f; p.y = (km & 2u) ? p.y : 0.f;
+          p.z = (km & 4u) ? p.z : 0.f; p.w = (km & 8u) ? p.w : 0.f;
+          keepbits |= km << (4 * q4);
         }
         p = round_tf32_4(p);                        // P is only ever a tensor-core operand
         const uint32_t addr = sP + g * (TQ * 128) + row * 128 + ((uint32_t)(q4 ^ (row & 7)) << 4);
@@ -207,7 +206,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     s_sum[g][row] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += s_sum[g ^ 1][row];
-    const float inv = 1.0f / l;
+    const float inv = (a.thresh != 0u ? a.keep_scale : 1.0f) / l;
     float* orow = a.O + (int64_t)(q_row0 + row) * a.ldo + h * HD + g * 32;
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {

@@ -108,6 +108,13 @@ __device__ __forceinline__ void dropout_keep4(uint64_t key, uint64_t quad, uint3
   m[2] = (hi & 0xFFFFu) >= thresh ? scale : 0.f;
   m[3] = (hi >> 16) >= thresh ? scale : 0.f;
 }
+// Same decisions as dropout_keep4 as a 4-bit mask (bit e = element 4*quad+e is kept).
+__device__ __forceinline__ uint32_t dropout_keepmask4(uint64_t key, uint64_t quad, uint32_t thresh) {
+  const uint64_t r = dropout_bits(key, quad);
+  const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+  return ((lo & 0xFFFFu) >= thresh ? 1u : 0u) | ((lo >> 16) >= thresh ? 2u : 0u) |
+         ((hi & 0xFFFFu) >= thresh ? 4u : 0u) | ((hi >> 16) >= thresh ? 8u : 0u);
+}
 static inline uint32_t dropout_threshold(float p) {
   double t = (double)p * 65536.0 + 0.5;
   if (t < 0) t = 0;

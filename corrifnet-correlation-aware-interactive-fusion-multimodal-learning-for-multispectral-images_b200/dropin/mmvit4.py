@@ -1,0 +1,222 @@
+"""Drop-in for the reference's ``mmvit4`` module: ``MMVit4(num_cls=1)`` with the same ``forward(x)``
+contract ([B,3,3,H,W] -> [B,3,1,224,224] sigmoid probabilities) and the SAME 1140 ``state_dict`` keys
+and shapes, so ``iremmodel{i}.pt`` / ``Finaliremmodel{i}.pt`` checkpoints load strictly in both
+directions (reference F4_TRAIN.py:84-86,180).
+
+What differs is only where the fusion hot path (reference mmvit4.py:456-529) runs: here it is one
+call to ``torch.ops.corrif.fusion_block`` (hand-written sm_100a kernels behind the C ABI, see
+include/corrif.h), forward and backward.  The modality encoders, the early-fusion blocks and the
+decoder are outside the hot path (SURVEY.md section 8f ranks them "next") and run on stock PyTorch /
+cuDNN; they are re-stated here from the architecture description, table-driven, because the class
+has to own their parameters under the reference's names.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+from corrif_b200 import fusion as _fusion  # noqa: E402
+from corrif_b200 import module as _module  # noqa: E402  (registers torch.ops.corrif.*)
+
+basic_dims = 8
+transformer_basic_dims = 512
+mlp_dim = 512
+num_heads = 8
+depth = 1
+num_modals = 3
+patch_size = 8
+
+_MODS = ("RGB", "NIR", "SWIR")
+
+
+# ----------------------------------------------------------------------------------------------
+# encoder: ResNet-50 topology inflated to (1,k,k) 3-D convolutions (reference mmvit4.py:83-212)
+# ----------------------------------------------------------------------------------------------
+def _conv2d_as_3d(cin, cout, k, stride, pad, depth_k=1):
+    return nn.Conv3d(cin, cout, (depth_k, k, k), stride=(1, stride, stride),
+                     padding=(depth_k // 2, pad, pad), bias=False)
+
+
+class Bottleneck3D(nn.Module):
+    def __init__(self, cin, planes, stride, project):
+        super().__init__()
+        self.conv1, self.bn1 = _conv2d_as_3d(cin, planes, 1, 1, 0), nn.BatchNorm3d(planes)
+        self.conv2, self.bn2 = _conv2d_as_3d(planes, planes, 3, stride, 1), nn.BatchNorm3d(planes)
+        self.conv3, self.bn3 = _conv2d_as_3d(planes, 4 * planes, 1, 1, 0), nn.BatchNorm3d(4 * planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = None
+        if project:
+            self.downsample = nn.Sequential(_conv2d_as_3d(cin, 4 * planes, 1, stride, 0),
+                                            nn.BatchNorm3d(4 * planes))
+
+    def forward(self, x):
+        y = self.relu(self.bn1(self.conv1(x)))
+        y = self.relu(self.bn2(self.conv2(y)))
+        y = self.bn3(self.conv3(y))
+        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+
+
+def _stage(cin, planes, blocks, stride):
+    layers = [Bottleneck3D(cin, planes, stride, True)]
+    layers += [Bottleneck3D(4 * planes, planes, 1, False) for _ in range(blocks - 1)]
+    return nn.Sequential(*layers)
+
+
+class Encoder(nn.Module):
+    """One modality encoder.  Returns the five adapted pyramid levels and x6 [B,64,8,8,8]."""
+
+    def __init__(self, inflate_time=3):
+        super().__init__()
+        self.e1_c1 = _conv2d_as_3d(1, 64, 7, 2, 3, depth_k=inflate_time)
+        self.e1_bn = nn.BatchNorm3d(64)
+        self.e1_relu = nn.ReLU(inplace=True)
+        self.e1_mp = nn.MaxPool3d(kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1))
+        self.e2 = _stage(64, 64, 3, 1)
+        self.e3 = _stage(256, 128, 4, 2)
+        self.e4 = _stage(512, 256, 6, 2)
+        self.e5 = _stage(1024, 512, 3, 2)
+        widths = (basic_dims, basic_dims * 2, basic_dims * 4, basic_dims * 8, basic_dims * 8)
+        self.conv6 = nn.Conv3d(sum(widths), basic_dims * 8, kernel_size=1)
+        for i, (cin, cout) in enumerate(zip((64, 256, 512, 1024, 2048), widths), start=1):
+            setattr(self, f"adapt{i}", nn.Conv3d(cin, cout, kernel_size=1))
+
+    def forward(self, x):
+        f1 = self.e1_mp(self.e1_bn(self.e1_relu(self.e1_c1(x))))      # ReLU before BN, as the reference
+        f2 = self.e2(f1)
+        f3 = self.e3(f2)
+        f4 = self.e4(f3)
+        f5 = self.e5(f4)
+        lv = [getattr(self, f"adapt{i}")(f) for i, f in enumerate((f1, f2, f3, f4, f5), start=1)]
+        pooled = [F.interpolate(t, size=(8, 8, 8), mode="trilinear", align_corners=True) for t in lv]
+        return (*lv, self.conv6(torch.cat(pooled, dim=1)))
+
+
+class EarlyFusionBlock(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        c = num_modals * in_channels
+        self.conv = nn.Conv3d(c, c, kernel_size=1)
+        self.act = nn.ReLU(inplace=True)
+        self.norm = nn.InstanceNorm3d(c)
+
+    def forward(self, a, b, c):
+        return self.norm(self.act(self.conv(torch.cat([a, b, c], dim=1))))
+
+
+# ----------------------------------------------------------------------------------------------
+# decoder (reference mmvit4.py:29-56, 222-292)
+# ----------------------------------------------------------------------------------------------
+class general_conv3d_prenorm(nn.Module):
+    def __init__(self, in_ch, out_ch, k_size=3, stride=1, padding=1, pad_type="zeros"):
+        super().__init__()
+        self.conv = nn.Conv3d(in_ch, out_ch, k_size, stride=stride, padding=padding,
+                              padding_mode=pad_type, bias=True)
+        self.norm = nn.InstanceNorm3d(out_ch)
+        self.activation = nn.ReLU(inplace=True)
+
+    def forward(self, x):
+        return self.norm(self.activation(self.conv(x)))
+
+
+class fusion_prenorm(nn.Module):
+    def __init__(self, in_channel):
+        super().__init__()
+        self.fusion_layer = nn.Sequential(
+            general_conv3d_prenorm(in_channel, in_channel, k_size=1, padding=0),
+            general_conv3d_prenorm(in_channel, in_channel, k_size=3, padding=1),
+            general_conv3d_prenorm(in_channel, in_channel, k_size=1, padding=0))
+
+    def forward(self, x):
+        return self.fusion_layer(x)
+
+
+class Decoder_fuse(nn.Module):
+    # (level, skip channels, in channels of *_c1, out channels, cube size the skip is resized to)
+    _LEVELS = ((4, 192, 128, 64, 16), (3, 96, 64, 32, 32), (2, 48, 32, 16, 64), (1, 24, 16, 8, 128))
+
+    def __init__(self, num_cls=1):
+        super().__init__()
+        rep = dict(pad_type="replicate")
+        for lvl, skip, cin, cout, _ in self._LEVELS:
+            c1_out = cin if lvl == 4 else cout
+            setattr(self, f"d{lvl}_c1", general_conv3d_prenorm(cin, c1_out, **rep))
+            setattr(self, f"d{lvl}_c2", general_conv3d_prenorm(skip + c1_out, cout, **rep))
+            setattr(self, f"d{lvl}_out", general_conv3d_prenorm(cout, cout, k_size=1, padding=0, **rep))
+            setattr(self, f"RFM{lvl}", fusion_prenorm(skip))
+        for name, cin in (("seg_d4", 64), ("seg_d3", 64), ("seg_d2", 32), ("seg_d1", 16), ("seg_layer", 8)):
+            setattr(self, name, nn.Conv3d(cin, num_cls, kernel_size=1))          # unused in forward
+        self.RFM5 = fusion_prenorm(192)
+        self.RFM5_reduce = nn.Conv3d(192, 128, kernel_size=1)
+        self.final_conv = nn.Conv3d(8, 3, kernel_size=1)
+        self.up2 = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)
+        self.up_to_224 = nn.Upsample(size=(1, 224, 224), mode="trilinear", align_corners=True)
+
+    def forward(self, x1, x2, x3, x4, x5):
+        y = self.RFM5_reduce(self.RFM5(x5))
+        for (lvl, _, _, _, cube), skip in zip(self._LEVELS, (x4, x3, x2, x1)):
+            y = getattr(self, f"d{lvl}_c1")(self.up2(y))
+            s = F.interpolate(getattr(self, f"RFM{lvl}")(skip), (cube, cube, cube))
+            y = getattr(self, f"d{lvl}_out")(getattr(self, f"d{lvl}_c2")(torch.cat((s, y), dim=1)))
+        return torch.sigmoid(self.final_conv(self.up_to_224(y)))
+
+
+# ----------------------------------------------------------------------------------------------
+class MMVit4(nn.Module):
+    def __init__(self, num_cls=1, dropout_rate=0.1, precision="tf32"):
+        super().__init__()
+        C, E = transformer_basic_dims, basic_dims * 8
+        self.dropout_rate, self.precision = dropout_rate, precision
+        self._step, self.base_seed = 0, 0x5EED
+        for m in _MODS:
+            setattr(self, f"{m}_encoder", Encoder())
+        for m in _MODS:
+            setattr(self, f"{m}_encode_conv", nn.Conv3d(E, C, 1))
+        self.fused6_encode_conv = nn.Conv3d(E * 3, C, 1)
+        for m in _MODS:
+            setattr(self, f"{m}_decode_conv", nn.Conv3d(C, E, 1))                 # unused in forward
+        for m in _MODS + ("fused6",):
+            setattr(self, f"{m}_pos", nn.Parameter(torch.zeros(1, patch_size ** 3, C)))
+        # transformer parameters live under the reference's dotted names
+        for prefix in [f"{m}_transformer" for m in _MODS] + ["multimodal_transformer"]:
+            for key in _fusion.transformer_keys(prefix).values():
+                shape = _module.fusion_param_shapes()[key]
+                p = nn.Parameter(torch.empty(shape))
+                if key.endswith("norm.weight"):
+                    nn.init.ones_(p)
+                elif key.endswith(".bias"):
+                    nn.init.zeros_(p)
+                else:
+                    nn.init.kaiming_uniform_(p, a=5 ** 0.5)
+                _module._attach(self, key, p)
+        for m in _MODS:
+            setattr(self, f"qkv_{m}", nn.Conv3d(C, C * 3, 1))
+        self.multimodal_decode_conv = nn.Conv3d(C * 4, E * 3, 1)
+        self.decoder_fuse = Decoder_fuse(num_cls=num_cls)
+        for i, c in enumerate((1, 2, 4, 8, 8, 8), start=1):
+            setattr(self, f"fusion{i}", EarlyFusionBlock(basic_dims * c))
+        for mod in self.modules():
+            if isinstance(mod, nn.Conv3d):
+                nn.init.kaiming_normal_(mod.weight)
+        self._fusion_names = _fusion.param_names()
+
+    def fusion_parameters(self):
+        named = dict(self.named_parameters())
+        return [named[n] for n in self._fusion_names]
+
+    def forward(self, x):
+        feats = [getattr(self, f"{m}_encoder")(x[:, i:i + 1]) for i, m in enumerate(_MODS)]
+        fused = [getattr(self, f"fusion{lv + 1}")(*(f[lv] for f in feats)) for lv in (0, 1, 2, 3, 5)]
+        fused_x1, fused_x2, fused_x3, fused_x4, fused_x6 = fused          # fusion5's output is unused
+        p = self.dropout_rate if self.training else 0.0
+        self._step += 1
+        x6_inter = torch.ops.corrif.fusion_block(feats[0][5], feats[1][5], feats[2][5], fused_x6,
+                                                 self.fusion_parameters(), p,
+                                                 self.base_seed + self._step, self.precision)
+        return self.decoder_fuse(fused_x1, fused_x2, fused_x3, fused_x4, x6_inter)

@@ -1,0 +1,171 @@
+"""The data-parallel unit of the reference: the step body of ``train_model`` (F4_TRAIN.py:52-71),
+without its two host synchronisations, plus batch-sharded data parallelism over NCCL.
+
+Reference step:  zero_grad -> model(images) -> BCEWithLogitsLoss(outputs, masks) on the already
+sigmoided outputs -> backward -> optim.step -> loss.item() [sync] -> Jaccard2(...) [sync inside the
+``if y.sum(0)==0``].  Here loss and metric stay on the device (corrif_b200.metrics resolves the
+empty-mask branch in the kernel) and are read once per epoch.
+
+Data parallelism (new: the reference is single-device).  One process per GPU; a rank runs its own
+micro-batches (the semantic micro-batch must not be split: train-mode BatchNorm and the inter_attn
+batch-mixing view couple the samples of a batch) and gradients are averaged with
+bucketed all-reduces launched from autograd hooks while the backward is still running.  Gradients
+live in one flat buffer per bucket (``param.grad`` are views), so there is no copy-in/copy-out.
+The parameters that never receive a gradient in MMVit4 (18 tensors: ``*_decode_conv``, ``seg_*``,
+``fusion5``) are discovered on the first step and left out of the buckets.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class GradBuckets:
+    """Flat gradient storage + overlapped all-reduce.  Works with any backend (gloo on CPU for tests,
+    NCCL over NVLink on the GPUs)."""
+
+    def __init__(self, params: List[nn.Parameter], bucket_bytes: int = 64 << 20,
+                 process_group=None):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.bucket_bytes = bucket_bytes
+        self.buckets: List[dict] = []
+        self._built = False
+        self._handles = []
+        self._sync_now = True
+        self._hooks = []
+
+    # -- first step: plain autograd, then find out who actually got a gradient --------------------
+    def build(self):
+        live = [p for p in self.params if p.grad is not None]
+        self.skipped = [p for p in self.params if p.grad is None]
+        order = list(reversed(live))                       # backward produces the last layers first
+        cur, cur_bytes = [], 0
+        groups = []
+        for p in order:
+            cur.append(p)
+            cur_bytes += p.numel() * p.element_size()
+            if cur_bytes >= self.bucket_bytes:
+                groups.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            groups.append(cur)
+        for gi, grp in enumerate(groups):
+            n = sum(p.numel() for p in grp)
+            flat = torch.zeros(n, dtype=grp[0].dtype, device=grp[0].device)
+            off = 0
+            for p in grp:
+                view = flat[off:off + p.numel()].view_as(p)
+                view.copy_(p.grad)
+                p.grad = view                               # autograd accumulates in place from now on
+                off += p.numel()
+            b = {"flat": flat, "params": grp, "pending": len(grp), "index": gi}
+            self.buckets.append(b)
+            for p in grp:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
+        self._built = True
+
+    def _make_hook(self, bucket):
+        def hook(_param):
+            if not self._sync_now:
+                return
+            bucket["pending"] -= 1
+            if bucket["pending"] == 0:
+                self._launch(bucket)
+        return hook
+
+    def _launch(self, bucket):
+        if self.world > 1:
+            self._handles.append(dist.all_reduce(bucket["flat"], group=self.group, async_op=True))
+
+    # -- per step ---------------------------------------------------------------------------------
+    def zero(self):
+        if self._built:
+            for b in self.buckets:
+                b["flat"].zero_()
+                b["pending"] = len(b["params"])
+            for p in self.skipped:
+                p.grad = None
+        else:
+            for p in self.params:
+                p.grad = None
+
+    def set_sync(self, sync: bool):
+        """False while accumulating micro-batches; True on the last one (hooks then all-reduce)."""
+        self._sync_now = sync
+
+    def finish(self, divisor: float = 1.0):
+        """Wait for the in-flight all-reduces and average.  On the first step (buckets not built yet)
+        do one blocking all-reduce per gradient, then build the buckets."""
+        if not self._built:
+            if self.world > 1:
+                for p in self.params:
+                    if p.grad is not None:
+                        dist.all_reduce(p.grad, group=self.group)
+            scale = 1.0 / (self.world * divisor)
+            if scale != 1.0:
+                for p in self.params:
+                    if p.grad is not None:
+                        p.grad.mul_(scale)
+            self.build()
+            return
+        for h in self._handles:
+            h.wait()
+        self._handles.clear()
+        scale = 1.0 / (self.world * divisor)
+        if scale != 1.0:
+            for b in self.buckets:
+                b["flat"].mul_(scale)
+
+    def grad_bytes(self) -> int:
+        return sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets)
+
+
+def broadcast_module(model: nn.Module, src: int = 0, process_group=None):
+    """Make every rank start from rank ``src``'s parameters and buffers (as DDP does at construction)."""
+    if not dist.is_initialized() or dist.get_world_size(process_group) == 1:
+        return
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src=src, group=process_group)
+
+
+class TrainStep:
+    """One optimisation step over ``len(micro_batches)`` local micro-batches (gradient accumulation)
+    followed by the data-parallel gradient average and ``optim.step()``.
+
+    Returns device tensors only: ``loss`` (mean over local micro-batches), ``jaccard_sum``
+    (sum of Jaccard2 * batchLoad, F4_TRAIN.py:70-71) and ``pixels`` (sum of batchLoad)."""
+
+    def __init__(self, model: nn.Module, optim: torch.optim.Optimizer, lim: int = 224,
+                 jaccard_fn=None, process_group=None, bucket_bytes: int = 64 << 20):
+        self.model, self.optim, self.lim = model, optim, lim
+        self.buckets = GradBuckets(list(model.parameters()), bucket_bytes, process_group)
+        if jaccard_fn is None:
+            from .metrics import Jaccard2 as jaccard_fn
+        self.jaccard_fn = jaccard_fn
+
+    def __call__(self, micro_batches) -> Dict[str, torch.Tensor]:
+        if isinstance(micro_batches, tuple):
+            micro_batches = [micro_batches]
+        self.buckets.zero()
+        n = len(micro_batches)
+        loss_acc, jac_acc, pixels = None, None, 0
+        for k, (images, masks) in enumerate(micro_batches):
+            self.buckets.set_sync(k == n - 1)
+            outputs = self.model(images)
+            loss = F.binary_cross_entropy_with_logits(outputs, masks)        # F4_TRAIN.py:58-60
+            loss.backward()                                                  # :61
+            with torch.no_grad():
+                load = masks.shape[0] * self.lim * self.lim                  # :65
+                jac = self.jaccard_fn(masks[:, 0].reshape(load, 1), outputs.detach()[:, 0].reshape(load, 1)) * load
+                loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
+                jac_acc = jac if jac_acc is None else jac_acc + jac
+                pixels += load
+        self.buckets.finish(divisor=float(n))
+        self.optim.step()                                                    # :62
+        return {"loss": loss_acc / n, "jaccard_sum": jac_acc, "pixels": pixels}

@@ -100,6 +100,34 @@ def make_params(seed: int, modalities=MODALITIES, dtype=torch.float32):
     return out
 
 
+def make_full_model_state(seed: int, inventory: dict, dtype=torch.float32):
+    """Deterministic values for EVERY entry of MMVit4.state_dict() (``inventory`` = key -> shape, the
+    committed tests/golden/mmvit4_state_dict_inventory.json).  Hot-path keys reuse make_params."""
+    hot = make_params(seed, dtype=dtype)
+    out = {}
+    for name, shape in inventory.items():
+        if name in hot:
+            out[name] = hot[name]
+            continue
+        rng = np.random.default_rng([int(seed), zlib.crc32(name.encode())])
+        if name.endswith("num_batches_tracked"):
+            out[name] = torch.zeros((), dtype=torch.int64)
+            continue
+        if name.endswith("running_var"):
+            a = 1.0 + 0.1 * rng.random(shape)
+        elif name.endswith("running_mean"):
+            a = 0.05 * rng.standard_normal(shape)
+        elif ("bn" in name.split(".")[-2] or "downsample.1" in name) and name.endswith(".weight"):
+            a = 1.0 + 0.1 * rng.standard_normal(shape)
+        elif name.endswith(".bias"):
+            a = 0.05 * rng.standard_normal(shape)
+        else:
+            fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else int(shape[0])
+            a = rng.standard_normal(shape) * math.sqrt(2.0 / fan_in)
+        out[name] = torch.from_numpy(np.asarray(a, dtype=np.float64)).to(dtype)
+    return out
+
+
 def make_inputs(seed: int, batch: int, modalities=MODALITIES, dtype=torch.float32):
     """x6 per modality [B,64,8,8,8], fused_x6 [B,192,8,8,8] and the upstream gradient
     [B,192,8,8,8] (SURVEY.md section 8d synthetic inputs)."""

@@ -217,3 +217,65 @@ if __name__ == "__main__":
     make_loss_golden()
     make_inter_attn_golden()
     make_block_golden()
+
+
+def make_state_dict_inventory():
+    """Key -> shape of the reference MMVit4.state_dict() (1140 entries): the drop-in must match it."""
+    import json
+    torch.manual_seed(0)
+    m = ref_mmvit4.MMVit4(num_cls=1)
+    inv = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(HERE, "mmvit4_state_dict_inventory.json"), "w") as f:
+        json.dump(inv, f, indent=0, sort_keys=True)
+    n_param = sum(p.numel() for p in m.parameters())
+    print("state_dict inventory: %d entries, %d parameters" % (len(inv), n_param))
+
+
+FULL_GRAD_KEYS = (
+    "RGB_encoder.e1_c1.weight", "NIR_encoder.e3.1.conv2.weight", "SWIR_encoder.conv6.weight",
+    "SWIR_encoder.e5.2.bn3.weight", "fusion1.conv.weight", "fusion6.conv.bias", "RGB_encode_conv.weight",
+    "NIR_pos", "multimodal_transformer.cross_attention_list.0.fn.fn.qkv.weight",
+    "RGB_transformer.cross_ffn_list.0.fn.fn.net.0.weight", "qkv_SWIR.weight",
+    "multimodal_decode_conv.weight", "decoder_fuse.RFM5.fusion_layer.1.conv.weight",
+    "decoder_fuse.d4_c2.conv.weight", "decoder_fuse.d1_c2.conv.weight", "decoder_fuse.final_conv.weight",
+)
+
+
+def make_full_model_golden():
+    """One full MMVit4 train-step forward/backward (F4_TRAIN.py:57-61) on a tiny batch, dropout off:
+    output, loss, gradient norms of selected tensors and the list of parameters that get no gradient.
+    Weights/inputs come from seeds (oracle.make_full_model_state), nothing large is stored."""
+    import json
+    inv = json.load(open(os.path.join(HERE, "mmvit4_state_dict_inventory.json")))
+    torch.manual_seed(0)
+    m = ref_mmvit4.MMVit4(num_cls=1)
+    m.load_state_dict(O.make_full_model_state(2024, inv), strict=True)
+    for mod in m.modules():
+        if isinstance(mod, nn.Dropout):
+            mod.p = 0.0
+    m.train()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 3, 64, 64, generator=g)
+    masks = (torch.rand(2, 1, 1, 224, 224, generator=g) < 0.3).float().repeat(1, 3, 1, 1, 1)
+    y = m(x)
+    loss = nn.BCEWithLogitsLoss()(y, masks)
+    loss.backward()
+    named = dict(m.named_parameters())
+    rec = {"x": x.numpy(), "masks": masks[:, :1].numpy(), "y": y.detach().numpy(),
+           "loss": np.array(loss.item())}
+    for k in FULL_GRAD_KEYS:
+        gk = named[k].grad.reshape(-1).double().numpy()
+        rec[f"gnorm/{k}"] = np.array(np.linalg.norm(gk))
+        rec[f"gsample/{k}"] = gk[sample_idx(gk.size)].astype(np.float32)
+    nograd = sorted(k for k, p in named.items() if p.grad is None)
+    rec["nograd"] = np.array(nograd)
+    jac = ref_jac.Jaccard2(masks[:, 0].reshape(-1, 1), y.detach()[:, 0].reshape(-1, 1))
+    rec["jaccard2"] = jac.numpy()
+    np.savez_compressed(os.path.join(HERE, "mmvit4_full_small.npz"), **rec)
+    print("full model golden: loss %.6f  y mean %.6f  no-grad tensors %d  jaccard2 %.6f" % (
+        loss.item(), y.mean().item(), len(nograd), jac.item()))
+
+
+if __name__ == "__main__" and os.environ.get("GOLDEN_EXTRA", "1") == "1":
+    make_state_dict_inventory()
+    make_full_model_golden()

@@ -1,0 +1,105 @@
+"""End-to-end parity of the drop-in MMVit4 train step (reference F4_TRAIN.py:52-71) on the B200
+against a fixture produced by the unmodified reference (make_golden.make_full_model_golden):
+sigmoid output, BCE loss, gradient norms/samples of 16 tensors spread over encoders, fusion block and
+decoder, the set of gradient-less parameters, Jaccard2.
+
+Encoders/decoder run on stock PyTorch (cuDNN, TF32 convs disabled here so they are a clean fp32
+comparison); the fusion block runs on libcorrif_b200.  Tolerances: precision="fp32" isolates wiring
+errors (1e-4: cuDNN fp32 vs CPU fp32 through ~160 BatchNorm layers), precision="tf32" is the hot path.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2, GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+DROPIN = os.path.join(ROOT, "corrifnet-correlation-aware-interactive-fusion-multimodal-learning-for-multispectral-images_b200", "dropin")
+
+
+def _sample_idx(n, k=2048):
+    return np.arange(n) if n <= k else np.linspace(0, n - 1, k).astype(np.int64)
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    sys.path.insert(0, DROPIN)
+    for name in ("mmvit4", "F4_TRAIN", "F5_JACCARD2", "F3_DATASET"):
+        sys.modules.pop(name, None)
+    import mmvit4
+    import F4_TRAIN
+    import F3_DATASET
+    yield mmvit4, F4_TRAIN, F3_DATASET
+    sys.path.remove(DROPIN)
+    for name in ("mmvit4", "F4_TRAIN", "F5_JACCARD2", "F3_DATASET"):
+        sys.modules.pop(name, None)
+
+
+@pytest.mark.parametrize("precision,tol_y,tol_g", [("fp32", 2e-4, 2e-3), ("tf32", 1e-3, 2e-2)])
+def test_full_model_train_step_matches_reference(dropin, precision, tol_y, tol_g):
+    from oracle import corrif_oracle as O
+    from corrif_b200 import metrics
+    mmvit4 = dropin[0]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(GOLDEN, "mmvit4_full_small.npz"))
+    inv = json.load(open(os.path.join(GOLDEN, "mmvit4_state_dict_inventory.json")))
+    model = mmvit4.MMVit4(num_cls=1, dropout_rate=0.0, precision=precision)
+    model.load_state_dict(O.make_full_model_state(2024, inv), strict=True)
+    model = model.to(dev).train()
+    x = torch.from_numpy(g["x"]).to(dev)
+    masks = torch.from_numpy(g["masks"]).to(dev).repeat(1, 3, 1, 1, 1)
+    y = model(x)
+    loss = torch.nn.BCEWithLogitsLoss()(y, masks)
+    loss.backward()
+    e_y = rel_l2(y.detach().cpu().numpy(), g["y"])
+    print(f"\n[full model {precision}] y rel err {e_y:.2e}  loss {loss.item():.6f} vs {float(g['loss']):.6f}")
+    assert e_y < tol_y
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * max(1.0, tol_y / 2e-4)
+    named = dict(model.named_parameters())
+    assert sorted(k for k, p in named.items() if p.grad is None) == sorted(g["nograd"].tolist())
+    worst = {}
+    for key in [k[6:] for k in g.files if k.startswith("gnorm/")]:
+        gk = named[key].grad.reshape(-1).double().cpu().numpy()
+        worst[key] = rel_l2(gk[_sample_idx(gk.size)], g[f"gsample/{key}"])
+    print("   grads:", ", ".join(f"{k.split('.')[0]}..{k.split('.')[-2]}:{v:.1e}" for k, v in worst.items()))
+    for k, v in worst.items():
+        assert v < tol_g, (k, v)
+    load = masks.shape[0] * 224 * 224
+    jac = metrics.Jaccard2(masks[:, 0].reshape(load, 1), y.detach()[:, 0].reshape(load, 1))
+    assert abs(jac.item() - float(g["jaccard2"][0])) < 1e-4
+
+
+def test_train_model_entry_point_runs_and_writes_reference_files(dropin, tmp_path):
+    """F4_TRAIN.train_model with the reference's 19-argument signature: one epoch, two batches, plus
+    validate; checks the text outputs and the two checkpoints (F4_TRAIN.py:74-86)."""
+    import io
+    mmvit4, F4_TRAIN, F3_DATASET = dropin
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = mmvit4.MMVit4(num_cls=1).to(dev)
+    images = torch.randn(4, 3, 3, 64, 64)
+    masks = (torch.rand(4, 1, 1, 224, 224) < 0.3).float().repeat(1, 3, 1, 1, 1)
+    dl = torch.utils.data.DataLoader(F3_DATASET.satellitedata(images, masks), batch_size=2, shuffle=False)
+    optim = torch.optim.Adam(model.parameters(), 1e-4)
+    sched = torch.optim.lr_scheduler.StepLR(optim, 5, 0.9)
+    files = [io.StringIO() for _ in range(6)]
+    lrF, trF, traF, treF, vaF, vaaF = files
+    w_before = dict(model.named_parameters())["RGB_transformer.cross_attention_list.0.fn.fn.qkv.weight"].detach().clone()
+    F4_TRAIN.train_model(1, "BCEWithLogitsLoss", "BCEWithLogitsLoss", "Jaccard", model, sched, lrF, dl, optim,
+                         224, trF, traF, treF, dl, vaF, vaaF, str(tmp_path), 0, "MMVit4")
+    w_after = dict(model.named_parameters())["RGB_transformer.cross_attention_list.0.fn.fn.qkv.weight"].detach()
+    assert not torch.equal(w_before, w_after)                       # the fusion block was trained
+    assert 0.3 < float(trF.getvalue().strip()) < 1.5                # BCE-on-probabilities range
+    assert 0.0 <= float(traF.getvalue().strip()) <= 1.0
+    assert treF.getvalue().strip() == "0"
+    assert 0.0 <= float(vaaF.getvalue().strip()) <= 1.0
+    assert "Training loss:" in lrF.getvalue() and "Validation accuracy:" in lrF.getvalue()
+    sd = torch.load(os.path.join(str(tmp_path), "Finaliremmodel0.pt"))
+    assert len(sd) == 1140 and os.path.exists(os.path.join(str(tmp_path), "iremmodel0.pt"))
