@@ -241,10 +241,7 @@ FULL_GRAD_KEYS = (
 )
 
 
-def make_full_model_golden():
-    """One full MMVit4 train-step forward/backward (F4_TRAIN.py:57-61) on a tiny batch, dropout off:
-    output, loss, gradient norms of selected tensors and the list of parameters that get no gradient.
-    Weights/inputs come from seeds (oracle.make_full_model_state), nothing large is stored."""
+def _full_model_run(dtype):
     import json
     inv = json.load(open(os.path.join(HERE, "mmvit4_state_dict_inventory.json")))
     torch.manual_seed(0)
@@ -253,27 +250,40 @@ def make_full_model_golden():
     for mod in m.modules():
         if isinstance(mod, nn.Dropout):
             mod.p = 0.0
-    m.train()
+    m = m.to(dtype).train()
     g = torch.Generator().manual_seed(3)
     x = torch.randn(2, 3, 3, 64, 64, generator=g)
     masks = (torch.rand(2, 1, 1, 224, 224, generator=g) < 0.3).float().repeat(1, 3, 1, 1, 1)
-    y = m(x)
-    loss = nn.BCEWithLogitsLoss()(y, masks)
+    y = m(x.to(dtype))
+    loss = nn.BCEWithLogitsLoss()(y, masks.to(dtype))
     loss.backward()
     named = dict(m.named_parameters())
-    rec = {"x": x.numpy(), "masks": masks[:, :1].numpy(), "y": y.detach().numpy(),
-           "loss": np.array(loss.item())}
-    for k in FULL_GRAD_KEYS:
-        gk = named[k].grad.reshape(-1).double().numpy()
-        rec[f"gnorm/{k}"] = np.array(np.linalg.norm(gk))
-        rec[f"gsample/{k}"] = gk[sample_idx(gk.size)].astype(np.float32)
+    grads = {k: named[k].grad.reshape(-1).double().numpy() for k in FULL_GRAD_KEYS}
     nograd = sorted(k for k, p in named.items() if p.grad is None)
+    return x, masks, y.detach(), loss.item(), grads, nograd
+
+
+def make_full_model_golden():
+    """One full MMVit4 train-step forward/backward (F4_TRAIN.py:57-61) on a tiny batch, dropout off.
+    Ground truth = the reference run in fp64; the reference's own fp32 run is compared against it and
+    the per-tensor spread stored, because this decoder is ill-conditioned in fp32 (its gradients move
+    by 1-4e-2 between fp32 and fp64) and a kernel cannot be held to more than the reference itself
+    delivers.  Weights/inputs come from seeds (oracle.make_full_model_state); nothing large is stored."""
+    x, masks, y64, loss64, g64, nograd = _full_model_run(torch.float64)
+    _, _, y32, loss32, g32, _ = _full_model_run(torch.float32)
+    rec = {"x": x.numpy(), "masks": masks[:, :1].numpy(), "y": y64.float().numpy(), "loss": np.array(loss64),
+           "ref_fp32_relerr/y": np.array(float((y32.double() - y64).norm() / y64.norm())),
+           "ref_fp32_loss": np.array(loss32)}
+    for k in FULL_GRAD_KEYS:
+        rec[f"gnorm/{k}"] = np.array(np.linalg.norm(g64[k]))
+        rec[f"gsample/{k}"] = g64[k][sample_idx(g64[k].size)].astype(np.float32)
+        rec[f"ref_fp32_relerr/{k}"] = np.array(np.linalg.norm(g32[k] - g64[k]) / np.linalg.norm(g64[k]))
     rec["nograd"] = np.array(nograd)
-    jac = ref_jac.Jaccard2(masks[:, 0].reshape(-1, 1), y.detach()[:, 0].reshape(-1, 1))
+    jac = ref_jac.Jaccard2(masks[:, 0].reshape(-1, 1), y64.float()[:, 0].reshape(-1, 1))
     rec["jaccard2"] = jac.numpy()
     np.savez_compressed(os.path.join(HERE, "mmvit4_full_small.npz"), **rec)
-    print("full model golden: loss %.6f  y mean %.6f  no-grad tensors %d  jaccard2 %.6f" % (
-        loss.item(), y.mean().item(), len(nograd), jac.item()))
+    print("full model golden (fp64): loss %.6f  no-grad tensors %d  jaccard2 %.6f  worst ref fp32 grad spread %.2e" % (
+        loss64, len(nograd), jac.item(), max(float(rec[f"ref_fp32_relerr/{k}"]) for k in FULL_GRAD_KEYS)))
 
 
 if __name__ == "__main__" and os.environ.get("GOLDEN_EXTRA", "1") == "1":

@@ -4,8 +4,15 @@ sigmoid output, BCE loss, gradient norms/samples of 16 tensors spread over encod
 decoder, the set of gradient-less parameters, Jaccard2.
 
 Encoders/decoder run on stock PyTorch (cuDNN, TF32 convs disabled here so they are a clean fp32
-comparison); the fusion block runs on libcorrif_b200.  Tolerances: precision="fp32" isolates wiring
-errors (1e-4: cuDNN fp32 vs CPU fp32 through ~160 BatchNorm layers), precision="tf32" is the hot path.
+comparison); the fusion block runs on libcorrif_b200.
+
+Tolerances.  Output: 2e-4 (fp32 mode) / 1e-3 (tf32 hot path).  Gradients: the fixture holds the
+reference's fp64 gradients AND how far the reference's own fp32 run is from them (1e-2 .. 4e-2 per
+tensor: the InstanceNorm chain of the decoder at 64^3/128^3 is ill-conditioned in fp32, it amplifies
+any perturbation ~30x).  fp32 mode must stay within 3x that spread (same arithmetic, different
+summation order on the GPU); the tf32 hot path within 0.15 (its 2e-3 block-level gradient error
+times the same amplification).  fusion-block-only gradient parity at 1e-6 / 2.4e-3 is pinned in
+test_gpu_fusion.py, where the upstream gradient is well conditioned.
 """
 import json
 import os
@@ -40,7 +47,7 @@ def dropin():
         sys.modules.pop(name, None)
 
 
-@pytest.mark.parametrize("precision,tol_y,tol_g", [("fp32", 2e-4, 2e-3), ("tf32", 1e-3, 2e-2)])
+@pytest.mark.parametrize("precision,tol_y,tol_g", [("fp32", 2e-4, None), ("tf32", 1e-3, 0.15)])
 def test_full_model_train_step_matches_reference(dropin, precision, tol_y, tol_g):
     from oracle import corrif_oracle as O
     from corrif_b200 import metrics
@@ -68,9 +75,10 @@ def test_full_model_train_step_matches_reference(dropin, precision, tol_y, tol_g
     for key in [k[6:] for k in g.files if k.startswith("gnorm/")]:
         gk = named[key].grad.reshape(-1).double().cpu().numpy()
         worst[key] = rel_l2(gk[_sample_idx(gk.size)], g[f"gsample/{key}"])
-    print("   grads:", ", ".join(f"{k.split('.')[0]}..{k.split('.')[-2]}:{v:.1e}" for k, v in worst.items()))
+    print("   grads:", ", ".join(f"{k[:14]}..{k[-12:]}:{v:.1e}" for k, v in worst.items()))
     for k, v in worst.items():
-        assert v < tol_g, (k, v)
+        bound = tol_g if tol_g is not None else max(3.0 * float(g[f"ref_fp32_relerr/{k}"]), 1e-4)
+        assert v < bound, (k, v, bound)
     load = masks.shape[0] * 224 * 224
     jac = metrics.Jaccard2(masks[:, 0].reshape(load, 1), y.detach()[:, 0].reshape(load, 1))
     assert abs(jac.item() - float(g["jaccard2"][0])) < 1e-4
