@@ -141,6 +141,9 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
+    # keep stdout clean for the single JSON line (NCCL prints its version banner to stdout)
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -304,7 +307,9 @@ def run_ours(args):
                          "sample": "oracle port of mmvit4.py:456-529 (torch CPU fp32, dropout masks drawn per step), "
                                    "batch %d, 3 steps after 1 warm-up, %.2f s/step" % (cpu_b, cpu_t)},
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

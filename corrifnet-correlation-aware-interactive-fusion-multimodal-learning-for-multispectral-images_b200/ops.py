@@ -47,20 +47,25 @@ class profile:
         global _prof
         _prof = None
 
+    def details(self):
+        """[(class, detail string, ms, work)] per launch, in launch order."""
+        torch.cuda.synchronize()
+        return [(r[0], r[4] if len(r) > 4 else "", r[2].elapsed_time(r[3]), r[1]) for r in self.records]
+
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for cls, work, e0, e1 in self.records:
+        for cls, work, e0, e1, *_ in self.records:
             n, ms, w = out.get(cls, (0, 0.0, 0.0))
             out[cls] = (n + 1, ms + e0.elapsed_time(e1), w + work)
         return out
 
 
 class _Rec:
-    __slots__ = ("cls", "work", "e0")
+    __slots__ = ("cls", "work", "e0", "detail")
 
-    def __init__(self, cls, work):
-        self.cls, self.work = cls, work
+    def __init__(self, cls, work, detail=""):
+        self.cls, self.work, self.detail = cls, work, detail
 
     def __enter__(self):
         self.e0 = torch.cuda.Event(enable_timing=True)
@@ -70,7 +75,7 @@ class _Rec:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         if _prof is not None:
-            _prof.append((self.cls, self.work, self.e0, e1))
+            _prof.append((self.cls, self.work, self.e0, e1, self.detail))
 
 
 class _NoRec:
@@ -84,8 +89,8 @@ class _NoRec:
 _NOREC = _NoRec()
 
 
-def _rec(cls: str, work: float):
-    return _NOREC if _prof is None else _Rec(cls, work)
+def _rec(cls: str, work: float, detail: str = ""):
+    return _NOREC if _prof is None else _Rec(cls, work, detail)
 
 
 def _stream() -> int:
@@ -135,7 +140,9 @@ def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K
     g.split_k, g.epilogue, g.precision, g.alpha = split_k, epilogue, precision, alpha
     g.flags = GEMM_ROUND_TF32 if round_out else 0
     cls = ("gemm_tf32" if precision == GEMM_TF32 else "gemm_fp32") + ("/" + tag if tag else "")
-    with _rec(cls, 2.0 * M * N * K * batch[0] * batch[1]):
+    det = "" if _prof is None else "M%d N%d K%d a%d b%d epi%d split%d z%d" % (
+        M, N, K, int(a_mn), int(b_mn), epilogue, split_k, batch[0] * batch[1])
+    with _rec(cls, 2.0 * M * N * K * batch[0] * batch[1], det):
         L.check(lib().corrif_gemm(C.byref(g), _stream()), "corrif_gemm")
     _count()
 
