@@ -10,7 +10,7 @@
 // Two kernels so that every tensor-core operand the threads have to write is K-major with
 // "thread = accumulator row":
 //   attn_bwd_dq : CTA owns a 128-row query tile (TMEM lane = q), loops over 64-key tiles:
-//                 S, dP -> dS (written to smem) -> dQ += dS . K_j       (K_j also staged MN-major)
+//                 S, dP -> dS (stored back to TMEM) -> dQ += dS . K_j   (K_j also staged MN-major)
 //   attn_bwd_dkv: CTA owns a 128-row key tile (TMEM lane = kv), loops over 64-query tiles and computes
 //                 the TRANSPOSED products S^T = K_j Q_i^T, dP^T = V_j dO_i^T directly, so P^T and dS^T
 //                 come out with kv as the row: dV += P^T . dO_i, dK += dS^T . Q_i  (Q_i, dO_i also MN-major)
@@ -114,14 +114,19 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// dQ kernel: S/dP double-buffered in TMEM, K/V tiles double-buffered in smem
+// dQ kernel.  S/dP double-buffered in TMEM; dS goes back to the tensor core THROUGH TMEM (tcgen05.st,
+// A-operand-in-TMEM MMA), which frees 32 KB of shared memory for a third K/V stage: with two stages a
+// stage was re-loaded (48 KB from L2) right before its next use and ~2500 cycles of TMA latency were
+// exposed on every tile (ncu: >50 % of stall samples in the two mbarrier waits).
 // ------------------------------------------------------------------------------------------------
 namespace dq {
-constexpr int OFF_Q = 0, OFF_DO = OFF_Q + TB * 256, OFF_DS = OFF_DO + TB * 256;
-constexpr int OFF_STAGE = OFF_DS + TB * TL * 4;
+constexpr int KV_STAGES = 3;
+constexpr int OFF_Q = 0, OFF_DO = OFF_Q + TB * 256;
+constexpr int OFF_STAGE = OFF_DO + TB * 256;
 constexpr int STAGE_BYTES = 3 * TL * 256;   // K (K-major), K (MN-major), V (K-major)
-constexpr int SMEM_BYTES = OFF_STAGE + 2 * STAGE_BYTES + 1024;
-constexpr uint32_t TMEM_COLS = 512;         // buffer u: S [128u, 128u+64) dP [128u+64, 128u+128); dQ [256,320)
+constexpr int SMEM_BYTES = OFF_STAGE + KV_STAGES * STAGE_BYTES + 1024;
+// TMEM columns: buffer u in {0,1}: S [128u, +64) dP [128u+64, +64); dQ [256,320); dS operand u: [320+64u, +64)
+constexpr uint32_t TMEM_COLS = 512;
 }  // namespace dq
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -130,10 +135,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const BwdArgs a) {
   using namespace dq;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t own_full, kv_full[2], kv_free[2], sdp_full[2], sdp_free[2], ds_full, ds_free, fin;
+  __shared__ __align__(8) uint64_t own_full, kv_full[KV_STAGES], kv_free[KV_STAGES], sdp_full[2], sdp_free[2],
+      ds_full[2], ds_free[2], fin;
   __shared__ uint32_t tmem_holder;
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = sb + OFF_Q, sDO = sb + OFF_DO, sDS = sb + OFF_DS;
+  const uint32_t sQ = sb + OFF_Q, sDO = sb + OFF_DO;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, bh = blockIdx.y;
   const int b = bh / a.H, h = bh % a.H, C = a.H * HD;
@@ -142,11 +148,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     mbar_init(&own_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1);
       mbar_init(&sdp_full[s], 1); mbar_init(&sdp_free[s], 256);
+      mbar_init(&ds_full[s], 256); mbar_init(&ds_free[s], 1);
     }
-    mbar_init(&ds_full, 256); mbar_init(&ds_free, 1); mbar_init(&fin, 1);
+    mbar_init(&fin, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_holder, TMEM_COLS);
@@ -154,15 +161,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_holder;
-  const uint32_t tDQ = tmem + 256;
+  const uint32_t tDQ = tmem + 256, tDS = tmem + 320;
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(&own_full, 2 * TB * 256);
     tma_tile(sQ, &tmQ, &own_full, h * HD, q_row0, TB);
     tma_tile(sDO, &tmDO, &own_full, h * HD, q_row0, TB);
     for (int j = 0; j < ntiles; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      const int s = j % KV_STAGES;
+      const uint32_t ph = (uint32_t)(j / KV_STAGES) & 1u;
       mbar_wait(&kv_free[s], ph ^ 1u);
       mbar_expect_tx(&kv_full[s], STAGE_BYTES);
       const uint32_t st = sb + OFF_STAGE + s * STAGE_BYTES;
@@ -175,11 +182,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t id_q = idesc_tf32(HD, false, true);    // [128 x 64] = dS . K (K MN-major)
     mbar_wait(&own_full, 0);
     auto issue_sdp = [&](int j) {
-      const int u = j & 1;
-      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-      const uint32_t st = sb + OFF_STAGE + u * STAGE_BYTES;
-      mbar_wait(&kv_full[u], ph);
-      mbar_wait(&sdp_free[u], ph ^ 1u);                        // element-wise done with buffer u (tile j-2)
+      const int u = j & 1, s = j % KV_STAGES;
+      const uint32_t st = sb + OFF_STAGE + s * STAGE_BYTES;
+      mbar_wait(&kv_full[s], (uint32_t)(j / KV_STAGES) & 1u);
+      mbar_wait(&sdp_free[u], ((uint32_t)(j >> 1) & 1u) ^ 1u);   // element-wise done with buffer u (tile j-2)
       tcgen05_fence_after();
       mma_headdim(tmem + 128 * u, sQ, TB, st, TL, id_s);                       // S  = Q  K_j^T
       mma_headdim(tmem + 128 * u + 64, sDO, TB, st + 2 * TL * 256, TL, id_s);  // dP = dO V_j^T
@@ -188,12 +194,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     issue_sdp(0);
     for (int j = 0; j < ntiles; ++j) {
       if (j + 1 < ntiles) issue_sdp(j + 1);                    // overlaps the element-wise work of tile j
-      const int u = j & 1;
-      mbar_wait(&ds_full, (uint32_t)j & 1u);
+      const int u = j & 1, s = j % KV_STAGES;
+      mbar_wait(&ds_full[u], (uint32_t)(j >> 1) & 1u);
       tcgen05_fence_after();
-      mma_tile64(tDQ, sDS, sb + OFF_STAGE + u * STAGE_BYTES + TL * 256, id_q, j > 0);   // dQ += dS K_j
-      tcgen05_commit(&ds_free);
-      tcgen05_commit(&kv_free[u]);
+      const uint32_t kmn = sb + OFF_STAGE + s * STAGE_BYTES + TL * 256;
+#pragma unroll
+      for (int t = 0; t < TL / 8; ++t)                          // dQ += dS(TMEM) . K_j
+        tcgen05_mma_tf32_ts(tDQ, tDS + 64 * u + 8 * t, smem_desc_mnmajor(kmn + t * 1024, TL * 128), id_q,
+                            (j > 0 || t > 0) ? 1u : 0u);
+      tcgen05_commit(&ds_free[u]);
+      tcgen05_commit(&kv_free[s]);
     }
     tcgen05_commit(&fin);
   } else if (warp >= 2) {
@@ -205,29 +215,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t rs[32], rp[32];
     for (int j = 0; j < ntiles; ++j) {
       const int u = j & 1;
+      const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
       const uint32_t bits = mrow ? mrow[j * 2 + g] : 0xffffffffu;
-      mbar_wait(&sdp_full[u], (uint32_t)(j >> 1) & 1u);
+      mbar_wait(&sdp_full[u], ph2);
       tcgen05_fence_after();
       tmem_ld32_nowait(tmem + 128 * u + lane_addr + g * 32, rs);
       tmem_ld32_nowait(tmem + 128 * u + 64 + lane_addr + g * 32, rp);
       tmem_wait_ld();
       tcgen05_fence_before();
       mbar_arrive(&sdp_free[u]);                               // S/dP buffer u may be refilled
-      mbar_wait(&ds_free, ((uint32_t)j & 1u) ^ 1u);            // dQ MMA of tile j-1 has read sDS
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 4 * q4 + e;
-          const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - lse);
-          const float dp = ((bits >> c) & 1u) ? __uint_as_float(rp[c]) * a.keep_scale : 0.f;
-          v[e] = round_tf32(p * (dp - dl) * a.scale);
-        }
-        st_swz(sDS, row, g * 8 + q4, make_float4(v[0], v[1], v[2], v[3]));
+      for (int c = 0; c < 32; ++c) {
+        const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - lse);
+        const float dp = ((bits >> c) & 1u) ? __uint_as_float(rp[c]) * a.keep_scale : 0.f;
+        rs[c] = __float_as_uint(round_tf32(p * (dp - dl) * a.scale));
       }
-      fence_proxy_async();
-      mbar_arrive(&ds_full);
+      mbar_wait(&ds_free[u], ph2 ^ 1u);                        // dQ MMA of tile j-2 has read dS buffer u
+      tcgen05_fence_after();
+      tmem_st32(tDS + 64 * u + lane_addr + g * 32, rs);
+      tcgen05_fence_before();
+      mbar_arrive(&ds_full[u]);
     }
     mbar_wait(&fin, 0);
     tcgen05_fence_after();
@@ -244,16 +251,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// dK / dV kernel
+// dK / dV kernel.  S^T/dP^T double-buffered in TMEM, P^T and dS^T handed to the tensor core through
+// TMEM, both query-tile images (K-major for S^T/dP^T, MN-major for dV/dK) double-buffered in smem.
 // ------------------------------------------------------------------------------------------------
 namespace dkv {
-constexpr int OFF_K = 0, OFF_V = OFF_K + TB * 256, OFF_PT = OFF_V + TB * 256, OFF_DST = OFF_PT + TB * TL * 4;
-constexpr int OFF_QK = OFF_DST + TB * TL * 4;       // Q_i  K-major
-constexpr int OFF_DOK = OFF_QK + TL * 256;          // dO_i K-major
-constexpr int OFF_QMN = OFF_DOK + TL * 256;         // Q_i  MN-major
-constexpr int OFF_DOMN = OFF_QMN + TL * 256;        // dO_i MN-major
-constexpr int SMEM_BYTES = OFF_DOMN + TL * 256 + 1024;
-constexpr uint32_t TMEM_COLS = 256;                 // S^T [0,64) dP^T [64,128) dV [128,192) dK [192,256)
+constexpr int OFF_K = 0, OFF_V = OFF_K + TB * 256;
+constexpr int OFF_KM = OFF_V + TB * 256;            // 2 stages x {Q_i K-major, dO_i K-major}
+constexpr int KM_BYTES = 2 * TL * 256;
+constexpr int OFF_MN = OFF_KM + 2 * KM_BYTES;       // 2 stages x {Q_i MN-major, dO_i MN-major}
+constexpr int MN_BYTES = 2 * TL * 256;
+constexpr int SMEM_BYTES = OFF_MN + 2 * MN_BYTES + 1024;
+// TMEM columns: buffer u: S^T [128u,+64) dP^T [128u+64,+64); dV [256,320) dK [320,384);
+//               P^T operand [384,448); dS^T operand [448,512)
+constexpr uint32_t TMEM_COLS = 512;
 }  // namespace dkv
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -265,13 +275,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
                     const BwdArgs a) {
   using namespace dkv;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t own_full, km_full, km_free, mn_full, mn_free, st_full, st_free, pds_full, pds_free, fin;
+  __shared__ __align__(8) uint64_t own_full, km_full[2], km_free[2], mn_full[2], mn_free[2], st_full[2], st_free[2],
+      pds_full, pds_free, fin;
   __shared__ uint32_t tmem_holder;
   __shared__ float s_lse[2][TL], s_delta[2][TL];
   __shared__ uint32_t s_bits[2][TL][4];              // keep bits of (query c, key word w) for this tile
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = sb + OFF_K, sV = sb + OFF_V, sPT = sb + OFF_PT, sDST = sb + OFF_DST;
-  const uint32_t sQK = sb + OFF_QK, sDOK = sb + OFF_DOK, sQMN = sb + OFF_QMN, sDOMN = sb + OFF_DOMN;
+  const uint32_t sK = sb + OFF_K, sV = sb + OFF_V;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, bh = blockIdx.y;
   const int b = bh / a.H, h = bh % a.H, C = a.H * HD;
@@ -279,9 +289,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
   const int ntiles = a.N / TL;
 
   if (warp == 0 && lane == 0) {
-    mbar_init(&own_full, 1); mbar_init(&km_full, 1); mbar_init(&km_free, 1); mbar_init(&mn_full, 1);
-    mbar_init(&mn_free, 1); mbar_init(&st_full, 1); mbar_init(&st_free, 256); mbar_init(&pds_full, 256);
-    mbar_init(&pds_free, 1); mbar_init(&fin, 1);
+    mbar_init(&own_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&km_full[s], 1); mbar_init(&km_free[s], 1); mbar_init(&mn_full[s], 1); mbar_init(&mn_free[s], 1);
+      mbar_init(&st_full[s], 1); mbar_init(&st_free[s], 256);
+    }
+    mbar_init(&pds_full, 256); mbar_init(&pds_free, 1); mbar_init(&fin, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_holder, TMEM_COLS);
@@ -289,42 +302,57 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_holder;
-  const uint32_t tST = tmem, tDPT = tmem + 64, tDV = tmem + 128, tDK = tmem + 192;
+  const uint32_t tDV = tmem + 256, tDK = tmem + 320, tPT = tmem + 384, tDST = tmem + 448;
 
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(&own_full, 2 * TB * 256);
     tma_tile(sK, &tmKVk, &own_full, C + h * HD, kv_row0, TB);
     tma_tile(sV, &tmKVk, &own_full, 2 * C + h * HD, kv_row0, TB);
     for (int i = 0; i < ntiles; ++i) {
-      const uint32_t ph = (uint32_t)i & 1u;
-      mbar_wait(&km_free, ph ^ 1u);
-      mbar_expect_tx(&km_full, 2 * TL * 256);
-      tma_tile(sQK, &tmQk, &km_full, h * HD, q_base + i * TL, TL);
-      tma_tile(sDOK, &tmDOk, &km_full, h * HD, q_base + i * TL, TL);
-      mbar_wait(&mn_free, ph ^ 1u);
-      mbar_expect_tx(&mn_full, 2 * TL * 256);
-      tma_tile(sQMN, &tmQmn, &mn_full, h * HD, q_base + i * TL, TL);
-      tma_tile(sDOMN, &tmDOmn, &mn_full, h * HD, q_base + i * TL, TL);
+      const int s = i & 1;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      mbar_wait(&km_free[s], ph ^ 1u);
+      mbar_expect_tx(&km_full[s], KM_BYTES);
+      tma_tile(sb + OFF_KM + s * KM_BYTES, &tmQk, &km_full[s], h * HD, q_base + i * TL, TL);
+      tma_tile(sb + OFF_KM + s * KM_BYTES + TL * 256, &tmDOk, &km_full[s], h * HD, q_base + i * TL, TL);
+      mbar_wait(&mn_free[s], ph ^ 1u);
+      mbar_expect_tx(&mn_full[s], MN_BYTES);
+      tma_tile(sb + OFF_MN + s * MN_BYTES, &tmQmn, &mn_full[s], h * HD, q_base + i * TL, TL);
+      tma_tile(sb + OFF_MN + s * MN_BYTES + TL * 256, &tmDOmn, &mn_full[s], h * HD, q_base + i * TL, TL);
     }
   } else if (warp == 1 && lane == 0) {
     constexpr uint32_t id_s = idesc_tf32(TL, false, false);
     constexpr uint32_t id_g = idesc_tf32(HD, false, true);
     mbar_wait(&own_full, 0);
+    auto issue_st = [&](int i) {
+      const int u = i & 1;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const uint32_t km = sb + OFF_KM + u * KM_BYTES;
+      mbar_wait(&km_full[u], ph);
+      mbar_wait(&st_free[u], ph ^ 1u);
+      tcgen05_fence_after();
+      mma_headdim(tmem + 128 * u, sK, TB, km, TL, id_s);                   // S^T  = K_j Q_i^T
+      mma_headdim(tmem + 128 * u + 64, sV, TB, km + TL * 256, TL, id_s);   // dP^T = V_j dO_i^T
+      tcgen05_commit(&km_free[u]);
+      tcgen05_commit(&st_full[u]);
+    };
+    issue_st(0);
     for (int i = 0; i < ntiles; ++i) {
-      const uint32_t ph = (uint32_t)i & 1u;
-      mbar_wait(&km_full, ph);
-      mbar_wait(&st_free, ph ^ 1u);
+      if (i + 1 < ntiles) issue_st(i + 1);
+      const int s = i & 1;
+      mbar_wait(&pds_full, (uint32_t)i & 1u);
+      mbar_wait(&mn_full[s], (uint32_t)(i >> 1) & 1u);
       tcgen05_fence_after();
-      mma_headdim(tST, sK, TB, sQK, TL, id_s);      // S^T  = K_j Q_i^T
-      mma_headdim(tDPT, sV, TB, sDOK, TL, id_s);    // dP^T = V_j dO_i^T
-      tcgen05_commit(&km_free);
-      tcgen05_commit(&st_full);
-      mbar_wait(&pds_full, ph);
-      mbar_wait(&mn_full, ph);
-      tcgen05_fence_after();
-      mma_tile64(tDV, sPT, sDOMN, id_g, i > 0);     // dV += P^T  dO_i
-      mma_tile64(tDK, sDST, sQMN, id_g, i > 0);     // dK += dS^T Q_i
-      tcgen05_commit(&mn_free);
+      const uint32_t mn = sb + OFF_MN + s * MN_BYTES;
+#pragma unroll
+      for (int t = 0; t < TL / 8; ++t)                                      // dV += P^T(TMEM)  dO_i
+        tcgen05_mma_tf32_ts(tDV, tPT + 8 * t, smem_desc_mnmajor(mn + TL * 256 + t * 1024, TL * 128), id_g,
+                            (i > 0 || t > 0) ? 1u : 0u);
+#pragma unroll
+      for (int t = 0; t < TL / 8; ++t)                                      // dK += dS^T(TMEM) Q_i
+        tcgen05_mma_tf32_ts(tDK, tDST + 8 * t, smem_desc_mnmajor(mn + t * 1024, TL * 128), id_g,
+                            (i > 0 || t > 0) ? 1u : 0u);
+      tcgen05_commit(&mn_free[s]);
       tcgen05_commit(&pds_free);
     }
     tcgen05_commit(&fin);
@@ -335,39 +363,37 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
     const int words = a.N / 32;
     uint32_t rs[32], rp[32];
     for (int i = 0; i < ntiles; ++i) {
-      const uint32_t ph = (uint32_t)i & 1u;
-      const int bf = i & 1;
+      const int u = i & 1;
+      const uint32_t ph2 = (uint32_t)(i >> 1) & 1u;
       // per-column statistics and keep bits of this query tile -> smem (double-buffered by tile parity)
-      if (t256 < TL) s_lse[bf][t256] = a.lse[(int64_t)bh * a.N + i * TL + t256];
-      else if (t256 < 2 * TL) s_delta[bf][t256 - TL] = a.delta[(int64_t)bh * a.N + i * TL + (t256 - TL)];
+      if (t256 < TL) s_lse[u][t256] = a.lse[(int64_t)bh * a.N + i * TL + t256];
+      else if (t256 < 2 * TL) s_delta[u][t256 - TL] = a.delta[(int64_t)bh * a.N + i * TL + (t256 - TL)];
       if (a.maskbits)
-        s_bits[bf][t256 >> 2][t256 & 3] =
+        s_bits[u][t256 >> 2][t256 & 3] =
             a.maskbits[((int64_t)bh * a.N + i * TL + (t256 >> 2)) * words + kt * 4 + (t256 & 3)];
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&st_full, ph);
+      mbar_wait(&st_full[u], ph2);
       tcgen05_fence_after();
-      tmem_ld32_nowait(tST + lane_addr + g * 32, rs);
-      tmem_ld32_nowait(tDPT + lane_addr + g * 32, rp);
+      tmem_ld32_nowait(tmem + 128 * u + lane_addr + g * 32, rs);
+      tmem_ld32_nowait(tmem + 128 * u + 64 + lane_addr + g * 32, rp);
       tmem_wait_ld();
       tcgen05_fence_before();
-      mbar_arrive(&st_free);
-      mbar_wait(&pds_free, ph ^ 1u);
+      mbar_arrive(&st_free[u]);
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        float pv[4], dv[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = g * 32 + 4 * q4 + e;                     // query column inside the tile
-          const float p = ex2_approx(__uint_as_float(rs[4 * q4 + e]) * a.scale_log2e - s_lse[bf][c]);
-          float keep = 1.0f;
-          if (a.maskbits) keep = ((s_bits[bf][c][quad] >> lane) & 1u) ? a.keep_scale : 0.f;
-          pv[e] = round_tf32(p * keep);
-          dv[e] = round_tf32(p * (__uint_as_float(rp[4 * q4 + e]) * keep - s_delta[bf][c]) * a.scale);
-        }
-        st_swz(sPT, row, g * 8 + q4, make_float4(pv[0], pv[1], pv[2], pv[3]));
-        st_swz(sDST, row, g * 8 + q4, make_float4(dv[0], dv[1], dv[2], dv[3]));
+      for (int c = 0; c < 32; ++c) {
+        const int qc = g * 32 + c;                               // query column inside the tile
+        const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - s_lse[u][qc]);
+        float keep = 1.0f;
+        if (a.maskbits) keep = ((s_bits[u][qc][quad] >> lane) & 1u) ? a.keep_scale : 0.f;
+        const float pd = p * keep;
+        rs[c] = __float_as_uint(round_tf32(pd));
+        rp[c] = __float_as_uint(round_tf32((pd * __uint_as_float(rp[c]) - p * s_delta[u][qc]) * a.scale));
       }
-      fence_proxy_async();
+      mbar_wait(&pds_free, ((uint32_t)i & 1u) ^ 1u);            // dV/dK MMAs of tile i-1 have read the operands
+      tcgen05_fence_after();
+      tmem_st32(tPT + lane_addr + g * 32, rs);
+      tmem_st32(tDST + lane_addr + g * 32, rp);
+      tcgen05_fence_before();
       mbar_arrive(&pds_full);
     }
     mbar_wait(&fin, 0);

@@ -9,14 +9,14 @@
 //               V is the B operand of P.V with the contraction (key) index slow in memory, i.e.
 //               MN-major -> 128B_ATOM_32B boxes)
 //   warp 1      tcgen05 issuer: S = Q K_j^T (TF32, fp32 accumulate, 64 TMEM columns), and, once the
-//               softmax warps have published P_j in shared memory, O_j = P_j V_j (64 more columns)
+//               softmax warps have stored P_j back into TMEM, O_j = P_j V_j with the A operand read
+//               from TMEM (no shared-memory round trip for P; the freed 32 KB double-buffer K/V)
 //   warps 2..9  online softmax, two warpgroups: thread = (query row = TMEM lane, column half g).
 //               Group g owns score columns [32g, 32g+32) of the tile and output columns [32g, 32g+32):
 //               one tcgen05.ld of S, row max exchanged between the halves through shared memory, running
 //               max / sum in the log2 domain (ex2.approx), counter-RNG dropout (keep bits saved for the
-//               backward), P_j written to shared memory in the SWIZZLE_128B K-major layout the tensor
-//               core expects, then O_j is pulled from TMEM and folded into a register accumulator with
-//               the usual rescale.
+//               backward), P_j stored to TMEM (tcgen05.st), then O_j is pulled from TMEM and folded
+//               into a register accumulator with the usual rescale.
 // Shared memory is ~97 KB and TMEM 128 columns per CTA, so two CTAs share an SM and one's softmax
 // overlaps the other's MMAs.  lse (log2-domain log-sum-exp) is saved for the backward.
 #include "tc05.cuh"
@@ -26,10 +26,11 @@ namespace attn {
 using namespace tc05;
 
 constexpr int TQ = 128, TK = 64, HD = 64;
-constexpr int Q_BYTES = TQ * HD * 4, K_BYTES = TK * HD * 4, V_BYTES = TK * HD * 4, P_BYTES = TQ * TK * 4;
-constexpr int OFF_Q = 0, OFF_K = Q_BYTES, OFF_V = OFF_K + K_BYTES, OFF_P = OFF_V + V_BYTES;
-constexpr int SMEM_BYTES = OFF_P + P_BYTES + 1024;
-constexpr uint32_t TMEM_COLS = 128;   // S: [0,64)  O_j: [64,128)
+constexpr int Q_BYTES = TQ * HD * 4, K_BYTES = TK * HD * 4, V_BYTES = TK * HD * 4;
+constexpr int KV_BYTES = K_BYTES + V_BYTES;
+constexpr int OFF_Q = 0, OFF_KV = Q_BYTES;            // two {K_j, V_j} stages
+constexpr int SMEM_BYTES = OFF_KV + 2 * KV_BYTES + 1024;
+constexpr uint32_t TMEM_COLS = 256;   // S: [0,64)  O_j: [64,128)  P_j (A operand of P.V): [128,192)
 
 struct FwdArgs {
   float* O;
@@ -52,12 +53,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, k_full, k_free, v_full, v_free, s_full, s_free, p_full, o_full;
+  __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_free[2], s_full, s_free, p_full, o_full;
   __shared__ uint32_t tmem_holder;
   __shared__ float s_max[2][2][TQ];    // [tile parity][column half][row]
   __shared__ float s_sum[2][TQ];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = sbase + OFF_Q, sK = sbase + OFF_K, sV = sbase + OFF_V, sP = sbase + OFF_P;
+  const uint32_t sQ = sbase + OFF_Q;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, bh = blockIdx.y;
   const int b = bh / a.H, h = bh % a.H;
@@ -70,8 +71,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmQ) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmV) : "memory");
-    mbar_init(&q_full, 1); mbar_init(&k_full, 1); mbar_init(&k_free, 1);
-    mbar_init(&v_full, 1); mbar_init(&v_free, 1); mbar_init(&s_full, 1);
+    mbar_init(&q_full, 1); mbar_init(&s_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1); }
     mbar_init(&s_free, 256); mbar_init(&p_full, 256); mbar_init(&o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -80,7 +81,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_holder;
-  const uint32_t tS = tmem, tO = tmem + 64;
+  const uint32_t tS = tmem, tO = tmem + 64, tP = tmem + 128;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -88,15 +89,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_load_2d(sQ, &tmQ, &q_full, h * HD, q_row0);
     tma_load_2d(sQ + TQ * 128, &tmQ, &q_full, h * HD + 32, q_row0);
     for (int j = 0; j < ntiles; ++j) {
-      const uint32_t ph = (uint32_t)j & 1u;
-      mbar_wait(&k_free, ph ^ 1u);
-      mbar_expect_tx(&k_full, K_BYTES);
-      tma_load_2d(sK, &tmK, &k_full, C + h * HD, kv_row0 + j * TK);
-      tma_load_2d(sK + TK * 128, &tmK, &k_full, C + h * HD + 32, kv_row0 + j * TK);
-      mbar_wait(&v_free, ph ^ 1u);
-      mbar_expect_tx(&v_full, V_BYTES);
-      tma_load_2d(sV, &tmV, &v_full, 2 * C + h * HD, kv_row0 + j * TK);
-      tma_load_2d(sV + TK * 128, &tmV, &v_full, 2 * C + h * HD + 32, kv_row0 + j * TK);
+      const int s = j & 1;
+      mbar_wait(&kv_free[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      mbar_expect_tx(&kv_full[s], KV_BYTES);
+      const uint32_t sK = sbase + OFF_KV + s * KV_BYTES, sV = sK + K_BYTES;
+      tma_load_2d(sK, &tmK, &kv_full[s], C + h * HD, kv_row0 + j * TK);
+      tma_load_2d(sK + TK * 128, &tmK, &kv_full[s], C + h * HD + 32, kv_row0 + j * TK);
+      tma_load_2d(sV, &tmV, &kv_full[s], 2 * C + h * HD, kv_row0 + j * TK);
+      tma_load_2d(sV + TK * 128, &tmV, &kv_full[s], 2 * C + h * HD + 32, kv_row0 + j * TK);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== tcgen05 issuer =====================
@@ -105,7 +105,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&q_full, 0);
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
-      mbar_wait(&k_full, ph);
+      const int s = j & 1;
+      const uint32_t sK = sbase + OFF_KV + s * KV_BYTES, sV = sK + K_BYTES;
+      mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1u);
       mbar_wait(&s_free, ph ^ 1u);                 // softmax finished reading S_{j-1}
       tcgen05_fence_after();
 #pragma unroll
@@ -114,18 +116,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint64_t bd = smem_desc_kmajor(sK + (t >> 2) * (TK * 128) + (t & 3) * 32);
         tcgen05_mma_tf32(tS, ad, bd, idesc_s, t > 0 ? 1u : 0u);
       }
-      tcgen05_commit(&k_free);
       tcgen05_commit(&s_full);
-      mbar_wait(&p_full, ph);                      // P_j in smem, O_{j-1} already consumed
-      mbar_wait(&v_full, ph);
+      mbar_wait(&p_full, ph);                      // P_j in TMEM, O_{j-1} already consumed
       tcgen05_fence_after();
 #pragma unroll
-      for (int t = 0; t < TK / 8; ++t) {
-        const uint64_t ad = smem_desc_kmajor(sP + (t >> 2) * (TQ * 128) + (t & 3) * 32);
-        const uint64_t bd = smem_desc_mnmajor(sV + t * 1024, TK * 128);
-        tcgen05_mma_tf32(tO, ad, bd, idesc_o, t > 0 ? 1u : 0u);
-      }
-      tcgen05_commit(&v_free);
+      for (int t = 0; t < TK / 8; ++t)             // O_j = P_j(TMEM) . V_j
+        tcgen05_mma_tf32_ts(tO, tP + 8 * t, smem_desc_mnmajor(sV + t * 1024, TK * 128), idesc_o, t > 0 ? 1u : 0u);
+      tcgen05_commit(&kv_free[s]);
       tcgen05_commit(&o_full);
     }
   } else if (warp >= 2) {
@@ -187,16 +184,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           keepbits |= km << (4 * q4);
         }
         p = round_tf32_4(p);                        // P is only ever a tensor-core operand
-        const uint32_t addr = sP + g * (TQ * 128) + row * 128 + ((uint32_t)(q4 ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
-                     :: "r"(addr), "f"(p.x), "f"(p.y), "f"(p.z), "f"(p.w) : "memory");
+        r[4 * q4 + 0] = __float_as_uint(p.x); r[4 * q4 + 1] = __float_as_uint(p.y);
+        r[4 * q4 + 2] = __float_as_uint(p.z); r[4 * q4 + 3] = __float_as_uint(p.w);
       }
       if (a.thresh != 0u && a.maskbits != nullptr)
         a.maskbits[((int64_t)bh * a.N + q_in_head) * (a.N / 32) + j * (TK / 32) + g] = keepbits;
       l = l * alpha + rs;
       tcgen05_fence_before();
       mbar_arrive(&s_free);                         // S may be overwritten by Q K_{j+1}^T
-      fence_proxy_async();                          // make the P stores visible to the tensor core
+      tmem_st32(tP + lane_addr + g * 32, r);        // P_j -> TMEM (its previous reader P.V_{j-1} is done)
+      tcgen05_fence_before();
       mbar_arrive(&p_full);
     }
     // last tile's O, then combine the two halves' partial row sums
