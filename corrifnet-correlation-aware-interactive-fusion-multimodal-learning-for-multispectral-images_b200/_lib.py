@@ -30,7 +30,9 @@ class GemmDesc(C.Structure):
         ("batch_outer", i32), ("batch_inner", i32),
         ("a_bo", i64), ("a_bi", i64), ("b_bo", i64), ("b_bi", i64), ("d_bo", i64), ("d_bi", i64),
         ("split_k", i32), ("epilogue", i32), ("precision", i32), ("alpha", f32),
-        ("flags", i32), ("reserved_", i32),
+        ("flags", i32),
+        ("drop_p", f32), ("drop_site_a", u32), ("drop_site_b", u32), ("reserved_", u32),
+        ("drop_seed", u64), ("drop_seed_dev", C.c_void_p),
     ]
 
 
@@ -45,8 +47,10 @@ PROTOTYPES = {
     "corrif_last_error": (C.c_char_p, []),
     "corrif_check_device": (C.c_int, []),
     "corrif_gemm": (C.c_int, [C.POINTER(GemmDesc), stream_t]),
+    "corrif_sizeof_gemm_desc": (C.c_int, []),
     "corrif_transpose": (C.c_int, [f32p, f32p, i64, i32, i32, i32, stream_t]),
     "corrif_round_tf32": (C.c_int, [f32p, f32p, i64, stream_t]),
+    "corrif_round_tf32_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, i32, stream_t]),
     "corrif_layernorm_fwd": (C.c_int, [f32p, f32p, i64, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, i32, stream_t]),
     "corrif_layernorm_bwd_scratch_floats": (i64, [i64, i32]),
     "corrif_layernorm_bwd": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, i32, stream_t]),
@@ -93,6 +97,8 @@ def load():
         fn.argtypes = args
     if lib.corrif_abi_version() != 1:
         raise CorrifError("libcorrif_b200.so ABI version mismatch")
+    if lib.corrif_sizeof_gemm_desc() != C.sizeof(GemmDesc):
+        raise CorrifError("corrif_gemm_desc layout mismatch between include/corrif.h and _lib.py")
     _lib = lib
     return lib
 

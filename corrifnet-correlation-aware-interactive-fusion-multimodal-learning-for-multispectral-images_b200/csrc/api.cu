@@ -33,6 +33,8 @@ extern "C" {
 
 int corrif_abi_version(void) { return CORRIF_ABI_VERSION; }
 
+int corrif_sizeof_gemm_desc(void) { return (int)sizeof(corrif_gemm_desc); }
+
 const char* corrif_last_error(void) { return corrif::g_last_error; }
 
 int corrif_check_device(void) {

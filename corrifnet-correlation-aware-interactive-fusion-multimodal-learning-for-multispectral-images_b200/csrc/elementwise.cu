@@ -322,8 +322,18 @@ colsum_partial_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int
     const float4 u = ld4_stream(x + r * ld + c);
     a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
   }
-  st4(partial + (int64_t)blockIdx.y * cols + c,
-      make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w));
+  float* dst = partial + c;   // `partial` is the output vector: add this block's share
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(dst), "f"(a0.x + a1.x), "f"(a0.y + a1.y), "f"(a0.z + a1.z), "f"(a0.w + a1.w) : "memory");
+}
+
+__global__ void round_tf32_multi_kernel(const float* const* __restrict__ src, float* const* __restrict__ dst,
+                                        const int64_t* __restrict__ n) {
+  const float* x = src[blockIdx.y];
+  float* o = dst[blockIdx.y];
+  const int64_t nq = n[blockIdx.y] >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x)
+    st4(o + q * 4, round_tf32_4(ld4(x + q * 4)));
 }
 
 __global__ void batchsum_kernel(const float* __restrict__ x, int64_t batch, int64_t stride,
@@ -529,22 +539,31 @@ static int colsum_chunks(int64_t rows, int32_t cols) {
 }
 
 int64_t corrif_colsum_scratch_floats(int64_t rows, int32_t cols) {
-  (void)rows;
-  return (int64_t)256 * cols;
+  (void)rows; (void)cols;
+  return 4;
 }
 
 int corrif_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out,
                   int accumulate, float* scratch, void* stream) {
-  CORRIF_REQUIRE(x && out && scratch && rows > 0 && cols > 0 && cols % 4 == 0 && ld % 4 == 0,
+  (void)scratch;
+  CORRIF_REQUIRE(x && out && rows > 0 && cols > 0 && cols % 4 == 0 && ld % 4 == 0,
                  "colsum: cols and ld must be multiples of 4");
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_last_error("colsum: memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
   const int chunks = colsum_chunks(rows, cols);
   dim3 grid((cols / 4 + 127) / 128, chunks);
-  colsum_partial_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, scratch);
-  int st = launch_status("colsum");
-  if (st) return st;
-  fold_partials_kernel<<<(cols + 31) / 32, dim3(32, 16), 0, (cudaStream_t)stream>>>(
-      scratch, chunks, cols, out, out, cols, accumulate);
-  return launch_status("colsum_fold");
+  colsum_partial_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, out);
+  return launch_status("colsum");
+}
+
+int corrif_round_tf32_multi(const float* const* src, float* const* dst, const int64_t* n, int32_t count,
+                            void* stream) {
+  CORRIF_REQUIRE(src && dst && n && count > 0 && count <= 65535, "round_tf32_multi: bad arguments");
+  dim3 grid(num_sms() * 2 / (count < 8 ? count : 8) + 1, count);
+  round_tf32_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+  return launch_status("round_tf32_multi");
 }
 
 int corrif_batchsum(const float* x, int64_t batch, int64_t stride, int64_t n, float* out,

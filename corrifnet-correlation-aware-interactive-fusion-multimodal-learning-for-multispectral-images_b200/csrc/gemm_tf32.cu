@@ -56,6 +56,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 
 struct KernelArgs {
   EpiArgs epi;
+  DropArgs drop;
   int K;
   int batch_inner, split_k;
   // TMA start coordinates per batch index: c0 is the contiguous dim of the operand in memory
@@ -161,6 +162,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full_bar, 0);
       tcgen05_fence_after();
       EpiArgs e = args.epi;
+      epi_setup_dropout(e, args.drop);
       const int64_t doff = bo * args.d_bo + bi * args.d_bi;
       e.D += doff;
       if (e.residual) e.residual += doff;
@@ -172,12 +174,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
         if (m < e.M) {
+          float4 pre[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = n0 + c * 32 + j * 4;
+            pre[j] = n < e.N ? epilogue_prefetch4(e, m, n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int n = n0 + c * 32 + j * 4;
             if (n < e.N)
-              epilogue_store4(e, m, n, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+              epilogue_apply4(e, m, n, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), pre[j]);
           }
         }
       }
@@ -326,18 +334,36 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int batch = z / args.split_k;
       const int bi = batch % args.batch_inner, bo = batch / args.batch_inner;
       EpiArgs e = args.epi;
+      epi_setup_dropout(e, args.drop);
       const int64_t doff = bo * args.d_bo + bi * args.d_bi;
       e.D += doff;
       if (e.residual) e.residual += doff;
       if (e.aux) e.aux += doff;
       const uint32_t buf = tc & 1u;
+      // Software-pipelined epilogue: the residual / saved pre-activation of a chunk is fetched one
+      // chunk ahead (the first one even before the accumulator is ready), so DRAM latency hides
+      // behind the main loop and the previous chunk's math instead of stalling every chunk.
+      constexpr int NCH = BN / 64;                             // chunks handled by this warp
+      const int mrow = m0 + quad * 32 + r_sub;
+      auto prefetch = [&](int c, float4 (&pre)[8]) {
+        const int n = n0 + c * 32 + c4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = mrow + 4 * i;
+          pre[i] = (m < e.M && n < e.N) ? epilogue_prefetch4(e, m, n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float4 pre[8], pre_next[8];
+      prefetch(half, pre);
       mbar_wait(&tfull_bar[buf], (tc >> 1) & 1u);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = half + 2 * ci;
         uint32_t r[32];
         tmem_ld32(tacc + (uint32_t)(c * 32), r);
+        if (ci + 1 < NCH) prefetch(c + 2, pre_next);
         if (n0 + c * 32 < e.N) {                      // warp-uniform: skip fully out-of-range chunks
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -345,13 +371,19 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                 make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                             __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           __syncwarp();
+          const int n = n0 + c * 32 + c4;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = r_sub + 4 * i;
-            const int m = m0 + quad * 32 + rr, n = n0 + c * 32 + c4;
-            if (m < e.M && n < e.N) epilogue_store4(e, m, n, *reinterpret_cast<const float4*>(&stg[rr][c4]));
+            const int m = m0 + quad * 32 + rr;
+            if (m < e.M && n < e.N)
+              epilogue_apply4(e, m, n, *reinterpret_cast<const float4*>(&stg[rr][c4]), pre[i]);
           }
           __syncwarp();
+        }
+        if (ci + 1 < NCH) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pre[i] = pre_next[i];
         }
       }
       tcgen05_fence_before();
@@ -376,8 +408,8 @@ static int launch_persistent_variant(const corrif_gemm_desc& g, const CUtensorMa
     configured = true;
   }
   KernelArgs a;
-  a.epi = EpiArgs{g.D, g.bias, g.residual, g.aux, g.ldd, g.ldr, g.ldaux, g.M, g.N, g.epilogue, g.alpha,
-                  (g.flags & CORRIF_GEMM_ROUND_TF32) != 0};
+  a.epi = make_epi_args(g);
+  a.drop = DropArgs{g.drop_p, g.drop_site_a, g.drop_site_b, g.drop_seed, g.drop_seed_dev};
   a.K = g.K; a.batch_inner = g.batch_inner; a.split_k = g.split_k;
   a.a_bo = g.a_bo; a.a_bi = g.a_bi; a.b_bo = g.b_bo; a.b_bi = g.b_bi; a.d_bo = g.d_bo; a.d_bi = g.d_bi;
   a.lda = g.lda; a.ldb = g.ldb;
@@ -409,8 +441,8 @@ static int launch_variant(const corrif_gemm_desc& g, const CUtensorMap& ta, cons
     configured = true;
   }
   KernelArgs a;
-  a.epi = EpiArgs{g.D, g.bias, g.residual, g.aux, g.ldd, g.ldr, g.ldaux, g.M, g.N, g.epilogue, g.alpha,
-                  (g.flags & CORRIF_GEMM_ROUND_TF32) != 0};
+  a.epi = make_epi_args(g);
+  a.drop = DropArgs{g.drop_p, g.drop_site_a, g.drop_site_b, g.drop_seed, g.drop_seed_dev};
   a.K = g.K; a.batch_inner = g.batch_inner; a.split_k = g.split_k;
   a.a_bo = g.a_bo; a.a_bi = g.a_bi; a.b_bo = g.b_bo; a.b_bi = g.b_bi; a.d_bo = g.d_bo; a.d_bi = g.d_bi;
   a.lda = g.lda; a.ldb = g.ldb;
@@ -512,6 +544,12 @@ extern "C" int corrif_gemm(const corrif_gemm_desc* d, void* stream) {
   if (g.epilogue == CORRIF_EPI_BIAS_RESIDUAL)
     CORRIF_REQUIRE(g.residual != nullptr && g.ldr % 4 == 0 && (uintptr_t)g.residual % 16 == 0,
                    "gemm: residual missing/unaligned");
+  if (g.drop_p != 0.f) {
+    CORRIF_REQUIRE(g.drop_p > 0.f && g.drop_p < 1.f, "gemm: drop_p");
+    CORRIF_REQUIRE(g.epilogue == CORRIF_EPI_BIAS_RESIDUAL || g.epilogue == CORRIF_EPI_BIAS_GELU ||
+                   g.epilogue == CORRIF_EPI_MUL_DGELU, "gemm: fused dropout needs BIAS_RESIDUAL, BIAS_GELU or MUL_DGELU");
+    CORRIF_REQUIRE(g.ldd == g.N && g.batch_outer * g.batch_inner == 1, "gemm: fused dropout needs ldd == N, no batching");
+  }
   if (g.epilogue == CORRIF_EPI_BIAS_GELU || g.epilogue == CORRIF_EPI_MUL_DGELU)
     CORRIF_REQUIRE(g.aux != nullptr && g.ldaux % 4 == 0 && (uintptr_t)g.aux % 16 == 0,
                    "gemm: aux missing/unaligned");

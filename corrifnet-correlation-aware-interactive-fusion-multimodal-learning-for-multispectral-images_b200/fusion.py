@@ -134,9 +134,17 @@ class FusionBlockEngine:
         return flat, views
 
     def refresh_weights(self):
-        if self.rnd:
-            for k in self.wnames:
-                ops.round_tf32(self.p[k], self.pw[k], self.p[k].numel())
+        """TF32 round-to-nearest copies of all matrix weights in ONE launch (device pointer table)."""
+        if not self.rnd:
+            return
+        if getattr(self, "_rt", None) is None:
+            i64 = dict(dtype=torch.int64, device=self.dev)
+            self._rt = (torch.tensor([self.p[k].data_ptr() for k in self.wnames], **i64),
+                        torch.tensor([self.pw[k].data_ptr() for k in self.wnames], **i64),
+                        torch.tensor([self.p[k].numel() for k in self.wnames], **i64),
+                        sum(self.p[k].numel() for k in self.wnames))
+        src, dst, cnt, total = self._rt
+        ops.round_tf32_multi(src, dst, cnt, len(self.wnames), total)
 
     # ------------------------------------------------------------------------------------------
     def workspace(self, B: int) -> dict:
@@ -184,6 +192,13 @@ class FusionBlockEngine:
 
     def _site(self, t: int, kind: int) -> int:
         return t * 8 + kind
+
+    def _drop(self, t: int, kind_a: int, kind_b: Optional[int] = None) -> dict:
+        """GEMM-epilogue dropout arguments for transformer t (empty when dropout is off)."""
+        if self.dropout_p <= 0:
+            return {}
+        return dict(drop_p=self.dropout_p, drop_seed=self.seed, drop_seed_dev=self.seed_dev,
+                    drop_sites=(self._site(t, kind_a), NO_SITE if kind_b is None else self._site(t, kind_b)))
 
     # ------------------------------------------------------------------------------------------
     def _attention_fwd(self, t: int, tb: _TBuf):
@@ -241,26 +256,18 @@ class FusionBlockEngine:
                           tb.mean1, tb.rstd1, R, round_out=self.rnd)
         self._linear(tb.h, self.pw[k["qkv_w"]], tb.qkv, R, 3 * C, C, round_out=self.rnd)
         self._attention_fwd(t, tb)
-        if p == 0:
-            self._linear(tb.O, self.pw[k["proj_w"]], tb.x2, R, C, C, bias=P_[k["proj_b"]],
-                         epilogue=EPI_BIAS_RESIDUAL, residual=tb.x1, ldr=C)
-        else:
-            self._linear(tb.O, self.pw[k["proj_w"]], tb.t0, R, C, C, bias=P_[k["proj_b"]], epilogue=EPI_BIAS)
-            ops.dropout_add(tb.t0, tb.x1, tb.x2, R * C, p, self.seed, self._site(t, SITE_PROJ),
-                            self._site(t, SITE_PRENORM), self.seed_dev)
+        # x2 = x1 + drop(drop(proj(O) + b)): both dropouts and the residual live in the GEMM epilogue
+        self._linear(tb.O, self.pw[k["proj_w"]], tb.x2, R, C, C, bias=P_[k["proj_b"]],
+                     epilogue=EPI_BIAS_RESIDUAL, residual=tb.x1, ldr=C,
+                     **self._drop(t, SITE_PROJ, SITE_PRENORM))
         ops.layernorm_fwd(tb.x2, None, 1, P_[k["ln2_w"]], P_[k["ln2_b"]], None, tb.h2, tb.mean2,
                           tb.rstd2, R, round_out=self.rnd)
         self._linear(tb.h2, self.pw[k["fc1_w"]], tb.f1, R, C, C, bias=P_[k["fc1_b"]],
-                     epilogue=EPI_BIAS_GELU, aux=tb.u, ldaux=C, round_out=self.rnd)
-        if p > 0:
-            ops.dropout(tb.f1, tb.f1, R * C, p, self.seed, self._site(t, SITE_FFN1), self.seed_dev)
-        if p == 0:
-            self._linear(tb.f1, self.pw[k["fc2_w"]], tb.x3, R, C, C, bias=P_[k["fc2_b"]],
-                         epilogue=EPI_BIAS_RESIDUAL, residual=tb.x2, ldr=C, round_out=self.rnd)
-        else:
-            self._linear(tb.f1, self.pw[k["fc2_w"]], tb.t0, R, C, C, bias=P_[k["fc2_b"]], epilogue=EPI_BIAS)
-            ops.dropout_add(tb.t0, tb.x2, tb.x3, R * C, p, self.seed, self._site(t, SITE_FFN2),
-                            NO_SITE, self.seed_dev)
+                     epilogue=EPI_BIAS_GELU, aux=tb.u, ldaux=C, round_out=self.rnd,
+                     **self._drop(t, SITE_FFN1))
+        self._linear(tb.f1, self.pw[k["fc2_w"]], tb.x3, R, C, C, bias=P_[k["fc2_b"]],
+                     epilogue=EPI_BIAS_RESIDUAL, residual=tb.x2, ldr=C, round_out=self.rnd,
+                     **self._drop(t, SITE_FFN2))
         return tb.x3
 
     def _transformer_bwd(self, t: int, dx3, tb: _TBuf, g: Dict[str, torch.Tensor], scratch):
@@ -275,9 +282,8 @@ class FusionBlockEngine:
             df2 = tb.t0
         self._wgrad(df2, tb.f1, g[k["fc2_w"]], R, C, C)
         ops.colsum(df2, C, R, C, g[k["fc2_b"]], scratch, accumulate=True)
-        self._dgrad(df2, self.pw[k["fc2_w"]], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C)
-        if p > 0:
-            ops.dropout(tb.t1, tb.t1, R * C, p, self.seed, self._site(t, SITE_FFN1), self.seed_dev)
+        self._dgrad(df2, self.pw[k["fc2_w"]], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C,
+                    **self._drop(t, SITE_FFN1))          # d(u) = (df2 . W2) * keep * gelu'(u)
         self._wgrad(tb.t1, tb.h2, g[k["fc1_w"]], R, C, C)
         ops.colsum(tb.t1, C, R, C, g[k["fc1_b"]], scratch, accumulate=True)
         self._dgrad(tb.t1, self.pw[k["fc1_w"]], tb.t2, R, C, C)                    # d(h2)

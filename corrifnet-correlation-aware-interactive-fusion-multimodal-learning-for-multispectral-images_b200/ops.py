@@ -125,7 +125,8 @@ def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K
          ldb: int, ldd: int, a_mn: bool = False, b_mn: bool = False, bias=None, residual=None,
          ldr: int = 0, aux=None, ldaux: int = 0, batch=(1, 1), a_step=(0, 0), b_step=(0, 0),
          d_step=(0, 0), split_k: int = 1, epilogue: int = EPI_STORE, precision: int = GEMM_TF32,
-         alpha: float = 1.0, round_out: bool = False, tag: str = ""):
+         alpha: float = 1.0, round_out: bool = False, tag: str = "", drop_p: float = 0.0,
+         drop_sites=(NO_SITE, NO_SITE), drop_seed: int = 0, drop_seed_dev=None):
     """D = epilogue(alpha * A . B^T); see corrif_gemm in include/corrif.h for the layout rules."""
     g = GemmDesc()
     g.A, g.B, g.D = _ptr(A), _ptr(B), _ptr(D)
@@ -139,6 +140,9 @@ def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K
     g.d_bo, g.d_bi = d_step
     g.split_k, g.epilogue, g.precision, g.alpha = split_k, epilogue, precision, alpha
     g.flags = GEMM_ROUND_TF32 if round_out else 0
+    if drop_p > 0:
+        g.drop_p, g.drop_site_a, g.drop_site_b = drop_p, drop_sites[0], drop_sites[1]
+        g.drop_seed, g.drop_seed_dev = drop_seed, _seed_dev(drop_seed_dev)
     cls = ("gemm_tf32" if precision == GEMM_TF32 else "gemm_fp32") + ("/" + tag if tag else "")
     det = "" if _prof is None else "M%d N%d K%d a%d b%d epi%d split%d z%d" % (
         M, N, K, int(a_mn), int(b_mn), epilogue, split_k, batch[0] * batch[1])
@@ -157,6 +161,15 @@ def transpose(x: TensorOrView, out: TensorOrView, batch: int, rows: int, cols: i
 def round_tf32(x: TensorOrView, out: TensorOrView, n: int):
     with _rec('round_tf32', 8.0 * n):
         L.check(lib().corrif_round_tf32(_ptr(x), _ptr(out), n, _stream()), "corrif_round_tf32")
+    _count()
+
+
+def round_tf32_multi(src_ptrs, dst_ptrs, counts, count: int, total_elems: int):
+    """src_ptrs/dst_ptrs/counts: int64 device tensors holding pointers / element counts."""
+    with _rec('round_tf32', 8.0 * total_elems):
+        L.check(lib().corrif_round_tf32_multi(_ptr(src_ptrs, torch.int64), _ptr(dst_ptrs, torch.int64),
+                                              _ptr(counts, torch.int64), count, _stream()),
+                "corrif_round_tf32_multi")
     _count()
 
 
@@ -247,7 +260,7 @@ def colsum(x, ld, rows, cols, out, scratch, accumulate=False):
     with _rec('colsum', 4.0 * rows * cols):
         L.check(lib().corrif_colsum(_ptr(x), ld, rows, cols, _ptr(out), int(accumulate), _ptr(scratch),
                                     _stream()), "corrif_colsum")
-    _count(2)
+    _count(1)
 
 
 def batchsum(x, batch, stride, n, out, accumulate=False):

@@ -80,10 +80,24 @@ typedef struct corrif_gemm_desc {
   int32_t precision;
   float alpha;
   int32_t flags;
-  int32_t reserved_;
+  /* Dropout fused into the epilogue (drop_p > 0; not with ATOMIC_ADD): the value that the epilogue
+   * would add the residual to / store is first multiplied by keep(site_a) * keep(site_b) / (1-p)^k,
+   * k = number of sites != CORRIF_NO_SITE, with the element index m*N + n (requires ldd == N):
+   *   BIAS_RESIDUAL: D = (v + bias) * keeps + residual   (proj_drop + PreNormDrop.dropout + Residual,
+   *                                                       mmvit4.py:314,339,322; FeedForward :355,322)
+   *   BIAS_GELU    : D = gelu(v + bias) * keep            (:352-353)
+   *   MUL_DGELU    : D = v * gelu'(aux) * keep            (backward of :352-353)
+   * Same decisions as corrif_dropout with the same (seed, seed_dev, site). */
+  float drop_p;
+  uint32_t drop_site_a, drop_site_b;
+  uint32_t reserved_;
+  uint64_t drop_seed;
+  const uint64_t* drop_seed_dev;
 } corrif_gemm_desc;
 
 int corrif_gemm(const corrif_gemm_desc* desc, void* stream);
+/* sizeof(corrif_gemm_desc) as compiled into the library (binding sanity check). */
+int corrif_sizeof_gemm_desc(void);
 
 /* ------------------------------------------------------------------------------------------
  * Layout: batched 2-D transpose  in [batch, rows, cols] -> out [batch, cols, rows].
@@ -92,8 +106,11 @@ int corrif_gemm(const corrif_gemm_desc* desc, void* stream);
  * ------------------------------------------------------------------------------------------ */
 int corrif_transpose(const float* in, float* out, int64_t batch, int32_t rows, int32_t cols,
                      int32_t round_tf32, void* stream);
-/* out = round-to-nearest-TF32(in): makes GEMM-ready copies of weights (in place allowed). */
+/* out = round-to-nearest-TF32(in): makes GEMM-ready copies of weights (in place allowed).
+ * _multi: `count` tensors in one launch; src/dst/n are DEVICE arrays of pointers / element counts. */
 int corrif_round_tf32(const float* in, float* out, int64_t n, void* stream);
+int corrif_round_tf32_multi(const float* const* src, float* const* dst, const int64_t* n, int32_t count,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (C == 512, eps 1e-5, affine) with the positional add fused:
@@ -171,7 +188,9 @@ int corrif_dropout_add(const float* x, const float* res, float* out, int64_t n, 
  *   colsum:   out[c] (+)= sum_r x[r*ld + c]          bias gradients
  *   batchsum: out[i] (+)= sum_b x[b*stride + i]      positional-embedding gradients
  *   add:      out[i] = a[i] + b[i]
- * `scratch` for colsum must hold corrif_colsum_scratch_floats(rows, cols) floats.
+ * colsum is one launch: per-block partial column sums are added to `out` with red.global.add (the
+ * summation order across blocks is not fixed); accumulate == 0 zeroes `out` first.  `scratch` is
+ * unused (kept for ABI stability; corrif_colsum_scratch_floats returns a small constant).
  * ------------------------------------------------------------------------------------------ */
 int64_t corrif_colsum_scratch_floats(int64_t rows, int32_t cols);
 int corrif_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out,

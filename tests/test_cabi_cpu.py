@@ -43,12 +43,11 @@ def test_ctypes_prototypes_cover_header(lib):
     assert lib.corrif_abi_version() == 1
 
 
-def test_gemm_desc_layout_matches_c_struct():
+def test_gemm_desc_layout_matches_c_struct(lib):
     from corrif_b200 import _lib
-    # 6 pointers, 5 int64, 7 int32 (+pad), 6 int64, 3 int32 + float + flags + reserved
-    assert ctypes.sizeof(_lib.GemmDesc) == 6 * 8 + 5 * 8 + 8 * 4 + 6 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.GemmDesc) == lib.corrif_sizeof_gemm_desc()
     assert _lib.GemmDesc.M.offset == 88 and _lib.GemmDesc.a_bo.offset == 120
-    assert _lib.GemmDesc.alpha.offset == 180
+    assert _lib.GemmDesc.alpha.offset == 180 and _lib.GemmDesc.drop_seed.offset % 8 == 0
 
 
 def test_argument_errors_are_reported_without_a_gpu(lib):
