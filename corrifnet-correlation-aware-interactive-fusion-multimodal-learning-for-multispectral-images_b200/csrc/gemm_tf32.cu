@@ -15,54 +15,10 @@
 //
 // Descriptor encodings follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor"
 // tables (cross-checked against cute/arch/mma_sm100_desc.hpp).
-#include <stdlib.h>
-#include "gemm.cuh"
-#include "tc05.cuh"
+#include "gemm_tc.cuh"
 
 namespace corrif {
 namespace tc {
-using namespace tc05;
-
-constexpr int BM = 128;
-constexpr int BK = 32;                 // fp32 elements per k-block = 128 bytes = one swizzle row
-constexpr int UMMA_K = 8;              // tf32: 32 bytes of K per instruction
-constexpr int ROW_BYTES = BK * 4;      // 128
-constexpr int A_BYTES = BM * ROW_BYTES;
-constexpr int NUM_THREADS = 192;
-
-// Shared-memory matrix descriptor (sm_100 "version 1").
-//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
-//   bits [46,48) = 1, bits [61,64) layout type.
-//   K-major : SWIZZLE_128B (type 2): rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
-//   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (type 1; 32-B chunks swizzled over
-//             4-row atoms, TMA mode 128B_ATOM_32B): [k][32 floats] boxes, 4-k-row atoms 512 B apart
-//             (SBO), the next 32 MN elements one box (BK*128 B) further (LBO).
-template <bool MN_MAJOR>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  constexpr uint64_t lbo = MN_MAJOR ? (uint64_t)(BK * ROW_BYTES) >> 4 : 1;
-  constexpr uint64_t sbo = MN_MAJOR ? (512 >> 4) : (1024 >> 4);
-  constexpr uint64_t layout = MN_MAJOR ? 1ull : 2ull;
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
-// Instruction descriptor, kind::tf32, fp32 accumulate:
-//   [4,6) c_format = 1 (F32), [7,10) a_format = 2 (TF32), [10,13) b_format = 2, bit 15 a_major,
-//   bit 16 b_major (1 = MN-major), [17,23) N >> 3, [24,29) M >> 4.
-template <int BN, bool A_MN, bool B_MN>
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-struct KernelArgs {
-  EpiArgs epi;
-  DropArgs drop;
-  int K;
-  int batch_inner, split_k;
-  // TMA start coordinates per batch index: c0 is the contiguous dim of the operand in memory
-  int64_t a_bo, a_bi, b_bo, b_bi, d_bo, d_bi;
-  int64_t lda, ldb;
-};
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
@@ -249,8 +205,8 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   auto decode = [&](int tile, int& z, int& m0, int& n0, int& kb_begin, int& num_kb) {
     z = tile / tiles_per_z;
     const int rem = tile - z * tiles_per_z;
-    n0 = (rem / mt) * BN;
-    m0 = (rem % mt) * BM;
+    n0 = (rem % nt) * BN;            // n fastest: CTAs running together share the A rows (read from
+    m0 = (rem / nt) * BM;            // DRAM once); B (weights, <= 3 MB) stays L2-resident anyway
     const int split = z % args.split_k;
     kb_begin = split * kb_per_split;
     num_kb = min(total_kb, kb_begin + kb_per_split) - kb_begin;
@@ -481,7 +437,12 @@ int gemm_tf32_launch(const corrif_gemm_desc& g, cudaStream_t stream) {
   using namespace tc;
   // Split-K weight gradients are many short, latency-bound CTAs: two co-resident non-persistent CTAs
   // per SM (v1) beat one persistent CTA there; everything else runs the persistent kernel (v2).
-  static const bool force_v1 = getenv("CORRIF_GEMM_V1") != nullptr;    // bring-up A/B switch
+  static const bool force_v1 = getenv("CORRIF_GEMM_V1") != nullptr;    // bring-up A/B switches
+  static const bool no_pair = getenv("CORRIF_GEMM_NOPAIR") != nullptr;
+  // CTA-pair 256 x 256 tiles (v3, gemm_tf32_pair.cu) whenever the problem is wide enough to fill them:
+  // they need a third less operand traffic per MAC than any single-CTA tile, which is what bounds
+  // TF32 GEMMs here.
+  if (!force_v1 && !no_pair && gemm_tf32_pair_supported(g)) return gemm_tf32_pair_launch(g, stream);
   const bool use_v1 = force_v1 || g.split_k > 1;
   const int BN = use_v1 ? (g.N <= 64 ? 64 : 128) : choose_bn(g);
   const bool batched = g.batch_outer * g.batch_inner > 1;

@@ -96,6 +96,16 @@ def test_gemm_epilogues(epi, precision):
     assert rel_l2(got, ref) < (2e-3 if precision == "tf32" else 2e-6)
 
 
+@pytest.mark.parametrize("epi", ["STORE", "BIAS", "BIAS_GELU", "BIAS_RESIDUAL", "MUL_DGELU", "ATOMIC_ADD"])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(2304, 640, 256, False, False), (1000, 260, 96, False, True),
+                                              (19200, 512, 64, False, False), (192, 2048, 512, True, True)])
+def test_gemm_pair_tiles_epilogues(M, N, K, a_mn, b_mn, epi):
+    """CTA-pair (cta_group::2) kernel with the TMA epilogue: several 256 x 256 tiles per cluster (the
+    residual / aux prefetch crosses tile boundaries), ragged M and N edges, every epilogue mode."""
+    got, ref = _gemm_case(M, N, K, a_mn, b_mn, ops.GEMM_TF32, epilogue=getattr(ops, "EPI_" + epi), seed=11)
+    assert rel_l2(got, ref) < 2e-3
+
+
 @pytest.mark.parametrize("split_k", [2, 7, 16])
 def test_gemm_split_k_wgrad_shape(split_k):
     # dW[512,512] += dY[4096,512]^T . X[4096,512]: both operands MN-major, atomics
