@@ -91,7 +91,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-
+// 16-column variant: thread i of the warp reads 16 consecutive columns of lane (base lane + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -203,8 +213,8 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor map over memory [dim1][ld] of which dim0 columns are addressable.
-inline int encode_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, int64_t ld,
-                      uint32_t box0, uint32_t box1, bool mn_major) {
+inline int encode_map_swz(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, int64_t ld,
+                          uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not found"); return CORRIF_EDRIVER; }
   cuuint64_t dims[2] = {dim0, dim1};
@@ -212,9 +222,8 @@ inline int encode_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): base %p dims %llu x %llu ld %lld box %u x %u",
                    (int)r, (const void*)base, (unsigned long long)dim0, (unsigned long long)dim1,
@@ -222,6 +231,11 @@ inline int encode_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64
     return CORRIF_EDRIVER;
   }
   return 0;
+}
+inline int encode_map(CUtensorMap* map, const float* base, uint64_t dim0, uint64_t dim1, int64_t ld,
+                      uint32_t box0, uint32_t box1, bool mn_major) {
+  return encode_map_swz(map, base, dim0, dim1, ld, box0, box1,
+                        mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 

@@ -184,9 +184,16 @@ class FusionBlockEngine:
                    tag="dgrad", **k)
 
     def _wgrad(self, dy, x, dw, R, N_out, K_in, ldy=None, ldx=None):
-        """dw[N_out,K_in] += dy[R,N_out]^T . x[R,K_in]: both operands MN-major, split-K + atomics."""
-        tiles = ((N_out + 127) // 128) * ((K_in + (63 if K_in <= 64 else 127)) // (64 if K_in <= 64 else 128))
-        split = _split_for(tiles, R // 32, self.sms)
+        """dw[N_out,K_in] += dy[R,N_out]^T . x[R,K_in]: both operands MN-major, split-K + reduce-add."""
+        kblocks = R // 32
+        if N_out > 128 and K_in > 128:
+            # CTA-pair kernel (256 x 256 tiles, one cluster per SM pair, persistent): exactly one wave of
+            # tiles - a 75th tile would double the kernel's duration
+            tiles = ((N_out + 255) // 256) * ((K_in + 255) // 256)
+            split = max(1, min((self.sms // 2) // tiles, max(1, kblocks // 4), 64))
+        else:
+            tiles = ((N_out + 127) // 128) * ((K_in + (63 if K_in <= 64 else 127)) // (64 if K_in <= 64 else 128))
+            split = _split_for(tiles, kblocks, self.sms)
         self._gemm(dy, x, dw, M=N_out, N=K_in, K=R, lda=ldy or N_out, ldb=ldx or K_in, ldd=K_in,
                    a_mn=True, b_mn=True, split_k=split, epilogue=EPI_ATOMIC_ADD, tag="wgrad")
 

@@ -16,6 +16,8 @@ ap.add_argument("--dropout", type=float, default=0.1)
 ap.add_argument("--gemm", type=int, nargs="*", default=None)
 ap.add_argument("--attn", type=int, nargs=2, default=None, help="B N: fused attention fwd+bwd only")
 ap.add_argument("--pdrop", type=float, default=0.1)
+ap.add_argument("--epi", type=int, default=0, help="--gemm: epilogue mode (include/corrif.h)")
+ap.add_argument("--gdrop", type=float, default=0.0, help="--gemm: fused epilogue dropout p")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 
@@ -26,6 +28,11 @@ if args.gemm:
     B = torch.randn(K, N, device=dev) if b_mn else torch.randn(N, K, device=dev)
     D = torch.empty(M, N, device=dev)
     kw = dict(M=M, N=N, K=K, lda=M if a_mn else K, ldb=N if b_mn else K, ldd=N, a_mn=a_mn, b_mn=b_mn)
+    if args.epi:
+        kw.update(epilogue=args.epi, bias=torch.randn(N, device=dev), residual=torch.randn(M, N, device=dev), ldr=N,
+                  aux=torch.randn(M, N, device=dev), ldaux=N)
+        if args.gdrop > 0:
+            kw.update(drop_p=args.gdrop, drop_sites=(1, 2 if args.epi == 3 else ops.NO_SITE), drop_seed=5)
     for _ in range(3):
         ops.gemm(A, B, D, **kw)
     torch.cuda.synchronize()
