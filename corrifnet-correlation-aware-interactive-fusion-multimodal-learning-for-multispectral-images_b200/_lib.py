@@ -31,8 +31,8 @@ class GemmDesc(C.Structure):
         ("a_bo", i64), ("a_bi", i64), ("b_bo", i64), ("b_bi", i64), ("d_bo", i64), ("d_bi", i64),
         ("split_k", i32), ("epilogue", i32), ("precision", i32), ("alpha", f32),
         ("flags", i32),
-        ("drop_p", f32), ("drop_site_a", u32), ("drop_site_b", u32), ("reserved_", u32),
-        ("drop_seed", u64), ("drop_seed_dev", C.c_void_p),
+        ("drop_p", f32), ("drop_site_a", u32), ("drop_site_b", u32), ("drop_site_bo", u32),
+        ("drop_seed", u64), ("drop_seed_dev", C.c_void_p), ("bias_bo", i64),
     ]
 
 
@@ -56,7 +56,7 @@ PROTOTYPES = {
     "corrif_layernorm_bwd": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, i32, stream_t]),
     "corrif_softmax_fwd": (C.c_int, [f32p, f32p, i64, i32, f32, u64, u64p, u32, i32, stream_t]),
     "corrif_softmax_bwd": (C.c_int, [f32p, f32p, i64, i32, f32, f32, u64, u64p, u32, stream_t]),
-    "corrif_attention_fwd": (C.c_int, [f32p, f32p, f32p, C.c_void_p, i32, i32, i32, i32, f32, f32, u64, u64p, u32, i32, stream_t]),
+    "corrif_attention_fwd": (C.c_int, [f32p, f32p, f32p, C.c_void_p, i32, i32, i32, i32, f32, f32, u64, u64p, u32, i32, u32, i32, stream_t]),
     "corrif_attention_bwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_void_p, f32p, f32p, i32, i32, i32, i32, f32, f32, stream_t]),
     "corrif_dropout": (C.c_int, [f32p, f32p, i64, f32, u64, u64p, u32, stream_t]),
     "corrif_dropout_mask": (C.c_int, [f32p, i64, f32, u64, u64p, u32, stream_t]),
@@ -95,7 +95,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.corrif_abi_version() != 1:
+    if lib.corrif_abi_version() != 2:
         raise CorrifError("libcorrif_b200.so ABI version mismatch")
     if lib.corrif_sizeof_gemm_desc() != C.sizeof(GemmDesc):
         raise CorrifError("corrif_gemm_desc layout mismatch between include/corrif.h and _lib.py")

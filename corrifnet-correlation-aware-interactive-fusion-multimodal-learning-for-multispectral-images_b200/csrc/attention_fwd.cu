@@ -44,6 +44,8 @@ struct FwdArgs {
   uint64_t seed;
   const uint64_t* seed_dev;
   uint32_t site;
+  int group_batches;          // > 0: batch b is module b / group_batches (own dropout site)
+  uint32_t group_site_stride;
   int round_out;
 };
 
@@ -133,8 +135,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int q_in_head = qt * TQ + row;
     uint64_t key = 0;
-    if (a.thresh != 0u) key = dropout_key(a.seed + (a.seed_dev ? *a.seed_dev : 0ull), a.site);
-    const uint64_t drop_row = ((uint64_t)bh * a.N + q_in_head) * (uint64_t)a.N;
+    const int grp = a.group_batches > 0 ? b / a.group_batches : 0;
+    const int bh_rng = a.group_batches > 0 ? (b - grp * a.group_batches) * a.H + h : bh;
+    if (a.thresh != 0u)
+      key = dropout_key(a.seed + (a.seed_dev ? *a.seed_dev : 0ull), a.site + (uint32_t)grp * a.group_site_stride);
+    const uint64_t drop_row = ((uint64_t)bh_rng * a.N + q_in_head) * (uint64_t)a.N;
     float m = -INFINITY, l = 0.f;
     float acc[32];
 #pragma unroll
@@ -229,8 +234,8 @@ using namespace corrif;
 extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint32_t* maskbits,
                                     int32_t B, int32_t N, int32_t H, int32_t D, float scale,
                                     float p_drop, uint64_t seed,
-                                    const uint64_t* seed_dev, uint32_t site, int32_t round_tf32,
-                                    void* stream) {
+                                    const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
+                                    uint32_t group_site_stride, int32_t round_tf32, void* stream) {
   using namespace corrif::attn;
   CORRIF_REQUIRE(qkv && O && lse && B > 0, "attention_fwd: null/empty");
   CORRIF_REQUIRE(D == HD, "attention_fwd: head_dim must be 64 (got %d)", D);
@@ -238,6 +243,8 @@ extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint
   CORRIF_REQUIRE((int64_t)B * H <= 65535, "attention_fwd: B*H too large");
   CORRIF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "attention_fwd: p_drop");
   CORRIF_REQUIRE(p_drop == 0.f || maskbits != nullptr, "attention_fwd: dropout needs a maskbits buffer");
+  CORRIF_REQUIRE(group_batches >= 0 && (group_batches == 0 || B % group_batches == 0),
+                 "attention_fwd: group_batches must divide B");
   CORRIF_REQUIRE(((uintptr_t)qkv % 16 == 0) && ((uintptr_t)O % 16 == 0), "attention_fwd: alignment");
   const int C = H * D;
   CUtensorMap tq, tk, tv;
@@ -259,6 +266,7 @@ extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint
   a.thresh = p_drop > 0.f ? dropout_threshold(p_drop) : 0u;
   a.keep_scale = 1.0f / (1.0f - p_drop);
   a.seed = seed; a.seed_dev = seed_dev; a.site = site; a.round_out = round_tf32;
+  a.group_batches = group_batches; a.group_site_stride = group_site_stride;
   dim3 grid(N / TQ, B * H);
   attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
   return launch_status("attention_fwd");

@@ -331,9 +331,13 @@ __global__ void round_tf32_multi_kernel(const float* const* __restrict__ src, fl
                                         const int64_t* __restrict__ n) {
   const float* x = src[blockIdx.y];
   float* o = dst[blockIdx.y];
-  const int64_t nq = n[blockIdx.y] >> 2;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x)
-    st4(o + q * 4, round_tf32_4(ld4(x + q * 4)));
+  const int64_t cnt = n[blockIdx.y];
+  const bool copy = cnt < 0;                      // negative count: plain copy (stacked biases)
+  const int64_t nq = (copy ? -cnt : cnt) >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = ld4(x + q * 4);
+    st4(o + q * 4, copy ? v : round_tf32_4(v));
+  }
 }
 
 __global__ void batchsum_kernel(const float* __restrict__ x, int64_t batch, int64_t stride,

@@ -28,14 +28,18 @@ struct DropArgs {
   uint32_t site_a, site_b;
   uint64_t seed;
   const uint64_t* seed_dev;
+  uint32_t site_bo;            // site increment per outer batch index
 };
-__device__ __forceinline__ void epi_setup_dropout(EpiArgs& e, const DropArgs& d) {
+inline DropArgs make_drop_args(const corrif_gemm_desc& g) {
+  return DropArgs{g.drop_p, g.drop_site_a, g.drop_site_b, g.drop_seed, g.drop_seed_dev, g.drop_site_bo};
+}
+__device__ __forceinline__ void epi_setup_dropout(EpiArgs& e, const DropArgs& d, int bo = 0) {
   if (d.p <= 0.f) return;
   const uint64_t seed = d.seed + (d.seed_dev ? *d.seed_dev : 0ull);
   const float ks = 1.0f / (1.0f - d.p);
   e.two_sites = d.site_b != CORRIF_NO_SITE;
-  e.key_a = dropout_key(seed, d.site_a);
-  e.key_b = e.two_sites ? dropout_key(seed, d.site_b) : 0ull;
+  e.key_a = dropout_key(seed, d.site_a + (uint32_t)bo * d.site_bo);
+  e.key_b = e.two_sites ? dropout_key(seed, d.site_b + (uint32_t)bo * d.site_bo) : 0ull;
   e.drop_scale = e.two_sites ? ks * ks : ks;
   double t = (double)d.p * 65536.0 + 0.5;
   e.drop_thresh = t > 65535.0 ? 65535u : (uint32_t)t;

@@ -12,14 +12,15 @@ constexpr int FK = 16;
 __global__ void __launch_bounds__(256)
 gemm_fp32_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t a_rs, int64_t a_ks,
                  int64_t b_rs, int64_t b_ks, int K, int batch_inner, int split_k, int64_t a_bo,
-                 int64_t a_bi, int64_t b_bo, int64_t b_bi, int64_t d_bo, int64_t d_bi, EpiArgs e,
-                 const DropArgs drop) {
-  epi_setup_dropout(e, drop);
+                 int64_t a_bi, int64_t b_bo, int64_t b_bi, int64_t d_bo, int64_t d_bi, int64_t bias_bo,
+                 EpiArgs e, const DropArgs drop) {
   __shared__ float As[FK][FT + 4];
   __shared__ float Bs[FK][FT + 4];
   const int z = blockIdx.z;
   const int split = z % split_k, batch = z / split_k;
   const int bi = batch % batch_inner, bo = batch / batch_inner;
+  epi_setup_dropout(e, drop, bo);
+  if (e.bias) e.bias += bo * bias_bo;
   A += bo * a_bo + bi * a_bi;
   B += bo * b_bo + bi * b_bi;
   const int64_t doff = bo * d_bo + bi * d_bi;
@@ -68,13 +69,13 @@ gemm_fp32_kernel(const float* __restrict__ A, const float* __restrict__ B, int64
 
 int gemm_fp32_launch(const corrif_gemm_desc& g, cudaStream_t stream) {
   EpiArgs e = make_epi_args(g);
-  const DropArgs drop{g.drop_p, g.drop_site_a, g.drop_site_b, g.drop_seed, g.drop_seed_dev};
+  const DropArgs drop = make_drop_args(g);
   const int64_t a_rs = g.a_mn_major ? 1 : g.lda, a_ks = g.a_mn_major ? g.lda : 1;
   const int64_t b_rs = g.b_mn_major ? 1 : g.ldb, b_ks = g.b_mn_major ? g.ldb : 1;
   dim3 grid((g.M + FT - 1) / FT, (g.N + FT - 1) / FT, g.batch_outer * g.batch_inner * g.split_k);
   gemm_fp32_kernel<<<grid, 256, 0, stream>>>(g.A, g.B, a_rs, a_ks, b_rs, b_ks, g.K, g.batch_inner,
                                              g.split_k, g.a_bo, g.a_bi, g.b_bo, g.b_bi, g.d_bo,
-                                             g.d_bi, e, drop);
+                                             g.d_bi, g.bias_bo, e, drop);
   return launch_status("gemm_fp32");
 }
 

@@ -48,6 +48,7 @@ struct KernelArgs {
   // TMA start coordinates per batch index: c0 is the contiguous dim of the operand in memory
   int64_t a_bo, a_bi, b_bo, b_bi, d_bo, d_bi;
   int64_t lda, ldb;
+  int64_t bias_bo;           // bias element offset per outer batch index
 };
 
 }  // namespace tc

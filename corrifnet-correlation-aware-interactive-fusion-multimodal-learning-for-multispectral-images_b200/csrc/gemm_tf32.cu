@@ -118,7 +118,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full_bar, 0);
       tcgen05_fence_after();
       EpiArgs e = args.epi;
-      epi_setup_dropout(e, args.drop);
+      epi_setup_dropout(e, args.drop, bo);
+      if (e.bias) e.bias += bo * args.bias_bo;
       const int64_t doff = bo * args.d_bo + bi * args.d_bi;
       e.D += doff;
       if (e.residual) e.residual += doff;
@@ -290,7 +291,8 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int batch = z / args.split_k;
       const int bi = batch % args.batch_inner, bo = batch / args.batch_inner;
       EpiArgs e = args.epi;
-      epi_setup_dropout(e, args.drop);
+      epi_setup_dropout(e, args.drop, bo);
+      if (e.bias) e.bias += bo * args.bias_bo;
       const int64_t doff = bo * args.d_bo + bi * args.d_bi;
       e.D += doff;
       if (e.residual) e.residual += doff;
@@ -365,10 +367,10 @@ static int launch_persistent_variant(const corrif_gemm_desc& g, const CUtensorMa
   }
   KernelArgs a;
   a.epi = make_epi_args(g);
-  a.drop = DropArgs{g.drop_p, g.drop_site_a, g.drop_site_b, g.drop_seed, g.drop_seed_dev};
+  a.drop = make_drop_args(g);
   a.K = g.K; a.batch_inner = g.batch_inner; a.split_k = g.split_k;
   a.a_bo = g.a_bo; a.a_bi = g.a_bi; a.b_bo = g.b_bo; a.b_bi = g.b_bi; a.d_bo = g.d_bo; a.d_bi = g.d_bi;
-  a.lda = g.lda; a.ldb = g.ldb;
+  a.lda = g.lda; a.ldb = g.ldb; a.bias_bo = g.bias_bo;
   const int mt = (g.M + BM - 1) / BM, nt = (g.N + BN - 1) / BN;
   const int total = mt * nt * g.batch_outer * g.batch_inner * g.split_k;
   const int grid = total < num_sms() ? total : num_sms();
@@ -398,10 +400,10 @@ static int launch_variant(const corrif_gemm_desc& g, const CUtensorMap& ta, cons
   }
   KernelArgs a;
   a.epi = make_epi_args(g);
-  a.drop = DropArgs{g.drop_p, g.drop_site_a, g.drop_site_b, g.drop_seed, g.drop_seed_dev};
+  a.drop = make_drop_args(g);
   a.K = g.K; a.batch_inner = g.batch_inner; a.split_k = g.split_k;
   a.a_bo = g.a_bo; a.a_bi = g.a_bi; a.b_bo = g.b_bo; a.b_bi = g.b_bi; a.d_bo = g.d_bo; a.d_bi = g.d_bi;
-  a.lda = g.lda; a.ldb = g.ldb;
+  a.lda = g.lda; a.ldb = g.ldb; a.bias_bo = g.bias_bo;
   dim3 grid((g.M + BM - 1) / BM, (g.N + BN - 1) / BN, g.batch_outer * g.batch_inner * g.split_k);
   kern<<<grid, NUM_THREADS, smem, stream>>>(ta, tb, a);
   return launch_status("gemm_tf32");
@@ -509,7 +511,7 @@ extern "C" int corrif_gemm(const corrif_gemm_desc* d, void* stream) {
     CORRIF_REQUIRE(g.drop_p > 0.f && g.drop_p < 1.f, "gemm: drop_p");
     CORRIF_REQUIRE(g.epilogue == CORRIF_EPI_BIAS_RESIDUAL || g.epilogue == CORRIF_EPI_BIAS_GELU ||
                    g.epilogue == CORRIF_EPI_MUL_DGELU, "gemm: fused dropout needs BIAS_RESIDUAL, BIAS_GELU or MUL_DGELU");
-    CORRIF_REQUIRE(g.ldd == g.N && g.batch_outer * g.batch_inner == 1, "gemm: fused dropout needs ldd == N, no batching");
+    CORRIF_REQUIRE(g.ldd == g.N, "gemm: fused dropout needs ldd == N");
   }
   if (g.epilogue == CORRIF_EPI_BIAS_GELU || g.epilogue == CORRIF_EPI_MUL_DGELU)
     CORRIF_REQUIRE(g.aux != nullptr && g.ldaux % 4 == 0 && (uintptr_t)g.aux % 16 == 0,

@@ -288,6 +288,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     EpiArgs e = args.epi;
     epi_setup_dropout(e, args.drop);
+    const float* const bias0 = e.bias;
+    int cur_bo = 0;
     const int mode = e.mode;
     const int sites = e.drop_thresh == 0u ? 0 : (e.two_sites ? 2 : 1);
     const bool has_in = pa.has_in != 0;
@@ -297,7 +299,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     // This warp's chunk sequence: per tile, chunk ci covers columns nb + 32 ci .. +16 (the two warps
     // of a lane quadrant interleave), rows m .. m+32; chunks beyond N are not visited.
-    struct It { int tile, ci, nvalid, m, nb, dc0, dc1; };
+    struct It { int tile, ci, nvalid, m, nb, dc0, dc1, bo; };
     auto load_tile = [&](It& t) {
       while (t.tile < total_tiles) {
         int z, m0, n0, kb_begin, num_kb;
@@ -312,6 +314,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           t.m = m0 + (int)rank * BM + quad * 32;
           t.dc0 = (int)(doff % pa.ldd) + t.nb;
           t.dc1 = (int)(doff / pa.ldd) + t.m;
+          t.bo = bo;
           t.ci = 0;
           return;
         }
@@ -321,7 +324,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     auto advance = [&](It& t) {
       if (++t.ci >= t.nvalid) { t.tile += num_clusters; load_tile(t); }
     };
-    It cur{cluster_id, 0, 0, 0, 0, 0, 0};
+    It cur{cluster_id, 0, 0, 0, 0, 0, 0, 0};
     load_tile(cur);
     It pf = cur;
     uint32_t cc = 0, tc = 0;
@@ -361,6 +364,11 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (cur.tile != cur_tile) {                     // first chunk of a new tile: accumulator ready?
         if (cur_tile >= 0) ++tc;
         cur_tile = cur.tile;
+        if (cur.bo != cur_bo) {                        // batched problems: own bias row / dropout sites
+          cur_bo = cur.bo;
+          if (bias0) e.bias = bias0 + (int64_t)cur_bo * args.bias_bo;
+          if (args.drop.site_bo) epi_setup_dropout(e, args.drop, cur_bo);
+        }
         if (has_bias) {                                // this warp's 8 x 16 bias values of the tile, one load
           const int nbias = cur.nb + (lane >> 2) * 2 * CW + (lane & 3) * 4;
           bias_tile = nbias < e.N ? __ldg(reinterpret_cast<const float4*>(e.bias + nbias)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -443,14 +451,14 @@ static int launch_pair_variant(const corrif_gemm_desc& g, const CUtensorMap (&tm
   PairArgs pa;
   KernelArgs& a = pa.k;
   a.epi = make_epi_args(g);
-  a.drop = DropArgs{g.drop_p, g.drop_site_a, g.drop_site_b, g.drop_seed, g.drop_seed_dev};
+  a.drop = make_drop_args(g);
   a.K = g.K; a.batch_inner = g.batch_inner;
   // no empty trailing split: the epilogue's chunk sequence assumes every tile is computed
   const int total_kb = (g.K + BK - 1) / BK;
   const int kb_per = (total_kb + g.split_k - 1) / g.split_k;
   a.split_k = (total_kb + kb_per - 1) / kb_per;
   a.a_bo = g.a_bo; a.a_bi = g.a_bi; a.b_bo = g.b_bo; a.b_bi = g.b_bi; a.d_bo = g.d_bo; a.d_bi = g.d_bi;
-  a.lda = g.lda; a.ldb = g.ldb;
+  a.lda = g.lda; a.ldb = g.ldb; a.bias_bo = g.bias_bo;
   pa.ldd = g.ldd;
   pa.has_in = (g.epilogue == CORRIF_EPI_BIAS_RESIDUAL || g.epilogue == CORRIF_EPI_MUL_DGELU) ? 1 : 0;
   pa.bpc = g.epilogue == CORRIF_EPI_BIAS_GELU ? 2 : 1;
@@ -516,6 +524,8 @@ bool gemm_tf32_pair_supported(const corrif_gemm_desc& g) {
   if (g.batch_outer * g.batch_inner > 1) {
     // batched problems address D through one map over the whole buffer: TMA cannot clip per batch
     if (g.M % 256 != 0 || g.N % 32 != 0) return false;
+    // ... and every problem's D must start at column 0 of a row of that map
+    if (g.d_bo % g.ldd != 0 || g.d_bi % g.ldd != 0 || g.N > g.ldd) return false;
     if (g.residual && g.ldr != g.ldd) return false;
     if (g.aux && g.ldaux != g.ldd) return false;
   }

@@ -69,19 +69,25 @@ def _split_for(out_tiles: int, kblocks: int, sms: int = 148) -> int:
 
 
 class _TBuf:
-    """Saved activations + gradient scratch of one Transformer at a given (B, N)."""
+    """Saved activations + gradient scratch of one Transformer at a given (B, N); with G > 1, of G
+    same-shaped transformers stacked on a leading dim (``sub(X)`` is the view of member X), so that
+    their GEMMs and attention run as single batched launches."""
 
-    def __init__(self, B: int, N: int, dev, fused_attn: bool, dropout: bool):
+    FIELDS = ("x1", "h", "qkv", "mean1", "rstd1", "mean2", "rstd2", "lse", "delta", "maskbits", "P", "dP",
+              "O", "x2", "h2", "u", "f1", "x3", "t0", "t1", "t2", "din", "dqkv")
+
+    def __init__(self, B: int, N: int, dev, fused_attn: bool, dropout: bool, G: int = 1):
         R = B * N
-        f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
-        self.B, self.N, self.R = B, N, R
+        lead = (G,) if G > 1 else ()
+        f = lambda *s: torch.empty(*lead, *s, device=dev, dtype=torch.float32)  # noqa: E731
+        self.B, self.N, self.R, self.G = B, N, R, G
         self.x1, self.h, self.qkv = f(R, C), f(R, C), f(R, 3 * C)
         self.mean1, self.rstd1, self.mean2, self.rstd2 = f(R), f(R), f(R), f(R)
         self.fused = fused_attn
+        self.P = self.dP = self.lse = self.delta = self.maskbits = None
         if fused_attn:    # fused tcgen05 attention: no N x N tensor in HBM, only lse (+ keep bits)
-            self.P = self.dP = None
             self.lse, self.delta = f(B * HEADS, N), f(B * HEADS, N)
-            self.maskbits = (torch.empty(B * HEADS, N, N // 32, device=dev, dtype=torch.int32)
+            self.maskbits = (torch.empty(*lead, B * HEADS, N, N // 32, device=dev, dtype=torch.int32)
                              if dropout else None)
         else:             # materialised path (fp32 checking mode)
             self.P, self.dP = f(B * HEADS, N, N), f(B * HEADS, N, N)
@@ -89,6 +95,14 @@ class _TBuf:
         # backward scratch
         self.t0, self.t1, self.t2, self.din = f(R, C), f(R, C), f(R, C), f(R, C)
         self.dqkv = f(R, 3 * C)
+
+    def sub(self, X: int) -> "_TBuf":
+        v = object.__new__(_TBuf)
+        v.B, v.N, v.R, v.G, v.fused = self.B, self.N, self.R, 1, self.fused
+        for k in self.FIELDS:
+            t = getattr(self, k)
+            setattr(v, k, None if t is None else t[X])
+        return v
 
 
 class FusionBlockEngine:
@@ -119,7 +133,31 @@ class FusionBlockEngine:
         self.fused_attn = self.prec == GEMM_TF32     # fused flash-style attention on the tcgen05 path
         self.wnames = [k for k in param_names()
                        if k.endswith(".weight") and "norm" not in k]
-        self.pw = {k: (torch.empty_like(params[k]) if self.rnd else params[k]) for k in self.wnames}
+        # The three intra-modal branches have identical shapes: on the tensor-core path their rounded
+        # weight copies (and plain bias copies) are STACKED [3, ...] so that each of their GEMMs is one
+        # batched launch (z = 3) instead of three small ones.
+        self.batched = self.rnd
+        self.pw, self.pws, self.pbs = {}, {}, {}
+        self._bias_copies = []                      # (parameter name, stacked destination row)
+        if self.batched:
+            wk = {kk: [self.tk[X][kk] for X in range(NM)] for kk in ("qkv_w", "proj_w", "fc1_w", "fc2_w")}
+            wk["enc_w"] = [f"{m}_encode_conv.weight" for m in MODALITIES]
+            wk["qkvc_w"] = [f"qkv_{m}.weight" for m in MODALITIES]
+            for kind, names in wk.items():
+                st = torch.empty(NM, *params[names[0]].shape, device=self.dev)
+                self.pws[kind] = st
+                for X, n in enumerate(names):
+                    self.pw[n] = st[X]
+            bk = {kk: [self.tk[X][kk] for X in range(NM)] for kk in ("proj_b", "fc1_b", "fc2_b")}
+            bk["enc_b"] = [f"{m}_encode_conv.bias" for m in MODALITIES]
+            bk["qkvc_b"] = [f"qkv_{m}.bias" for m in MODALITIES]
+            for kind, names in bk.items():
+                st = torch.empty(NM, params[names[0]].numel(), device=self.dev)
+                self.pbs[kind] = st
+                self._bias_copies += [(n, st[X]) for X, n in enumerate(names)]
+        for k in self.wnames:
+            if k not in self.pw:
+                self.pw[k] = torch.empty_like(params[k]) if self.rnd else params[k]
 
     def new_grad_buffers(self):
         """(flat, {name: view}): one zero-filled flat fp32 buffer holding every parameter gradient in
@@ -139,12 +177,13 @@ class FusionBlockEngine:
             return
         if getattr(self, "_rt", None) is None:
             i64 = dict(dtype=torch.int64, device=self.dev)
-            self._rt = (torch.tensor([self.p[k].data_ptr() for k in self.wnames], **i64),
-                        torch.tensor([self.pw[k].data_ptr() for k in self.wnames], **i64),
-                        torch.tensor([self.p[k].numel() for k in self.wnames], **i64),
-                        sum(self.p[k].numel() for k in self.wnames))
-        src, dst, cnt, total = self._rt
-        ops.round_tf32_multi(src, dst, cnt, len(self.wnames), total)
+            src = [self.p[k].data_ptr() for k in self.wnames] + [self.p[n].data_ptr() for n, _ in self._bias_copies]
+            dst = [self.pw[k].data_ptr() for k in self.wnames] + [d.data_ptr() for _, d in self._bias_copies]
+            cnt = [self.p[k].numel() for k in self.wnames] + [-self.p[n].numel() for n, _ in self._bias_copies]
+            self._rt = (torch.tensor(src, **i64), torch.tensor(dst, **i64), torch.tensor(cnt, **i64),
+                        len(src), sum(abs(c) for c in cnt))
+        src, dst, cnt, count, total = self._rt
+        ops.round_tf32_multi(src, dst, cnt, count, total)
 
     # ------------------------------------------------------------------------------------------
     def workspace(self, B: int) -> dict:
@@ -157,8 +196,7 @@ class FusionBlockEngine:
             "x6tok": f(NM, B * S, ENC), "skip": f(NM, B * S, C), "qkvi": f(NM, B * S, 3 * C),
             "fx6tok": f(B * S, ENC * NM), "tokens": f(B, (NM + 1) * S, C), "posmm": f((NM + 1) * S, C),
             "ytok": f(B * S, ENC * NM), "out": f(B, ENC * NM, S),
-            "tb": [_TBuf(B, S, dev, self.fused_attn, self.dropout_p > 0) for _ in range(NM)]
-                  + [_TBuf(B, (NM + 1) * S, dev, self.fused_attn, self.dropout_p > 0)],
+            "tbm": _TBuf(B, (NM + 1) * S, dev, self.fused_attn, self.dropout_p > 0),
             # backward
             "dytok": f(B * S, ENC * NM), "dtokc": f(NM + 1, B * S, C), "dqkvi": f(NM, B * S, 3 * C),
             "dtok": f(B * S, C), "dx6tok": f(B * S, ENC), "dfx6tok": f(B * S, ENC * NM),
@@ -166,6 +204,12 @@ class FusionBlockEngine:
             "scratch": f(max(ops.layernorm_bwd_scratch_floats(B * 4 * S),
                              ops.colsum_scratch_floats(B * 4 * S, 3 * C))),
         }
+        if self.batched:
+            ws["tbi"] = _TBuf(B, S, dev, self.fused_attn, self.dropout_p > 0, G=NM)
+            ws["tb"] = [ws["tbi"].sub(X) for X in range(NM)] + [ws["tbm"]]
+            ws["dtok3"], ws["dx6tok3"] = f(NM, B * S, C), f(NM, B * S, ENC)
+        else:
+            ws["tb"] = [_TBuf(B, S, dev, self.fused_attn, self.dropout_p > 0) for _ in range(NM)] + [ws["tbm"]]
         self._ws[B] = ws
         return ws
 
@@ -314,6 +358,129 @@ class FusionBlockEngine:
         return tb.t0
 
     # ------------------------------------------------------------------------------------------
+    # Batched intra-modal path (tensor-core precision): the three modalities' same-shaped GEMMs are one
+    # launch with batch_outer = 3 over stacked activations / weights / biases, their attention one
+    # launch over 3B "batches" (per-module dropout sites), so 8192-row problems become 24576-row ones.
+    def _blinear(self, x, w, out, R, N, K, bias=None, **k):
+        self._gemm(x, w, out, M=R, N=N, K=K, lda=K, ldb=K, ldd=N, bias=bias, batch=(NM, 1),
+                   a_step=(R * K, 0), b_step=(N * K, 0), d_step=(R * N, 0),
+                   bias_step=N if bias is not None else 0, tag="linear", **k)
+
+    def _bdgrad(self, dy, w, dx, R, N_out, K_in, **k):
+        self._gemm(dy, w, dx, M=R, N=K_in, K=N_out, lda=N_out, ldb=K_in, ldd=K_in, b_mn=True, batch=(NM, 1),
+                   a_step=(R * N_out, 0), b_step=(N_out * K_in, 0), d_step=(R * K_in, 0), tag="dgrad", **k)
+
+    def _bwgrad(self, dy, x, dws, R, N_out, K_in):
+        """dws: the three modalities' weight-gradient tensors; batched when they sit at a constant,
+        row-aligned stride (the flat gradient buffer of new_grad_buffers), else one launch each."""
+        d01 = (dws[1].data_ptr() - dws[0].data_ptr()) // 4
+        d12 = (dws[2].data_ptr() - dws[1].data_ptr()) // 4
+        if d01 != d12 or d01 <= 0 or d01 % K_in != 0:
+            for X in range(NM):
+                self._wgrad(dy[X], x[X], dws[X], R, N_out, K_in)
+            return
+        kblocks = R // 32
+        if N_out > 128 and K_in > 128:
+            tiles = NM * ((N_out + 255) // 256) * ((K_in + 255) // 256)
+            split = max(1, min((self.sms // 2) // tiles, max(1, kblocks // 4), 64))
+        else:
+            tiles = NM * ((N_out + 127) // 128) * ((K_in + (63 if K_in <= 64 else 127)) // (64 if K_in <= 64 else 128))
+            split = _split_for(tiles, kblocks, self.sms)
+        self._gemm(dy, x, dws[0], M=N_out, N=K_in, K=R, lda=N_out, ldb=K_in, ldd=K_in, a_mn=True, b_mn=True,
+                   batch=(NM, 1), a_step=(R * N_out, 0), b_step=(R * K_in, 0), d_step=(d01, 0),
+                   split_k=split, epilogue=EPI_ATOMIC_ADD, tag="wgrad")
+
+    def _bdrop(self, kind_a: int, kind_b: Optional[int] = None) -> dict:
+        d = self._drop(0, kind_a, kind_b)
+        if d:
+            d["drop_site_step"] = 8
+        return d
+
+    def _intra_fwd_batched(self, x6, ws):
+        """Tokenise + the three IntraFormers + qkv_* convs (mmvit4.py:457-479), batched."""
+        B, P_, p = self._B, self.p, self.dropout_p
+        R = B * S
+        tb, tk, W, Bs = ws["tbi"], self.tk, self.pws, self.pbs
+        for X in range(NM):
+            ops.transpose(x6[X], ws["x6tok"][X], B, ENC, S, round_out=self.rnd)
+        self._blinear(ws["x6tok"], W["enc_w"], ws["skip"], R, C, ENC, bias=Bs["enc_b"], epilogue=EPI_BIAS)
+        for X, m in enumerate(MODALITIES):
+            ops.layernorm_fwd(ws["skip"][X], P_[f"{m}_pos"], S, P_[tk[X]["ln1_w"]], P_[tk[X]["ln1_b"]], tb.x1[X],
+                              tb.h[X], tb.mean1[X], tb.rstd1[X], R, round_out=self.rnd)
+        self._blinear(tb.h, W["qkv_w"], tb.qkv, R, 3 * C, C, round_out=self.rnd)
+        ops.attention_fwd(tb.qkv, tb.O, tb.lse, tb.maskbits, NM * B, S, HEADS, HD, HD ** -0.5, p, self.seed,
+                          self.seed_dev, self._site(0, SITE_ATTN), round_out=self.rnd, group_batches=B,
+                          group_site_stride=8)
+        self._blinear(tb.O, W["proj_w"], tb.x2, R, C, C, bias=Bs["proj_b"], epilogue=EPI_BIAS_RESIDUAL,
+                      residual=tb.x1, ldr=C, **self._bdrop(SITE_PROJ, SITE_PRENORM))
+        for X in range(NM):
+            ops.layernorm_fwd(tb.x2[X], None, 1, P_[tk[X]["ln2_w"]], P_[tk[X]["ln2_b"]], None, tb.h2[X],
+                              tb.mean2[X], tb.rstd2[X], R, round_out=self.rnd)
+        self._blinear(tb.h2, W["fc1_w"], tb.f1, R, C, C, bias=Bs["fc1_b"], epilogue=EPI_BIAS_GELU, aux=tb.u,
+                      ldaux=C, round_out=self.rnd, **self._bdrop(SITE_FFN1))
+        self._blinear(tb.f1, W["fc2_w"], tb.x3, R, C, C, bias=Bs["fc2_b"], epilogue=EPI_BIAS_RESIDUAL,
+                      residual=tb.x2, ldr=C, round_out=self.rnd, **self._bdrop(SITE_FFN2))
+        self._blinear(tb.x3, W["qkvc_w"], ws["qkvi"], R, 3 * C, C, bias=Bs["qkvc_b"], epilogue=EPI_BIAS)
+
+    def _intra_bwd_batched(self, ws, g, sc):
+        """Backward of _intra_fwd_batched given ws["dqkvi"] (d qkv_* outputs) and ws["dtokc"][:3] (the
+        skip-path token gradients); fills ws["dx6"] and accumulates the parameter gradients."""
+        B, P_, p = self._B, self.p, self.dropout_p
+        R = B * S
+        tb, tk, W = ws["tbi"], self.tk, self.pws
+        gk = lambda kk: [g[tk[X][kk]] for X in range(NM)]  # noqa: E731
+        dq = ws["dqkvi"]
+        self._bwgrad(dq, tb.x3, [g[f"qkv_{m}.weight"] for m in MODALITIES], R, 3 * C, C)
+        for X, m in enumerate(MODALITIES):
+            ops.colsum(dq[X], 3 * C, R, 3 * C, g[f"qkv_{m}.bias"], sc, accumulate=True)
+        self._bdgrad(dq, W["qkvc_w"], tb.din, R, 3 * C, C)                          # d(trans_X)
+        # ---- FeedForward branch
+        df2 = tb.din
+        if p > 0:
+            for X in range(NM):
+                ops.dropout(tb.din[X], tb.t0[X], R * C, p, self.seed, self._site(X, SITE_FFN2), self.seed_dev)
+            df2 = tb.t0
+        self._bwgrad(df2, tb.f1, gk("fc2_w"), R, C, C)
+        for X in range(NM):
+            ops.colsum(df2[X], C, R, C, g[tk[X]["fc2_b"]], sc, accumulate=True)
+        self._bdgrad(df2, W["fc2_w"], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C,
+                     **self._bdrop(SITE_FFN1))
+        self._bwgrad(tb.t1, tb.h2, gk("fc1_w"), R, C, C)
+        for X in range(NM):
+            ops.colsum(tb.t1[X], C, R, C, g[tk[X]["fc1_b"]], sc, accumulate=True)
+        self._bdgrad(tb.t1, W["fc1_w"], tb.t2, R, C, C)                            # d(h2)
+        for X in range(NM):
+            ops.layernorm_bwd(tb.t2[X], tb.x2[X], P_[tk[X]["ln2_w"]], tb.mean2[X], tb.rstd2[X], tb.din[X],
+                              tb.t1[X], g[tk[X]["ln2_w"]], g[tk[X]["ln2_b"]], sc, R, accumulate=True)
+        dx2 = tb.t1
+        # ---- attention branch
+        dy = dx2
+        if p > 0:
+            for X in range(NM):
+                ops.dropout_add(dx2[X], None, tb.t0[X], R * C, p, self.seed, self._site(X, SITE_PROJ),
+                                self._site(X, SITE_PRENORM), self.seed_dev)
+            dy = tb.t0
+        self._bwgrad(dy, tb.O, gk("proj_w"), R, C, C)
+        for X in range(NM):
+            ops.colsum(dy[X], C, R, C, g[tk[X]["proj_b"]], sc, accumulate=True)
+        self._bdgrad(dy, W["proj_w"], tb.t2, R, C, C)                              # d(O)
+        ops.attention_bwd(tb.qkv, tb.O, tb.t2, tb.lse, tb.maskbits, tb.delta, tb.dqkv, NM * B, S, HEADS, HD,
+                          HD ** -0.5, p)
+        self._bwgrad(tb.dqkv, tb.h, gk("qkv_w"), R, 3 * C, C)
+        self._bdgrad(tb.dqkv, W["qkv_w"], tb.t2, R, 3 * C, C)                      # d(h)
+        for X, m in enumerate(MODALITIES):
+            ops.layernorm_bwd(tb.t2[X], tb.x1[X], P_[tk[X]["ln1_w"]], tb.mean1[X], tb.rstd1[X], dx2[X], tb.t0[X],
+                              g[tk[X]["ln1_w"]], g[tk[X]["ln1_b"]], sc, R, accumulate=True)   # t0 = d(x1)
+            ops.batchsum(tb.t0[X], B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
+            ops.add_rows(tb.t0[X], C, ws["dtokc"][X], C, ws["dtok3"][X], C, R, C)       # + skip path (:505)
+        # ---- encode convs
+        self._bwgrad(ws["dtok3"], ws["x6tok"], [g[f"{m}_encode_conv.weight"] for m in MODALITIES], R, C, ENC)
+        for X, m in enumerate(MODALITIES):
+            ops.colsum(ws["dtok3"][X], C, R, C, g[f"{m}_encode_conv.bias"], sc, accumulate=True)
+        self._bdgrad(ws["dtok3"], W["enc_w"], ws["dx6tok3"], R, C, ENC)
+        ops.transpose(ws["dx6tok3"], ws["dx6"], NM * B, S, ENC)
+
+    # ------------------------------------------------------------------------------------------
     def forward(self, x6: List[torch.Tensor], fused_x6: torch.Tensor) -> torch.Tensor:
         """x6: three [B,64,8,8,8]; fused_x6 [B,192,8,8,8] -> x6_inter [B,192,8,8,8] (workspace-owned;
         clone it if it must survive the next forward)."""
@@ -322,13 +489,16 @@ class FusionBlockEngine:
         self._B = B
         self.refresh_weights()
         W = self.pw
-        for X, m in enumerate(MODALITIES):
-            ops.transpose(x6[X], ws["x6tok"][X], B, ENC, S, round_out=self.rnd)            # :459
-            self._linear(ws["x6tok"][X], W[f"{m}_encode_conv.weight"], ws["skip"][X], B * S, C, ENC,
-                         bias=P_[f"{m}_encode_conv.bias"], epilogue=EPI_BIAS)              # :458
-            x3 = self._transformer_fwd(X, ws["skip"][X], P_[f"{m}_pos"], S, ws["tb"][X])   # :462
-            self._linear(x3, W[f"qkv_{m}.weight"], ws["qkvi"][X], B * S, 3 * C, C,
-                         bias=P_[f"qkv_{m}.bias"], epilogue=EPI_BIAS)                      # :477-479
+        if self.batched:
+            self._intra_fwd_batched(x6, ws)
+        else:
+            for X, m in enumerate(MODALITIES):
+                ops.transpose(x6[X], ws["x6tok"][X], B, ENC, S, round_out=self.rnd)            # :459
+                self._linear(ws["x6tok"][X], W[f"{m}_encode_conv.weight"], ws["skip"][X], B * S, C, ENC,
+                             bias=P_[f"{m}_encode_conv.bias"], epilogue=EPI_BIAS)              # :458
+                x3 = self._transformer_fwd(X, ws["skip"][X], P_[f"{m}_pos"], S, ws["tb"][X])   # :462
+                self._linear(x3, W[f"qkv_{m}.weight"], ws["qkvi"][X], B * S, 3 * C, C,
+                             bias=P_[f"qkv_{m}.bias"], epilogue=EPI_BIAS)                      # :477-479
         ops.inter_corr_fwd(ws["qkvi"], ws["skip"], ws["tokens"], NM, B, S, C)              # :481-507
         ops.transpose(fused_x6, ws["fx6tok"], B, ENC * NM, S, round_out=self.rnd)
         self._gemm(ws["fx6tok"], W["fused6_encode_conv.weight"], (ws["tokens"], NM * S * C),
@@ -373,6 +543,9 @@ class FusionBlockEngine:
         ops.transpose(ws["dfx6tok"], ws["dfused"], B, S, ENC * NM)
         # ---- inter-modal correlation
         ops.inter_corr_bwd(ws["qkvi"], dtokens, ws["dqkvi"], NM, B, S, C)
+        if self.batched:
+            self._intra_bwd_batched(ws, g, sc)
+            return (ws["dx6"].view(NM, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * NM, 8, 8, 8), grads)
         for X, m in enumerate(MODALITIES):
             tb = ws["tb"][X]
             dq = ws["dqkvi"][X]

@@ -126,7 +126,8 @@ def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K
          ldr: int = 0, aux=None, ldaux: int = 0, batch=(1, 1), a_step=(0, 0), b_step=(0, 0),
          d_step=(0, 0), split_k: int = 1, epilogue: int = EPI_STORE, precision: int = GEMM_TF32,
          alpha: float = 1.0, round_out: bool = False, tag: str = "", drop_p: float = 0.0,
-         drop_sites=(NO_SITE, NO_SITE), drop_seed: int = 0, drop_seed_dev=None):
+         drop_sites=(NO_SITE, NO_SITE), drop_seed: int = 0, drop_seed_dev=None, bias_step: int = 0,
+         drop_site_step: int = 0):
     """D = epilogue(alpha * A . B^T); see corrif_gemm in include/corrif.h for the layout rules."""
     g = GemmDesc()
     g.A, g.B, g.D = _ptr(A), _ptr(B), _ptr(D)
@@ -143,6 +144,8 @@ def gemm(A: TensorOrView, B: TensorOrView, D: TensorOrView, *, M: int, N: int, K
     if drop_p > 0:
         g.drop_p, g.drop_site_a, g.drop_site_b = drop_p, drop_sites[0], drop_sites[1]
         g.drop_seed, g.drop_seed_dev = drop_seed, _seed_dev(drop_seed_dev)
+        g.drop_site_bo = drop_site_step
+    g.bias_bo = bias_step
     cls = ("gemm_tf32" if precision == GEMM_TF32 else "gemm_fp32") + ("/" + tag if tag else "")
     det = "" if _prof is None else "M%d N%d K%d a%d b%d epi%d split%d z%d" % (
         M, N, K, int(a_mn), int(b_mn), epilogue, split_k, batch[0] * batch[1])
@@ -214,11 +217,11 @@ def softmax_bwd(P, dP, rows, cols, scale, p=0.0, seed=0, seed_dev=None, site=0):
 
 
 def attention_fwd(qkv, O, lse, maskbits, B, N, H=8, D=64, scale=0.125, p=0.0, seed=0, seed_dev=None,
-                  site=0, round_out=False):
+                  site=0, round_out=False, group_batches=0, group_site_stride=0):
     with _rec("attn_fwd", 4.0 * B * H * N * N * D):
         L.check(lib().corrif_attention_fwd(_ptr(qkv), _ptr(O), _ptr(lse), _ptr(maskbits, torch.int32), B, N,
-                                           H, D, scale, p, seed, _seed_dev(seed_dev), site,
-                                           int(round_out), _stream()), "corrif_attention_fwd")
+                                           H, D, scale, p, seed, _seed_dev(seed_dev), site, group_batches,
+                                           group_site_stride, int(round_out), _stream()), "corrif_attention_fwd")
     _count()
 
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CORRIF_ABI_VERSION 1
+#define CORRIF_ABI_VERSION 2
 
 #define CORRIF_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
 #define CORRIF_EARCH  (-2)  /* device is not sm_100 */
@@ -90,9 +90,10 @@ typedef struct corrif_gemm_desc {
    * Same decisions as corrif_dropout with the same (seed, seed_dev, site). */
   float drop_p;
   uint32_t drop_site_a, drop_site_b;
-  uint32_t reserved_;
+  uint32_t drop_site_bo;   /* batched problems: problem (bo, bi) draws from sites site_a/_b + bo * drop_site_bo */
   uint64_t drop_seed;
   const uint64_t* drop_seed_dev;
+  int64_t bias_bo;         /* batched problems: problem (bo, bi) adds bias + bo * bias_bo (element offset) */
 } corrif_gemm_desc;
 
 int corrif_gemm(const corrif_gemm_desc* desc, void* stream);
@@ -107,7 +108,8 @@ int corrif_sizeof_gemm_desc(void);
 int corrif_transpose(const float* in, float* out, int64_t batch, int32_t rows, int32_t cols,
                      int32_t round_tf32, void* stream);
 /* out = round-to-nearest-TF32(in): makes GEMM-ready copies of weights (in place allowed).
- * _multi: `count` tensors in one launch; src/dst/n are DEVICE arrays of pointers / element counts. */
+ * _multi: `count` tensors in one launch; src/dst/n are DEVICE arrays of pointers / element counts;
+ *         a NEGATIVE count -n copies n elements unrounded (stacked bias copies for batched GEMMs). */
 int corrif_round_tf32(const float* in, float* out, int64_t n, void* stream);
 int corrif_round_tf32_multi(const float* const* src, float* const* dst, const int64_t* n, int32_t count,
                             void* stream);
@@ -155,10 +157,15 @@ int corrif_softmax_bwd(const float* P, float* dP, int64_t rows, int32_t cols, fl
  *                            p_drop > 0 (counter RNG keyed by seed/site/element index as corrif_dropout),
  *                            read by bwd; may be NULL when p_drop == 0
  *   delta    [B*H, N]        scratch of bwd (rowsum(dO*O))
+ * Several independent attention modules of the same shape (the three intra-modal transformers) run
+ * as ONE launch over their stacked buffers: with group_batches = G > 0, batch b belongs to module
+ * b / G and draws its dropout decisions from site + (b / G) * group_site_stride with the element
+ * index of batch b % G - exactly what G-batch launches per module would draw.  0 = one module.
  * ------------------------------------------------------------------------------------------ */
 int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint32_t* maskbits, int32_t B,
                          int32_t N, int32_t H, int32_t D, float scale, float p_drop, uint64_t seed,
-                         const uint64_t* seed_dev, uint32_t site, int32_t round_tf32, void* stream);
+                         const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
+                         uint32_t group_site_stride, int32_t round_tf32, void* stream);
 int corrif_attention_bwd(const float* qkv, const float* O, const float* dO, const float* lse,
                          const uint32_t* maskbits, float* delta, float* dqkv, int32_t B, int32_t N,
                          int32_t H, int32_t D, float scale, float p_drop, void* stream);
