@@ -16,6 +16,7 @@
 //                 come out with kv as the row: dV += P^T . dO_i, dK += dS^T . Q_i  (Q_i, dO_i also MN-major)
 // fp32 tensor-core operands cannot share one smem image between K-major and MN-major use (MN-major
 // 32-bit operands only exist in the 128B_BASE32B swizzle), hence the duplicate TMA loads.
+#include <stdlib.h>
 #include "tc05.cuh"
 
 namespace corrif {
@@ -61,12 +62,15 @@ __device__ __forceinline__ void st_swz(uint32_t tile, int row, int col4, float4 
 }
 
 struct BwdArgs {
+  const float* qkv;          // [B*N, 3C]
+  const float* dO;           // [B*N, C]
   const float* lse;          // [B*H, N]  log2 domain
   const float* delta;        // [B*H, N]
   const uint32_t* maskbits;  // [B*H, N, N/32] or nullptr (no dropout)
   float* dqkv;               // [B*N, 3C]
   int N, H;
   float scale, scale_log2e, keep_scale;
+  unsigned long long* dbg;   // CORRIF_ATTN_TIMING=1: wait cycles of CTA 0 (bring-up aid), else null
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -97,7 +101,14 @@ attn_delta_kernel(const float* __restrict__ O, const float* __restrict__ dO, flo
 // (thread = (accumulator row = TMEM lane, column half g)); no cross-thread reduction is needed in the
 // backward because lse and delta are given.
 // ------------------------------------------------------------------------------------------------
-constexpr int BWD_THREADS = 320;
+// 16 element-wise warps (4 per TMEM lane quadrant, 16 accumulator columns each): with 8, every
+// scheduler had two warps running ~640-instruction dependent chains per tile and the kernels sat at
+// ~36 % issue utilisation, 4x off their instruction-issue bound (one CTA per SM: 512 TMEM columns).
+constexpr int EW = 16;                       // element-wise warps
+constexpr int EWT = 32 * EW;                 // element-wise threads
+constexpr int CG = 64 / (EW / 4);            // accumulator columns per thread
+constexpr int BWD_THREADS = 64 + EWT;
+static_assert(CG == 16, "tmem helpers below move 16 columns");
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -111,35 +122,75 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// dQ kernel.  S/dP double-buffered in TMEM; dS goes back to the tensor core THROUGH TMEM (tcgen05.st,
-// A-operand-in-TMEM MMA), which frees 32 KB of shared memory for a third K/V stage: with two stages a
-// stage was re-loaded (48 KB from L2) right before its next use and ~2500 cycles of TMA latency were
-// exposed on every tile (ncu: >50 % of stall samples in the two mbarrier waits).
+// Both kernels are bound by shared-memory bandwidth, not by math: a 128 x 64 x 8 TF32 MMA with both
+// operands in shared memory fetches 6 KB (48 clk at 128 B/clk) for 32 clk of tensor work, and TMA
+// writes the tiles into the same memory.  So the CTA's OWN tile (Q, dO / K, V) is parked in TMEM for
+// its lifetime as the A operand of the score products, the thread-produced operands (dS / P^T, dS^T)
+// overwrite the scores they were computed from IN PLACE, and everything left in shared memory is the
+// loop tile.  Re-use of a TMEM buffer needs no barrier: the tensor pipe executes in issue order, and
+// the score MMAs of tile j+2 are issued behind the gradient MMAs of tile j that read the buffer.
 // ------------------------------------------------------------------------------------------------
+// dQ kernel.  CTA = 128 queries (TMEM lane = q), loop over 64-key tiles.
 namespace dq {
-constexpr int KV_STAGES = 3;
-constexpr int OFF_Q = 0, OFF_DO = OFF_Q + TB * 256;
-constexpr int OFF_STAGE = OFF_DO + TB * 256;
+constexpr int KV_STAGES = 4;
 constexpr int STAGE_BYTES = 3 * TL * 256;   // K (K-major), K (MN-major), V (K-major)
-constexpr int SMEM_BYTES = OFF_STAGE + KV_STAGES * STAGE_BYTES + 1024;
-// TMEM columns: buffer u in {0,1}: S [128u, +64) dP [128u+64, +64); dQ [256,320); dS operand u: [320+64u, +64)
+constexpr int SMEM_BYTES = KV_STAGES * STAGE_BYTES + 1024;
+// TMEM columns: buffer u in {0,1}: S -> dS [128u, +64), dP [128u+64, +64); dQ [256,320); Q [320,384); dO [384,448)
 constexpr uint32_t TMEM_COLS = 512;
 }  // namespace dq
 
+// 8 TS-mode MMAs over the 64-wide head dim: A = 64 TMEM columns, B = K-major [rows x 64] smem tile
+__device__ __forceinline__ void mma_headdim_ts(uint32_t tm, uint32_t tA, uint32_t sB, int rowsB, uint32_t idesc) {
+#pragma unroll
+  for (int t = 0; t < HD / 8; ++t)
+    tcgen05_mma_tf32_ts(tm, tA + 8 * t, smem_desc_kmajor(sB + (t >> 2) * (rowsB * 128) + (t & 3) * 32), idesc,
+                        t > 0 ? 1u : 0u);
+}
+// my CG columns of one row of a [rows, ld] matrix -> TMEM (optionally rounded to TF32)
+__device__ __forceinline__ void row_slice_to_tmem(const float* src, uint32_t taddr, bool round) {
+  uint32_t r[CG];
+#pragma unroll
+  for (int q4 = 0; q4 < CG / 4; ++q4) {
+    const float4 v = ld4(src + 4 * q4);
+    r[4 * q4] = __float_as_uint(v.x); r[4 * q4 + 1] = __float_as_uint(v.y);
+    r[4 * q4 + 2] = __float_as_uint(v.z); r[4 * q4 + 3] = __float_as_uint(v.w);
+  }
+  if (round) {
+#pragma unroll
+    for (int c = 0; c < CG; ++c) r[c] += 0x1000u;
+  }
+  tmem_st16(taddr, r);
+}
+
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
-                   const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmKmn,
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmKmn,
                    const BwdArgs a) {
   using namespace dq;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t own_full, kv_full[KV_STAGES], kv_free[KV_STAGES], sdp_full[2], sdp_free[2],
-      ds_full[2], ds_free[2], fin;
+  __shared__ __align__(8) uint64_t own_full, kv_full[KV_STAGES], kv_free[KV_STAGES], sdp_full[2], ds_full[2], fin;
   __shared__ uint32_t tmem_holder;
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = sb + OFF_Q, sDO = sb + OFF_DO;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, bh = blockIdx.y;
   const int b = bh / a.H, h = bh % a.H, C = a.H * HD;
@@ -147,12 +198,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int ntiles = a.N / TL;
 
   if (warp == 0 && lane == 0) {
-    mbar_init(&own_full, 1);
+    mbar_init(&own_full, EWT);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&sdp_full[s], 1); mbar_init(&sdp_free[s], 256);
-      mbar_init(&ds_full[s], 256); mbar_init(&ds_free[s], 1);
-    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], EWT); }
     mbar_init(&fin, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -161,87 +209,92 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_holder;
-  const uint32_t tDQ = tmem + 256, tDS = tmem + 320;
+  const uint32_t tDQ = tmem + 256, tQ = tmem + 320, tDO = tmem + 384;
 
   if (warp == 0 && lane == 0) {
-    mbar_expect_tx(&own_full, 2 * TB * 256);
-    tma_tile(sQ, &tmQ, &own_full, h * HD, q_row0, TB);
-    tma_tile(sDO, &tmDO, &own_full, h * HD, q_row0, TB);
     for (int j = 0; j < ntiles; ++j) {
       const int s = j % KV_STAGES;
       const uint32_t ph = (uint32_t)(j / KV_STAGES) & 1u;
       mbar_wait(&kv_free[s], ph ^ 1u);
       mbar_expect_tx(&kv_full[s], STAGE_BYTES);
-      const uint32_t st = sb + OFF_STAGE + s * STAGE_BYTES;
+      const uint32_t st = sb + s * STAGE_BYTES;
       tma_tile(st, &tmKk, &kv_full[s], C + h * HD, kv_row0 + j * TL, TL);              // K  K-major
       tma_tile(st + TL * 256, &tmKmn, &kv_full[s], C + h * HD, kv_row0 + j * TL, TL);  // K  MN-major
       tma_tile(st + 2 * TL * 256, &tmKk, &kv_full[s], 2 * C + h * HD, kv_row0 + j * TL, TL);  // V K-major
     }
-  } else if (warp == 1 && lane == 0) {
-    constexpr uint32_t id_s = idesc_tf32(TL, false, false);   // [128 x 64] = own . loop^T over d
-    constexpr uint32_t id_q = idesc_tf32(HD, false, true);    // [128 x 64] = dS . K (K MN-major)
-    mbar_wait(&own_full, 0);
+  } else if (warp == 1) {
+    // whole warp walks the loop (uniform control flow), one elected lane issues: see elect_one()
+    constexpr uint32_t id_s = idesc_tf32(TL, false, false);   // [128 x 64] = own(TMEM) . loop^T over d
+    constexpr uint32_t id_q = idesc_tf32(HD, false, true);    // [128 x 64] = dS(TMEM) . K (K MN-major)
+    mbar_wait(&own_full, 0);                                   // Q and dO are in TMEM
     auto issue_sdp = [&](int j) {
       const int u = j & 1, s = j % KV_STAGES;
-      const uint32_t st = sb + OFF_STAGE + s * STAGE_BYTES;
+      const uint32_t st = sb + s * STAGE_BYTES;
       mbar_wait(&kv_full[s], (uint32_t)(j / KV_STAGES) & 1u);
-      mbar_wait(&sdp_free[u], ((uint32_t)(j >> 1) & 1u) ^ 1u);   // element-wise done with buffer u (tile j-2)
       tcgen05_fence_after();
-      mma_headdim(tmem + 128 * u, sQ, TB, st, TL, id_s);                       // S  = Q  K_j^T
-      mma_headdim(tmem + 128 * u + 64, sDO, TB, st + 2 * TL * 256, TL, id_s);  // dP = dO V_j^T
-      tcgen05_commit(&sdp_full[u]);
+      if (elect_one()) {
+        mma_headdim_ts(tmem + 128 * u, tQ, st, TL, id_s);                        // S  = Q  K_j^T
+        mma_headdim_ts(tmem + 128 * u + 64, tDO, st + 2 * TL * 256, TL, id_s);   // dP = dO V_j^T
+        tcgen05_commit(&sdp_full[u]);
+      }
+      __syncwarp();
     };
-    issue_sdp(0);
+    issue_sdp(0);                                     // S/dP run two tiles ahead of the element-wise warps
+    if (ntiles > 1) issue_sdp(1);
     for (int j = 0; j < ntiles; ++j) {
-      if (j + 1 < ntiles) issue_sdp(j + 1);                    // overlaps the element-wise work of tile j
       const int u = j & 1, s = j % KV_STAGES;
       mbar_wait(&ds_full[u], (uint32_t)(j >> 1) & 1u);
       tcgen05_fence_after();
-      const uint32_t kmn = sb + OFF_STAGE + s * STAGE_BYTES + TL * 256;
+      const uint32_t kmn = sb + s * STAGE_BYTES + TL * 256;
+      if (elect_one()) {
 #pragma unroll
-      for (int t = 0; t < TL / 8; ++t)                          // dQ += dS(TMEM) . K_j
-        tcgen05_mma_tf32_ts(tDQ, tDS + 64 * u + 8 * t, smem_desc_mnmajor(kmn + t * 1024, TL * 128), id_q,
-                            (j > 0 || t > 0) ? 1u : 0u);
-      tcgen05_commit(&ds_free[u]);
-      tcgen05_commit(&kv_free[s]);
+        for (int t = 0; t < TL / 8; ++t)                          // dQ += dS(TMEM, in S's columns) . K_j
+          tcgen05_mma_tf32_ts(tDQ, tmem + 128 * u + 8 * t, smem_desc_mnmajor(kmn + t * 1024, TL * 128), id_q,
+                              (j > 0 || t > 0) ? 1u : 0u);
+        tcgen05_commit(&kv_free[s]);
+        if (j == ntiles - 1) tcgen05_commit(&fin);
+      }
+      __syncwarp();
+      if (j + 2 < ntiles) issue_sdp(j + 2);           // overwrites buffer u behind dQ(j): pipe order
     }
-    tcgen05_commit(&fin);
   } else if (warp >= 2) {
     const int quad = warp & 3, g = (warp - 2) >> 2, row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int col0 = g * CG;                                   // my columns of every 64-wide tile
     const int q = qt * TB + row;
+    row_slice_to_tmem(a.qkv + (int64_t)(q_row0 + row) * (3 * C) + h * HD + col0, tQ + lane_addr + col0, false);
+    row_slice_to_tmem(a.dO + (int64_t)(q_row0 + row) * C + h * HD + col0, tDO + lane_addr + col0, true);
+    tcgen05_fence_before();
+    mbar_arrive(&own_full);
     const float lse = a.lse[(int64_t)bh * a.N + q], dl = a.delta[(int64_t)bh * a.N + q];
     const uint32_t* mrow = a.maskbits ? a.maskbits + ((int64_t)bh * a.N + q) * (a.N / 32) : nullptr;
-    uint32_t rs[32], rp[32];
+    uint32_t rs[CG], rp[CG];
     for (int j = 0; j < ntiles; ++j) {
       const int u = j & 1;
       const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
-      const uint32_t bits = mrow ? mrow[j * 2 + g] : 0xffffffffu;
+      const uint32_t bits = mrow ? (mrow[j * 2 + (col0 >> 5)] >> (col0 & 31)) : 0xffffffffu;
       mbar_wait(&sdp_full[u], ph2);
       tcgen05_fence_after();
-      tmem_ld32_nowait(tmem + 128 * u + lane_addr + g * 32, rs);
-      tmem_ld32_nowait(tmem + 128 * u + 64 + lane_addr + g * 32, rp);
+      tmem_ld16_nowait(tmem + 128 * u + lane_addr + col0, rs);
+      tmem_ld16_nowait(tmem + 128 * u + 64 + lane_addr + col0, rp);
       tmem_wait_ld();
-      tcgen05_fence_before();
-      mbar_arrive(&sdp_free[u]);                               // S/dP buffer u may be refilled
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < CG; ++c) {
         const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - lse);
         const float dp = ((bits >> c) & 1u) ? __uint_as_float(rp[c]) * a.keep_scale : 0.f;
-        rs[c] = __float_as_uint(round_tf32(p * (dp - dl) * a.scale));
+        rs[c] = __float_as_uint(round_tf32_operand(p * (dp - dl) * a.scale));
       }
-      mbar_wait(&ds_free[u], ph2 ^ 1u);                        // dQ MMA of tile j-2 has read dS buffer u
-      tcgen05_fence_after();
-      tmem_st32(tDS + 64 * u + lane_addr + g * 32, rs);
+      tmem_st16(tmem + 128 * u + lane_addr + col0, rs);          // dS replaces S in place
       tcgen05_fence_before();
       mbar_arrive(&ds_full[u]);
     }
     mbar_wait(&fin, 0);
     tcgen05_fence_after();
-    float* orow = a.dqkv + (int64_t)(q_row0 + row) * (3 * C) + h * HD + g * 32;
-    tmem_ld32(tDQ + lane_addr + g * 32, rs);
+    float* orow = a.dqkv + (int64_t)(q_row0 + row) * (3 * C) + h * HD + col0;
+    tmem_ld16_nowait(tDQ + lane_addr + col0, rs);
+    tmem_wait_ld();
 #pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4)
+    for (int q4 = 0; q4 < CG / 4; ++q4)
       st4(orow + 4 * q4, make_float4(__uint_as_float(rs[4 * q4]), __uint_as_float(rs[4 * q4 + 1]),
                                      __uint_as_float(rs[4 * q4 + 2]), __uint_as_float(rs[4 * q4 + 3])));
   }
@@ -251,37 +304,34 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// dK / dV kernel.  S^T/dP^T double-buffered in TMEM, P^T and dS^T handed to the tensor core through
-// TMEM, both query-tile images (K-major for S^T/dP^T, MN-major for dV/dK) double-buffered in smem.
+// dK / dV kernel.  CTA = 128 keys (TMEM lane = kv), loop over 64-query tiles; computes the TRANSPOSED
+// scores S^T = K_j Q_i^T, dP^T = V_j dO_i^T so that P^T / dS^T come out with "thread = accumulator row".
 // ------------------------------------------------------------------------------------------------
 namespace dkv {
-constexpr int OFF_K = 0, OFF_V = OFF_K + TB * 256;
-constexpr int OFF_KM = OFF_V + TB * 256;            // 2 stages x {Q_i K-major, dO_i K-major}
-constexpr int KM_BYTES = 2 * TL * 256;
-constexpr int OFF_MN = OFF_KM + 2 * KM_BYTES;       // 2 stages x {Q_i MN-major, dO_i MN-major}
-constexpr int MN_BYTES = 2 * TL * 256;
-constexpr int SMEM_BYTES = OFF_MN + 2 * MN_BYTES + 1024;
-// TMEM columns: buffer u: S^T [128u,+64) dP^T [128u+64,+64); dV [256,320) dK [320,384);
-//               P^T operand [384,448); dS^T operand [448,512)
+constexpr int STAGES = 3;
+constexpr int KM_BYTES = 2 * TL * 256;              // {Q_i K-major, dO_i K-major}
+constexpr int MN_BYTES = 2 * TL * 256;              // {Q_i MN-major, dO_i MN-major}
+constexpr int OFF_KM = 0, OFF_MN = STAGES * KM_BYTES;
+constexpr int SMEM_BYTES = OFF_MN + STAGES * MN_BYTES + 1024;
+// TMEM columns: buffer u: S^T -> P^T [128u,+64), dP^T -> dS^T [128u+64,+64); dV [256,320) dK [320,384);
+//               K [384,448) V [448,512)
 constexpr uint32_t TMEM_COLS = 512;
 }  // namespace dkv
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
-attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {32,128} K-major (K_j, V_j)
-                    const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {32, 64} K-major (Q_i)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {32, 64} K-major (Q_i)
                     const __grid_constant__ CUtensorMap tmQmn,   // qkv,  box {32, 64} MN-major (Q_i)
                     const __grid_constant__ CUtensorMap tmDOk,   // dO,   box {32, 64} K-major
                     const __grid_constant__ CUtensorMap tmDOmn,  // dO,   box {32, 64} MN-major
                     const BwdArgs a) {
   using namespace dkv;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t own_full, km_full[2], km_free[2], mn_full[2], mn_free[2], st_full[2], st_free[2],
-      pds_full, pds_free, fin;
+  __shared__ __align__(8) uint64_t own_full, km_full[STAGES], km_free[STAGES], mn_full[STAGES], mn_free[STAGES],
+      st_full[2], pds_full[2], fin;
   __shared__ uint32_t tmem_holder;
-  __shared__ float s_lse[2][TL], s_delta[2][TL];
+  __shared__ __align__(16) float s_lse[2][TL], s_delta[2][TL];
   __shared__ uint32_t s_bits[2][TL][4];              // keep bits of (query c, key word w) for this tile
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sK = sb + OFF_K, sV = sb + OFF_V;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, bh = blockIdx.y;
   const int b = bh / a.H, h = bh % a.H, C = a.H * HD;
@@ -289,12 +339,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
   const int ntiles = a.N / TL;
 
   if (warp == 0 && lane == 0) {
-    mbar_init(&own_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    mbar_init(&own_full, EWT);
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&km_full[s], 1); mbar_init(&km_free[s], 1); mbar_init(&mn_full[s], 1); mbar_init(&mn_free[s], 1);
-      mbar_init(&st_full[s], 1); mbar_init(&st_free[s], 256);
     }
-    mbar_init(&pds_full, 256); mbar_init(&pds_free, 1); mbar_init(&fin, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&pds_full[s], EWT); }
+    mbar_init(&fin, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_holder, TMEM_COLS);
@@ -302,15 +352,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_holder;
-  const uint32_t tDV = tmem + 256, tDK = tmem + 320, tPT = tmem + 384, tDST = tmem + 448;
+  const uint32_t tDV = tmem + 256, tDK = tmem + 320, tK = tmem + 384, tV = tmem + 448;
 
   if (warp == 0 && lane == 0) {
-    mbar_expect_tx(&own_full, 2 * TB * 256);
-    tma_tile(sK, &tmKVk, &own_full, C + h * HD, kv_row0, TB);
-    tma_tile(sV, &tmKVk, &own_full, 2 * C + h * HD, kv_row0, TB);
     for (int i = 0; i < ntiles; ++i) {
-      const int s = i & 1;
-      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const int s = i % STAGES;
+      const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
       mbar_wait(&km_free[s], ph ^ 1u);
       mbar_expect_tx(&km_full[s], KM_BYTES);
       tma_tile(sb + OFF_KM + s * KM_BYTES, &tmQk, &km_full[s], h * HD, q_base + i * TL, TL);
@@ -320,91 +367,127 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKVk,   // qkv,  box {3
       tma_tile(sb + OFF_MN + s * MN_BYTES, &tmQmn, &mn_full[s], h * HD, q_base + i * TL, TL);
       tma_tile(sb + OFF_MN + s * MN_BYTES + TL * 256, &tmDOmn, &mn_full[s], h * HD, q_base + i * TL, TL);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    // whole warp walks the loop (uniform control flow), one elected lane issues: see elect_one()
     constexpr uint32_t id_s = idesc_tf32(TL, false, false);
     constexpr uint32_t id_g = idesc_tf32(HD, false, true);
-    mbar_wait(&own_full, 0);
+    mbar_wait(&own_full, 0);                                   // K and V are in TMEM
     auto issue_st = [&](int i) {
-      const int u = i & 1;
-      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-      const uint32_t km = sb + OFF_KM + u * KM_BYTES;
-      mbar_wait(&km_full[u], ph);
-      mbar_wait(&st_free[u], ph ^ 1u);
+      const int u = i & 1, s = i % STAGES;
+      const uint32_t km = sb + OFF_KM + s * KM_BYTES;
+      long long t0 = a.dbg ? clock64() : 0;
+      mbar_wait(&km_full[s], (uint32_t)(i / STAGES) & 1u);
+      if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) atomicAdd(&a.dbg[0], (unsigned long long)(clock64() - t0));
       tcgen05_fence_after();
-      mma_headdim(tmem + 128 * u, sK, TB, km, TL, id_s);                   // S^T  = K_j Q_i^T
-      mma_headdim(tmem + 128 * u + 64, sV, TB, km + TL * 256, TL, id_s);   // dP^T = V_j dO_i^T
-      tcgen05_commit(&km_free[u]);
-      tcgen05_commit(&st_full[u]);
+      if (elect_one()) {
+        mma_headdim_ts(tmem + 128 * u, tK, km, TL, id_s);                    // S^T  = K_j Q_i^T
+        mma_headdim_ts(tmem + 128 * u + 64, tV, km + TL * 256, TL, id_s);    // dP^T = V_j dO_i^T
+        tcgen05_commit(&km_free[s]);
+        tcgen05_commit(&st_full[u]);
+      }
+      __syncwarp();
     };
-    issue_st(0);
+    issue_st(0);                                      // S^T/dP^T run two tiles ahead of the element-wise warps
+    if (ntiles > 1) issue_st(1);
     for (int i = 0; i < ntiles; ++i) {
-      if (i + 1 < ntiles) issue_st(i + 1);
-      const int s = i & 1;
-      mbar_wait(&pds_full, (uint32_t)i & 1u);
-      mbar_wait(&mn_full[s], (uint32_t)(i >> 1) & 1u);
+      const int u = i & 1, s = i % STAGES;
+      long long t0 = a.dbg ? clock64() : 0;
+      mbar_wait(&pds_full[u], (uint32_t)(i >> 1) & 1u);
+      long long t1 = a.dbg ? clock64() : 0;
+      mbar_wait(&mn_full[s], (uint32_t)(i / STAGES) & 1u);
+      if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+        atomicAdd(&a.dbg[2], (unsigned long long)(t1 - t0)); atomicAdd(&a.dbg[3], (unsigned long long)(clock64() - t1));
+      }
       tcgen05_fence_after();
       const uint32_t mn = sb + OFF_MN + s * MN_BYTES;
+      if (elect_one()) {
 #pragma unroll
-      for (int t = 0; t < TL / 8; ++t)                                      // dV += P^T(TMEM)  dO_i
-        tcgen05_mma_tf32_ts(tDV, tPT + 8 * t, smem_desc_mnmajor(mn + TL * 256 + t * 1024, TL * 128), id_g,
-                            (i > 0 || t > 0) ? 1u : 0u);
+        for (int t = 0; t < TL / 8; ++t)                                      // dV += P^T(TMEM)  dO_i
+          tcgen05_mma_tf32_ts(tDV, tmem + 128 * u + 8 * t, smem_desc_mnmajor(mn + TL * 256 + t * 1024, TL * 128),
+                              id_g, (i > 0 || t > 0) ? 1u : 0u);
 #pragma unroll
-      for (int t = 0; t < TL / 8; ++t)                                      // dK += dS^T(TMEM) Q_i
-        tcgen05_mma_tf32_ts(tDK, tDST + 8 * t, smem_desc_mnmajor(mn + t * 1024, TL * 128), id_g,
-                            (i > 0 || t > 0) ? 1u : 0u);
-      tcgen05_commit(&mn_free[s]);
-      tcgen05_commit(&pds_free);
+        for (int t = 0; t < TL / 8; ++t)                                      // dK += dS^T(TMEM) Q_i
+          tcgen05_mma_tf32_ts(tDK, tmem + 128 * u + 64 + 8 * t, smem_desc_mnmajor(mn + t * 1024, TL * 128), id_g,
+                              (i > 0 || t > 0) ? 1u : 0u);
+        tcgen05_commit(&mn_free[s]);
+        if (i == ntiles - 1) tcgen05_commit(&fin);
+      }
+      __syncwarp();
+      if (i + 2 < ntiles) issue_st(i + 2);            // overwrites buffer u behind dV/dK(i): pipe order
     }
-    tcgen05_commit(&fin);
   } else if (warp >= 2) {
     const int quad = warp & 3, g = (warp - 2) >> 2, row = quad * 32 + lane;   // kv row == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const int t256 = threadIdx.x - 64;                           // 0..255 among the 8 warps
+    const int t = threadIdx.x - 64;                              // 0..EWT-1 among the element-wise warps
+    const int col0 = g * CG;
     const int words = a.N / 32;
-    uint32_t rs[32], rp[32];
+    {
+      const float* krow = a.qkv + (int64_t)(kv_row0 + row) * (3 * C) + C + h * HD + col0;
+      row_slice_to_tmem(krow, tK + lane_addr + col0, false);
+      row_slice_to_tmem(krow + C, tV + lane_addr + col0, false);
+      tcgen05_fence_before();
+      mbar_arrive(&own_full);
+    }
+    uint32_t rs[CG], rp[CG];
     for (int i = 0; i < ntiles; ++i) {
       const int u = i & 1;
       const uint32_t ph2 = (uint32_t)(i >> 1) & 1u;
       // per-column statistics and keep bits of this query tile -> smem (double-buffered by tile parity)
-      if (t256 < TL) s_lse[u][t256] = a.lse[(int64_t)bh * a.N + i * TL + t256];
-      else if (t256 < 2 * TL) s_delta[u][t256 - TL] = a.delta[(int64_t)bh * a.N + i * TL + (t256 - TL)];
-      if (a.maskbits)
-        s_bits[u][t256 >> 2][t256 & 3] =
-            a.maskbits[((int64_t)bh * a.N + i * TL + (t256 >> 2)) * words + kt * 4 + (t256 & 3)];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&st_full[u], ph2);
-      tcgen05_fence_after();
-      tmem_ld32_nowait(tmem + 128 * u + lane_addr + g * 32, rs);
-      tmem_ld32_nowait(tmem + 128 * u + 64 + lane_addr + g * 32, rp);
-      tmem_wait_ld();
-      tcgen05_fence_before();
-      mbar_arrive(&st_free[u]);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int qc = g * 32 + c;                               // query column inside the tile
-        const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - s_lse[u][qc]);
-        float keep = 1.0f;
-        if (a.maskbits) keep = ((s_bits[u][qc][quad] >> lane) & 1u) ? a.keep_scale : 0.f;
-        const float pd = p * keep;
-        rs[c] = __float_as_uint(round_tf32(pd));
-        rp[c] = __float_as_uint(round_tf32((pd * __uint_as_float(rp[c]) - p * s_delta[u][qc]) * a.scale));
+      if (t < TL) s_lse[u][t] = a.lse[(int64_t)bh * a.N + i * TL + t];
+      else if (t < 2 * TL) s_delta[u][t - TL] = a.delta[(int64_t)bh * a.N + i * TL + (t - TL)];
+      else if (a.maskbits && t >= 256) {
+        const int e = t - 256;                                   // (query c = e / 4, key word e % 4)
+        s_bits[u][e >> 2][e & 3] = a.maskbits[((int64_t)bh * a.N + i * TL + (e >> 2)) * words + kt * 4 + (e & 3)];
       }
-      mbar_wait(&pds_free, ((uint32_t)i & 1u) ^ 1u);            // dV/dK MMAs of tile i-1 have read the operands
+      const long long e0 = a.dbg ? clock64() : 0;
+      asm volatile("bar.sync 1, %0;" :: "n"(EWT) : "memory");
+      const long long e1 = a.dbg ? clock64() : 0;
+      mbar_wait(&st_full[u], ph2);
+      const long long e2 = a.dbg ? clock64() : 0;
       tcgen05_fence_after();
-      tmem_st32(tPT + lane_addr + g * 32, rs);
-      tmem_st32(tDST + lane_addr + g * 32, rp);
+      tmem_ld16_nowait(tmem + 128 * u + lane_addr + col0, rs);
+      tmem_ld16_nowait(tmem + 128 * u + 64 + lane_addr + col0, rp);
+      tmem_wait_ld();
+      const long long e3 = a.dbg ? clock64() : 0;
+#pragma unroll
+      for (int c4 = 0; c4 < CG / 4; ++c4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(&s_lse[u][col0 + 4 * c4]);
+        const float4 d4 = *reinterpret_cast<const float4*>(&s_delta[u][col0 + 4 * c4]);
+        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * c4 + k, qc = col0 + c;               // query column inside the tile
+          const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - ls[k]);
+          float keep = 1.0f;
+          if (a.maskbits) keep = ((s_bits[u][qc][quad] >> lane) & 1u) ? a.keep_scale : 0.f;
+          const float pd = p * keep;
+          rs[c] = __float_as_uint(round_tf32_operand(pd));
+          rp[c] = __float_as_uint(round_tf32_operand((pd * __uint_as_float(rp[c]) - p * ds[k]) * a.scale));
+        }
+      }
+      const long long e4 = a.dbg ? clock64() : 0;
+      tmem_st16(tmem + 128 * u + lane_addr + col0, rs);          // P^T  replaces S^T  in place
+      tmem_st16(tmem + 128 * u + 64 + lane_addr + col0, rp);     // dS^T replaces dP^T in place
       tcgen05_fence_before();
-      mbar_arrive(&pds_full);
+      mbar_arrive(&pds_full[u]);
+      if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) {
+        atomicAdd(&a.dbg[4], (unsigned long long)(e1 - e0));   // smem stats load + named barrier
+        atomicAdd(&a.dbg[5], (unsigned long long)(e2 - e1));   // wait S^T/dP^T
+        atomicAdd(&a.dbg[6], (unsigned long long)(e3 - e2));   // tmem ld
+        atomicAdd(&a.dbg[7], (unsigned long long)(e4 - e3));   // math
+        atomicAdd(&a.dbg[9], (unsigned long long)(clock64() - e4));   // tmem st
+        atomicAdd(&a.dbg[10], 1ull);
+      }
     }
     mbar_wait(&fin, 0);
     tcgen05_fence_after();
-    float* krow = a.dqkv + (int64_t)(kv_row0 + row) * (3 * C) + C + h * HD + g * 32;
+    float* krow = a.dqkv + (int64_t)(kv_row0 + row) * (3 * C) + C + h * HD + col0;
     float* vrow = krow + C;
-    tmem_ld32_nowait(tDV + lane_addr + g * 32, rs);
-    tmem_ld32_nowait(tDK + lane_addr + g * 32, rp);
+    tmem_ld16_nowait(tDV + lane_addr + col0, rs);
+    tmem_ld16_nowait(tDK + lane_addr + col0, rp);
     tmem_wait_ld();
 #pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4) {
+    for (int q4 = 0; q4 < CG / 4; ++q4) {
       st4(vrow + 4 * q4, make_float4(__uint_as_float(rs[4 * q4]), __uint_as_float(rs[4 * q4 + 1]),
                                      __uint_as_float(rs[4 * q4 + 2]), __uint_as_float(rs[4 * q4 + 3])));
       st4(krow + 4 * q4, make_float4(__uint_as_float(rp[4 * q4]), __uint_as_float(rp[4 * q4 + 1]),
@@ -439,12 +522,10 @@ extern "C" int corrif_attention_bwd(const float* qkv, const float* O, const floa
   int rc = launch_status("attention_delta");
   if (rc) return rc;
 
-  CUtensorMap q128, do128, k64, k64mn, kv128, q64, q64mn, do64, do64mn;
-  if ((rc = tc05::encode_map(&q128, qkv, 3 * C, rows, 3 * C, 32, TB, false))) return rc;
-  if ((rc = tc05::encode_map(&do128, dO, C, rows, C, 32, TB, false))) return rc;
+  CUtensorMap k64, k64mn, q64, q64mn, do64, do64mn;
   if ((rc = tc05::encode_map(&k64, qkv, 3 * C, rows, 3 * C, 32, TL, false))) return rc;
   if ((rc = tc05::encode_map(&k64mn, qkv, 3 * C, rows, 3 * C, 32, TL, true))) return rc;
-  kv128 = q128; q64 = k64; q64mn = k64mn;
+  q64 = k64; q64mn = k64mn;
   if ((rc = tc05::encode_map(&do64, dO, C, rows, C, 32, TL, false))) return rc;
   if ((rc = tc05::encode_map(&do64mn, dO, C, rows, C, 32, TL, true))) return rc;
   static bool configured = false;
@@ -456,12 +537,28 @@ extern "C" int corrif_attention_bwd(const float* qkv, const float* O, const floa
     configured = true;
   }
   BwdArgs a;
-  a.lse = lse; a.delta = delta; a.maskbits = p_drop > 0.f ? maskbits : nullptr; a.dqkv = dqkv;
+  a.qkv = qkv; a.dO = dO; a.lse = lse; a.delta = delta; a.maskbits = p_drop > 0.f ? maskbits : nullptr; a.dqkv = dqkv;
   a.N = N; a.H = H; a.scale = scale; a.scale_log2e = scale * 1.4426950408889634f;
   a.keep_scale = 1.0f / (1.0f - p_drop);
+  static const bool timing = getenv("CORRIF_ATTN_TIMING") != nullptr;
+  static unsigned long long* dbg = nullptr;
+  a.dbg = nullptr;
+  if (timing) {
+    if (!dbg) cudaMalloc(&dbg, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), st);
+    a.dbg = dbg;
+  }
   dim3 grid(N / TB, B * H);
-  attn_bwd_dq_kernel<<<grid, BWD_THREADS, dq::SMEM_BYTES, st>>>(q128, do128, k64, k64mn, a);
+  attn_bwd_dq_kernel<<<grid, BWD_THREADS, dq::SMEM_BYTES, st>>>(k64, k64mn, a);
   if ((rc = launch_status("attention_bwd_dq"))) return rc;
-  attn_bwd_dkv_kernel<<<grid, BWD_THREADS, dkv::SMEM_BYTES, st>>>(kv128, q64, q64mn, do64, do64mn, a);
+  attn_bwd_dkv_kernel<<<grid, BWD_THREADS, dkv::SMEM_BYTES, st>>>(q64, q64mn, do64, do64mn, a);
+  if (timing) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[attn dkv N%d] CTA0: mma wait q/do %llu  pds_full %llu  mn_full %llu | ew: stats+bar %llu  wait S %llu"
+            "  tmem ld %llu  math %llu  tmem st %llu  tiles %llu\n", N, h[0], h[2], h[3], h[4],
+            h[5], h[6], h[7], h[9], h[10]);
+  }
   return launch_status("attention_bwd_dkv");
 }

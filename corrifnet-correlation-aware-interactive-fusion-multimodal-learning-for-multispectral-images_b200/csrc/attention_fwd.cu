@@ -28,11 +28,16 @@ using namespace tc05;
 constexpr int TQ = 128, TK = 64, HD = 64;
 constexpr int Q_BYTES = TQ * HD * 4, K_BYTES = TK * HD * 4, V_BYTES = TK * HD * 4;
 constexpr int KV_BYTES = K_BYTES + V_BYTES;
-constexpr int OFF_Q = 0, OFF_KV = Q_BYTES;            // two {K_j, V_j} stages
-constexpr int SMEM_BYTES = OFF_KV + 2 * KV_BYTES + 1024;
-constexpr uint32_t TMEM_COLS = 256;   // S: [0,64)  O_j: [64,128)  P_j (A operand of P.V): [128,192)
+constexpr int KV_STAGES = 3;                          // {K_j, V_j} ring
+constexpr int OFF_KV = 0;
+constexpr int SMEM_BYTES = OFF_KV + KV_STAGES * KV_BYTES + 1024;
+// TMEM columns.  S: [0,64)  O_j: [64,128)  P_j (A operand of P.V): [128,192)  Q (A operand of Q.K^T): [192,256)
+// Q lives in TMEM for the CTA's lifetime: with both operands in shared memory a 128 x 64 x 8 TF32 MMA
+// has to fetch 6 KB (48 clk at 128 B/clk) for 32 clk of math; with A in TMEM only K_j's 2 KB remain.
+constexpr uint32_t TMEM_COLS = 256;
 
 struct FwdArgs {
+  const float* qkv;
   float* O;
   float* lse;
   uint32_t* maskbits;   // [B*H, N, N/32] keep bits (written when dropout is on), or nullptr
@@ -55,12 +60,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_free[2], s_full, s_free, p_full, o_full;
+  __shared__ __align__(8) uint64_t q_full, kv_full[KV_STAGES], kv_free[KV_STAGES], s_full, s_free, p_full, o_full;
   __shared__ uint32_t tmem_holder;
   __shared__ float s_max[2][2][TQ];    // [tile parity][column half][row]
   __shared__ float s_sum[2][TQ];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = sbase + OFF_Q;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, bh = blockIdx.y;
   const int b = bh / a.H, h = bh % a.H;
@@ -70,11 +74,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int ntiles = a.N / TK;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmQ) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmV) : "memory");
-    mbar_init(&q_full, 1); mbar_init(&s_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1); }
+    mbar_init(&q_full, 256); mbar_init(&s_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1); }
     mbar_init(&s_free, 256); mbar_init(&p_full, 256); mbar_init(&o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -83,16 +86,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_holder;
-  const uint32_t tS = tmem, tO = tmem + 64, tP = tmem + 128;
+  const uint32_t tS = tmem, tO = tmem + 64, tP = tmem + 128, tQ = tmem + 192;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    mbar_expect_tx(&q_full, Q_BYTES);
-    tma_load_2d(sQ, &tmQ, &q_full, h * HD, q_row0);
-    tma_load_2d(sQ + TQ * 128, &tmQ, &q_full, h * HD + 32, q_row0);
     for (int j = 0; j < ntiles; ++j) {
-      const int s = j & 1;
-      mbar_wait(&kv_free[s], ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      const int s = j % KV_STAGES;
+      mbar_wait(&kv_free[s], ((uint32_t)(j / KV_STAGES) & 1u) ^ 1u);
       mbar_expect_tx(&kv_full[s], KV_BYTES);
       const uint32_t sK = sbase + OFF_KV + s * KV_BYTES, sV = sK + K_BYTES;
       tma_load_2d(sK, &tmK, &kv_full[s], C + h * HD, kv_row0 + j * TK);
@@ -100,32 +100,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_load_2d(sV, &tmV, &kv_full[s], 2 * C + h * HD, kv_row0 + j * TK);
       tma_load_2d(sV + TK * 128, &tmV, &kv_full[s], 2 * C + h * HD + 32, kv_row0 + j * TK);
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== tcgen05 issuer =====================
+  } else if (warp == 1) {
+    // ===================== tcgen05 issuer (uniform warp, one elected lane: see elect_one()) =========
     constexpr uint32_t idesc_s = idesc_tf32(TK, false, false);   // S[128 x 64] = Q . K^T
     constexpr uint32_t idesc_o = idesc_tf32(HD, false, true);    // O[128 x 64] = P . V (V MN-major)
-    mbar_wait(&q_full, 0);
+    mbar_wait(&q_full, 0);                           // the softmax warps have put Q into TMEM
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
-      const int s = j & 1;
+      const int s = j % KV_STAGES;
       const uint32_t sK = sbase + OFF_KV + s * KV_BYTES, sV = sK + K_BYTES;
-      mbar_wait(&kv_full[s], (uint32_t)(j >> 1) & 1u);
+      mbar_wait(&kv_full[s], (uint32_t)(j / KV_STAGES) & 1u);
       mbar_wait(&s_free, ph ^ 1u);                 // softmax finished reading S_{j-1}
       tcgen05_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int t = 0; t < HD / 8; ++t) {
-        const uint64_t ad = smem_desc_kmajor(sQ + (t >> 2) * (TQ * 128) + (t & 3) * 32);
-        const uint64_t bd = smem_desc_kmajor(sK + (t >> 2) * (TK * 128) + (t & 3) * 32);
-        tcgen05_mma_tf32(tS, ad, bd, idesc_s, t > 0 ? 1u : 0u);
+        for (int t = 0; t < HD / 8; ++t) {           // S = Q(TMEM) . K_j^T
+          const uint64_t bd = smem_desc_kmajor(sK + (t >> 2) * (TK * 128) + (t & 3) * 32);
+          tcgen05_mma_tf32_ts(tS, tQ + 8 * t, bd, idesc_s, t > 0 ? 1u : 0u);
+        }
+        tcgen05_commit(&s_full);
       }
-      tcgen05_commit(&s_full);
+      __syncwarp();
       mbar_wait(&p_full, ph);                      // P_j in TMEM, O_{j-1} already consumed
       tcgen05_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int t = 0; t < TK / 8; ++t)             // O_j = P_j(TMEM) . V_j
-        tcgen05_mma_tf32_ts(tO, tP + 8 * t, smem_desc_mnmajor(sV + t * 1024, TK * 128), idesc_o, t > 0 ? 1u : 0u);
-      tcgen05_commit(&kv_free[s]);
-      tcgen05_commit(&o_full);
+        for (int t = 0; t < TK / 8; ++t)             // O_j = P_j(TMEM) . V_j
+          tcgen05_mma_tf32_ts(tO, tP + 8 * t, smem_desc_mnmajor(sV + t * 1024, TK * 128), idesc_o, t > 0 ? 1u : 0u);
+        tcgen05_commit(&kv_free[s]);
+        tcgen05_commit(&o_full);
+      }
+      __syncwarp();
     }
   } else if (warp >= 2) {
     // ===================== online softmax (8 warps) =====================
@@ -145,6 +150,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int d = 0; d < 32; ++d) acc[d] = 0.f;
     uint32_t r[32];
+    {   // my half of my query row -> TMEM (qkv is already TF32-rounded by its producer)
+      const float* qrow = a.qkv + (int64_t)(q_row0 + row) * (3 * C) + h * HD + g * 32;
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 v = ld4(qrow + 4 * q4);
+        r[4 * q4] = __float_as_uint(v.x); r[4 * q4 + 1] = __float_as_uint(v.y);
+        r[4 * q4 + 2] = __float_as_uint(v.z); r[4 * q4 + 3] = __float_as_uint(v.w);
+      }
+      tmem_st32(tQ + lane_addr + g * 32, r);
+      tcgen05_fence_before();
+      mbar_arrive(&q_full);
+    }
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
       // add my half of O_{j-1} (its P.V has finished: the P buffer is free again too); the rescale
@@ -188,7 +205,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           p.z = (km & 4u) ? p.z : 0.f; p.w = (km & 8u) ? p.w : 0.f;
           keepbits |= km << (4 * q4);
         }
-        p = round_tf32_4(p);                        // P is only ever a tensor-core operand
+        p.x = round_tf32_operand(p.x); p.y = round_tf32_operand(p.y);   // P is only ever a tensor-core operand
+        p.z = round_tf32_operand(p.z); p.w = round_tf32_operand(p.w);
         r[4 * q4 + 0] = __float_as_uint(p.x); r[4 * q4 + 1] = __float_as_uint(p.y);
         r[4 * q4 + 2] = __float_as_uint(p.z); r[4 * q4 + 3] = __float_as_uint(p.w);
       }
@@ -261,7 +279,7 @@ extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint
     configured = true;
   }
   FwdArgs a;
-  a.O = O; a.lse = lse; a.maskbits = maskbits; a.N = N; a.H = H; a.ldo = C;
+  a.qkv = qkv; a.O = O; a.lse = lse; a.maskbits = maskbits; a.N = N; a.H = H; a.ldo = C;
   a.scale_log2e = scale * 1.4426950408889634f;
   a.thresh = p_drop > 0.f ? dropout_threshold(p_drop) : 0u;
   a.keep_scale = 1.0f / (1.0f - p_drop);

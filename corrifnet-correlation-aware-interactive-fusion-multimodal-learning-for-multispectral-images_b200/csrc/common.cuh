@@ -67,6 +67,13 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// For values that go STRAIGHT into a tensor-core operand (registers -> TMEM): adding half a TF32 ulp
+// and letting the MMA truncate the low 13 bits IS round-to-nearest (ties away, like cvt.rna) - one
+// integer add instead of the four instructions cvt.rna.tf32 expands to on sm_100 (add, Inf test,
+// select, mask).  Only for finite values (P in [0,1], dS); the low bits are left dirty.
+__device__ __forceinline__ float round_tf32_operand(float x) {
+  return __uint_as_float(__float_as_uint(x) + 0x1000u);
+}
 __device__ __forceinline__ float4 round_tf32_4(float4 v) {
   return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
 }

@@ -37,6 +37,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       :: "r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// One lane of a fully converged warp.  Single-thread tcgen05 / TMA issue code must be guarded by THIS
+// (warp-uniform control flow + elect.sync), not by `lane == 0`: under a lane test the compiler treats
+// every operand as thread-divergent and wraps each UTCHMMA in an ELECT / R2UR / BRA.U.ANY waterfall
+// (~19 instructions, ~80 cycles per MMA - more than the 32 cycles a 128x64x8 TF32 MMA computes for).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
