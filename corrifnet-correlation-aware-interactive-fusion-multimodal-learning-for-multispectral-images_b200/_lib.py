@@ -63,6 +63,7 @@ PROTOTYPES = {
     "corrif_dropout_add": (C.c_int, [f32p, f32p, f32p, i64, f32, u64, u64p, u32, u32, stream_t]),
     "corrif_colsum_scratch_floats": (i64, [i64, i32]),
     "corrif_colsum": (C.c_int, [f32p, i64, i64, i32, f32p, C.c_int, f32p, stream_t]),
+    "corrif_colsum_batched": (C.c_int, [f32p, i64, i64, i32, f32p, i32, i64, i64, C.c_int, stream_t]),
     "corrif_batchsum": (C.c_int, [f32p, i64, i64, i64, f32p, C.c_int, stream_t]),
     "corrif_add_rows": (C.c_int, [f32p, i64, f32p, i64, f32p, i64, i64, i32, stream_t]),
     "corrif_inter_corr_fwd": (C.c_int, [f32p, f32p, f32p, i32, i32, i32, i32, stream_t]),

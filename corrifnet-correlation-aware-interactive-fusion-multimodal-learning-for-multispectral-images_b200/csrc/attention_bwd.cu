@@ -269,10 +269,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
     const float lse = a.lse[(int64_t)bh * a.N + q], dl = a.delta[(int64_t)bh * a.N + q];
     const uint32_t* mrow = a.maskbits ? a.maskbits + ((int64_t)bh * a.N + q) * (a.N / 32) : nullptr;
     uint32_t rs[CG], rp[CG];
+    uint32_t bits_next = mrow ? mrow[col0 >> 5] : 0xffffffffu;   // keep-bit word, fetched one tile ahead
     for (int j = 0; j < ntiles; ++j) {
       const int u = j & 1;
       const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
-      const uint32_t bits = mrow ? (mrow[j * 2 + (col0 >> 5)] >> (col0 & 31)) : 0xffffffffu;
+      const uint32_t bits = bits_next >> (col0 & 31);
+      if (mrow && j + 1 < ntiles) bits_next = mrow[(j + 1) * 2 + (col0 >> 5)];
       mbar_wait(&sdp_full[u], ph2);
       tcgen05_fence_after();
       tmem_ld16_nowait(tmem + 128 * u + lane_addr + col0, rs);
@@ -429,18 +431,29 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
       mbar_arrive(&own_full);
     }
     uint32_t rs[CG], rp[CG];
+    // Per-column statistics (lse, delta) and keep bits of a query tile go through smem, double-buffered
+    // by tile parity and fetched from HBM ONE TILE AHEAD into a register (thread t owns one value), so
+    // no global-load latency sits between the named barrier and the math.
+    const int role = t < TL ? 0 : (t < 2 * TL ? 1 : ((a.maskbits && t >= 256) ? 2 : 3));
+    const int e = t - 256;                                       // role 2: (query c = e / 4, key word e % 4)
+    auto fetch = [&](int i) -> uint32_t {
+      if (role == 0) return __float_as_uint(a.lse[(int64_t)bh * a.N + i * TL + t]);
+      if (role == 1) return __float_as_uint(a.delta[(int64_t)bh * a.N + i * TL + (t - TL)]);
+      if (role == 2) return a.maskbits[((int64_t)bh * a.N + i * TL + (e >> 2)) * words + kt * 4 + (e & 3)];
+      return 0u;
+    };
+    auto stash = [&](int u, uint32_t v) {
+      if (role == 0) s_lse[u][t] = __uint_as_float(v);
+      else if (role == 1) s_delta[u][t - TL] = __uint_as_float(v);
+      else if (role == 2) s_bits[u][e >> 2][e & 3] = v;
+    };
+    stash(0, fetch(0));
     for (int i = 0; i < ntiles; ++i) {
       const int u = i & 1;
       const uint32_t ph2 = (uint32_t)(i >> 1) & 1u;
-      // per-column statistics and keep bits of this query tile -> smem (double-buffered by tile parity)
-      if (t < TL) s_lse[u][t] = a.lse[(int64_t)bh * a.N + i * TL + t];
-      else if (t < 2 * TL) s_delta[u][t - TL] = a.delta[(int64_t)bh * a.N + i * TL + (t - TL)];
-      else if (a.maskbits && t >= 256) {
-        const int e = t - 256;                                   // (query c = e / 4, key word e % 4)
-        s_bits[u][e >> 2][e & 3] = a.maskbits[((int64_t)bh * a.N + i * TL + (e >> 2)) * words + kt * 4 + (e & 3)];
-      }
       const long long e0 = a.dbg ? clock64() : 0;
-      asm volatile("bar.sync 1, %0;" :: "n"(EWT) : "memory");
+      asm volatile("bar.sync 1, %0;" :: "n"(EWT) : "memory");    // tile i's stats visible; buffer u^1 is free
+      const uint32_t nxt = i + 1 < ntiles ? fetch(i + 1) : 0u;
       const long long e1 = a.dbg ? clock64() : 0;
       mbar_wait(&st_full[u], ph2);
       const long long e2 = a.dbg ? clock64() : 0;
@@ -465,6 +478,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
           rp[c] = __float_as_uint(round_tf32_operand((pd * __uint_as_float(rp[c]) - p * ds[k]) * a.scale));
         }
       }
+      if (i + 1 < ntiles) stash(u ^ 1, nxt);
       const long long e4 = a.dbg ? clock64() : 0;
       tmem_st16(tmem + 128 * u + lane_addr + col0, rs);          // P^T  replaces S^T  in place
       tmem_st16(tmem + 128 * u + 64 + lane_addr + col0, rp);     // dS^T replaces dP^T in place

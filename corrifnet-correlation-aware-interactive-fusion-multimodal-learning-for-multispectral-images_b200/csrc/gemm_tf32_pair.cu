@@ -342,14 +342,19 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
     long long t_wait = 0, t_work = 0, t_ld = 0, t_tm = 0;
+    const long long t_loop0 = pa.dbg ? clock64() : 0;
     while (cur.tile < total_tiles) {
       const uint32_t box = boxes + (uint32_t)box_i * BOX_BYTES;
       const int box2_i = box_i + 1 == nbox ? 0 : box_i + 1;
       const uint32_t box2 = boxes + (uint32_t)box2_i * BOX_BYTES;      // BIAS_GELU: pre-activation out
       if (lane == 0) {
-        // at most one store group pending: the store of chunk cc-2 has finished reading its box, which
-        // is the one the prefetch below refills (and, without loads, the one chunk cc writes)
-        bulk_wait_read<1>();
+        // the box about to be refilled must have been read by its TMA store.  Loading / two-output
+        // epilogues refill the box of chunk cc-2 (one store group may stay pending); store-only ones
+        // rotate through all nbox boxes, so nbox-1 groups may stay pending - the stores queue behind
+        // the operand loads in the TMA unit and need more than two chunks of time to drain.
+        if (has_in || bpc == 2 || nbox == 2) bulk_wait_read<1>();
+        else if (nbox == 4) bulk_wait_read<3>();
+        else bulk_wait_read<5>();
         if (has_in && pf.tile < total_tiles) {
           mbar_expect_tx(&ld_bar[ew][pf_box], BOX_BYTES);
           tma_load_2d(boxes + pf_box * BOX_BYTES, &tmIn, &ld_bar[ew][pf_box], pf.dc0 + pf.ci * 2 * CW, pf.dc1);
@@ -431,6 +436,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       atomicAdd(&pa.dbg[6], (unsigned long long)cc);
       atomicAdd(&pa.dbg[7], (unsigned long long)t_ld);
       atomicAdd(&pa.dbg[8], (unsigned long long)t_tm);
+      atomicAdd(&pa.dbg[9], (unsigned long long)(clock64() - t_loop0));
     }
   }
   tcgen05_fence_before();
@@ -500,6 +506,7 @@ static int launch_pair_variant(const corrif_gemm_desc& g, const CUtensorMap (&tm
     cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
     if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / 2; }
     max_clusters = n < num_sms() / 2 ? n : num_sms() / 2;
+    if (const char* ov = getenv("CORRIF_PAIR_CLUSTERS")) { const int v = atoi(ov); if (v > 0 && v <= max_clusters) max_clusters = v; }
     if (timing) fprintf(stderr, "[pair] max co-resident clusters: %d\n", max_clusters);
   }
   const int clusters = total < max_clusters ? total : max_clusters;
@@ -511,8 +518,8 @@ static int launch_pair_variant(const corrif_gemm_desc& g, const CUtensorMap (&tm
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[pair M%d N%d K%d split%d epi%d] cluster0 cycles: prod wait empty %llu/%llu  mma wait tempty %llu"
-            "  mma wait full %llu  epi wait acc %llu  epi work %llu (tmem ld %llu, wait in %llu)  chunks %llu\n", g.M, g.N, g.K, a.split_k,
-            g.epilogue, h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[7], h[6]);
+            "  mma wait full %llu  epi wait acc %llu  epi work %llu (tmem ld %llu, wait in %llu)  chunks %llu  epi loop total %llu\n", g.M, g.N, g.K, a.split_k,
+            g.epilogue, h[0], h[1], h[2], h[3], h[4], h[5], h[8], h[7], h[6], h[9]);
   }
   return launch_status("gemm_tf32_pair");
 }

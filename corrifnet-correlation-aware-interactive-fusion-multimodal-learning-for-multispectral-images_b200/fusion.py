@@ -390,6 +390,17 @@ class FusionBlockEngine:
                    batch=(NM, 1), a_step=(R * N_out, 0), b_step=(R * K_in, 0), d_step=(d01, 0),
                    split_k=split, epilogue=EPI_ATOMIC_ADD, tag="wgrad")
 
+    def _bcolsum(self, x, cols, R, outs, sc):
+        """Bias gradients of the three branches: x [3, R, cols] -> outs[X] (+=), one launch when the
+        outputs sit at a constant stride."""
+        d01 = (outs[1].data_ptr() - outs[0].data_ptr()) // 4
+        d12 = (outs[2].data_ptr() - outs[1].data_ptr()) // 4
+        if d01 == d12 and d01 > 0 and d01 % 4 == 0:
+            ops.colsum_batched(x, cols, R, cols, outs[0], NM, R * cols, d01, accumulate=True)
+        else:
+            for X in range(NM):
+                ops.colsum(x[X], cols, R, cols, outs[X], sc, accumulate=True)
+
     def _bdrop(self, kind_a: int, kind_b: Optional[int] = None) -> dict:
         d = self._drop(0, kind_a, kind_b)
         if d:
@@ -431,8 +442,7 @@ class FusionBlockEngine:
         gk = lambda kk: [g[tk[X][kk]] for X in range(NM)]  # noqa: E731
         dq = ws["dqkvi"]
         self._bwgrad(dq, tb.x3, [g[f"qkv_{m}.weight"] for m in MODALITIES], R, 3 * C, C)
-        for X, m in enumerate(MODALITIES):
-            ops.colsum(dq[X], 3 * C, R, 3 * C, g[f"qkv_{m}.bias"], sc, accumulate=True)
+        self._bcolsum(dq, 3 * C, R, [g[f"qkv_{m}.bias"] for m in MODALITIES], sc)
         self._bdgrad(dq, W["qkvc_w"], tb.din, R, 3 * C, C)                          # d(trans_X)
         # ---- FeedForward branch
         df2 = tb.din
@@ -441,13 +451,11 @@ class FusionBlockEngine:
                 ops.dropout(tb.din[X], tb.t0[X], R * C, p, self.seed, self._site(X, SITE_FFN2), self.seed_dev)
             df2 = tb.t0
         self._bwgrad(df2, tb.f1, gk("fc2_w"), R, C, C)
-        for X in range(NM):
-            ops.colsum(df2[X], C, R, C, g[tk[X]["fc2_b"]], sc, accumulate=True)
+        self._bcolsum(df2, C, R, gk("fc2_b"), sc)
         self._bdgrad(df2, W["fc2_w"], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C,
                      **self._bdrop(SITE_FFN1))
         self._bwgrad(tb.t1, tb.h2, gk("fc1_w"), R, C, C)
-        for X in range(NM):
-            ops.colsum(tb.t1[X], C, R, C, g[tk[X]["fc1_b"]], sc, accumulate=True)
+        self._bcolsum(tb.t1, C, R, gk("fc1_b"), sc)
         self._bdgrad(tb.t1, W["fc1_w"], tb.t2, R, C, C)                            # d(h2)
         for X in range(NM):
             ops.layernorm_bwd(tb.t2[X], tb.x2[X], P_[tk[X]["ln2_w"]], tb.mean2[X], tb.rstd2[X], tb.din[X],
@@ -461,8 +469,7 @@ class FusionBlockEngine:
                                 self._site(X, SITE_PRENORM), self.seed_dev)
             dy = tb.t0
         self._bwgrad(dy, tb.O, gk("proj_w"), R, C, C)
-        for X in range(NM):
-            ops.colsum(dy[X], C, R, C, g[tk[X]["proj_b"]], sc, accumulate=True)
+        self._bcolsum(dy, C, R, gk("proj_b"), sc)
         self._bdgrad(dy, W["proj_w"], tb.t2, R, C, C)                              # d(O)
         ops.attention_bwd(tb.qkv, tb.O, tb.t2, tb.lse, tb.maskbits, tb.delta, tb.dqkv, NM * B, S, HEADS, HD,
                           HD ** -0.5, p)
@@ -475,8 +482,7 @@ class FusionBlockEngine:
             ops.add_rows(tb.t0[X], C, ws["dtokc"][X], C, ws["dtok3"][X], C, R, C)       # + skip path (:505)
         # ---- encode convs
         self._bwgrad(ws["dtok3"], ws["x6tok"], [g[f"{m}_encode_conv.weight"] for m in MODALITIES], R, C, ENC)
-        for X, m in enumerate(MODALITIES):
-            ops.colsum(ws["dtok3"][X], C, R, C, g[f"{m}_encode_conv.bias"], sc, accumulate=True)
+        self._bcolsum(ws["dtok3"], C, R, [g[f"{m}_encode_conv.bias"] for m in MODALITIES], sc)
         self._bdgrad(ws["dtok3"], W["enc_w"], ws["dx6tok3"], R, C, ENC)
         ops.transpose(ws["dx6tok3"], ws["dx6"], NM * B, S, ENC)
 

@@ -266,6 +266,13 @@ def colsum(x, ld, rows, cols, out, scratch, accumulate=False):
     _count(1)
 
 
+def colsum_batched(x, ld, rows, cols, out, batch, x_bstride, out_bstride, accumulate=False):
+    with _rec('colsum', 4.0 * rows * cols * batch):
+        L.check(lib().corrif_colsum_batched(_ptr(x), ld, rows, cols, _ptr(out), batch, x_bstride, out_bstride,
+                                            int(accumulate), _stream()), "corrif_colsum_batched")
+    _count(1)
+
+
 def batchsum(x, batch, stride, n, out, accumulate=False):
     with _rec('batchsum', 4.0 * (batch + 1) * n):
         L.check(lib().corrif_batchsum(_ptr(x), batch, stride, n, _ptr(out), int(accumulate), _stream()),

@@ -202,6 +202,10 @@ int corrif_dropout_add(const float* x, const float* res, float* out, int64_t n, 
 int64_t corrif_colsum_scratch_floats(int64_t rows, int32_t cols);
 int corrif_colsum(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out,
                   int accumulate, float* scratch, void* stream);
+/* `batch` independent column sums in one launch: problem b reads x + b*x_bstride and adds into
+ * out + b*out_bstride (the three intra-modal branches' bias gradients). */
+int corrif_colsum_batched(const float* x, int64_t ld, int64_t rows, int32_t cols, float* out, int32_t batch,
+                          int64_t x_bstride, int64_t out_bstride, int accumulate, void* stream);
 int corrif_batchsum(const float* x, int64_t batch, int64_t stride, int64_t n, float* out,
                     int accumulate, void* stream);
 /* out[r*ldo + c] = a[r*lda + c] + b[r*ldb + c]   (rows x cols, cols % 4 == 0) */
