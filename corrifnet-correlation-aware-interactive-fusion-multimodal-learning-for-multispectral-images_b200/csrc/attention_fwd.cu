@@ -19,6 +19,7 @@
 //               into a register accumulator with the usual rescale.
 // Shared memory is ~97 KB and TMEM 128 columns per CTA, so two CTAs share an SM and one's softmax
 // overlaps the other's MMAs.  lse (log2-domain log-sum-exp) is saved for the backward.
+#include <stdlib.h>
 #include "tc05.cuh"
 
 namespace corrif {
@@ -52,10 +53,13 @@ struct FwdArgs {
   int group_batches;          // > 0: batch b is module b / group_batches (own dropout site)
   uint32_t group_site_stride;
   int round_out;
+  unsigned long long* dbg;    // CORRIF_ATTN_TIMING=1: softmax-warp wait cycles of CTA 0, else null
 };
 
 constexpr int NUM_THREADS = 320;     // producer warp, MMA warp, 8 softmax warps
 
+// DROP is a template parameter so that the dropout code is straight-line (no branch per float4 group).
+template <bool DROP>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs a) {
@@ -142,7 +146,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t key = 0;
     const int grp = a.group_batches > 0 ? b / a.group_batches : 0;
     const int bh_rng = a.group_batches > 0 ? (b - grp * a.group_batches) * a.H + h : bh;
-    if (a.thresh != 0u)
+    if (DROP)
       key = dropout_key(a.seed + (a.seed_dev ? *a.seed_dev : 0ull), a.site + (uint32_t)grp * a.group_site_stride);
     const uint64_t drop_row = ((uint64_t)bh_rng * a.N + q_in_head) * (uint64_t)a.N;
     float m = -INFINITY, l = 0.f;
@@ -166,6 +170,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t ph = (uint32_t)j & 1u;
       // add my half of O_{j-1} (its P.V has finished: the P buffer is free again too); the rescale
       // by this tile's alpha follows once the new row max is known
+      const long long c0 = a.dbg ? clock64() : 0;
       if (j > 0) {
         mbar_wait(&o_full, ph ^ 1u);
         tcgen05_fence_after();
@@ -173,14 +178,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(r[c]);
       }
+      const long long c1 = a.dbg ? clock64() : 0;
       mbar_wait(&s_full, ph);
+      const long long c2 = a.dbg ? clock64() : 0;
       tcgen05_fence_after();
       tmem_ld32(tS + lane_addr + g * 32, r);                 // my 32 score columns (kept in registers)
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
       s_max[ph][g][row] = mx;
+      const long long c3 = a.dbg ? clock64() : 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      const long long c4 = a.dbg ? clock64() : 0;
       mx = fmaxf(mx, s_max[ph][g ^ 1][row]);
       const float m_new = fmaxf(m, mx * a.scale_log2e);
       const float alpha = ex2_approx(m - m_new);
@@ -190,6 +199,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // p = 2^(s*scale*log2e - m), partial row sum, dropout, publish my k-block of P_j
       float rs = 0.f;
       uint32_t keepbits = 0u;
+      const uint64_t q0 = (drop_row + (uint64_t)(j * TK + g * 32)) >> 2;
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         float4 p;
@@ -198,9 +208,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         p.z = ex2_approx(__uint_as_float(r[4 * q4 + 2]) * a.scale_log2e - m);
         p.w = ex2_approx(__uint_as_float(r[4 * q4 + 3]) * a.scale_log2e - m);
         rs += (p.x + p.y) + (p.z + p.w);
-        if (a.thresh != 0u) {     // 1/(1-p) is applied once to the output, not per element
-          const uint64_t e = drop_row + (uint64_t)(j * TK + g * 32 + 4 * q4);
-          const uint32_t km = dropout_keepmask4(key, e >> 2, a.thresh);
+        if (DROP) {               // 1/(1-p) is applied once to the output, not per element
+          const uint32_t km = dropout_keepmask4(key, q0 + q4, a.thresh);
           p.x = (km & 1u) ? p.x : 0.f; p.y = (km & 2u) ? p.y : 0.f;
           p.z = (km & 4u) ? p.z : 0.f; p.w = (km & 8u) ? p.w : 0.f;
           keepbits |= km << (4 * q4);
@@ -210,7 +219,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         r[4 * q4 + 0] = __float_as_uint(p.x); r[4 * q4 + 1] = __float_as_uint(p.y);
         r[4 * q4 + 2] = __float_as_uint(p.z); r[4 * q4 + 3] = __float_as_uint(p.w);
       }
-      if (a.thresh != 0u && a.maskbits != nullptr)
+      if (DROP && a.maskbits != nullptr)
         a.maskbits[((int64_t)bh * a.N + q_in_head) * (a.N / 32) + j * (TK / 32) + g] = keepbits;
       l = l * alpha + rs;
       tcgen05_fence_before();
@@ -218,6 +227,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_st32(tP + lane_addr + g * 32, r);        // P_j -> TMEM (its previous reader P.V_{j-1} is done)
       tcgen05_fence_before();
       mbar_arrive(&p_full);
+      if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) {
+        atomicAdd(&a.dbg[0], (unsigned long long)(c1 - c0));   // wait O_{j-1} + fold
+        atomicAdd(&a.dbg[1], (unsigned long long)(c2 - c1));   // wait S_j
+        atomicAdd(&a.dbg[2], (unsigned long long)(c3 - c2));   // tmem ld + row max
+        atomicAdd(&a.dbg[3], (unsigned long long)(c4 - c3));   // max exchange barrier
+        atomicAdd(&a.dbg[4], (unsigned long long)(clock64() - c4));   // exp / dropout / P store
+        atomicAdd(&a.dbg[5], 1ull);
+      }
     }
     // last tile's O, then combine the two halves' partial row sums
     mbar_wait(&o_full, (uint32_t)(ntiles - 1) & 1u);
@@ -226,7 +243,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     s_sum[g][row] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += s_sum[g ^ 1][row];
-    const float inv = (a.thresh != 0u ? a.keep_scale : 1.0f) / l;
+    const float inv = (DROP ? a.keep_scale : 1.0f) / l;
     float* orow = a.O + (int64_t)(q_row0 + row) * a.ldo + h * HD + g * 32;
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {
@@ -274,7 +291,9 @@ extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint
   if (st) return st;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { set_last_error("attention_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
@@ -285,7 +304,23 @@ extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint
   a.keep_scale = 1.0f / (1.0f - p_drop);
   a.seed = seed; a.seed_dev = seed_dev; a.site = site; a.round_out = round_tf32;
   a.group_batches = group_batches; a.group_site_stride = group_site_stride;
+  static const bool timing = getenv("CORRIF_ATTN_TIMING") != nullptr;
+  static unsigned long long* dbg = nullptr;
+  a.dbg = nullptr;
+  if (timing) {
+    if (!dbg) cudaMalloc(&dbg, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), (cudaStream_t)stream);
+    a.dbg = dbg;
+  }
   dim3 grid(N / TQ, B * H);
-  attn_fwd_kernel<<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  if (a.thresh != 0u) attn_fwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  else attn_fwd_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  if (timing) {
+    unsigned long long h[16];
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[attn fwd N%d] CTA0 softmax warp: wait O+fold %llu  wait S %llu  ld+max %llu  max barrier %llu"
+            "  exp/drop/store %llu  tiles %llu\n", N, h[0], h[1], h[2], h[3], h[4], h[5]);
+  }
   return launch_status("attention_fwd");
 }
