@@ -233,8 +233,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
       mbar_wait(&kv_full[s], (uint32_t)(j / KV_STAGES) & 1u);
       tcgen05_fence_after();
       if (elect_one()) {
-        mma_headdim_ts(tmem + 128 * u, tQ, st, TL, id_s);                        // S  = Q  K_j^T
-        mma_headdim_ts(tmem + 128 * u + 64, tDO, st + 2 * TL * 256, TL, id_s);   // dP = dO V_j^T
+        mma8_ts_kmajor<TL>(tmem + 128 * u, tQ, desc_lo_kmajor(st), id_s, false);                        // S  = Q  K_j^T
+        mma8_ts_kmajor<TL>(tmem + 128 * u + 64, tDO, desc_lo_kmajor(st + 2 * TL * 256), id_s, false);   // dP = dO V_j^T
         tcgen05_commit(&sdp_full[u]);
       }
       __syncwarp();
@@ -246,11 +246,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
       mbar_wait(&ds_full[u], (uint32_t)(j >> 1) & 1u);
       tcgen05_fence_after();
       const uint32_t kmn = sb + s * STAGE_BYTES + TL * 256;
-      if (elect_one()) {
-#pragma unroll
-        for (int t = 0; t < TL / 8; ++t)                          // dQ += dS(TMEM, in S's columns) . K_j
-          tcgen05_mma_tf32_ts(tDQ, tmem + 128 * u + 8 * t, smem_desc_mnmajor(kmn + t * 1024, TL * 128), id_q,
-                              (j > 0 || t > 0) ? 1u : 0u);
+      if (elect_one()) {                              // dQ += dS(TMEM, in S's columns) . K_j
+        mma8_ts_mnmajor(tDQ, tmem + 128 * u, desc_lo_mnmajor(kmn, TL * 128), id_q, j > 0);
         tcgen05_commit(&kv_free[s]);
         if (j == ntiles - 1) tcgen05_commit(&fin);
       }
@@ -382,8 +379,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
       if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) atomicAdd(&a.dbg[0], (unsigned long long)(clock64() - t0));
       tcgen05_fence_after();
       if (elect_one()) {
-        mma_headdim_ts(tmem + 128 * u, tK, km, TL, id_s);                    // S^T  = K_j Q_i^T
-        mma_headdim_ts(tmem + 128 * u + 64, tV, km + TL * 256, TL, id_s);    // dP^T = V_j dO_i^T
+        mma8_ts_kmajor<TL>(tmem + 128 * u, tK, desc_lo_kmajor(km), id_s, false);                    // S^T  = K_j Q_i^T
+        mma8_ts_kmajor<TL>(tmem + 128 * u + 64, tV, desc_lo_kmajor(km + TL * 256), id_s, false);    // dP^T = V_j dO_i^T
         tcgen05_commit(&km_free[s]);
         tcgen05_commit(&st_full[u]);
       }
@@ -403,14 +400,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
       tcgen05_fence_after();
       const uint32_t mn = sb + OFF_MN + s * MN_BYTES;
       if (elect_one()) {
-#pragma unroll
-        for (int t = 0; t < TL / 8; ++t)                                      // dV += P^T(TMEM)  dO_i
-          tcgen05_mma_tf32_ts(tDV, tmem + 128 * u + 8 * t, smem_desc_mnmajor(mn + TL * 256 + t * 1024, TL * 128),
-                              id_g, (i > 0 || t > 0) ? 1u : 0u);
-#pragma unroll
-        for (int t = 0; t < TL / 8; ++t)                                      // dK += dS^T(TMEM) Q_i
-          tcgen05_mma_tf32_ts(tDK, tmem + 128 * u + 64 + 8 * t, smem_desc_mnmajor(mn + t * 1024, TL * 128), id_g,
-                              (i > 0 || t > 0) ? 1u : 0u);
+        mma8_ts_mnmajor(tDV, tmem + 128 * u, desc_lo_mnmajor(mn + TL * 256, TL * 128), id_g, i > 0);   // dV += P^T  dO_i
+        mma8_ts_mnmajor(tDK, tmem + 128 * u + 64, desc_lo_mnmajor(mn, TL * 128), id_g, i > 0);         // dK += dS^T Q_i
         tcgen05_commit(&mn_free[s]);
         if (i == ntiles - 1) tcgen05_commit(&fin);
       }

@@ -116,21 +116,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&kv_full[s], (uint32_t)(j / KV_STAGES) & 1u);
       mbar_wait(&s_free, ph ^ 1u);                 // softmax finished reading S_{j-1}
       tcgen05_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int t = 0; t < HD / 8; ++t) {           // S = Q(TMEM) . K_j^T
-          const uint64_t bd = smem_desc_kmajor(sK + (t >> 2) * (TK * 128) + (t & 3) * 32);
-          tcgen05_mma_tf32_ts(tS, tQ + 8 * t, bd, idesc_s, t > 0 ? 1u : 0u);
-        }
+      if (elect_one()) {                           // S = Q(TMEM) . K_j^T
+        mma8_ts_kmajor<TK>(tS, tQ, desc_lo_kmajor(sK), idesc_s, false);
         tcgen05_commit(&s_full);
       }
       __syncwarp();
       mbar_wait(&p_full, ph);                      // P_j in TMEM, O_{j-1} already consumed
       tcgen05_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int t = 0; t < TK / 8; ++t)             // O_j = P_j(TMEM) . V_j
-          tcgen05_mma_tf32_ts(tO, tP + 8 * t, smem_desc_mnmajor(sV + t * 1024, TK * 128), idesc_o, t > 0 ? 1u : 0u);
+      if (elect_one()) {                           // O_j = P_j(TMEM) . V_j
+        mma8_ts_mnmajor(tO, tP, desc_lo_mnmajor(sV, TK * 128), idesc_o, false);
         tcgen05_commit(&kv_free[s]);
         tcgen05_commit(&o_full);
       }

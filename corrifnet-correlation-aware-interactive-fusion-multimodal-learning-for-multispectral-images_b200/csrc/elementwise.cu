@@ -95,8 +95,16 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ dres,
-                     float* __restrict__ dx, float* __restrict__ partial, int64_t rows) {
-  __shared__ float red[8][2][LN_C];
+                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
+                     float* __restrict__ dx_drop, uint32_t thresh, float keep_scale, uint64_t seed,
+                     const uint64_t* seed_dev, uint32_t site_a, uint32_t site_b) {
+  __shared__ __align__(16) float red[8][2][LN_C];
+  uint64_t key_a = 0, key_b = 0;
+  if (dx_drop != nullptr) {      // fused dropout of the outgoing gradient (backward of the next block's
+    if (seed_dev != nullptr) seed += *seed_dev;   // proj_drop + PreNormDrop.dropout, mmvit4.py:314,339)
+    key_a = dropout_key(seed, site_a);
+    key_b = site_b != CORRIF_NO_SITE ? dropout_key(seed, site_b) : 0ull;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 g[LN_V], dg[LN_V], db[LN_V];
 #pragma unroll
@@ -136,6 +144,14 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       st4(dx + row * LN_C + lane * 4 + j * 128, o);
+      if (dx_drop != nullptr) {
+        const uint64_t quad = (uint64_t)(row * LN_C + lane * 4 + j * 128) >> 2;
+        uint32_t km = dropout_keepmask4(key_a, quad, thresh);
+        if (site_b != CORRIF_NO_SITE) km &= dropout_keepmask4(key_b, quad, thresh);
+        st4(dx_drop + row * LN_C + lane * 4 + j * 128,
+            make_float4((km & 1u) ? o.x * keep_scale : 0.f, (km & 2u) ? o.y * keep_scale : 0.f,
+                        (km & 4u) ? o.z * keep_scale : 0.f, (km & 8u) ? o.w * keep_scale : 0.f));
+      }
     }
   }
 #pragma unroll
@@ -144,12 +160,17 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
     st4(&red[warp][1][lane * 4 + j * 128], db[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * LN_C; i += 256) {
-    const int which = i / LN_C, c = i % LN_C;
-    float s = 0.f;
+  {   // block totals straight into dgamma / dbeta (256 threads x float4 = 2 x 512 columns)
+    const int which = threadIdx.x >> 7, c = (threadIdx.x & 127) * 4;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][which][c];
-    partial[(int64_t)blockIdx.x * 2 * LN_C + i] = s;
+    for (int w = 0; w < 8; ++w) {
+      const float4 v = ld4(&red[w][which][c]);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    float* dst = (which ? dbeta : dgamma) + c;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
   }
 }
 
@@ -462,20 +483,27 @@ int64_t corrif_layernorm_bwd_scratch_floats(int64_t rows, int32_t C) {
 int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, const float* mean,
                          const float* rstd, const float* dres, float* dx, float* dgamma,
                          float* dbeta, float* scratch, int64_t rows, int32_t C, int32_t accumulate,
-                         void* stream) {
+                         float* dx_drop, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                         uint32_t site_a, uint32_t site_b, void* stream) {
+  (void)scratch;
   CORRIF_REQUIRE(C == LN_C, "layernorm: C must be 512, got %d", C);
-  CORRIF_REQUIRE(dy && x1 && gamma && mean && rstd && dx && dgamma && dbeta && scratch && rows > 0,
+  CORRIF_REQUIRE(dy && x1 && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0,
                  "layernorm_bwd: null/empty");
+  CORRIF_REQUIRE(dx_drop == nullptr || (p_drop > 0.f && p_drop < 1.f), "layernorm_bwd: dx_drop needs 0 < p < 1");
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dgamma, 0, LN_C * sizeof(float), (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dbeta, 0, LN_C * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_last_error("layernorm_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
   int blocks = (int)((rows + 7) / 8);
   const int cap = num_sms() * 4 < LN_BWD_MAX_BLOCKS ? num_sms() * 4 : LN_BWD_MAX_BLOCKS;
   if (blocks > cap) blocks = cap;
-  layernorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, x1, gamma, mean, rstd, dres,
-                                                                 dx, scratch, rows);
-  int st = launch_status("layernorm_bwd");
-  if (st) return st;
-  fold_partials_kernel<<<(2 * LN_C + 31) / 32, dim3(32, 16), 0, (cudaStream_t)stream>>>(
-      scratch, blocks, 2 * LN_C, dgamma, dbeta, LN_C, accumulate);
-  return launch_status("layernorm_bwd_fold");
+  float ks = 1.0f;
+  if (dx_drop) { ks = 1.0f / (1.0f - p_drop); if (site_b != CORRIF_NO_SITE) ks *= ks; }
+  layernorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, dx_drop, dx_drop ? dropout_threshold(p_drop) : 0u,
+      ks, seed, seed_dev, site_a, site_b);
+  return launch_status("layernorm_bwd");
 }
 
 int corrif_softmax_fwd(float* S, float* Pdrop, int64_t rows, int32_t cols, float p_drop,

@@ -200,6 +200,39 @@ __device__ __forceinline__ uint64_t smem_desc_mnmajor(uint32_t saddr, uint32_t l
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) |
          ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
+// The issuing warp shares its scheduler with four math warps, so every instruction between two MMAs
+// costs ~5 cycles of round-robin latency (measured: ~8 instructions per MMA made the issuer, not the
+// tensor pipe, the limit of the attention backward).  These helpers keep the descriptor's constant
+// upper word apart and derive each k-step's descriptor with ONE 32-bit add of a compile-time offset
+// (the 14-bit address field cannot carry: shared memory is < 256 KB).
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+constexpr uint32_t DESC_HI_KMAJOR = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);      // SBO, bit 46, SWIZZLE_128B
+constexpr uint32_t DESC_HI_MNMAJOR = (uint32_t)(512 >> 4) | (1u << 14) | (1u << 29);     // SBO, bit 46, 128B_BASE32B
+__device__ __forceinline__ uint32_t desc_lo_kmajor(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+// 8 TS-mode MMAs over a 64-long contraction, A = 64 TMEM columns starting at tA.
+//   K-major B tile [ROWS x 64] stored as two [ROWS x 128 B] k-blocks
+template <int ROWS>
+__device__ __forceinline__ void mma8_ts_kmajor(uint32_t tD, uint32_t tA, uint32_t b_lo, uint32_t idesc, bool acc) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+    tcgen05_mma_tf32_ts(tD, tA + 8 * t, desc_from(b_lo + (uint32_t)(((t >> 2) * (ROWS * 128) + (t & 3) * 32) >> 4),
+                                                    DESC_HI_KMAJOR), idesc, (acc || t > 0) ? 1u : 0u);
+}
+//   MN-major B tile [64 k x 64 n]: k-step t is 1024 B further
+__device__ __forceinline__ void mma8_ts_mnmajor(uint32_t tD, uint32_t tA, uint32_t b_lo, uint32_t idesc, bool acc) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+    tcgen05_mma_tf32_ts(tD, tA + 8 * t, desc_from(b_lo + (uint32_t)((t * 1024) >> 4), DESC_HI_MNMAJOR), idesc,
+                        (acc || t > 0) ? 1u : 0u);
+}
+
 // Instruction descriptor, kind::tf32, fp32 accumulate, M = 128.
 __device__ __forceinline__ constexpr uint32_t idesc_tf32(int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |

@@ -338,15 +338,14 @@ class FusionBlockEngine:
         self._wgrad(tb.t1, tb.h2, g[k["fc1_w"]], R, C, C)
         ops.colsum(tb.t1, C, R, C, g[k["fc1_b"]], scratch, accumulate=True)
         self._dgrad(tb.t1, self.pw[k["fc1_w"]], tb.t2, R, C, C)                    # d(h2)
+        # t1 = d(x2); with dropout the kernel also emits t0 = d(x2) * keep(proj_drop) * keep(PreNormDrop)
+        dd = dict(dx_drop=tb.t0, p=p, seed=self.seed, seed_dev=self.seed_dev, site_a=self._site(t, SITE_PROJ),
+                  site_b=self._site(t, SITE_PRENORM)) if p > 0 else {}
         ops.layernorm_bwd(tb.t2, tb.x2, P_[k["ln2_w"]], tb.mean2, tb.rstd2, dx3, tb.t1,
-                          g[k["ln2_w"]], g[k["ln2_b"]], scratch, R, accumulate=True)   # t1 = d(x2)
+                          g[k["ln2_w"]], g[k["ln2_b"]], scratch, R, accumulate=True, **dd)
         dx2 = tb.t1
         # ---- attention branch: x2 = x1 + drop(drop(proj(attn(LN1(x1)))))
-        dy = dx2
-        if p > 0:
-            ops.dropout_add(dx2, None, tb.t0, R * C, p, self.seed, self._site(t, SITE_PROJ),
-                            self._site(t, SITE_PRENORM), self.seed_dev)
-            dy = tb.t0
+        dy = tb.t0 if p > 0 else dx2
         self._wgrad(dy, tb.O, g[k["proj_w"]], R, C, C)
         ops.colsum(dy, C, R, C, g[k["proj_b"]], scratch, accumulate=True)
         self._dgrad(dy, self.pw[k["proj_w"]], tb.t2, R, C, C)                      # d(O)
@@ -457,17 +456,14 @@ class FusionBlockEngine:
         self._bwgrad(tb.t1, tb.h2, gk("fc1_w"), R, C, C)
         self._bcolsum(tb.t1, C, R, gk("fc1_b"), sc)
         self._bdgrad(tb.t1, W["fc1_w"], tb.t2, R, C, C)                            # d(h2)
-        for X in range(NM):
+        for X in range(NM):     # t1 = d(x2); with dropout also t0 = d(x2) * keep(proj_drop) * keep(PreNormDrop)
+            dd = dict(dx_drop=tb.t0[X], p=p, seed=self.seed, seed_dev=self.seed_dev,
+                      site_a=self._site(X, SITE_PROJ), site_b=self._site(X, SITE_PRENORM)) if p > 0 else {}
             ops.layernorm_bwd(tb.t2[X], tb.x2[X], P_[tk[X]["ln2_w"]], tb.mean2[X], tb.rstd2[X], tb.din[X],
-                              tb.t1[X], g[tk[X]["ln2_w"]], g[tk[X]["ln2_b"]], sc, R, accumulate=True)
+                              tb.t1[X], g[tk[X]["ln2_w"]], g[tk[X]["ln2_b"]], sc, R, accumulate=True, **dd)
         dx2 = tb.t1
         # ---- attention branch
-        dy = dx2
-        if p > 0:
-            for X in range(NM):
-                ops.dropout_add(dx2[X], None, tb.t0[X], R * C, p, self.seed, self._site(X, SITE_PROJ),
-                                self._site(X, SITE_PRENORM), self.seed_dev)
-            dy = tb.t0
+        dy = tb.t0 if p > 0 else dx2
         self._bwgrad(dy, tb.O, gk("proj_w"), R, C, C)
         self._bcolsum(dy, C, R, gk("proj_b"), sc)
         self._bdgrad(dy, W["proj_w"], tb.t2, R, C, C)                              # d(O)

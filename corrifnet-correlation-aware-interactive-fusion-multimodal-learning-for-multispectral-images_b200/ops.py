@@ -189,13 +189,15 @@ def layernorm_bwd_scratch_floats(rows, C_=512) -> int:
 
 
 def layernorm_bwd(dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, scratch, rows, C_=512,
-                  accumulate=False):
-    with _rec('layernorm_bwd', (16.0 if dres is not None else 12.0) * rows * C_):
+                  accumulate=False, dx_drop=None, p=0.0, seed=0, seed_dev=None, site_a=NO_SITE, site_b=NO_SITE):
+    nbytes = (16.0 if dres is not None else 12.0) + (4.0 if dx_drop is not None else 0.0)
+    with _rec('layernorm_bwd', nbytes * rows * C_):
         L.check(lib().corrif_layernorm_bwd(_ptr(dy), _ptr(x1), _ptr(gamma), _ptr(mean), _ptr(rstd),
                                            _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                                           _ptr(scratch), rows, C_, int(accumulate), _stream()),
+                                           _ptr(scratch), rows, C_, int(accumulate), _ptr(dx_drop), p, seed,
+                                           _seed_dev(seed_dev), site_a, site_b, _stream()),
                     "corrif_layernorm_bwd")
-    _count(2)
+    _count(1)
 
 
 def _seed_dev(seed_dev):

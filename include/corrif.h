@@ -124,12 +124,16 @@ int corrif_layernorm_fwd(const float* x, const float* pos, int64_t pos_rows, con
                          const float* beta, float* x1_out, float* y, float* mean, float* rstd,
                          int64_t rows, int32_t C, int32_t round_tf32, void* stream);
 /* dx = LN'(dy) (+ dres if not NULL).  dgamma/dbeta [C] are overwritten, or added to when
- * accumulate != 0.  `scratch` must hold corrif_layernorm_bwd_scratch_floats(rows, C) floats. */
+ * accumulate != 0 (block totals are added with red.global.add: the summation order is not fixed).
+ * `scratch` is unused (kept for source compatibility).  When dx_drop != NULL the kernel also writes
+ * dx_drop = dx * keep(site_a) * keep(site_b) / (1-p)^k - the backward of the dropouts that followed
+ * this tensor in the forward (mmvit4.py:314,339) - with the decisions of corrif_dropout_add. */
 int64_t corrif_layernorm_bwd_scratch_floats(int64_t rows, int32_t C);
 int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, const float* mean,
                          const float* rstd, const float* dres, float* dx, float* dgamma,
                          float* dbeta, float* scratch, int64_t rows, int32_t C, int32_t accumulate,
-                         void* stream);
+                         float* dx_drop, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                         uint32_t site_a, uint32_t site_b, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row softmax in place, for the materialised attention path: P = softmax(S) over `cols`
