@@ -328,8 +328,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
   __shared__ __align__(8) uint64_t own_full, km_full[STAGES], km_free[STAGES], mn_full[STAGES], mn_free[STAGES],
       st_full[2], pds_full[2], fin;
   __shared__ uint32_t tmem_holder;
-  __shared__ __align__(16) float s_lse[2][TL], s_delta[2][TL];
-  __shared__ uint32_t s_bits[2][TL][4];              // keep bits of (query c, key word w) for this tile
+  // per element-wise warp and tile parity: lse[16] | delta[16] | keep-bit words[16] of the warp's 16 query
+  // columns.  Warp-private, so the warps need no CTA-wide barrier per tile and drift apart freely.
+  __shared__ __align__(16) uint32_t s_stats[EW][2][48];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, bh = blockIdx.y;
@@ -422,29 +423,31 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
       mbar_arrive(&own_full);
     }
     uint32_t rs[CG], rp[CG];
-    // Per-column statistics (lse, delta) and keep bits of a query tile go through smem, double-buffered
-    // by tile parity and fetched from HBM ONE TILE AHEAD into a register (thread t owns one value), so
-    // no global-load latency sits between the named barrier and the math.
-    const int role = t < TL ? 0 : (t < 2 * TL ? 1 : ((a.maskbits && t >= 256) ? 2 : 3));
-    const int e = t - 256;                                       // role 2: (query c = e / 4, key word e % 4)
-    auto fetch = [&](int i) -> uint32_t {
-      if (role == 0) return __float_as_uint(a.lse[(int64_t)bh * a.N + i * TL + t]);
-      if (role == 1) return __float_as_uint(a.delta[(int64_t)bh * a.N + i * TL + (t - TL)]);
-      if (role == 2) return a.maskbits[((int64_t)bh * a.N + i * TL + (e >> 2)) * words + kt * 4 + (e & 3)];
-      return 0u;
+    // Per-column statistics (lse, delta) and keep-bit words of the warp's 16 query columns go through a
+    // warp-private smem slot, double-buffered by tile parity and fetched from HBM ONE TILE AHEAD into
+    // registers (lane L: lse[L] or delta[L-16], and bit word L), so no global-load latency and no
+    // CTA-wide barrier sit on the per-tile path.
+    uint32_t (*slot)[48] = s_stats[warp - 2];
+    const bool drop = a.maskbits != nullptr;
+    auto fetch0 = [&](int i) -> uint32_t {
+      const int64_t qi = (int64_t)bh * a.N + i * TL + col0 + (lane & 15);
+      return __float_as_uint(lane < 16 ? a.lse[qi] : a.delta[qi]);
     };
-    auto stash = [&](int u, uint32_t v) {
-      if (role == 0) s_lse[u][t] = __uint_as_float(v);
-      else if (role == 1) s_delta[u][t - TL] = __uint_as_float(v);
-      else if (role == 2) s_bits[u][e >> 2][e & 3] = v;
+    auto fetch1 = [&](int i) -> uint32_t {
+      if (!drop || lane >= 16) return 0u;
+      return a.maskbits[((int64_t)bh * a.N + i * TL + col0 + lane) * words + kt * 4 + quad];
     };
-    stash(0, fetch(0));
+    auto stash = [&](int u, uint32_t v0, uint32_t v1) {
+      slot[u][lane] = v0;
+      if (lane < 16) slot[u][32 + lane] = v1;
+    };
+    stash(0, fetch0(0), fetch1(0));
     for (int i = 0; i < ntiles; ++i) {
       const int u = i & 1;
       const uint32_t ph2 = (uint32_t)(i >> 1) & 1u;
       const long long e0 = a.dbg ? clock64() : 0;
-      asm volatile("bar.sync 1, %0;" :: "n"(EWT) : "memory");    // tile i's stats visible; buffer u^1 is free
-      const uint32_t nxt = i + 1 < ntiles ? fetch(i + 1) : 0u;
+      __syncwarp();                                              // tile i's slot visible; slot u^1 is free
+      const uint32_t nxt0 = i + 1 < ntiles ? fetch0(i + 1) : 0u, nxt1 = i + 1 < ntiles ? fetch1(i + 1) : 0u;
       const long long e1 = a.dbg ? clock64() : 0;
       mbar_wait(&st_full[u], ph2);
       const long long e2 = a.dbg ? clock64() : 0;
@@ -455,21 +458,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
       const long long e3 = a.dbg ? clock64() : 0;
 #pragma unroll
       for (int c4 = 0; c4 < CG / 4; ++c4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(&s_lse[u][col0 + 4 * c4]);
-        const float4 d4 = *reinterpret_cast<const float4*>(&s_delta[u][col0 + 4 * c4]);
+        const float4 l4 = *reinterpret_cast<const float4*>(&slot[u][4 * c4]);
+        const float4 d4 = *reinterpret_cast<const float4*>(&slot[u][16 + 4 * c4]);
+        const uint4 b4 = *reinterpret_cast<const uint4*>(&slot[u][32 + 4 * c4]);
         const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
+        const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int c = 4 * c4 + k, qc = col0 + c;               // query column inside the tile
+          const int c = 4 * c4 + k;                              // query column inside my 16
           const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - ls[k]);
           float keep = 1.0f;
-          if (a.maskbits) keep = ((s_bits[u][qc][quad] >> lane) & 1u) ? a.keep_scale : 0.f;
+          if (drop) keep = ((bw[k] >> lane) & 1u) ? a.keep_scale : 0.f;
           const float pd = p * keep;
           rs[c] = __float_as_uint(round_tf32_operand(pd));
           rp[c] = __float_as_uint(round_tf32_operand((pd * __uint_as_float(rp[c]) - p * ds[k]) * a.scale));
         }
       }
-      if (i + 1 < ntiles) stash(u ^ 1, nxt);
+      if (i + 1 < ntiles) stash(u ^ 1, nxt0, nxt1);
       const long long e4 = a.dbg ? clock64() : 0;
       tmem_st16(tmem + 128 * u + lane_addr + col0, rs);          // P^T  replaces S^T  in place
       tmem_st16(tmem + 128 * u + 64 + lane_addr + col0, rp);     // dS^T replaces dP^T in place
