@@ -220,18 +220,28 @@ def run_ours(args):
     hout = torch.empty(B, 192, 8, 8, 8).pin_memory()
     plist = blk.ordered_params()
 
+    from corrif_b200.staging import PinnedPipeline
+    pipe = PinnedPipeline(dev)
+    host_in = hx6 + [hfused, hgout]
+    pipe.prefetch(host_in)
+
     def e2e_step(i):
-        xs = [t_.to(dev, non_blocking=True).requires_grad_(True) for t_ in hx6]
-        fx = hfused.to(dev, non_blocking=True).requires_grad_(True)
-        go = hgout.to(dev, non_blocking=True)
+        # every step: H2D of ITS inputs from pinned memory (enqueued one step ahead on the copy stream),
+        # forward + backward through the registered op, D2H of its result
+        bufs = pipe.get()
+        pipe.prefetch(host_in)                       # next step's inputs travel while this step computes
+        xs = [b_.detach().requires_grad_(True) for b_ in bufs[:3]]
+        fx = bufs[3].detach().requires_grad_(True)
+        go = bufs[4]
         for p_ in plist:
             p_.grad = None
         out = blk(xs, fx)
         out.backward(go)
+        pipe.release()
         if world > 1:
             fl = torch.cat([p_.grad.reshape(-1) for p_ in plist])
             dist.all_reduce(fl)
-        hout.copy_(out.detach(), non_blocking=True)
+        pipe.put(out.detach(), hout)
 
     for i in range(max(2, args.warmup // 2)):
         e2e_step(i)
@@ -239,8 +249,10 @@ def run_ours(args):
     e0.record()
     for i in range(args.steps):
         e2e_step(i)
+    torch.cuda.current_stream().wait_stream(pipe.copy_stream)    # the last D2H is inside the timed region
     e1.record()
     barrier()
+    pipe.synchronize()
     e2e_ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([e2e_ms], device=dev)
     if world > 1:
@@ -308,7 +320,8 @@ def run_ours(args):
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": sum(t_.numel() for t_ in hx6 + [hfused, hgout]) * 4,
                 "d2h_bytes_per_step": hout.numel() * 4,
-                "api": "torch.ops.corrif.fusion_block via corrif_b200.module.CorrIFusionBlock + autograd"},
+                "api": "torch.ops.corrif.fusion_block via corrif_b200.module.CorrIFusionBlock + autograd; "
+                       "corrif_b200.staging.PinnedPipeline (copy stream, double-buffered inputs)"},
         "gpu_launches": launches,
         "roofline": dominant,
         other_key: other,
