@@ -111,3 +111,31 @@ def test_train_model_entry_point_runs_and_writes_reference_files(dropin, tmp_pat
     assert "Training loss:" in lrF.getvalue() and "Validation accuracy:" in lrF.getvalue()
     sd = torch.load(os.path.join(str(tmp_path), "Finaliremmodel0.pt"))
     assert len(sd) == 1140 and os.path.exists(os.path.join(str(tmp_path), "iremmodel0.pt"))
+
+
+@pytest.mark.gpu
+def test_pinned_pipeline_round_trip():
+    """staging.PinnedPipeline: prefetched inputs arrive intact and in order, results come back, slots are
+    not overwritten while a step still uses them."""
+    import torch
+    from corrif_b200.staging import PinnedPipeline
+    dev = torch.device("cuda:0")
+    pipe = PinnedPipeline(dev, depth=2)
+    host = [torch.full((1 << 20,), float(i)).pin_memory() for i in range(6)]
+    outs = [torch.empty(1 << 20).pin_memory() for _ in range(6)]
+    pipe.prefetch([host[0]])
+    for i in range(6):
+        (x,) = pipe.get()
+        if i + 1 < 6:
+            pipe.prefetch([host[i + 1]])
+        y = x * 2 + 1
+        for _ in range(20):                    # keep the compute stream busy while the next copy runs
+            y = y + 0
+        pipe.release()
+        pipe.put(y, outs[i])
+    torch.cuda.synchronize()
+    pipe.synchronize()
+    for i in range(6):
+        assert torch.equal(outs[i], torch.full((1 << 20,), 2.0 * i + 1))
+    with pytest.raises(RuntimeError):
+        pipe.get()
