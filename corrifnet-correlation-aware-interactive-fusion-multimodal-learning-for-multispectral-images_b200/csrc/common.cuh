@@ -118,6 +118,32 @@ __host__ __device__ __forceinline__ uint64_t dropout_bits(uint64_t key, uint64_t
   }
   return ((uint64_t)c1 << 32) | c0;
 }
+// Same stream with the five round keys (k + r * golden) and the key's upper word precomputed: inside
+// the attention forward the compiler re-derived them for every quad (5 extra adds per hash).
+struct DropRoundKeys { uint32_t k[5]; uint32_t hi; };
+__device__ __forceinline__ DropRoundKeys dropout_round_keys(uint64_t key) {
+  DropRoundKeys rk;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) rk.k[r] = (uint32_t)key + (uint32_t)r * 0x9E3779B9u;
+  rk.hi = (uint32_t)(key >> 32);
+  return rk;
+}
+__device__ __forceinline__ uint64_t dropout_bits(const DropRoundKeys& rk, uint64_t quad) {
+  uint32_t c0 = (uint32_t)quad, c1 = (uint32_t)(quad >> 32) ^ rk.hi;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const uint64_t p = (uint64_t)c0 * 0xD256D193u;
+    c0 = (uint32_t)(p >> 32) ^ c1 ^ rk.k[r];
+    c1 = (uint32_t)p;
+  }
+  return ((uint64_t)c1 << 32) | c0;
+}
+__device__ __forceinline__ uint32_t dropout_keepmask4(const DropRoundKeys& rk, uint64_t quad, uint32_t thresh) {
+  const uint64_t r = dropout_bits(rk, quad);
+  const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+  return ((lo & 0xFFFFu) >= thresh ? 1u : 0u) | ((lo >> 16) >= thresh ? 2u : 0u) |
+         ((hi & 0xFFFFu) >= thresh ? 4u : 0u) | ((hi >> 16) >= thresh ? 8u : 0u);
+}
 __device__ __forceinline__ void dropout_keep4(uint64_t key, uint64_t quad, uint32_t thresh, float scale,
                                               float (&m)[4]) {
   const uint64_t r = dropout_bits(key, quad);
