@@ -107,7 +107,12 @@ attn_delta_kernel(const float* __restrict__ O, const float* __restrict__ dO, flo
 constexpr int EW = 16;                       // element-wise warps
 constexpr int EWT = 32 * EW;                 // element-wise threads
 constexpr int CG = 64 / (EW / 4);            // accumulator columns per thread
-constexpr int BWD_THREADS = 64 + EWT;
+// warp 0 = TMA producer, warp 1 = score-MMA issuer, warps 2..17 = element-wise, warp 18 = gradient-MMA
+// issuer.  TWO issuing warps on different schedulers: a single issuer shares its scheduler with four
+// math warps and needed ~1.5 k cycles per tile to get its 32 MMAs + waits issued - as long as the
+// math itself.
+constexpr int BWD_THREADS = 64 + EWT + 32;
+constexpr int GRAD_WARP = 2 + EW;
 static_assert(CG == 16, "tmem helpers below move 16 columns");
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
@@ -188,7 +193,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
                    const BwdArgs a) {
   using namespace dq;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t own_full, kv_full[KV_STAGES], kv_free[KV_STAGES], sdp_full[2], ds_full[2], fin;
+  __shared__ __align__(8) uint64_t own_full, kv_full[KV_STAGES], kv_free[KV_STAGES], sdp_full[2], ds_full[2],
+      buf_free[2], fin;
   __shared__ uint32_t tmem_holder;
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -200,7 +206,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
   if (warp == 0 && lane == 0) {
     mbar_init(&own_full, EWT);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], EWT); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], EWT); mbar_init(&buf_free[s], 1); }
     mbar_init(&fin, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -225,12 +231,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
   } else if (warp == 1) {
     // whole warp walks the loop (uniform control flow), one elected lane issues: see elect_one()
     constexpr uint32_t id_s = idesc_tf32(TL, false, false);   // [128 x 64] = own(TMEM) . loop^T over d
-    constexpr uint32_t id_q = idesc_tf32(HD, false, true);    // [128 x 64] = dS(TMEM) . K (K MN-major)
     mbar_wait(&own_full, 0);                                   // Q and dO are in TMEM
-    auto issue_sdp = [&](int j) {
+    // score issuer: S/dP of tile j go into TMEM buffer j & 1 once dQ(j-2) has finished reading dS from it
+    for (int j = 0; j < ntiles; ++j) {
       const int u = j & 1, s = j % KV_STAGES;
       const uint32_t st = sb + s * STAGE_BYTES;
       mbar_wait(&kv_full[s], (uint32_t)(j / KV_STAGES) & 1u);
+      if (j >= 2) mbar_wait(&buf_free[u], (uint32_t)((j - 2) >> 1) & 1u);
       tcgen05_fence_after();
       if (elect_one()) {
         mma8_ts_kmajor<TL>(tmem + 128 * u, tQ, desc_lo_kmajor(st), id_s, false);                        // S  = Q  K_j^T
@@ -238,23 +245,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
         tcgen05_commit(&sdp_full[u]);
       }
       __syncwarp();
-    };
-    issue_sdp(0);                                     // S/dP run two tiles ahead of the element-wise warps
-    if (ntiles > 1) issue_sdp(1);
+    }
+  } else if (warp == GRAD_WARP) {
+    constexpr uint32_t id_q = idesc_tf32(HD, false, true);    // [128 x 64] = dS(TMEM) . K (K MN-major)
     for (int j = 0; j < ntiles; ++j) {
       const int u = j & 1, s = j % KV_STAGES;
+      mbar_wait(&kv_full[s], (uint32_t)(j / KV_STAGES) & 1u);
       mbar_wait(&ds_full[u], (uint32_t)(j >> 1) & 1u);
       tcgen05_fence_after();
       const uint32_t kmn = sb + s * STAGE_BYTES + TL * 256;
       if (elect_one()) {                              // dQ += dS(TMEM, in S's columns) . K_j
         mma8_ts_mnmajor(tDQ, tmem + 128 * u, desc_lo_mnmajor(kmn, TL * 128), id_q, j > 0);
         tcgen05_commit(&kv_free[s]);
+        tcgen05_commit(&buf_free[u]);
         if (j == ntiles - 1) tcgen05_commit(&fin);
       }
       __syncwarp();
-      if (j + 2 < ntiles) issue_sdp(j + 2);           // overwrites buffer u behind dQ(j): pipe order
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < GRAD_WARP) {
     const int quad = warp & 3, g = (warp - 2) >> 2, row = quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int col0 = g * CG;                                   // my columns of every 64-wide tile
@@ -326,7 +334,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
   using namespace dkv;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t own_full, km_full[STAGES], km_free[STAGES], mn_full[STAGES], mn_free[STAGES],
-      st_full[2], pds_full[2], fin;
+      st_full[2], pds_full[2], buf_free[2], fin;
   __shared__ uint32_t tmem_holder;
   // per element-wise warp and tile parity: lse[16] | delta[16] | keep-bit words[16] of the warp's 16 query
   // columns.  Warp-private, so the warps need no CTA-wide barrier per tile and drift apart freely.
@@ -343,7 +351,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&km_full[s], 1); mbar_init(&km_free[s], 1); mbar_init(&mn_full[s], 1); mbar_init(&mn_free[s], 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&pds_full[s], EWT); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&st_full[s], 1); mbar_init(&pds_full[s], EWT); mbar_init(&buf_free[s], 1); }
     mbar_init(&fin, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -370,13 +378,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
   } else if (warp == 1) {
     // whole warp walks the loop (uniform control flow), one elected lane issues: see elect_one()
     constexpr uint32_t id_s = idesc_tf32(TL, false, false);
-    constexpr uint32_t id_g = idesc_tf32(HD, false, true);
     mbar_wait(&own_full, 0);                                   // K and V are in TMEM
-    auto issue_st = [&](int i) {
+    // score issuer: S^T/dP^T of tile i go into TMEM buffer i & 1 once dV/dK(i-2) has read its operands
+    for (int i = 0; i < ntiles; ++i) {
       const int u = i & 1, s = i % STAGES;
       const uint32_t km = sb + OFF_KM + s * KM_BYTES;
       long long t0 = a.dbg ? clock64() : 0;
       mbar_wait(&km_full[s], (uint32_t)(i / STAGES) & 1u);
+      if (i >= 2) mbar_wait(&buf_free[u], (uint32_t)((i - 2) >> 1) & 1u);
       if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) atomicAdd(&a.dbg[0], (unsigned long long)(clock64() - t0));
       tcgen05_fence_after();
       if (elect_one()) {
@@ -386,9 +395,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
         tcgen05_commit(&st_full[u]);
       }
       __syncwarp();
-    };
-    issue_st(0);                                      // S^T/dP^T run two tiles ahead of the element-wise warps
-    if (ntiles > 1) issue_st(1);
+    }
+  } else if (warp == GRAD_WARP) {
+    constexpr uint32_t id_g = idesc_tf32(HD, false, true);
     for (int i = 0; i < ntiles; ++i) {
       const int u = i & 1, s = i % STAGES;
       long long t0 = a.dbg ? clock64() : 0;
@@ -404,12 +413,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
         mma8_ts_mnmajor(tDV, tmem + 128 * u, desc_lo_mnmajor(mn + TL * 256, TL * 128), id_g, i > 0);   // dV += P^T  dO_i
         mma8_ts_mnmajor(tDK, tmem + 128 * u + 64, desc_lo_mnmajor(mn, TL * 128), id_g, i > 0);         // dK += dS^T Q_i
         tcgen05_commit(&mn_free[s]);
+        tcgen05_commit(&buf_free[u]);
         if (i == ntiles - 1) tcgen05_commit(&fin);
       }
       __syncwarp();
-      if (i + 2 < ntiles) issue_st(i + 2);            // overwrites buffer u behind dV/dK(i): pipe order
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < GRAD_WARP) {
     const int quad = warp & 3, g = (warp - 2) >> 2, row = quad * 32 + lane;   // kv row == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int t = threadIdx.x - 64;                              // 0..EWT-1 among the element-wise warps
