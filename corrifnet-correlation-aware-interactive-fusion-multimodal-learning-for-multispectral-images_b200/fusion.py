@@ -110,7 +110,7 @@ class FusionBlockEngine:
     CUDA fp32 tensors (conv weights may keep their [out,in,1,1,1] shape)."""
 
     def __init__(self, params: Dict[str, torch.Tensor], dropout_p: float = 0.0,
-                 precision: str = "tf32"):
+                 precision: str = "tf32", use_graphs: bool = False):
         ops.check_device()
         self.p = params
         for k in param_names():
@@ -124,7 +124,14 @@ class FusionBlockEngine:
         self.tk.append(transformer_keys("multimodal_transformer"))
         self._ws: Dict[int, dict] = {}
         self.seed = 0
-        self.seed_dev: Optional[torch.Tensor] = None   # int64[1] device step counter (graph replay)
+        self.seed_dev: Optional[torch.Tensor] = None   # int64[1] device seed offset (graph replay)
+        # CUDA graphs: after two eager calls on the same input buffers, forward and backward are each
+        # captured once and replayed (95 launches -> 2 graph launches; measured 4.86 -> 4.67 ms/step).
+        # Kernel arguments are baked into a graph, so the per-step seed travels through `seed_dev`.
+        self.use_graphs = bool(use_graphs)
+        self._graphs: Dict[tuple, dict] = {}
+        if self.use_graphs:
+            self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         # The tensor core truncates fp32 operands to TF32; GEMM-only tensors are therefore rounded to
         # nearest where they are produced, and matrix weights get rounded copies (refreshed each
@@ -483,9 +490,57 @@ class FusionBlockEngine:
         ops.transpose(ws["dx6tok3"], ws["dx6"], NM * B, S, ENC)
 
     # ------------------------------------------------------------------------------------------
+    def set_seed(self, seed: int) -> None:
+        """Seed of the next forward/backward pair (dropout masks are a pure function of it)."""
+        if self.use_graphs:
+            self.seed = 0
+            self.seed_dev.fill_(int(seed))
+        else:
+            self.seed = int(seed)
+
+    def _graphed(self, key: tuple, fn):
+        """Run ``fn`` eagerly twice per key, then capture it once and replay."""
+        if ops._prof is not None:                       # per-launch profiling needs real launches
+            return fn()
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 16:                 # inputs keep moving (no static staging buffers):
+                return fn()                             # stay on stream launches
+            ent = self._graphs[key] = {"calls": 0}
+        if "graph" in ent:
+            ent["graph"].replay()
+            ops._count(ent["launches"])
+            return ent["out"]
+        ent["calls"] += 1
+        if ent["calls"] <= 2:
+            return fn()
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(g):
+            out = fn()
+        ent.update(graph=g, out=out, launches=ops.launch_count() - n0)
+        g.replay()                                      # capture does not execute
+        return out
+
     def forward(self, x6: List[torch.Tensor], fused_x6: torch.Tensor) -> torch.Tensor:
         """x6: three [B,64,8,8,8]; fused_x6 [B,192,8,8,8] -> x6_inter [B,192,8,8,8] (workspace-owned;
         clone it if it must survive the next forward)."""
+        if not self.use_graphs:
+            return self._forward(x6, fused_x6)
+        self._B = fused_x6.shape[0]
+        key = ("fwd",) + tuple(t.data_ptr() for t in x6) + (fused_x6.data_ptr(), fused_x6.shape[0])
+        return self._graphed(key, lambda: self._forward(x6, fused_x6))
+
+    def backward(self, gout: torch.Tensor, grads: Optional[Dict[str, torch.Tensor]] = None):
+        """gout [B,192,8,8,8] -> (dx6 [3,B,64,8,8,8], dfused_x6 [B,192,8,8,8], {param: grad}).
+        If ``grads`` is given the parameter gradients are accumulated into it."""
+        if not self.use_graphs or grads is None:
+            return self._backward(gout, grads)
+        key = ("bwd", gout.data_ptr(), self._B) + tuple(grads[n].data_ptr() for n in param_names()[:4])
+        return self._graphed(key, lambda: self._backward(gout, grads))
+
+    def _forward(self, x6: List[torch.Tensor], fused_x6: torch.Tensor) -> torch.Tensor:
         B = fused_x6.shape[0]
         ws, P_ = self.workspace(B), self.p
         self._B = B
@@ -516,9 +571,7 @@ class FusionBlockEngine:
         ops.transpose(ws["ytok"], ws["out"], B, S, ENC * NM)                               # :527-528
         return ws["out"].view(B, ENC * NM, 8, 8, 8)
 
-    def backward(self, gout: torch.Tensor, grads: Optional[Dict[str, torch.Tensor]] = None):
-        """gout [B,192,8,8,8] -> (dx6 [3,B,64,8,8,8], dfused_x6 [B,192,8,8,8], {param: grad}).
-        If ``grads`` is given the parameter gradients are accumulated into it."""
+    def _backward(self, gout: torch.Tensor, grads: Optional[Dict[str, torch.Tensor]] = None):
         B = self._B
         ws, P_ = self.workspace(B), self.p
         if grads is None:

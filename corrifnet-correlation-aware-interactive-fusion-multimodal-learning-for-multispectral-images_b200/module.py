@@ -12,6 +12,10 @@ from . import fusion
 from .fusion import FusionBlockEngine, param_names
 
 _ENGINES: Dict[Tuple, FusionBlockEngine] = {}
+# forward / backward of the op are captured into CUDA graphs once the same input buffers have been seen
+# three times (a training loop with static staging buffers); CORRIF_NO_GRAPHS=1 keeps stream launches
+import os as _os
+USE_GRAPHS = _os.environ.get("CORRIF_NO_GRAPHS") is None
 
 
 def _engine_for(params: Sequence[Tensor], dropout_p: float, precision: str) -> FusionBlockEngine:
@@ -23,7 +27,8 @@ def _engine_for(params: Sequence[Tensor], dropout_p: float, precision: str) -> F
         if len(_ENGINES) > 8:
             _ENGINES.clear()
         named = {n: p.detach() for n, p in zip(param_names(), params)}
-        eng = FusionBlockEngine(named, dropout_p=dropout_p, precision=precision)
+        eng = FusionBlockEngine(named, dropout_p=dropout_p, precision=precision, use_graphs=USE_GRAPHS)
+        eng._flat_grads = eng.new_grad_buffers()          # persistent: graph replay needs fixed addresses
         _ENGINES[key] = eng
     return eng
 
@@ -33,7 +38,7 @@ def fusion_block_op(x6_rgb: Tensor, x6_nir: Tensor, x6_swir: Tensor, fused_x6: T
                     params: Sequence[Tensor], dropout_p: float, seed: int, precision: str) -> Tensor:
     """x6_inter = CorrIFNet fusion block (mmvit4.py:456-529).  ``params`` in ``param_names()`` order."""
     eng = _engine_for(params, dropout_p, precision)
-    eng.seed = int(seed)
+    eng.set_seed(seed)
     out = eng.forward([x6_rgb.contiguous(), x6_nir.contiguous(), x6_swir.contiguous()],
                       fused_x6.contiguous())
     return out.clone()
@@ -50,10 +55,11 @@ def fusion_block_backward_op(gout: Tensor, params: Sequence[Tensor], dropout_p: 
     """Backward of the most recent corrif::fusion_block call on the same parameter set.  Returns
     [d x6_rgb, d x6_nir, d x6_swir, d fused_x6, flat parameter gradients (param_names() order)]."""
     eng = _engine_for(params, dropout_p, precision)
-    eng.seed = int(seed)
-    flat, views = eng.new_grad_buffers()
+    eng.set_seed(seed)
+    flat, views = eng._flat_grads
+    flat.zero_()
     dx6, dfused, _ = eng.backward(gout.contiguous(), views)
-    return [dx6[0].clone(), dx6[1].clone(), dx6[2].clone(), dfused.clone(), flat]
+    return [dx6[0].clone(), dx6[1].clone(), dx6[2].clone(), dfused.clone(), flat.clone()]
 
 
 @fusion_block_backward_op.register_fake

@@ -149,3 +149,31 @@ def test_dropout_train_mode_matches_oracle_with_exported_masks(precision):
               "multimodal_transformer.cross_attention_list.0.fn.fn.qkv.weight",
               "RGB_transformer.cross_attention_list.0.fn.fn.qkv.weight"):
         assert rel_l2(grads[k].cpu().numpy(), ref_g[k].numpy()) < tol["pgrad"], k
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_matches_stream_launches():
+    """use_graphs=True: forward/backward captured after two eager calls and replayed must give exactly
+    the eager results for the same seed (dropout on: the seed travels through seed_dev)."""
+    dev = torch.device("cuda:0")
+    params = {k: v.to(dev) for k, v in O.make_params(3).items()}
+    x6, fused, gout = O.make_inputs(3, 2)
+    x6 = [t.to(dev) for t in x6]
+    fused, gout = fused.to(dev), gout.to(dev)
+    ref = fusion.FusionBlockEngine(params, dropout_p=0.1, precision="tf32")
+    eng = fusion.FusionBlockEngine(params, dropout_p=0.1, precision="tf32", use_graphs=True)
+    flat, grads = eng.new_grad_buffers()
+    for step in range(5):                      # steps 3.. are graph replays
+        ref.seed = 100 + step
+        r_out = ref.forward(x6, fused).clone()
+        r_dx6, r_df, r_g = ref.backward(gout)
+        eng.set_seed(100 + step)
+        flat.zero_()
+        out = eng.forward(x6, fused)
+        dx6, df, _ = eng.backward(gout, grads)
+        torch.cuda.synchronize()
+        assert torch.equal(out, r_out), step
+        assert torch.equal(dx6, r_dx6) and torch.equal(df, r_df), step
+        worst = max(float((grads[n] - r_g[n]).abs().max() / (r_g[n].abs().max() + 1e-30)) for n in grads)
+        assert worst < 1e-5, (step, worst)     # weight gradients: reduce-add order is not fixed
+    assert sum("graph" in e for e in eng._graphs.values()) == 2
