@@ -572,10 +572,10 @@ int corrif_dropout_add(const float* x, const float* res, float* out, int64_t n, 
 
 static int colsum_chunks(int64_t rows, int32_t cols) {
   const int bx = (cols / 4 + 127) / 128;
-  int64_t want = ((int64_t)num_sms() * 4 + bx - 1) / bx;
+  int64_t want = ((int64_t)num_sms() * 8 + bx - 1) / bx;
   if (want > (rows + 15) / 16) want = (rows + 15) / 16;
   if (want < 1) want = 1;
-  if (want > 256) want = 256;
+  if (want > 1024) want = 1024;
   return (int)want;
 }
 

@@ -31,9 +31,12 @@ inter_corr_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ s
   const int64_t total = (int64_t)B * S * cq;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
+  // sample index faster than the token index: the q, k of sample b are needed by the three output
+  // samples (m B + b) / 3, a third of the batch apart; with all samples of a token row in flight
+  // together those re-reads hit L2 (DRAM traffic was 1.7x the algorithmic bytes with b' slowest)
   const int c = (int)(idx % cq) * 4;
-  const int s = (int)((idx / cq) % S);
-  const int bp = (int)(idx / ((int64_t)cq * S));
+  const int bp = (int)((idx / cq) % B);
+  const int s = (int)(idx / ((int64_t)cq * B));
   const int64_t C3 = 3 * (int64_t)C;
   const int64_t mod_stride = (int64_t)B * S * C3;
 
