@@ -70,6 +70,7 @@ PROTOTYPES = {
     "corrif_inter_corr_fwd": (C.c_int, [f32p, f32p, f32p, i32, i32, i32, i32, stream_t]),
     "corrif_inter_corr_bwd": (C.c_int, [f32p, f32p, f32p, i32, i32, i32, i32, stream_t]),
     "corrif_jaccard_sums": (C.c_int, [f32p, f32p, i64, f64p, stream_t]),
+    "corrif_loss_jaccard_fused": (C.c_int, [f32p, f32p, i64, i32, i64, f32, f64p, f32p, f64p, stream_t]),
     "corrif_jaccard_finish": (C.c_int, [f64p, f32, f32p, stream_t]),
     "corrif_confusion_counts": (C.c_int, [u8p, u8p, i64, i32, u64p, stream_t]),
     "corrif_bce_probs_fwd_bwd": (C.c_int, [f32p, f32p, i64, f32, f64p, f32p, stream_t]),

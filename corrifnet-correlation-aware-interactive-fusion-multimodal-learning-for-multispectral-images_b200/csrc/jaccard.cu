@@ -43,6 +43,48 @@ jaccard_sums_kernel(const float* __restrict__ y, const float* __restrict__ yp, i
   if (blockIdx.x == 0 && threadIdx.x == 3) atomicAdd(sums + 3, (double)P);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Train-step tail in ONE pass (F4_TRAIN.py:58-71): BCE-with-logits of ALL B*CH*P output elements
+// (loss sum in fp64, optional gradient) and, on channel 0 only, the three Jaccard sums that
+// F4_TRAIN.py:70 feeds to Jaccard2 - the reference reads outputs and masks ~8 times for this and
+// synchronises the host twice.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+loss_jaccard_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t nquads, int64_t Pq,
+                    int CH, float grad_scale, double* __restrict__ loss_sum, float* __restrict__ dx,
+                    double* __restrict__ sums, double pixels) {
+  __shared__ double red[8][4];
+  double ls = 0.0, sy = 0.0, sp = 0.0, syp = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
+    const float4 xv = ld4_stream(x + q * 4), yv = ld4_stream(y + q * 4);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+    float g[4], l4 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      l4 += fmaxf(xs[e], 0.f) - xs[e] * ys[e] + log1pf(expf(-fabsf(xs[e])));   // as bce_probs_kernel
+      g[e] = (1.0f / (1.0f + expf(-xs[e])) - ys[e]) * grad_scale;
+    }
+    ls += (double)l4;
+    if (dx != nullptr) st4(dx + q * 4, make_float4(g[0], g[1], g[2], g[3]));
+    if ((q / Pq) % CH == 0) {                       // channel 0: the plane the metric is taken on
+      sy += (double)((ys[0] + ys[1]) + (ys[2] + ys[3]));
+      sp += (double)((xs[0] + xs[1]) + (xs[2] + xs[3]));
+      syp += (double)ys[0] * xs[0] + (double)ys[1] * xs[1] + (double)ys[2] * xs[2] + (double)ys[3] * xs[3];
+    }
+  }
+  ls = warp_sum(ls); sy = warp_sum(sy); sp = warp_sum(sp); syp = warp_sum(syp);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[warp][0] = ls; red[warp][1] = sy; red[warp][2] = sp; red[warp][3] = syp; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(threadIdx.x == 0 ? loss_sum : sums + (threadIdx.x - 1), t);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 4) atomicAdd(sums + 3, pixels);   // number of metric pixels
+}
+
 __device__ __forceinline__ float jac_ratio(float tp, float fp, float fn, float eps) {
   // (TP+eps) / (TP+FP+FN+eps), left to right as F5_JACCARD2.py:19
   return __fdiv_rn(__fadd_rn(tp, eps), __fadd_rn(__fadd_rn(__fadd_rn(tp, fp), fn), eps));
@@ -127,6 +169,21 @@ int corrif_jaccard_sums(const float* y, const float* y_pred, int64_t P, double* 
   if (blocks < 1) blocks = 1;
   jaccard_sums_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, y_pred, P, sums);
   return launch_status("jaccard_sums");
+}
+
+int corrif_loss_jaccard_fused(const float* x, const float* y, int64_t B, int32_t CH, int64_t P,
+                              float grad_scale, double* loss_sum, float* dx, double* sums, void* stream) {
+  CORRIF_REQUIRE(x && y && loss_sum && sums && B > 0 && CH > 0 && P > 0, "loss_jaccard: null/empty");
+  CORRIF_REQUIRE(P % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
+                     (dx == nullptr || (uintptr_t)dx % 16 == 0),
+                 "loss_jaccard: the plane size must be a multiple of 4 and the tensors 16-byte aligned");
+  const int64_t nquads = B * CH * P / 4;
+  int64_t blocks = (nquads + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  loss_jaccard_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, nquads, P / 4, CH, grad_scale,
+                                                                          loss_sum, dx, sums, (double)B * (double)P);
+  return launch_status("loss_jaccard");
 }
 
 int corrif_jaccard_finish(const double* sums, float epsilon, float* out3, void* stream) {

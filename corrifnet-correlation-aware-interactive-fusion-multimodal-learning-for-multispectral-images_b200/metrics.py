@@ -36,6 +36,26 @@ def jaccard_all(y: torch.Tensor, y_pred: torch.Tensor, epsilon: float = 1e-8):
     return out, sums
 
 
+def loss_and_jaccard(outputs: torch.Tensor, masks: torch.Tensor, want_grad: bool = True, epsilon: float = 1e-8):
+    """The train-step tail of F4_TRAIN.py:58-71 in one pass over ``outputs`` / ``masks`` [B, CH, 1, H, W]:
+    returns (loss, d loss / d outputs or None, Jaccard2 of channel 0 as float32[1], pixels).
+    loss = nn.BCEWithLogitsLoss()(outputs, masks) (mean over all elements); no host synchronisation."""
+    if not (outputs.is_cuda and masks.is_cuda):
+        raise ValueError("corrif_b200 loss/metric tail needs CUDA tensors (no CPU fallback)")
+    x, y = outputs.detach().float().contiguous(), masks.detach().float().contiguous()
+    if x.shape != y.shape or x.dim() < 3:
+        raise ValueError("outputs and masks must have the same [B, CH, ...] shape")
+    B, CH = x.shape[0], x.shape[1]
+    P = x[0, 0].numel()
+    loss_sum = torch.zeros(1, dtype=torch.float64, device=x.device)
+    sums = torch.zeros(4, dtype=torch.float64, device=x.device)
+    dx = torch.empty_like(x) if want_grad else None
+    out3 = torch.empty(3, dtype=torch.float32, device=x.device)
+    ops.loss_jaccard_fused(x, y, B, CH, P, 1.0 / x.numel(), loss_sum, dx, sums)
+    ops.jaccard_finish(sums, float(epsilon), out3)
+    return (loss_sum / x.numel()).float().reshape(()), dx, out3[1:2], B * P
+
+
 def Jaccard(y, y_pred, epsilon=1e-8):
     return jaccard_all(y, y_pred, epsilon)[0][0:1]
 

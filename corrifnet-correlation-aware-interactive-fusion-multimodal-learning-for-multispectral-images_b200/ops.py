@@ -310,6 +310,14 @@ def jaccard_sums(y, y_pred, P, sums):
     _count()
 
 
+def loss_jaccard_fused(x, y, B, CH, P, grad_scale, loss_sum, dx, sums):
+    with _rec('loss_jaccard', (12.0 if dx is not None else 8.0) * B * CH * P):
+        L.check(lib().corrif_loss_jaccard_fused(_ptr(x), _ptr(y), B, CH, P, grad_scale, _ptr(loss_sum, torch.float64),
+                                                _ptr(dx), _ptr(sums, torch.float64), _stream()),
+                "corrif_loss_jaccard_fused")
+    _count()
+
+
 def jaccard_finish(sums, epsilon, out3):
     L.check(lib().corrif_jaccard_finish(_ptr(sums, torch.float64), epsilon, _ptr(out3), _stream()),
             "corrif_jaccard_finish")

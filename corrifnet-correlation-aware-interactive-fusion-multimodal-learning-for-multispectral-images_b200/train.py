@@ -23,6 +23,8 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .metrics import loss_and_jaccard
+
 
 class GradBuckets:
     """Flat gradient storage + overlapped all-reduce.  Works with any backend (gloo on CPU for tests,
@@ -145,6 +147,8 @@ class TrainStep:
                  jaccard_fn=None, process_group=None, bucket_bytes: int = 64 << 20):
         self.model, self.optim, self.lim = model, optim, lim
         self.buckets = GradBuckets(list(model.parameters()), bucket_bytes, process_group)
+        # the default metric runs fused with the loss; a custom jaccard_fn keeps the two-step tail
+        self.fused_tail = jaccard_fn is None
         if jaccard_fn is None:
             from .metrics import Jaccard2 as jaccard_fn
         self.jaccard_fn = jaccard_fn
@@ -158,11 +162,18 @@ class TrainStep:
         for k, (images, masks) in enumerate(micro_batches):
             self.buckets.set_sync(k == n - 1)
             outputs = self.model(images)
-            loss = F.binary_cross_entropy_with_logits(outputs, masks)        # F4_TRAIN.py:58-60
-            loss.backward()                                                  # :61
+            if self.fused_tail:
+                # loss (F4_TRAIN.py:58-60), its gradient and the Jaccard sums of :65-71 in one pass
+                loss, dout, jac1, load = loss_and_jaccard(outputs, masks)
+                outputs.backward(dout)                                       # :61
+                jac = jac1 * load
+            else:
+                loss = F.binary_cross_entropy_with_logits(outputs, masks)    # F4_TRAIN.py:58-60
+                loss.backward()                                              # :61
+                with torch.no_grad():
+                    load = masks.shape[0] * self.lim * self.lim              # :65
+                    jac = self.jaccard_fn(masks[:, 0].reshape(load, 1), outputs.detach()[:, 0].reshape(load, 1)) * load
             with torch.no_grad():
-                load = masks.shape[0] * self.lim * self.lim                  # :65
-                jac = self.jaccard_fn(masks[:, 0].reshape(load, 1), outputs.detach()[:, 0].reshape(load, 1)) * load
                 loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
                 jac_acc = jac if jac_acc is None else jac_acc + jac
                 pixels += load

@@ -245,6 +245,13 @@ int corrif_inter_corr_bwd(const float* qkv, const float* g_tokens, float* dqkv, 
  * ------------------------------------------------------------------------------------------ */
 int corrif_jaccard_sums(const float* y, const float* y_pred, int64_t P, double* sums,
                         void* stream);
+/* Train-step tail in one pass (F4_TRAIN.py:58-71): x = model outputs [B, CH, P] (sigmoid probabilities
+ * fed to BCEWithLogitsLoss as the reference does), y = masks.  Adds sum_i bce(x_i, y_i) over ALL
+ * elements to *loss_sum (fp64), writes dx = (sigmoid(x) - y) * grad_scale when dx != NULL, and adds the
+ * Jaccard sums of channel 0 (sum y, sum x, sum x*y, B*P) to sums[0..3] - feed those to
+ * corrif_jaccard_finish.  loss_sum and sums must be zeroed by the caller.  P % 4 == 0. */
+int corrif_loss_jaccard_fused(const float* x, const float* y, int64_t B, int32_t CH, int64_t P,
+                              float grad_scale, double* loss_sum, float* dx, double* sums, void* stream);
 int corrif_jaccard_finish(const double* sums, float epsilon, float* out3, void* stream);
 int corrif_confusion_counts(const uint8_t* label, const uint8_t* pred, int64_t P,
                             int32_t num_classes, unsigned long long* counts, void* stream);

@@ -410,3 +410,35 @@ def test_fused_attention_fwd_bwd(B, N, p):
     for i, nm in enumerate("qkv"):
         e = rel_l2(got[:, i].cpu().numpy(), g[:, i].cpu().numpy())
         assert e < 3e-3, f"d{nm}: {e:.3e}"
+
+
+def test_fused_loss_and_jaccard_tail():
+    """F4_TRAIN.py:58-71 in one pass: BCEWithLogits over all elements (+ gradient) and Jaccard2 of
+    channel 0, against torch and against the stand-alone Jaccard2 kernel (bit-exact on {0,1} masks and
+    hard predictions, within fp32 rounding on probabilities)."""
+    from corrif_b200 import metrics
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, CH, H = 3, 3, 224
+    masks = (torch.rand(B, 1, 1, H, H, generator=g) < 0.3).float().repeat(1, CH, 1, 1, 1).to(dev())
+    for hard in (False, True):
+        probs = torch.rand(B, CH, 1, H, H, generator=g)
+        if hard:
+            probs = (probs < 0.4).float()
+        probs = probs.to(dev()).requires_grad_(True)
+        ref_loss = torch.nn.functional.binary_cross_entropy_with_logits(probs, masks)
+        ref_loss.backward()
+        loss, dx, jac, pixels = metrics.loss_and_jaccard(probs, masks)
+        assert pixels == B * H * H
+        assert abs(loss.item() - ref_loss.item()) < 2e-6 * abs(ref_loss.item())
+        assert rel_l2(dx.cpu().numpy(), probs.grad.cpu().numpy()) < 1e-6
+        load = B * H * H
+        j_ref = metrics.Jaccard2(masks[:, 0].reshape(load, 1), probs.detach()[:, 0].reshape(load, 1))
+        if hard:
+            assert jac.item() == j_ref.item()
+        else:
+            assert abs(jac.item() - j_ref.item()) < 1e-6
+    # empty mask: the inversion branch of F5_JACCARD2.py:12-14
+    z = torch.zeros(2, 3, 1, 8, 8, device=dev())
+    p = (torch.rand(2, 3, 1, 8, 8, generator=g) < 0.5).float().to(dev())
+    _, _, jac, _ = metrics.loss_and_jaccard(p, z, want_grad=False)
+    assert jac.item() == metrics.Jaccard2(z[:, 0].reshape(-1, 1), p[:, 0].reshape(-1, 1)).item()
