@@ -13,10 +13,11 @@
 //               from TMEM (no shared-memory round trip for P; the freed 32 KB double-buffer K/V)
 //   warps 2..9  online softmax, two warpgroups: thread = (query row = TMEM lane, column half g).
 //               Group g owns score columns [32g, 32g+32) of the tile and output columns [32g, 32g+32):
-//               one tcgen05.ld of S, row max exchanged between the halves through shared memory, running
-//               max / sum in the log2 domain (ex2.approx), counter-RNG dropout (keep bits saved for the
-//               backward), P_j stored to TMEM (tcgen05.st), then O_j is pulled from TMEM and folded
-//               into a register accumulator with the usual rescale.
+//               one tcgen05.ld of S, row max exchanged between the halves through shared memory, reference
+//               exponent / row sum in the log2 domain (FFMA2 + ex2.approx + FADD2), counter-RNG dropout
+//               (keep bits saved for the backward), P_j stored to TMEM (tcgen05.st).  O accumulates in
+//               TMEM over all key tiles; it is rescaled there only when a row maximum outgrows the
+//               reference exponent by 2^8 (lazy rescale), and read once at the end.
 // Shared memory is ~97 KB and TMEM 128 columns per CTA, so two CTAs share an SM and one's softmax
 // overlaps the other's MMAs.  lse (log2-domain log-sum-exp) is saved for the backward.
 #include <stdlib.h>
@@ -36,6 +37,11 @@ constexpr int SMEM_BYTES = OFF_KV + KV_STAGES * KV_BYTES + 1024;
 // Q lives in TMEM for the CTA's lifetime: with both operands in shared memory a 128 x 64 x 8 TF32 MMA
 // has to fetch 6 KB (48 clk at 128 B/clk) for 32 clk of math; with A in TMEM only K_j's 2 KB remain.
 constexpr uint32_t TMEM_COLS = 256;
+constexpr float RESCALE_LOG2 = 8.0f;          // lazy rescale threshold (log2 domain)
+// TS-mode kind::tf32 reads the low 13 mantissa bits of P as zero.  For p = 2^x the mantissa f is
+// log-uniform on [1,2), so the mean relative truncation loss is 2^-11 * E[1/f] = 2^-11 * 0.7213 = 3.522e-4.
+constexpr float TRUNC_COMP_SCALE = 1.0f + 3.522e-4f;
+constexpr float TRUNC_COMP = 5.0806e-4f;      // log2(TRUNC_COMP_SCALE)
 
 struct FwdArgs {
   const float* qkv;
@@ -53,7 +59,6 @@ struct FwdArgs {
   int group_batches;          // > 0: batch b is module b / group_batches (own dropout site)
   uint32_t group_site_stride;
   int round_out;
-  unsigned long long* dbg;    // CORRIF_ATTN_TIMING=1: softmax-warp wait cycles of CTA 0, else null
 };
 
 constexpr int NUM_THREADS = 320;     // producer warp, MMA warp, 8 softmax warps
@@ -133,7 +138,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&p_full, ph);                      // P_j in TMEM, O_{j-1} already consumed
       tcgen05_fence_after();
       if (elect_one()) {                           // O_j = P_j(TMEM) . V_j
-        mma8_ts_mnmajor(tO, tP, desc_lo_mnmajor(sV, TK * 128), idesc_o, false);
+        mma8_ts_mnmajor(tO, tP, desc_lo_mnmajor(sV, TK * 128), idesc_o, j > 0);   // O accumulates in TMEM
         tcgen05_commit(&kv_free[s]);
         tcgen05_commit(&o_full);
       }
@@ -153,10 +158,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       key = dropout_key(a.seed + (a.seed_dev ? *a.seed_dev : 0ull), a.site + (uint32_t)grp * a.group_site_stride);
     const DropRoundKeys rk = dropout_round_keys(key);
     const uint64_t drop_row = ((uint64_t)bh_rng * a.N + q_in_head) * (uint64_t)a.N;
-    float m = -INFINITY, l = 0.f;
-    float acc[32];
-#pragma unroll
-    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+    float m = -INFINITY, l = 0.f;      // m: the reference exponent in use (log2 domain), l: row sum of 2^(s - m)
     uint32_t r[32];
     {   // my half of my query row -> TMEM (qkv is already TF32-rounded by its producer)
       const float* qrow = a.qkv + (int64_t)(q_row0 + row) * (3 * C) + h * HD + g * 32;
@@ -170,12 +172,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tcgen05_fence_before();
       mbar_arrive(&q_full);
     }
+    const uint64_t sc2 = pack2(a.scale_log2e, a.scale_log2e);
+    const uint32_t th_lo = a.thresh, th_hi = a.thresh << 16;
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
-      const long long c0 = a.dbg ? clock64() : 0;
-      const long long c1 = c0;
       mbar_wait(&s_full, ph);
-      const long long c2 = a.dbg ? clock64() : 0;
       tcgen05_fence_after();
       tmem_ld32(tS + lane_addr + g * 32, r);                 // my 32 score columns (kept in registers)
       tcgen05_fence_before();
@@ -184,86 +185,95 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
       s_max[ph][g][row] = mx;
-      const long long c3 = a.dbg ? clock64() : 0;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const long long c4 = a.dbg ? clock64() : 0;
-      mx = fmaxf(mx, s_max[ph][g ^ 1][row]);
-      const float m_new = fmaxf(m, mx * a.scale_log2e);
-      const float alpha = ex2_approx(m - m_new);
-      m = m_new;
-      // p = 2^(s*scale*log2e - m), partial row sum, dropout, publish my k-block of P_j
-      float rs = 0.f;
+      mx = fmaxf(mx, s_max[ph][g ^ 1][row]) * a.scale_log2e;
+      // Lazy rescale: O_j accumulates in TMEM across tiles; the reference exponent m only moves when the
+      // row maximum outgrows it by 2^RESCALE_LOG2 (P then stays <= 256, l <= N * 256), which after the
+      // first tile is rare - the old per-tile "(acc + O_j) * alpha" fold cost 2 of the ~22 instructions per
+      // score element plus a TMEM load of O every tile.  Both column halves of a row see the same m and mx,
+      // so they take the same per-row decision; a warp enters when any of its rows does (alpha = 1 elsewhere).
+      const bool grow = mx > m + RESCALE_LOG2;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mx : m;
+        const float alpha = ex2_approx(m - m_new);           // first tile: 2^(-inf) = 0
+        l *= alpha;
+        m = m_new;
+        if (j > 0) {
+          mbar_wait(&o_full, ph ^ 1u);                       // P_{j-1} . V_{j-1} has landed in O
+          tcgen05_fence_after();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o16[16];
+            tmem_ld16(tO + lane_addr + g * 32 + hh * 16, o16);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o16[c] = __float_as_uint(__uint_as_float(o16[c]) * alpha);
+            tmem_st16(tO + lane_addr + g * 32 + hh * 16, o16);
+          }
+          tcgen05_fence_before();
+        }
+      }
+      // p' = 2^(s*scale*log2e - m + TRUNC_COMP), partial row sum, dropout, publish my k-block of P_j.
+      // P is only ever a TS-mode tensor-core operand, which TRUNCATES to TF32: instead of rounding every
+      // element (one integer add each) all of P is scaled up by 2^TRUNC_COMP = 1 + E[truncation loss]
+      // (free: folded into the exponent offset) and taken out again in the final 1 / l.
+      const float nm = TRUNC_COMP - m;
+      const uint64_t nm2 = pack2(nm, nm);
+      uint64_t rs_a = pack2(0.f, 0.f), rs_b = rs_a;
       uint32_t keepbits = 0u;
       const uint64_t q0 = (drop_row + (uint64_t)(j * TK + g * 32)) >> 2;
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
-        float4 p;
-        p.x = ex2_approx(__uint_as_float(r[4 * q4 + 0]) * a.scale_log2e - m);
-        p.y = ex2_approx(__uint_as_float(r[4 * q4 + 1]) * a.scale_log2e - m);
-        p.z = ex2_approx(__uint_as_float(r[4 * q4 + 2]) * a.scale_log2e - m);
-        p.w = ex2_approx(__uint_as_float(r[4 * q4 + 3]) * a.scale_log2e - m);
-        rs += (p.x + p.y) + (p.z + p.w);
+        float p0, p1, p2, p3;
+        unpack2(fma2(pack2u(r[4 * q4 + 0], r[4 * q4 + 1]), sc2, nm2), p0, p1);
+        unpack2(fma2(pack2u(r[4 * q4 + 2], r[4 * q4 + 3]), sc2, nm2), p2, p3);
+        p0 = ex2_approx(p0); p1 = ex2_approx(p1); p2 = ex2_approx(p2); p3 = ex2_approx(p3);
+        rs_a = add2(rs_a, pack2(p0, p1));
+        rs_b = add2(rs_b, pack2(p2, p3));
         if (DROP) {               // 1/(1-p) is applied once to the output, not per element
-          const uint32_t km = dropout_keepmask4(rk, q0 + q4, a.thresh);
-          p.x = (km & 1u) ? p.x : 0.f; p.y = (km & 2u) ? p.y : 0.f;
-          p.z = (km & 4u) ? p.z : 0.f; p.w = (km & 8u) ? p.w : 0.f;
-          keepbits |= km << (4 * q4);
+          const uint64_t hbits = dropout_bits(rk, q0 + q4);          // same decisions as dropout_keepmask4
+          const uint32_t lo = (uint32_t)hbits, hi = (uint32_t)(hbits >> 32);
+          const bool k0 = (lo & 0xFFFFu) >= th_lo, k1 = lo >= th_hi, k2 = (hi & 0xFFFFu) >= th_lo, k3 = hi >= th_hi;
+          p0 = k0 ? p0 : 0.f; p1 = k1 ? p1 : 0.f; p2 = k2 ? p2 : 0.f; p3 = k3 ? p3 : 0.f;
+          if (k0) keepbits |= 1u << (4 * q4);
+          if (k1) keepbits |= 2u << (4 * q4);
+          if (k2) keepbits |= 4u << (4 * q4);
+          if (k3) keepbits |= 8u << (4 * q4);
         }
-        p.x = round_tf32_operand(p.x); p.y = round_tf32_operand(p.y);   // P is only ever a tensor-core operand
-        p.z = round_tf32_operand(p.z); p.w = round_tf32_operand(p.w);
-        r[4 * q4 + 0] = __float_as_uint(p.x); r[4 * q4 + 1] = __float_as_uint(p.y);
-        r[4 * q4 + 2] = __float_as_uint(p.z); r[4 * q4 + 3] = __float_as_uint(p.w);
+        r[4 * q4 + 0] = __float_as_uint(p0); r[4 * q4 + 1] = __float_as_uint(p1);
+        r[4 * q4 + 2] = __float_as_uint(p2); r[4 * q4 + 3] = __float_as_uint(p3);
       }
       if (DROP && a.maskbits != nullptr)
         a.maskbits[((int64_t)bh * a.N + q_in_head) * (a.N / 32) + j * (TK / 32) + g] = keepbits;
-      l = l * alpha + rs;
-      // fold my half of O_{j-1} only now: its P.V was issued a whole exp / dropout pass ago, so this
-      // wait is free (at the top of the tile it cost ~800 cycles), and acc = (acc + O_{j-1}) * alpha_j
-      const long long c5 = a.dbg ? clock64() : 0;
-      if (j > 0) {
-        mbar_wait(&o_full, ph ^ 1u);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t o16[16];
-          tmem_ld16(tO + lane_addr + g * 32 + hh * 16, o16);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) acc[hh * 16 + c] = (acc[hh * 16 + c] + __uint_as_float(o16[c])) * alpha;
-        }
+      {
+        float s0, s1;
+        unpack2(add2(rs_a, rs_b), s0, s1);
+        l += s0 + s1;
       }
-      const long long c6 = a.dbg ? clock64() : 0;
-      tcgen05_fence_before();
-      tmem_st32(tP + lane_addr + g * 32, r);        // P_j -> TMEM (its previous reader P.V_{j-1} is done)
+      if (j > 0) {                                  // P_{j-1} . V_{j-1} must have finished reading P_{j-1}; it was
+        mbar_wait(&o_full, ph ^ 1u);                // issued a whole exp / dropout pass ago, so this does not block
+        tcgen05_fence_after();
+      }
+      tmem_st32(tP + lane_addr + g * 32, r);        // P_j -> TMEM
       tcgen05_fence_before();
       mbar_arrive(&p_full);
-      if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) {
-        atomicAdd(&a.dbg[0], (unsigned long long)(c6 - c5));   // wait O_{j-1} + fold
-        atomicAdd(&a.dbg[1], (unsigned long long)(c2 - c1));   // wait S_j
-        atomicAdd(&a.dbg[2], (unsigned long long)(c3 - c2));   // tmem ld + row max
-        atomicAdd(&a.dbg[3], (unsigned long long)(c4 - c3));   // max exchange barrier
-        atomicAdd(&a.dbg[4], (unsigned long long)(clock64() - c4 - (c6 - c5)));   // exp / dropout / P store
-        atomicAdd(&a.dbg[5], 1ull);
-      }
     }
-    // last tile's O, then combine the two halves' partial row sums
+    // O = sum_j P_j V_j sits in TMEM; combine the two halves' partial row sums
     mbar_wait(&o_full, (uint32_t)(ntiles - 1) & 1u);
     tcgen05_fence_after();
     tmem_ld32(tO + lane_addr + g * 32, r);
     s_sum[g][row] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += s_sum[g ^ 1][row];
-    const float inv = (DROP ? a.keep_scale : 1.0f) / l;
+    const float inv = (DROP ? a.keep_scale : 1.0f) * TRUNC_COMP_SCALE / l;
     float* orow = a.O + (int64_t)(q_row0 + row) * a.ldo + h * HD + g * 32;
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {
-      float4 v = make_float4((acc[4 * q4] + __uint_as_float(r[4 * q4])) * inv,
-                             (acc[4 * q4 + 1] + __uint_as_float(r[4 * q4 + 1])) * inv,
-                             (acc[4 * q4 + 2] + __uint_as_float(r[4 * q4 + 2])) * inv,
-                             (acc[4 * q4 + 3] + __uint_as_float(r[4 * q4 + 3])) * inv);
+      float4 v = make_float4(__uint_as_float(r[4 * q4]) * inv, __uint_as_float(r[4 * q4 + 1]) * inv,
+                             __uint_as_float(r[4 * q4 + 2]) * inv, __uint_as_float(r[4 * q4 + 3]) * inv);
       if (a.round_out) v = round_tf32_4(v);
       st4(orow + 4 * q4, v);
     }
-    if (g == 0) a.lse[(int64_t)bh * a.N + q_in_head] = m + log2f(l);
+    if (g == 0) a.lse[(int64_t)bh * a.N + q_in_head] = m + log2f(l) - TRUNC_COMP;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -313,23 +323,8 @@ extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint
   a.keep_scale = 1.0f / (1.0f - p_drop);
   a.seed = seed; a.seed_dev = seed_dev; a.site = site; a.round_out = round_tf32;
   a.group_batches = group_batches; a.group_site_stride = group_site_stride;
-  static const bool timing = getenv("CORRIF_ATTN_TIMING") != nullptr;
-  static unsigned long long* dbg = nullptr;
-  a.dbg = nullptr;
-  if (timing) {
-    if (!dbg) cudaMalloc(&dbg, 16 * sizeof(unsigned long long));
-    cudaMemsetAsync(dbg, 0, 16 * sizeof(unsigned long long), (cudaStream_t)stream);
-    a.dbg = dbg;
-  }
   dim3 grid(N / TQ, B * H);
   if (a.thresh != 0u) attn_fwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
   else attn_fwd_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
-  if (timing) {
-    unsigned long long h[16];
-    cudaStreamSynchronize((cudaStream_t)stream);
-    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[attn fwd N%d] CTA0 softmax warp: wait O+fold %llu  wait S %llu  ld+max %llu  max barrier %llu"
-            "  exp/drop/store %llu  tiles %llu\n", N, h[0], h[1], h[2], h[3], h[4], h[5]);
-  }
   return launch_status("attention_fwd");
 }
