@@ -26,6 +26,8 @@ using namespace tc05;
 constexpr int HD = 64;
 constexpr int TB = 128;   // owner tile rows (TMEM lanes)
 constexpr int TL = 64;    // loop tile rows
+// mean relative loss of TF32 truncation of a TS-mode operand (2^-11 * E[1/mantissa], see attention_fwd.cu)
+constexpr float TRUNC_COMP_SCALE = 1.0f + 3.522e-4f;
 
 // 8 MMAs over the 64-wide head dim: both operands K-major tiles of [rows x 64] stored as two
 // [rows x 128 B] k-blocks.
@@ -69,7 +71,7 @@ struct BwdArgs {
   const uint32_t* maskbits;  // [B*H, N, N/32] or nullptr (no dropout)
   float* dqkv;               // [B*N, 3C]
   int N, H;
-  float scale, scale_log2e, keep_scale;
+  float scale, scale_log2e, keep_scale, inv_keep_scale;
   unsigned long long* dbg;   // CORRIF_ATTN_TIMING=1: wait cycles of CTA 0 (bring-up aid), else null
 };
 
@@ -271,7 +273,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
     row_slice_to_tmem(a.dO + (int64_t)(q_row0 + row) * C + h * HD + col0, tDO + lane_addr + col0, true);
     tcgen05_fence_before();
     mbar_arrive(&own_full);
-    const float lse = a.lse[(int64_t)bh * a.N + q], dl = a.delta[(int64_t)bh * a.N + q];
+    // Constant factors leave the per-element path: dS = scale * ks * P * (keep * dP_raw - delta / ks), so the
+    // loop computes P * (keep ? dP_raw : 0 - delta') and dQ is multiplied by scale * ks once at the end.
+    // dS is only ever a TS-mode tensor-core operand, which truncates to TF32 (towards zero, mean relative
+    // loss 3.5e-4, see attention_fwd.cu): the same final factor carries the compensation instead of one
+    // rounding add per element.  Pairs of columns go through FFMA2 / FADD2 / FMUL2: 4.5 instructions per
+    // score element instead of ~10 (the element-wise warps are issue-bound).
+    const float nlse = -a.lse[(int64_t)bh * a.N + q], ndl = -a.delta[(int64_t)bh * a.N + q] * a.inv_keep_scale;
+    const uint64_t sc2 = pack2(a.scale_log2e, a.scale_log2e), nl2 = pack2(nlse, nlse), ndl2 = pack2(ndl, ndl);
     const uint32_t* mrow = a.maskbits ? a.maskbits + ((int64_t)bh * a.N + q) * (a.N / 32) : nullptr;
     uint32_t rs[CG], rp[CG];
     uint32_t bits_next = mrow ? mrow[col0 >> 5] : 0xffffffffu;   // keep-bit word, fetched one tile ahead
@@ -286,10 +295,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
       tmem_ld16_nowait(tmem + 128 * u + 64 + lane_addr + col0, rp);
       tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < CG; ++c) {
-        const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - lse);
-        const float dp = ((bits >> c) & 1u) ? __uint_as_float(rp[c]) * a.keep_scale : 0.f;
-        rs[c] = __float_as_uint(round_tf32_operand(p * (dp - dl) * a.scale));
+      for (int c = 0; c < CG; c += 2) {
+        float p0, p1;
+        unpack2(fma2(pack2u(rs[c], rs[c + 1]), sc2, nl2), p0, p1);
+        p0 = ex2_approx(p0); p1 = ex2_approx(p1);
+        const uint32_t d0 = (bits & (1u << c)) ? rp[c] : 0u, d1 = (bits & (2u << c)) ? rp[c + 1] : 0u;
+        const uint64_t ds = mul2(pack2(p0, p1), add2(pack2u(d0, d1), ndl2));
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(rs[c]), "=r"(rs[c + 1]) : "l"(ds));
       }
       tmem_st16(tmem + 128 * u + lane_addr + col0, rs);          // dS replaces S in place
       tcgen05_fence_before();
@@ -300,10 +312,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
     float* orow = a.dqkv + (int64_t)(q_row0 + row) * (3 * C) + h * HD + col0;
     tmem_ld16_nowait(tDQ + lane_addr + col0, rs);
     tmem_wait_ld();
+    const float fq = a.scale * a.keep_scale * TRUNC_COMP_SCALE;
 #pragma unroll
     for (int q4 = 0; q4 < CG / 4; ++q4)
-      st4(orow + 4 * q4, make_float4(__uint_as_float(rs[4 * q4]), __uint_as_float(rs[4 * q4 + 1]),
-                                     __uint_as_float(rs[4 * q4 + 2]), __uint_as_float(rs[4 * q4 + 3])));
+      st4(orow + 4 * q4, make_float4(__uint_as_float(rs[4 * q4]) * fq, __uint_as_float(rs[4 * q4 + 1]) * fq,
+                                     __uint_as_float(rs[4 * q4 + 2]) * fq, __uint_as_float(rs[4 * q4 + 3]) * fq));
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -438,65 +451,59 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
     // CTA-wide barrier sit on the per-tile path.
     uint32_t (*slot)[48] = s_stats[warp - 2];
     const bool drop = a.maskbits != nullptr;
+    // slot: -lse[16] | -delta/ks[16] | keep-bit words[16]   (constant factors and the TF32 truncation
+    // compensation are applied once to dV / dK at the end, see the dQ kernel)
     auto fetch0 = [&](int i) -> uint32_t {
       const int64_t qi = (int64_t)bh * a.N + i * TL + col0 + (lane & 15);
-      return __float_as_uint(lane < 16 ? a.lse[qi] : a.delta[qi]);
+      return __float_as_uint(lane < 16 ? -a.lse[qi] : -a.delta[qi] * a.inv_keep_scale);
     };
     auto fetch1 = [&](int i) -> uint32_t {
-      if (!drop || lane >= 16) return 0u;
+      if (lane >= 16) return 0u;
+      if (!drop) return 0xffffffffu;
       return a.maskbits[((int64_t)bh * a.N + i * TL + col0 + lane) * words + kt * 4 + quad];
     };
     auto stash = [&](int u, uint32_t v0, uint32_t v1) {
       slot[u][lane] = v0;
       if (lane < 16) slot[u][32 + lane] = v1;
     };
+    const uint64_t sc2 = pack2(a.scale_log2e, a.scale_log2e);
+    const uint32_t lanebit = 1u << lane;
     stash(0, fetch0(0), fetch1(0));
     for (int i = 0; i < ntiles; ++i) {
       const int u = i & 1;
       const uint32_t ph2 = (uint32_t)(i >> 1) & 1u;
-      const long long e0 = a.dbg ? clock64() : 0;
       __syncwarp();                                              // tile i's slot visible; slot u^1 is free
       const uint32_t nxt0 = i + 1 < ntiles ? fetch0(i + 1) : 0u, nxt1 = i + 1 < ntiles ? fetch1(i + 1) : 0u;
-      const long long e1 = a.dbg ? clock64() : 0;
       mbar_wait(&st_full[u], ph2);
-      const long long e2 = a.dbg ? clock64() : 0;
       tcgen05_fence_after();
       tmem_ld16_nowait(tmem + 128 * u + lane_addr + col0, rs);
       tmem_ld16_nowait(tmem + 128 * u + 64 + lane_addr + col0, rp);
       tmem_wait_ld();
-      const long long e3 = a.dbg ? clock64() : 0;
 #pragma unroll
       for (int c4 = 0; c4 < CG / 4; ++c4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(&slot[u][4 * c4]);
-        const float4 d4 = *reinterpret_cast<const float4*>(&slot[u][16 + 4 * c4]);
+        const uint4 l4 = *reinterpret_cast<const uint4*>(&slot[u][4 * c4]);
+        const uint4 d4 = *reinterpret_cast<const uint4*>(&slot[u][16 + 4 * c4]);
         const uint4 b4 = *reinterpret_cast<const uint4*>(&slot[u][32 + 4 * c4]);
-        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
+        const uint64_t nl[2] = {pack2u(l4.x, l4.y), pack2u(l4.z, l4.w)}, nd[2] = {pack2u(d4.x, d4.y), pack2u(d4.z, d4.w)};
         const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = 4 * c4 + k;                              // query column inside my 16
-          const float p = ex2_approx(__uint_as_float(rs[c]) * a.scale_log2e - ls[k]);
-          float keep = 1.0f;
-          if (drop) keep = ((bw[k] >> lane) & 1u) ? a.keep_scale : 0.f;
-          const float pd = p * keep;
-          rs[c] = __float_as_uint(round_tf32_operand(pd));
-          rp[c] = __float_as_uint(round_tf32_operand((pd * __uint_as_float(rp[c]) - p * ds[k]) * a.scale));
+        for (int k = 0; k < 2; ++k) {
+          const int c = 4 * c4 + 2 * k;                          // query columns c, c+1 inside my 16
+          float p0, p1;
+          unpack2(fma2(pack2u(rs[c], rs[c + 1]), sc2, nl[k]), p0, p1);
+          p0 = ex2_approx(p0); p1 = ex2_approx(p1);
+          const float pd0 = (bw[2 * k] & lanebit) ? p0 : 0.f, pd1 = (bw[2 * k + 1] & lanebit) ? p1 : 0.f;
+          // dS^T / (scale ks) = P keep dP_raw - P delta / ks
+          const uint64_t dst = fma2(pack2(pd0, pd1), pack2u(rp[c], rp[c + 1]), mul2(pack2(p0, p1), nd[k]));
+          rs[c] = __float_as_uint(pd0); rs[c + 1] = __float_as_uint(pd1);
+          asm("mov.b64 {%0, %1}, %2;" : "=r"(rp[c]), "=r"(rp[c + 1]) : "l"(dst));
         }
       }
       if (i + 1 < ntiles) stash(u ^ 1, nxt0, nxt1);
-      const long long e4 = a.dbg ? clock64() : 0;
       tmem_st16(tmem + 128 * u + lane_addr + col0, rs);          // P^T  replaces S^T  in place
       tmem_st16(tmem + 128 * u + 64 + lane_addr + col0, rp);     // dS^T replaces dP^T in place
       tcgen05_fence_before();
       mbar_arrive(&pds_full[u]);
-      if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && warp == 2 && lane == 0) {
-        atomicAdd(&a.dbg[4], (unsigned long long)(e1 - e0));   // smem stats load + named barrier
-        atomicAdd(&a.dbg[5], (unsigned long long)(e2 - e1));   // wait S^T/dP^T
-        atomicAdd(&a.dbg[6], (unsigned long long)(e3 - e2));   // tmem ld
-        atomicAdd(&a.dbg[7], (unsigned long long)(e4 - e3));   // math
-        atomicAdd(&a.dbg[9], (unsigned long long)(clock64() - e4));   // tmem st
-        atomicAdd(&a.dbg[10], 1ull);
-      }
     }
     mbar_wait(&fin, 0);
     tcgen05_fence_after();
@@ -505,12 +512,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
     tmem_ld16_nowait(tDV + lane_addr + col0, rs);
     tmem_ld16_nowait(tDK + lane_addr + col0, rp);
     tmem_wait_ld();
+    const float fv = a.keep_scale * TRUNC_COMP_SCALE, fk = fv * a.scale;
 #pragma unroll
     for (int q4 = 0; q4 < CG / 4; ++q4) {
-      st4(vrow + 4 * q4, make_float4(__uint_as_float(rs[4 * q4]), __uint_as_float(rs[4 * q4 + 1]),
-                                     __uint_as_float(rs[4 * q4 + 2]), __uint_as_float(rs[4 * q4 + 3])));
-      st4(krow + 4 * q4, make_float4(__uint_as_float(rp[4 * q4]), __uint_as_float(rp[4 * q4 + 1]),
-                                     __uint_as_float(rp[4 * q4 + 2]), __uint_as_float(rp[4 * q4 + 3])));
+      st4(vrow + 4 * q4, make_float4(__uint_as_float(rs[4 * q4]) * fv, __uint_as_float(rs[4 * q4 + 1]) * fv,
+                                     __uint_as_float(rs[4 * q4 + 2]) * fv, __uint_as_float(rs[4 * q4 + 3]) * fv));
+      st4(krow + 4 * q4, make_float4(__uint_as_float(rp[4 * q4]) * fk, __uint_as_float(rp[4 * q4 + 1]) * fk,
+                                     __uint_as_float(rp[4 * q4 + 2]) * fk, __uint_as_float(rp[4 * q4 + 3]) * fk));
     }
   }
   tcgen05_fence_before();
@@ -559,6 +567,7 @@ extern "C" int corrif_attention_bwd(const float* qkv, const float* O, const floa
   a.qkv = qkv; a.dO = dO; a.lse = lse; a.delta = delta; a.maskbits = p_drop > 0.f ? maskbits : nullptr; a.dqkv = dqkv;
   a.N = N; a.H = H; a.scale = scale; a.scale_log2e = scale * 1.4426950408889634f;
   a.keep_scale = 1.0f / (1.0f - p_drop);
+  a.inv_keep_scale = 1.0f - p_drop;
   static const bool timing = getenv("CORRIF_ATTN_TIMING") != nullptr;
   static unsigned long long* dbg = nullptr;
   a.dbg = nullptr;

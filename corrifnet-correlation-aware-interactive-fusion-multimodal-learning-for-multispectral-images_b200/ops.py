@@ -220,7 +220,7 @@ def softmax_bwd(P, dP, rows, cols, scale, p=0.0, seed=0, seed_dev=None, site=0):
 
 def attention_fwd(qkv, O, lse, maskbits, B, N, H=8, D=64, scale=0.125, p=0.0, seed=0, seed_dev=None,
                   site=0, round_out=False, group_batches=0, group_site_stride=0):
-    with _rec("attn_fwd", 4.0 * B * H * N * N * D):
+    with _rec("attn_fwd", 4.0 * B * H * N * N * D, "B%d N%d" % (B, N)):
         L.check(lib().corrif_attention_fwd(_ptr(qkv), _ptr(O), _ptr(lse), _ptr(maskbits, torch.int32), B, N,
                                            H, D, scale, p, seed, _seed_dev(seed_dev), site, group_batches,
                                            group_site_stride, int(round_out), _stream()), "corrif_attention_fwd")
@@ -229,7 +229,7 @@ def attention_fwd(qkv, O, lse, maskbits, B, N, H=8, D=64, scale=0.125, p=0.0, se
 
 def attention_bwd(qkv, O, dO, lse, maskbits, delta, dqkv, B, N, H=8, D=64, scale=0.125, p=0.0):
     # algorithmic FLOPs of the backward: dV, dP, dQ, dK = 4 products (recomputing S is not counted)
-    with _rec("attn_bwd", 8.0 * B * H * N * N * D):
+    with _rec("attn_bwd", 8.0 * B * H * N * N * D, "B%d N%d" % (B, N)):
         L.check(lib().corrif_attention_bwd(_ptr(qkv), _ptr(O), _ptr(dO), _ptr(lse),
                                            _ptr(maskbits, torch.int32), _ptr(delta), _ptr(dqkv), B, N, H,
                                            D, scale, p, _stream()), "corrif_attention_bwd")
