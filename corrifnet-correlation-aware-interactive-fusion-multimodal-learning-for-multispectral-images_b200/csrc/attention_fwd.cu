@@ -5,13 +5,13 @@
 // N = 2048).
 //
 // One CTA = one 128-row query tile of one (b, h); it walks the keys in tiles of 64:
-//   warp 0      TMA producer: Q once, then K_j / V_j tiles (SWIZZLE_128B K-major for Q and K;
+//   warp 8      TMA producer: Q once, then K_j / V_j tiles (SWIZZLE_128B K-major for Q and K;
 //               V is the B operand of P.V with the contraction (key) index slow in memory, i.e.
 //               MN-major -> 128B_ATOM_32B boxes)
-//   warp 1      tcgen05 issuer: S = Q K_j^T (TF32, fp32 accumulate, 64 TMEM columns), and, once the
+//   warp 9      tcgen05 issuer: S = Q K_j^T (TF32, fp32 accumulate, 64 TMEM columns), and, once the
 //               softmax warps have stored P_j back into TMEM, O_j = P_j V_j with the A operand read
 //               from TMEM (no shared-memory round trip for P; the freed 32 KB double-buffer K/V)
-//   warps 2..9  online softmax, two warpgroups: thread = (query row = TMEM lane, column half g).
+//   warps 0..7  online softmax, two warpgroups: thread = (query row = TMEM lane, column half g).
 //               Group g owns score columns [32g, 32g+32) of the tile and output columns [32g, 32g+32):
 //               one tcgen05.ld of S, row max exchanged between the halves through shared memory, reference
 //               exponent / row sum in the log2 domain (FFMA2 + ex2.approx + FADD2), counter-RNG dropout
@@ -61,7 +61,9 @@ struct FwdArgs {
   int round_out;
 };
 
-constexpr int NUM_THREADS = 320;     // producer warp, MMA warp, 8 softmax warps
+constexpr int NUM_THREADS = 320;     // 8 softmax warps, producer warp, MMA warp
+// The scheduler arbitrates highest-warp-id-first, so the single-thread issuers sit above the softmax warps.
+constexpr int PROD_WARP = 8, MMA_WARP = 9;
 
 // DROP is a template parameter so that the dropout code is straight-line (no branch per float4 group).
 template <bool DROP>
@@ -82,7 +84,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int kv_row0 = b * a.N;
   const int ntiles = a.N / TK;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == PROD_WARP && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t)&tmV) : "memory");
     mbar_init(&q_full, 256); mbar_init(&s_full, 1);
@@ -90,14 +92,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(&s_free, 256); mbar_init(&p_full, 256); mbar_init(&o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(&tmem_holder, TMEM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(&tmem_holder, TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_holder;
   const uint32_t tS = tmem, tO = tmem + 64, tP = tmem + 128, tQ = tmem + 192;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == PROD_WARP && lane == 0) {
     // ===================== TMA producer =====================
     for (int j = 0; j < ntiles; ++j) {
       const int s = j % KV_STAGES;
@@ -109,7 +111,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_load_2d(sV, &tmV, &kv_full[s], 2 * C + h * HD, kv_row0 + j * TK);
       tma_load_2d(sV + TK * 128, &tmV, &kv_full[s], 2 * C + h * HD + 32, kv_row0 + j * TK);
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ===================== tcgen05 issuer (uniform warp, one elected lane: see elect_one()) =========
     constexpr uint32_t idesc_s = idesc_tf32(TK, false, false);   // S[128 x 64] = Q . K^T
     constexpr uint32_t idesc_o = idesc_tf32(HD, false, true);    // O[128 x 64] = P . V (V MN-major)
@@ -144,10 +146,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       __syncwarp();
     }
-  } else if (warp >= 2) {
+  } else if (warp < 8) {
     // ===================== online softmax (8 warps) =====================
     const int quad = warp & 3;                               // TMEM lane quadrant this warp may access
-    const int g = (warp - 2) >> 2;                           // column half
+    const int g = warp >> 2;                                 // column half
     const int row = quad * 32 + lane;                        // query row in the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int q_in_head = qt * TQ + row;
@@ -277,7 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace attn
