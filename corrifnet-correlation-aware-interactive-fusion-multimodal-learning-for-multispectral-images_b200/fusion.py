@@ -130,6 +130,8 @@ class FusionBlockEngine:
         # Kernel arguments are baked into a graph, so the per-step seed travels through `seed_dev`.
         self.use_graphs = bool(use_graphs)
         self._graphs: Dict[tuple, dict] = {}
+        self._graph_mode: Dict[tuple, str] = {}
+        self._stage: Dict[int, dict] = {}
         if self.use_graphs:
             self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
@@ -504,8 +506,8 @@ class FusionBlockEngine:
             return fn()
         ent = self._graphs.get(key)
         if ent is None:
-            if len(self._graphs) >= 16:                 # inputs keep moving (no static staging buffers):
-                return fn()                             # stay on stream launches
+            if len(self._graphs) >= 16:                 # many batch sizes / gradient buffers: stay on stream launches
+                return fn()
             ent = self._graphs[key] = {"calls": 0}
         if "graph" in ent:
             ent["graph"].replay()
@@ -523,13 +525,45 @@ class FusionBlockEngine:
         g.replay()                                      # capture does not execute
         return out
 
+    # Graph keys.  A captured graph has its input addresses baked in, so graphs are keyed by the callers'
+    # buffers - free for a loop with static (or double-buffered) staging buffers such as bench.py's.  When
+    # a THIRD set of addresses shows up for the same batch size the inputs evidently keep moving (the full
+    # model: x6 / fused_x6 come out of the encoders wherever the caching allocator put them; measured 257
+    # ms per step of repeated captures), and the engine switches to its own staging buffers for good: a few
+    # MB of device-to-device copies per call, one graph per direction.
+    MAX_POINTER_KEYED = 2
+
+    def _static_mode(self, kind: str, B: int, key: tuple) -> bool:
+        if self._graph_mode.get((kind, B)) == "static":
+            return True
+        if key in self._graphs:
+            return False
+        if sum(1 for k in self._graphs if k[0] == kind and k[-1] == B) >= self.MAX_POINTER_KEYED:
+            self._graph_mode[(kind, B)] = "static"
+            return True
+        return False
+
+    def _staging(self, B: int) -> dict:
+        st = self._stage.get(B)
+        if st is None:
+            f = lambda *shape: torch.empty(*shape, device=self.dev, dtype=torch.float32)  # noqa: E731
+            st = self._stage[B] = {"x6": [f(B, ENC, 8, 8, 8) for _ in range(NM)], "fused": f(B, ENC * NM, 8, 8, 8),
+                                   "gout": f(B, ENC * NM, 8, 8, 8)}
+        return st
+
     def forward(self, x6: List[torch.Tensor], fused_x6: torch.Tensor) -> torch.Tensor:
         """x6: three [B,64,8,8,8]; fused_x6 [B,192,8,8,8] -> x6_inter [B,192,8,8,8] (workspace-owned;
         clone it if it must survive the next forward)."""
         if not self.use_graphs:
             return self._forward(x6, fused_x6)
-        self._B = fused_x6.shape[0]
-        key = ("fwd",) + tuple(t.data_ptr() for t in x6) + (fused_x6.data_ptr(), fused_x6.shape[0])
+        B = self._B = fused_x6.shape[0]
+        key = ("fwd",) + tuple(t.data_ptr() for t in x6) + (fused_x6.data_ptr(), B)
+        if self._static_mode("fwd", B, key):
+            st = self._staging(B)
+            for dst, src in zip(st["x6"], x6):
+                dst.copy_(src)
+            st["fused"].copy_(fused_x6)
+            return self._graphed(("fwd", "static", B), lambda: self._forward(st["x6"], st["fused"]))
         return self._graphed(key, lambda: self._forward(x6, fused_x6))
 
     def backward(self, gout: torch.Tensor, grads: Optional[Dict[str, torch.Tensor]] = None):
@@ -537,7 +571,12 @@ class FusionBlockEngine:
         If ``grads`` is given the parameter gradients are accumulated into it."""
         if not self.use_graphs or grads is None:
             return self._backward(gout, grads)
-        key = ("bwd", gout.data_ptr(), self._B) + tuple(grads[n].data_ptr() for n in param_names()[:4])
+        gkey = tuple(grads[n].data_ptr() for n in param_names()[:4])
+        key = ("bwd", gout.data_ptr()) + gkey + (self._B,)
+        if self._static_mode("bwd", self._B, key):
+            st = self._staging(self._B)
+            st["gout"].copy_(gout)
+            return self._graphed(("bwd", "static") + gkey + (self._B,), lambda: self._backward(st["gout"], grads))
         return self._graphed(key, lambda: self._backward(gout, grads))
 
     def _forward(self, x6: List[torch.Tensor], fused_x6: torch.Tensor) -> torch.Tensor:

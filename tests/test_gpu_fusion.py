@@ -177,3 +177,34 @@ def test_cuda_graph_replay_matches_stream_launches():
         worst = max(float((grads[n] - r_g[n]).abs().max() / (r_g[n].abs().max() + 1e-30)) for n in grads)
         assert worst < 1e-5, (step, worst)     # weight gradients: reduce-add order is not fixed
     assert sum("graph" in e for e in eng._graphs.values()) == 2
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_with_moving_inputs_switches_to_engine_staging():
+    """Inputs at a new address every call (the full model: x6 / fused_x6 come out of the encoders wherever
+    the allocator put them): after MAX_POINTER_KEYED address sets the engine copies into its own staging
+    buffers and replays ONE graph per direction; results equal stream launches for the same seed."""
+    dev = torch.device("cuda:0")
+    params = {k: v.to(dev) for k, v in O.make_params(4).items()}
+    ref = fusion.FusionBlockEngine(params, dropout_p=0.1, precision="tf32")
+    eng = fusion.FusionBlockEngine(params, dropout_p=0.1, precision="tf32", use_graphs=True)
+    flat, grads = eng.new_grad_buffers()
+    keep = []
+    for step in range(8):
+        x6, fused, gout = O.make_inputs(10 + step, 2)
+        x6 = [t.to(dev) for t in x6]
+        fused, gout = fused.to(dev), gout.to(dev)
+        keep.append((x6, fused, gout))             # keep them alive: every step sees fresh addresses
+        ref.seed = 200 + step
+        r_out = ref.forward(x6, fused).clone()
+        r_dx6, r_df, r_g = ref.backward(gout)
+        eng.set_seed(200 + step)
+        flat.zero_()
+        out = eng.forward(x6, fused)
+        dx6, df, _ = eng.backward(gout, grads)
+        torch.cuda.synchronize()
+        assert torch.equal(out, r_out), step
+        assert torch.equal(dx6, r_dx6) and torch.equal(df, r_df), step
+    assert eng._graph_mode == {("fwd", 2): "static", ("bwd", 2): "static"}
+    assert sum("graph" in e for e in eng._graphs.values()) == 2
+

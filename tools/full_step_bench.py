@@ -1,0 +1,64 @@
+"""Whole-model train step (BASELINE.json configs[2] micro-batch): the drop-in mmvit4.MMVit4 (encoders, early
+fusion and decoder on stock PyTorch/cuDNN, the fusion block on corrif_b200 kernels) through
+corrif_b200.train.TrainStep with Adam, batch 8 of synthetic 256x256 DSTL-shaped tiles on one B200.
+Prints one JSON line: imgs/s, ms/step and the share of the step spent in the fusion block (timed with
+CUDA events around the registered op's forward and backward).  Not the bench.py headline (that is the
+fusion block, configs[1]); this is the "callers either side of the path" context for it."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "corrifnet-correlation-aware-interactive-fusion-multimodal-learning-for-multispectral-images_b200", "dropin"))
+
+import mmvit4  # noqa: E402  (the drop-in)
+from corrif_b200 import fusion, train  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+model = mmvit4.MMVit4(num_cls=1).to(dev).train()
+optim = torch.optim.Adam(model.parameters(), 1e-4)
+step = train.TrainStep(model, optim, lim=224)
+images = torch.randn(B, 3, 3, 256, 256, device=dev)
+masks = (torch.rand(B, 1, 1, 224, 224, device=dev) < 0.3).float().repeat(1, 3, 1, 1, 1)
+
+# fusion-block share: CUDA events around FusionBlockEngine.forward / backward
+spans = []
+for name in ("forward", "backward"):
+    orig = getattr(fusion.FusionBlockEngine, name)
+
+    def timed(self, *a, _orig=orig, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = _orig(self, *a, **k)
+        e1.record()
+        spans.append((e0, e1))
+        return out
+    setattr(fusion.FusionBlockEngine, name, timed)
+
+for _ in range(8):      # the registered op captures its CUDA graphs after the same buffers were seen three times
+    out = step((images, masks))
+torch.cuda.synchronize()
+spans.clear()
+t0 = time.perf_counter()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(STEPS):
+    out = step((images, masks))
+e1.record()
+torch.cuda.synchronize()
+wall = time.perf_counter() - t0
+ms = e0.elapsed_time(e1) / STEPS
+fus = sum(a.elapsed_time(b) for a, b in spans) / STEPS
+print(json.dumps({"metric": "CorrIFNet (mmvit4) full train step imgs/s, 256x256 tiles, 1 B200", "value": B / (ms * 1e-3),
+                  "unit": "imgs/s", "ms_per_step": ms, "wall_ms_per_step": wall * 1e3 / STEPS, "batch": B, "steps": STEPS,
+                  "fusion_block_ms_per_step": fus, "fusion_block_share": fus / ms,
+                  "loss": float(out["loss"]), "peak_mem_GiB": torch.cuda.max_memory_allocated() / 2 ** 30,
+                  "note": "encoders / early fusion / decoder run on stock PyTorch (cuDNN, allow_tf32 defaults); "
+                          "fusion block, loss + Jaccard tail on corrif_b200 kernels"}))
