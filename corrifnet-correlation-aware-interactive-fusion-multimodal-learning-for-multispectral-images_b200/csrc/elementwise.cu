@@ -297,6 +297,52 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
   }
 }
 
+// dropout of a [rows, cols] gradient PLUS its column sums (the bias gradient of the layer it feeds, e.g.
+// FeedForward's second Linear: mmvit4.py:354-355 backward) in one pass - the stand-alone colsum re-read
+// the dropped tensor.  256 threads = 256 / (cols/4) rows per sweep, thread -> fixed column quad, 4 rows in
+// flight; block totals go out as red.global.add.v4.  Same keep decisions as dropout_kernel (quad = flat / 4).
+__global__ void __launch_bounds__(256)
+dropout_colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t rows, int cq,
+                      uint32_t thresh, float keep_scale, uint64_t seed, const uint64_t* seed_dev,
+                      uint32_t site, float* __restrict__ colsum) {
+  __shared__ __align__(16) float red[256][4];
+  if (seed_dev != nullptr) seed += *seed_dev;
+  const uint64_t key = dropout_key(seed, site);
+  const int rpi = 256 / cq, c = threadIdx.x % cq, roff = threadIdx.x / cq;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t stride = (int64_t)gridDim.x * rpi;
+  for (int64_t r0 = (int64_t)blockIdx.x * rpi + roff; r0 < rows; r0 += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u * stride;
+      v[u] = r < rows ? ld4_stream(x + (r * cq + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < rows) {
+        float m[4];
+        dropout_keep4(key, (uint64_t)(r * cq + c), thresh, keep_scale, m);
+        const float4 o = make_float4(v[u].x * m[0], v[u].y * m[1], v[u].z * m[2], v[u].w * m[3]);
+        st4(out + (r * cq + c) * 4, o);
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+    }
+  }
+  st4(&red[threadIdx.x][0], acc);
+  __syncthreads();
+  if (threadIdx.x < cq) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < rpi; ++g) {
+      const float4 w = ld4(&red[g * cq + threadIdx.x][0]);
+      t.x += w.x; t.y += w.y; t.z += w.z; t.w += w.w;
+    }
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(colsum + threadIdx.x * 4), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+  }
+}
+
 __global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t nquads) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads;
        q += (int64_t)gridDim.x * blockDim.x)
@@ -549,6 +595,23 @@ int corrif_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed
   dropout_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
       x, out, n / 4, dropout_threshold(p), 1.0f / (1.0f - p), seed, seed_dev, site, 0);
   return launch_status("dropout");
+}
+
+int corrif_dropout_colsum(const float* x, float* out, int64_t rows, int32_t cols, float p, uint64_t seed,
+                          const uint64_t* seed_dev, uint32_t site, float* colsum, void* stream) {
+  CORRIF_REQUIRE(x && out && colsum && rows > 0, "dropout_colsum: null/empty");
+  CORRIF_REQUIRE(cols > 0 && cols % 4 == 0 && cols <= 1024 && 256 % (cols / 4) == 0,
+                 "dropout_colsum: cols / 4 must divide 256 (got cols = %d)", cols);
+  CORRIF_REQUIRE(p >= 0.f && p < 1.f, "dropout_colsum: p");
+  CORRIF_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)colsum % 16 == 0),
+                 "dropout_colsum: alignment");
+  const int cq = cols / 4, rpi = 256 / cq;
+  int64_t blocks = (rows + 4 * rpi - 1) / (4 * rpi);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  dropout_colsum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      x, out, rows, cq, dropout_threshold(p), 1.0f / (1.0f - p), seed, seed_dev, site, colsum);
+  return launch_status("dropout_colsum");
 }
 
 int corrif_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev,

@@ -337,11 +337,12 @@ class FusionBlockEngine:
         k, P_, R, p = self.tk[t], self.p, tb.R, self.dropout_p
         # ---- FeedForward branch: x3 = x2 + drop(fc2(drop(gelu(fc1(LN2(x2))))))
         df2 = dx3
-        if p > 0:
-            ops.dropout(dx3, tb.t0, R * C, p, self.seed, self._site(t, SITE_FFN2), self.seed_dev)
+        if p > 0:      # dropout of the incoming gradient and the fc2 bias gradient (its column sums) in one pass
+            ops.dropout_colsum(dx3, tb.t0, R, C, p, self.seed, self._site(t, SITE_FFN2), g[k["fc2_b"]], self.seed_dev)
             df2 = tb.t0
+        else:
+            ops.colsum(df2, C, R, C, g[k["fc2_b"]], scratch, accumulate=True)
         self._wgrad(df2, tb.f1, g[k["fc2_w"]], R, C, C)
-        ops.colsum(df2, C, R, C, g[k["fc2_b"]], scratch, accumulate=True)
         self._dgrad(df2, self.pw[k["fc2_w"]], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C,
                     **self._drop(t, SITE_FFN1))          # d(u) = (df2 . W2) * keep * gelu'(u)
         self._wgrad(tb.t1, tb.h2, g[k["fc1_w"]], R, C, C)
@@ -456,10 +457,12 @@ class FusionBlockEngine:
         df2 = tb.din
         if p > 0:
             for X in range(NM):
-                ops.dropout(tb.din[X], tb.t0[X], R * C, p, self.seed, self._site(X, SITE_FFN2), self.seed_dev)
+                ops.dropout_colsum(tb.din[X], tb.t0[X], R, C, p, self.seed, self._site(X, SITE_FFN2),
+                                   g[tk[X]["fc2_b"]], self.seed_dev)
             df2 = tb.t0
+        else:
+            self._bcolsum(df2, C, R, gk("fc2_b"), sc)
         self._bwgrad(df2, tb.f1, gk("fc2_w"), R, C, C)
-        self._bcolsum(df2, C, R, gk("fc2_b"), sc)
         self._bdgrad(df2, W["fc2_w"], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C,
                      **self._bdrop(SITE_FFN1))
         self._bwgrad(tb.t1, tb.h2, gk("fc1_w"), R, C, C)

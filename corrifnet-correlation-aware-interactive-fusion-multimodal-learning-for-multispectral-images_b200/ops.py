@@ -243,6 +243,14 @@ def dropout(x, out, n, p, seed, site, seed_dev=None):
     _count()
 
 
+def dropout_colsum(x, out, rows, cols, p, seed, site, colsum, seed_dev=None):
+    """out = dropout(x) ([rows, cols]) and colsum += column sums of out, one pass."""
+    with _rec('dropout_colsum', 8.0 * rows * cols):
+        L.check(lib().corrif_dropout_colsum(_ptr(x), _ptr(out), rows, cols, p, seed, _seed_dev(seed_dev), site,
+                                            _ptr(colsum), _stream()), "corrif_dropout_colsum")
+    _count()
+
+
 def dropout_mask(mask, n, p, seed, site, seed_dev=None):
     with _rec('dropout', 4.0 * n):
         L.check(lib().corrif_dropout_mask(_ptr(mask), n, p, seed, _seed_dev(seed_dev), site, _stream()),

@@ -30,6 +30,8 @@ class GradBuckets:
     """Flat gradient storage + overlapped all-reduce.  Works with any backend (gloo on CPU for tests,
     NCCL over NVLink on the GPUs)."""
 
+    ALIGN = 64      # elements
+
     def __init__(self, params: List[nn.Parameter], bucket_bytes: int = 64 << 20,
                  process_group=None):
         self.group = process_group
@@ -58,15 +60,18 @@ class GradBuckets:
         if cur:
             groups.append(cur)
         for gi, grp in enumerate(groups):
-            n = sum(p.numel() for p in grp)
-            flat = torch.zeros(n, dtype=grp[0].dtype, device=grp[0].device)
-            off = 0
+            # every tensor starts on a 256-byte boundary (FlatAdam re-points the PARAMETERS into a buffer
+            # of the same layout and the kernels need 16-byte aligned weights / biases); the gaps stay zero
+            offs, n = [], 0
             for p in grp:
+                offs.append(n)
+                n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            flat = torch.zeros(n, dtype=grp[0].dtype, device=grp[0].device)
+            for p, off in zip(grp, offs):
                 view = flat[off:off + p.numel()].view_as(p)
                 view.copy_(p.grad)
                 p.grad = view                               # autograd accumulates in place from now on
-                off += p.numel()
-            b = {"flat": flat, "params": grp, "pending": len(grp), "index": gi}
+            b = {"flat": flat, "params": grp, "offsets": offs, "pending": len(grp), "index": gi}
             self.buckets.append(b)
             for p in grp:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
@@ -128,6 +133,56 @@ class GradBuckets:
         return sum(b["flat"].numel() * b["flat"].element_size() for b in self.buckets)
 
 
+class FlatAdam:
+    """``torch.optim.Adam.step()`` of the reference (F2_MAIN.py:168-169, F4_TRAIN.py:62) as ONE kernel launch
+    per gradient bucket.  The stock foreach implementation needs 13.9 ms per step for CorrIFNet's ~600
+    parameter tensors (85 M elements: 2.4 GB of traffic, 0.4 ms at HBM speed); here parameters are re-pointed
+    into flat buffers laid out like the gradient buckets, with flat exp_avg / exp_avg_sq beside them, and
+    ``corrif_adam_step`` walks each bucket once.  The wrapped optimizer stays the owner of the hyper-parameters
+    (LR schedulers keep working on its ``param_groups``) and its ``state`` is filled with views of the flat
+    moments, so ``state_dict()`` is what stock Adam would hold."""
+
+    @staticmethod
+    def eligible(optim) -> bool:
+        if type(optim) is not torch.optim.Adam or len(optim.param_groups) != 1 or len(optim.state) != 0:
+            return False
+        g = optim.param_groups[0]
+        return (g.get("weight_decay", 0) == 0 and not g.get("amsgrad", False) and not g.get("maximize", False)
+                and not g.get("capturable", False) and not g.get("differentiable", False)
+                and all(p.is_cuda and p.dtype == torch.float32 for p in g["params"]))
+
+    def __init__(self, optim, buckets: "GradBuckets"):
+        self.optim, self.buckets, self.t, self.slabs = optim, buckets, 0, None
+        self.step_t = torch.zeros((), dtype=torch.float32)
+
+    def _build(self):
+        self.slabs = []
+        for b in self.buckets.buckets:
+            flat_p = torch.zeros_like(b["flat"])
+            m, v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
+            for p, off in zip(b["params"], b["offsets"]):
+                n = p.numel()
+                view = flat_p[off:off + n].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                self.optim.state[p] = {"step": self.step_t, "exp_avg": m[off:off + n].view_as(p),
+                                       "exp_avg_sq": v[off:off + n].view_as(p)}
+            self.slabs.append((flat_p, b["flat"], m, v))
+        from . import module
+        module._ENGINES.clear()              # engines are keyed by parameter addresses, which just moved
+
+    def step(self):
+        from . import ops
+        if self.slabs is None:
+            self._build()
+        g = self.optim.param_groups[0]
+        self.t += 1
+        self.step_t.fill_(float(self.t))
+        for flat_p, flat_g, m, v in self.slabs:
+            ops.adam_step(flat_p, flat_g, m, v, flat_p.numel(), float(g["lr"]), float(g["betas"][0]),
+                          float(g["betas"][1]), float(g["eps"]), 1.0, self.t)
+
+
 def broadcast_module(model: nn.Module, src: int = 0, process_group=None):
     """Make every rank start from rank ``src``'s parameters and buffers (as DDP does at construction)."""
     if not dist.is_initialized() or dist.get_world_size(process_group) == 1:
@@ -144,9 +199,11 @@ class TrainStep:
     (sum of Jaccard2 * batchLoad, F4_TRAIN.py:70-71) and ``pixels`` (sum of batchLoad)."""
 
     def __init__(self, model: nn.Module, optim: torch.optim.Optimizer, lim: int = 224,
-                 jaccard_fn=None, process_group=None, bucket_bytes: int = 64 << 20):
+                 jaccard_fn=None, process_group=None, bucket_bytes: int = 64 << 20, flat_adam: bool = True):
         self.model, self.optim, self.lim = model, optim, lim
         self.buckets = GradBuckets(list(model.parameters()), bucket_bytes, process_group)
+        # a stock Adam with the reference's settings runs as one kernel per bucket (see FlatAdam)
+        self.flat_adam = FlatAdam(optim, self.buckets) if flat_adam and FlatAdam.eligible(optim) else None
         # the default metric runs fused with the loss; a custom jaccard_fn keeps the two-step tail
         self.fused_tail = jaccard_fn is None
         if jaccard_fn is None:
@@ -178,5 +235,8 @@ class TrainStep:
                 jac_acc = jac if jac_acc is None else jac_acc + jac
                 pixels += load
         self.buckets.finish(divisor=float(n))
-        self.optim.step()                                                    # :62
+        if self.flat_adam is not None:
+            self.flat_adam.step()                                            # :62
+        else:
+            self.optim.step()                                                # :62
         return {"loss": loss_acc / n, "jaccard_sum": jac_acc, "pixels": pixels}

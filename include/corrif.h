@@ -188,6 +188,11 @@ int corrif_attention_bwd(const float* qkv, const float* O, const float* dO, cons
 #define CORRIF_NO_SITE 0xFFFFFFFFu
 int corrif_dropout(const float* x, float* out, int64_t n, float p, uint64_t seed,
                    const uint64_t* seed_dev, uint32_t site, void* stream);
+/* out = dropout(x) over a [rows, cols] matrix and colsum[c] += sum_r out[r, c] in the same pass (the bias
+ * gradient of the Linear the dropped gradient feeds: backward of mmvit4.py:354-355).  Keep decisions are
+ * those of corrif_dropout on the flat tensor.  cols / 4 must divide 256; colsum is ACCUMULATED into. */
+int corrif_dropout_colsum(const float* x, float* out, int64_t rows, int32_t cols, float p, uint64_t seed,
+                          const uint64_t* seed_dev, uint32_t site, float* colsum, void* stream);
 int corrif_dropout_mask(float* mask, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev,
                         uint32_t site, void* stream);
 int corrif_dropout_add(const float* x, const float* res, float* out, int64_t n, float p,

@@ -27,7 +27,7 @@ def lib():
 def test_header_declares_expected_surface():
     syms = header_symbols()
     for must in ("corrif_gemm", "corrif_inter_corr_fwd", "corrif_inter_corr_bwd", "corrif_layernorm_fwd",
-                 "corrif_layernorm_bwd", "corrif_softmax_fwd", "corrif_jaccard_sums", "corrif_loss_jaccard_fused",
+                 "corrif_layernorm_bwd", "corrif_softmax_fwd", "corrif_jaccard_sums", "corrif_loss_jaccard_fused", "corrif_dropout_colsum",
                  "corrif_confusion_counts", "corrif_adam_step"):
         assert must in syms
 

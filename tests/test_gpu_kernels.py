@@ -224,6 +224,18 @@ def test_dropout_is_counter_based_and_unbiased():
     assert torch.allclose(y, x * m1 * m2 / (1 - p) ** 2 + r, rtol=1e-5, atol=1e-6)
 
 
+def test_dropout_colsum_fused():
+    """dropout + column sums in one pass == dropout kernel followed by a column sum (same keep decisions)."""
+    for rows, cols in ((1000, 512), (8192, 512), (37, 64)):
+        x = _rand(rows, cols, seed=rows)
+        ref, out = torch.empty_like(x), torch.empty_like(x)
+        ops.dropout(x, ref, rows * cols, 0.1, seed=11, site=5)
+        cs = torch.ones(cols, device=dev())
+        ops.dropout_colsum(x, out, rows, cols, 0.1, 11, 5, cs)
+        assert torch.equal(out, ref)
+        assert rel_l2(cs.cpu().numpy(), (1.0 + ref.double().sum(0)).cpu().numpy()) < 1e-6
+
+
 def test_softmax_dropout_consistency():
     rows, cols, p = 64, 512, 0.1
     s = _rand(rows, cols, seed=1)

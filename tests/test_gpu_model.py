@@ -139,3 +139,32 @@ def test_pinned_pipeline_round_trip():
         assert torch.equal(outs[i], torch.full((1 << 20,), 2.0 * i + 1))
     with pytest.raises(RuntimeError):
         pipe.get()
+
+
+def test_flat_adam_matches_torch_adam():
+    """TrainStep's one-kernel Adam (flat parameters / moments laid out like the gradient buckets) against
+    torch.optim.Adam on a small conv model: parameters after 4 steps, optimizer state views, LR schedule."""
+    import copy
+    from corrif_b200 import train
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Conv3d(3, 8, (1, 3, 3), padding=(0, 1, 1)), torch.nn.ReLU(),
+                              torch.nn.Conv3d(8, 3, 1), torch.nn.Sigmoid()).to(dev)
+    ref = copy.deepcopy(net)
+    o1, o2 = torch.optim.Adam(net.parameters(), 1e-2), torch.optim.Adam(ref.parameters(), 1e-2)
+    s1, s2 = torch.optim.lr_scheduler.StepLR(o1, 2, 0.5), torch.optim.lr_scheduler.StepLR(o2, 2, 0.5)
+    st1 = train.TrainStep(net, o1, lim=16)
+    st2 = train.TrainStep(ref, o2, lim=16, flat_adam=False)
+    assert st1.flat_adam is not None and st2.flat_adam is None
+    for step in range(4):
+        x = torch.randn(2, 3, 1, 16, 16, device=dev)
+        y = (torch.rand(2, 3, 1, 16, 16, device=dev) < 0.3).float()
+        a, b = st1((x, y)), st2((x, y))
+        s1.step(); s2.step()
+        assert abs(a["loss"].item() - b["loss"].item()) < 1e-5
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert torch.allclose(p, q, rtol=2e-5, atol=1e-7)
+        assert torch.allclose(o1.state[p]["exp_avg"], o2.state[q]["exp_avg"], rtol=1e-4, atol=1e-9)
+        assert torch.allclose(o1.state[p]["exp_avg_sq"], o2.state[q]["exp_avg_sq"], rtol=1e-4, atol=1e-12)
+    assert float(o1.state[next(net.parameters())]["step"]) == 4.0
+

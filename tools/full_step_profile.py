@@ -1,0 +1,29 @@
+"""torch.profiler table of one whole-model train step (batch 8, 256x256): where the time outside the
+fusion block goes (encoders / early fusion / decoder on stock PyTorch) - input for the "next" rows N1/N2."""
+import os
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "corrifnet-correlation-aware-interactive-fusion-multimodal-learning-for-multispectral-images_b200", "dropin"))
+import mmvit4  # noqa: E402
+from corrif_b200 import train  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+model = mmvit4.MMVit4(num_cls=1).to(dev).train()
+optim = torch.optim.Adam(model.parameters(), 1e-4)
+step = train.TrainStep(model, optim, lim=224)
+images = torch.randn(B, 3, 3, 256, 256, device=dev)
+masks = (torch.rand(B, 1, 1, 224, 224, device=dev) < 0.3).float().repeat(1, 3, 1, 1, 1)
+for _ in range(6):
+    step((images, masks))
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    step((images, masks))
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=35, max_name_column_width=60))
