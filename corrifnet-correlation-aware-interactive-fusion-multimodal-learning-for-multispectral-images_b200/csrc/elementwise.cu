@@ -91,7 +91,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos,
 // scratch and a second kernel folds the partials (deterministic, no atomics).
 constexpr int LN_BWD_MAX_BLOCKS = 592;  // 4 per SM
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ dres,
@@ -115,12 +115,21 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
   }
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[LN_V], d[LN_V];
+    float4 xh[LN_V], d[LN_V], rres[LN_V];
     float c1 = 0.f, c2 = 0.f;
+    // all 12 loads of the row are issued before the first use (the residual gradient used to be fetched
+    // after the two warp reductions: a second, dependent DRAM round trip per row)
+#pragma unroll
+    for (int j = 0; j < LN_V; ++j) xh[j] = ld4_stream(x1 + row * LN_C + lane * 4 + j * 128);
+#pragma unroll
+    for (int j = 0; j < LN_V; ++j) d[j] = ld4_stream(dy + row * LN_C + lane * 4 + j * 128);
+    if (dres != nullptr) {
+#pragma unroll
+      for (int j = 0; j < LN_V; ++j) rres[j] = ld4_stream(dres + row * LN_C + lane * 4 + j * 128);
+    }
 #pragma unroll
     for (int j = 0; j < LN_V; ++j) {
-      const float4 xv = ld4_stream(x1 + row * LN_C + lane * 4 + j * 128);
-      d[j] = ld4_stream(dy + row * LN_C + lane * 4 + j * 128);
+      const float4 xv = xh[j];
       xh[j].x = (xv.x - mu) * rs; xh[j].y = (xv.y - mu) * rs;
       xh[j].z = (xv.z - mu) * rs; xh[j].w = (xv.w - mu) * rs;
       dg[j].x += d[j].x * xh[j].x; dg[j].y += d[j].y * xh[j].y;
@@ -140,7 +149,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
       o.z = rs * (d[j].z - c1 - xh[j].z * c2);
       o.w = rs * (d[j].w - c1 - xh[j].w * c2);
       if (dres != nullptr) {
-        const float4 r = ld4_stream(dres + row * LN_C + lane * 4 + j * 128);
+        const float4 r = rres[j];
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       st4(dx + row * LN_C + lane * 4 + j * 128, o);
@@ -542,7 +551,7 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
     if (e != cudaSuccess) { set_last_error("layernorm_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
   }
   int blocks = (int)((rows + 7) / 8);
-  const int cap = num_sms() * 4 < LN_BWD_MAX_BLOCKS ? num_sms() * 4 : LN_BWD_MAX_BLOCKS;
+  const int cap = num_sms() * 2;     // 128 registers x 256 threads: two resident blocks per SM, one wave
   if (blocks > cap) blocks = cap;
   float ks = 1.0f;
   if (dx_drop) { ks = 1.0f / (1.0f - p_drop); if (site_b != CORRIF_NO_SITE) ks *= ks; }
