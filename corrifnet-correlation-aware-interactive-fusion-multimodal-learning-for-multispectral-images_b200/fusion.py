@@ -19,6 +19,9 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional
 
+import contextlib
+import os
+
 import torch
 
 from . import ops
@@ -135,6 +138,12 @@ class FusionBlockEngine:
         if self.use_graphs:
             self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        # Weight-gradient work (wgrad GEMMs, bias / pos column sums) only feeds the gradient buffers, so in the
+        # backward it runs on a second stream beside the dgrad -> LayerNorm -> attention chain: the persistent
+        # GEMMs leave SMs idle in their last wave (32768 x 512 x 512 is 3.46 waves of CTA pairs) and between
+        # launches, and the other stream's CTAs move in.  CORRIF_NO_SIDE_STREAM=1 keeps one stream.
+        self._side = (torch.cuda.Stream(self.dev)
+                      if self.dev.type == "cuda" and os.environ.get("CORRIF_NO_SIDE_STREAM") is None else None)
         # The tensor core truncates fp32 operands to TF32; GEMM-only tensors are therefore rounded to
         # nearest where they are produced, and matrix weights get rounded copies (refreshed each
         # forward, 41 MB).  In fp32 checking mode nothing is rounded.
@@ -225,6 +234,23 @@ class FusionBlockEngine:
     # ------------------------------------------------------------------------------------------
     def _gemm(self, *a, **k):
         ops.gemm(*a, precision=self.prec, **k)
+
+    # ---- second stream for the weight-gradient work of the backward ------------------------------------
+    def _side_on(self) -> bool:
+        return self._side is not None and ops._prof is None      # per-launch profiling stays serial
+
+    def _fork(self):
+        """The side stream may go on once everything enqueued so far on the main stream is done."""
+        if self._side_on():
+            self._side.wait_stream(torch.cuda.current_stream(self.dev))
+
+    def _join(self):
+        """The main stream waits for the side stream (before a buffer the side work reads is overwritten)."""
+        if self._side_on():
+            torch.cuda.current_stream(self.dev).wait_stream(self._side)
+
+    def _side_ctx(self):
+        return torch.cuda.stream(self._side) if self._side_on() else contextlib.nullcontext()
 
     def _linear(self, x, w, out, M, N, K, bias=None, epilogue=EPI_STORE, **k):
         """out[M,N] = x[M,K] . w[N,K]^T (+ epilogue)."""
@@ -342,26 +368,36 @@ class FusionBlockEngine:
             df2 = tb.t0
         else:
             ops.colsum(df2, C, R, C, g[k["fc2_b"]], scratch, accumulate=True)
-        self._wgrad(df2, tb.f1, g[k["fc2_w"]], R, C, C)
+        self._fork()
+        with self._side_ctx():
+            self._wgrad(df2, tb.f1, g[k["fc2_w"]], R, C, C)
         self._dgrad(df2, self.pw[k["fc2_w"]], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C,
                     **self._drop(t, SITE_FFN1))          # d(u) = (df2 . W2) * keep * gelu'(u)
-        self._wgrad(tb.t1, tb.h2, g[k["fc1_w"]], R, C, C)
-        ops.colsum(tb.t1, C, R, C, g[k["fc1_b"]], scratch, accumulate=True)
+        self._fork()
+        with self._side_ctx():
+            self._wgrad(tb.t1, tb.h2, g[k["fc1_w"]], R, C, C)
+            ops.colsum(tb.t1, C, R, C, g[k["fc1_b"]], scratch, accumulate=True)
         self._dgrad(tb.t1, self.pw[k["fc1_w"]], tb.t2, R, C, C)                    # d(h2)
         # t1 = d(x2); with dropout the kernel also emits t0 = d(x2) * keep(proj_drop) * keep(PreNormDrop)
         dd = dict(dx_drop=tb.t0, p=p, seed=self.seed, seed_dev=self.seed_dev, site_a=self._site(t, SITE_PROJ),
                   site_b=self._site(t, SITE_PRENORM)) if p > 0 else {}
+        self._join()                                     # t0 / t1 are about to be overwritten
         ops.layernorm_bwd(tb.t2, tb.x2, P_[k["ln2_w"]], tb.mean2, tb.rstd2, dx3, tb.t1,
                           g[k["ln2_w"]], g[k["ln2_b"]], scratch, R, accumulate=True, **dd)
         dx2 = tb.t1
         # ---- attention branch: x2 = x1 + drop(drop(proj(attn(LN1(x1)))))
         dy = tb.t0 if p > 0 else dx2
-        self._wgrad(dy, tb.O, g[k["proj_w"]], R, C, C)
-        ops.colsum(dy, C, R, C, g[k["proj_b"]], scratch, accumulate=True)
+        self._fork()
+        with self._side_ctx():
+            self._wgrad(dy, tb.O, g[k["proj_w"]], R, C, C)
+            ops.colsum(dy, C, R, C, g[k["proj_b"]], scratch, accumulate=True)
         self._dgrad(dy, self.pw[k["proj_w"]], tb.t2, R, C, C)                      # d(O)
         self._attention_bwd(t, tb, tb.t2)
-        self._wgrad(tb.dqkv, tb.h, g[k["qkv_w"]], R, 3 * C, C)
+        self._fork()
+        with self._side_ctx():
+            self._wgrad(tb.dqkv, tb.h, g[k["qkv_w"]], R, 3 * C, C)
         self._dgrad(tb.dqkv, self.pw[k["qkv_w"]], tb.t2, R, 3 * C, C)              # d(h)
+        self._join()                                     # t0 (dy) is about to be overwritten
         ops.layernorm_bwd(tb.t2, tb.x1, P_[k["ln1_w"]], tb.mean1, tb.rstd1, dx2, tb.t0,
                           g[k["ln1_w"]], g[k["ln1_b"]], scratch, R, accumulate=True)   # t0 = d(x1)
         return tb.t0
@@ -450,8 +486,10 @@ class FusionBlockEngine:
         tb, tk, W = ws["tbi"], self.tk, self.pws
         gk = lambda kk: [g[tk[X][kk]] for X in range(NM)]  # noqa: E731
         dq = ws["dqkvi"]
-        self._bwgrad(dq, tb.x3, [g[f"qkv_{m}.weight"] for m in MODALITIES], R, 3 * C, C)
-        self._bcolsum(dq, 3 * C, R, [g[f"qkv_{m}.bias"] for m in MODALITIES], sc)
+        self._fork()
+        with self._side_ctx():
+            self._bwgrad(dq, tb.x3, [g[f"qkv_{m}.weight"] for m in MODALITIES], R, 3 * C, C)
+            self._bcolsum(dq, 3 * C, R, [g[f"qkv_{m}.bias"] for m in MODALITIES], sc)
         self._bdgrad(dq, W["qkvc_w"], tb.din, R, 3 * C, C)                          # d(trans_X)
         # ---- FeedForward branch
         df2 = tb.din
@@ -462,12 +500,17 @@ class FusionBlockEngine:
             df2 = tb.t0
         else:
             self._bcolsum(df2, C, R, gk("fc2_b"), sc)
-        self._bwgrad(df2, tb.f1, gk("fc2_w"), R, C, C)
+        self._fork()
+        with self._side_ctx():
+            self._bwgrad(df2, tb.f1, gk("fc2_w"), R, C, C)
         self._bdgrad(df2, W["fc2_w"], tb.t1, R, C, C, epilogue=EPI_MUL_DGELU, aux=tb.u, ldaux=C,
                      **self._bdrop(SITE_FFN1))
-        self._bwgrad(tb.t1, tb.h2, gk("fc1_w"), R, C, C)
-        self._bcolsum(tb.t1, C, R, gk("fc1_b"), sc)
+        self._fork()
+        with self._side_ctx():
+            self._bwgrad(tb.t1, tb.h2, gk("fc1_w"), R, C, C)
+            self._bcolsum(tb.t1, C, R, gk("fc1_b"), sc)
         self._bdgrad(tb.t1, W["fc1_w"], tb.t2, R, C, C)                            # d(h2)
+        self._join()                                     # t0 / t1 are about to be overwritten
         for X in range(NM):     # t1 = d(x2); with dropout also t0 = d(x2) * keep(proj_drop) * keep(PreNormDrop)
             dd = dict(dx_drop=tb.t0[X], p=p, seed=self.seed, seed_dev=self.seed_dev,
                       site_a=self._site(X, SITE_PROJ), site_b=self._site(X, SITE_PRENORM)) if p > 0 else {}
@@ -476,23 +519,32 @@ class FusionBlockEngine:
         dx2 = tb.t1
         # ---- attention branch
         dy = tb.t0 if p > 0 else dx2
-        self._bwgrad(dy, tb.O, gk("proj_w"), R, C, C)
-        self._bcolsum(dy, C, R, gk("proj_b"), sc)
+        self._fork()
+        with self._side_ctx():
+            self._bwgrad(dy, tb.O, gk("proj_w"), R, C, C)
+            self._bcolsum(dy, C, R, gk("proj_b"), sc)
         self._bdgrad(dy, W["proj_w"], tb.t2, R, C, C)                              # d(O)
         ops.attention_bwd(tb.qkv, tb.O, tb.t2, tb.lse, tb.maskbits, tb.delta, tb.dqkv, NM * B, S, HEADS, HD,
                           HD ** -0.5, p)
-        self._bwgrad(tb.dqkv, tb.h, gk("qkv_w"), R, 3 * C, C)
+        self._fork()
+        with self._side_ctx():
+            self._bwgrad(tb.dqkv, tb.h, gk("qkv_w"), R, 3 * C, C)
         self._bdgrad(tb.dqkv, W["qkv_w"], tb.t2, R, 3 * C, C)                      # d(h)
+        self._join()                                     # t0 (dy) is about to be overwritten
         for X, m in enumerate(MODALITIES):
             ops.layernorm_bwd(tb.t2[X], tb.x1[X], P_[tk[X]["ln1_w"]], tb.mean1[X], tb.rstd1[X], dx2[X], tb.t0[X],
                               g[tk[X]["ln1_w"]], g[tk[X]["ln1_b"]], sc, R, accumulate=True)   # t0 = d(x1)
-            ops.batchsum(tb.t0[X], B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
             ops.add_rows(tb.t0[X], C, ws["dtokc"][X], C, ws["dtok3"][X], C, R, C)       # + skip path (:505)
-        # ---- encode convs
-        self._bwgrad(ws["dtok3"], ws["x6tok"], [g[f"{m}_encode_conv.weight"] for m in MODALITIES], R, C, ENC)
-        self._bcolsum(ws["dtok3"], C, R, [g[f"{m}_encode_conv.bias"] for m in MODALITIES], sc)
+        # ---- encode convs (weight / bias / pos gradients beside the last dgrad)
+        self._fork()
+        with self._side_ctx():
+            for X, m in enumerate(MODALITIES):
+                ops.batchsum(tb.t0[X], B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
+            self._bwgrad(ws["dtok3"], ws["x6tok"], [g[f"{m}_encode_conv.weight"] for m in MODALITIES], R, C, ENC)
+            self._bcolsum(ws["dtok3"], C, R, [g[f"{m}_encode_conv.bias"] for m in MODALITIES], sc)
         self._bdgrad(ws["dtok3"], W["enc_w"], ws["dx6tok3"], R, C, ENC)
         ops.transpose(ws["dx6tok3"], ws["dx6"], NM * B, S, ENC)
+        self._join()
 
     # ------------------------------------------------------------------------------------------
     def set_seed(self, seed: int) -> None:
@@ -623,25 +675,29 @@ class FusionBlockEngine:
         # ---- decode conv
         ops.transpose(gout, ws["dytok"], B, ENC * NM, S, round_out=self.rnd)
         tbm = ws["tb"][NM]
-        self._wgrad(ws["dytok"], tbm.x3, g["multimodal_decode_conv.weight"], R, ENC * NM, (NM + 1) * C)
-        ops.colsum(ws["dytok"], ENC * NM, R, ENC * NM, g["multimodal_decode_conv.bias"], sc, accumulate=True)
+        self._fork()
+        with self._side_ctx():
+            self._wgrad(ws["dytok"], tbm.x3, g["multimodal_decode_conv.weight"], R, ENC * NM, (NM + 1) * C)
+            ops.colsum(ws["dytok"], ENC * NM, R, ENC * NM, g["multimodal_decode_conv.bias"], sc, accumulate=True)
         self._dgrad(ws["dytok"], self.pw["multimodal_decode_conv.weight"], tbm.din, R, ENC * NM, (NM + 1) * C)
         # ---- multimodal transformer
         dtokens = self._transformer_bwd(NM, tbm.din, tbm, g, sc)                  # [B,2048,512]
-        for X, m in enumerate(MODALITIES + ("fused6",)):      # pos grads of the concatenated [2048,512]
-            ops.batchsum((dtokens, X * S * C), B, (NM + 1) * S * C, S * C, g[f"{m}_pos"], accumulate=True)
         # contiguous per-group copies of the token gradient: [4][B*S][512]
         ws["dtokc"].view(NM + 1, B, S, C).copy_(dtokens.view(B, NM + 1, S, C).transpose(0, 1))
-        # ---- fused6 encode conv
+        # ---- fused6 encode conv; pos grads of the concatenated [2048,512] beside it
         df6 = ws["dtokc"][NM]
-        self._wgrad(df6, ws["fx6tok"], g["fused6_encode_conv.weight"], R, C, ENC * NM)
-        ops.colsum(df6, C, R, C, g["fused6_encode_conv.bias"], sc, accumulate=True)
+        self._fork()
+        with self._side_ctx():
+            for X, m in enumerate(MODALITIES + ("fused6",)):
+                ops.batchsum((dtokens, X * S * C), B, (NM + 1) * S * C, S * C, g[f"{m}_pos"], accumulate=True)
+            self._wgrad(df6, ws["fx6tok"], g["fused6_encode_conv.weight"], R, C, ENC * NM)
+            ops.colsum(df6, C, R, C, g["fused6_encode_conv.bias"], sc, accumulate=True)
         self._dgrad(df6, self.pw["fused6_encode_conv.weight"], ws["dfx6tok"], R, C, ENC * NM)
         ops.transpose(ws["dfx6tok"], ws["dfused"], B, S, ENC * NM)
         # ---- inter-modal correlation
         ops.inter_corr_bwd(ws["qkvi"], dtokens, ws["dqkvi"], NM, B, S, C)
         if self.batched:
-            self._intra_bwd_batched(ws, g, sc)
+            self._intra_bwd_batched(ws, g, sc)          # joins the side stream at its end
             return (ws["dx6"].view(NM, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * NM, 8, 8, 8), grads)
         for X, m in enumerate(MODALITIES):
             tb = ws["tb"][X]
@@ -656,4 +712,5 @@ class FusionBlockEngine:
             ops.colsum(ws["dtok"], C, R, C, g[f"{m}_encode_conv.bias"], sc, accumulate=True)
             self._dgrad(ws["dtok"], self.pw[f"{m}_encode_conv.weight"], ws["dx6tok"], R, C, ENC)
             ops.transpose(ws["dx6tok"], ws["dx6"][X], B, S, ENC)
+        self._join()
         return (ws["dx6"].view(NM, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * NM, 8, 8, 8), grads)
