@@ -430,7 +430,15 @@ __global__ void batchsum_kernel(const float* __restrict__ x, int64_t batch, int6
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads;
        q += (int64_t)gridDim.x * blockDim.x) {
     float4 a = accumulate ? ld4(out + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t b = 0; b < batch; ++b) {
+    int64_t b = 0;
+    for (; b + 8 <= batch; b += 8) {       // 8 independent loads in flight (one at a time ran at 1.5 TB/s)
+      float4 u[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = ld4_stream(x + (b + i) * stride + q * 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a.x += u[i].x; a.y += u[i].y; a.z += u[i].z; a.w += u[i].w; }
+    }
+    for (; b < batch; ++b) {
       const float4 u = ld4_stream(x + b * stride + q * 4);
       a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
     }
