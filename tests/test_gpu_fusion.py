@@ -208,3 +208,38 @@ def test_cuda_graph_replay_with_moving_inputs_switches_to_engine_staging():
     assert eng._graph_mode == {("fwd", 2): "static", ("bwd", 2): "static"}
     assert sum("graph" in e for e in eng._graphs.values()) == 2
 
+
+def test_full_size_batch16_tf32_path_against_fp32_checking_mode_and_linearity():
+    """BASELINE.json configs[1] size (batch 16), where the CPU oracle no longer finishes in seconds:
+    (a) the tcgen05 TF32 path against the library's own fp32 checking mode (itself pinned to the reference
+        fixtures at B = 1..3 and to the oracle at B = 8) - output and input gradients;
+    (b) train mode, fixed seed: the backward is linear in the upstream gradient,
+        bwd(2 g1 - 3 g2) == 2 bwd(g1) - 3 bwd(g2), and the forward is bit-reproducible."""
+    batch, seed = 16, 99
+    a = _run_engine(batch, "tf32", seed=seed)
+    b = _run_engine(batch, "fp32", seed=seed)
+    tol = TOL["tf32"]
+    assert rel_l2(a[0].cpu().numpy(), b[0].cpu().numpy()) < tol["out"]
+    assert rel_l2(a[1].cpu().numpy(), b[1].cpu().numpy()) < tol["xgrad"]
+    assert rel_l2(a[2].cpu().numpy(), b[2].cpu().numpy()) < tol["xgrad"]
+    for k in ("multimodal_transformer.cross_attention_list.0.fn.fn.qkv.weight", "qkv_RGB.weight", "NIR_pos",
+              "multimodal_decode_conv.bias"):
+        assert rel_l2(a[3][k].cpu().numpy(), b[3][k].cpu().numpy()) < tol["pgrad"], k
+    del a, b
+    dev = torch.device("cuda:0")
+    params = {k: v.to(dev).contiguous() for k, v in O.make_params(seed).items()}
+    x6, fused, g1 = O.make_inputs(seed, batch)
+    g2 = O.make_inputs(seed + 1, batch)[2]
+    x6, fused, g1, g2 = [t.to(dev) for t in x6], fused.to(dev), g1.to(dev), g2.to(dev)
+    eng = fusion.FusionBlockEngine(params, dropout_p=0.1, precision="tf32")
+    res = []
+    for g in (g1, g2, 2.0 * g1 - 3.0 * g2):
+        eng.seed = 5
+        out = eng.forward(x6, fused).clone()
+        dx6, df, _ = eng.backward(g)
+        res.append((out, dx6.clone(), df.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][0], res[2][0])
+    for i in (1, 2):
+        lin = 2.0 * res[0][i] - 3.0 * res[1][i]
+        assert rel_l2(res[2][i].cpu().numpy(), lin.cpu().numpy()) < 2e-3, i
+
