@@ -186,11 +186,11 @@ __device__ __forceinline__ void mma_headdim_ts(uint32_t tm, uint32_t tA, uint32_
                         t > 0 ? 1u : 0u);
 }
 // my CG columns of one row of TWO [rows, ld] matrices -> TMEM (the second optionally rounded to TF32).
-// All eight 16-byte loads are issued before the first tcgen05.st: the own-tile prologue is pure global-load
-// latency (measured 7.7 k cycles per CTA when the two slices were loaded one after the other).
-__device__ __forceinline__ void row_slices_to_tmem(const float* src0, uint32_t taddr0, const float* src1,
-                                                   uint32_t taddr1, bool round1) {
-  uint32_t r0[CG], r1[CG];
+// All eight 16-byte loads are issued together and BEFORE the kernel's setup barrier (barrier init, TMEM
+// allocation): the own-tile prologue is pure global-load latency (measured 7.7 k cycles per CTA when the two
+// slices were loaded one after the other, behind the setup).
+__device__ __forceinline__ void row_slices_load(const float* src0, const float* src1, bool round1,
+                                                uint32_t (&r0)[CG], uint32_t (&r1)[CG]) {
 #pragma unroll
   for (int q4 = 0; q4 < CG / 4; ++q4) {
     const float4 v = ld4(src0 + 4 * q4);
@@ -207,8 +207,6 @@ __device__ __forceinline__ void row_slices_to_tmem(const float* src0, uint32_t t
 #pragma unroll
     for (int c = 0; c < CG; ++c) r1[c] += 0x1000u;
   }
-  tmem_st16(taddr0, r0);
-  tmem_st16(taddr1, r1);
 }
 // Gradient tile [128 x 64] (thread = row, my CG columns, scaled by f) -> SWIZZLE_128B image in shared memory
 // for a TMA store: direct st.global from "thread = row" registers is 32 half-filled sectors per
@@ -237,6 +235,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
   const int q_row0 = b * a.N + qt * TB, kv_row0 = b * a.N;
   const int ntiles = a.N / TL;
 
+  uint32_t own0[CG], own1[CG];            // my slices of the CTA's own Q / dO rows, in flight across the setup
+  if (warp < EW) {
+    const int orow = (warp & 3) * 32 + lane, oc0 = (warp >> 2) * CG;
+    row_slices_load(a.qkv + (int64_t)(q_row0 + orow) * (3 * C) + h * HD + oc0,
+                    a.dO + (int64_t)(q_row0 + orow) * C + h * HD + oc0, true, own0, own1);
+  }
   if (warp == PROD_WARP && lane == 0) {
     mbar_init(&own_full, EWT);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_free[s], 1); }
@@ -301,8 +305,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int col0 = g * CG;                                   // my columns of every 64-wide tile
     const int q = qt * TB + row;
-    row_slices_to_tmem(a.qkv + (int64_t)(q_row0 + row) * (3 * C) + h * HD + col0, tQ + lane_addr + col0,
-                       a.dO + (int64_t)(q_row0 + row) * C + h * HD + col0, tDO + lane_addr + col0, true);
+    tmem_st16(tQ + lane_addr + col0, own0);
+    tmem_st16(tDO + lane_addr + col0, own1);
     tcgen05_fence_before();
     mbar_arrive(&own_full);
     // Constant factors leave the per-element path: dS = scale * ks * P * (keep * dP_raw - delta / ks), so the
@@ -399,6 +403,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
   const int kv_row0 = b * a.N + kt * TB, q_base = b * a.N;
   const int ntiles = a.N / TL;
 
+  uint32_t own0[CG], own1[CG];            // my slices of the CTA's own K / V rows, in flight across the setup
+  if (warp < EW) {
+    const float* krow0 = a.qkv + (int64_t)(kv_row0 + (warp & 3) * 32 + lane) * (3 * C) + C + h * HD + (warp >> 2) * CG;
+    row_slices_load(krow0, krow0 + C, false, own0, own1);
+  }
   if (warp == PROD_WARP && lane == 0) {
     mbar_init(&own_full, EWT);
     for (int s = 0; s < STAGES; ++s) {
@@ -478,8 +487,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk,    // qkv,  box {3
     const int col0 = g * CG;
     const int words = a.N / 32;
     {
-      const float* krow = a.qkv + (int64_t)(kv_row0 + row) * (3 * C) + C + h * HD + col0;
-      row_slices_to_tmem(krow, tK + lane_addr + col0, krow + C, tV + lane_addr + col0, false);
+      tmem_st16(tK + lane_addr + col0, own0);
+      tmem_st16(tV + lane_addr + col0, own1);
       tcgen05_fence_before();
       mbar_arrive(&own_full);
     }
