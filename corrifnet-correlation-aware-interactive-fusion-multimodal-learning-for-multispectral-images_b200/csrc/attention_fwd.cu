@@ -66,7 +66,11 @@ constexpr int NUM_THREADS = 320;     // 8 softmax warps, producer warp, MMA warp
 constexpr int PROD_WARP = 8, MMA_WARP = 9;
 
 // DROP is a template parameter so that the dropout code is straight-line (no branch per float4 group).
-template <bool DROP>
+// PRE (with DROP): the keep bits were produced ahead of time by attn_keepbits_kernel (same decisions) and are
+// only READ here, one word per thread and tile, fetched a tile ahead: the counter hash, the 16-bit compares and
+// the keep-bit word are 4.3 of the 12.5 instructions per score element of this issue-bound loop, and they do
+// not depend on the data - the engine runs them on a second stream under the GEMMs that precede the attention.
+template <bool DROP, bool PRE>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FwdArgs a) {
@@ -183,8 +187,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     const uint64_t sc2 = pack2(a.scale_log2e, a.scale_log2e);
     const uint32_t th_lo = a.thresh, th_hi = a.thresh << 16;
+    const uint32_t* mrow = a.maskbits + ((int64_t)bh * a.N + q_in_head) * (a.N / 32) + g;
+    uint32_t bits_next = (DROP && PRE) ? mrow[0] : 0u;
     for (int j = 0; j < ntiles; ++j) {
       const uint32_t ph = (uint32_t)j & 1u;
+      const uint32_t bits_cur = bits_next;
+      if (DROP && PRE && j + 1 < ntiles) bits_next = mrow[(j + 1) * (TK / 32)];   // no arithmetic on it before the next tile
       mbar_wait(&s_full, ph);
       tcgen05_fence_after();
       tmem_ld32(tS + lane_addr + g * 32, r);                 // my 32 score columns (kept in registers)
@@ -238,7 +246,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         p0 = ex2_approx(p0); p1 = ex2_approx(p1); p2 = ex2_approx(p2); p3 = ex2_approx(p3);
         rs_a = add2(rs_a, pack2(p0, p1));
         rs_b = add2(rs_b, pack2(p2, p3));
-        if (DROP) {               // 1/(1-p) is applied once to the output, not per element
+        if (DROP && PRE) {
+          p0 = (bits_cur & (1u << (4 * q4))) ? p0 : 0.f; p1 = (bits_cur & (2u << (4 * q4))) ? p1 : 0.f;
+          p2 = (bits_cur & (4u << (4 * q4))) ? p2 : 0.f; p3 = (bits_cur & (8u << (4 * q4))) ? p3 : 0.f;
+        }
+        if (DROP && !PRE) {       // 1/(1-p) is applied once to the output, not per element
           const uint64_t hbits = dropout_bits(rk, q0 + q4);          // same decisions as dropout_keepmask4
           const uint32_t lo = (uint32_t)hbits, hi = (uint32_t)(hbits >> 32);
           const bool k0 = (lo & 0xFFFFu) >= th_lo, k1 = lo >= th_hi, k2 = (hi & 0xFFFFu) >= th_lo, k3 = hi >= th_hi;
@@ -251,7 +263,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         r[4 * q4 + 0] = __float_as_uint(p0); r[4 * q4 + 1] = __float_as_uint(p1);
         r[4 * q4 + 2] = __float_as_uint(p2); r[4 * q4 + 3] = __float_as_uint(p3);
       }
-      if (DROP && a.maskbits != nullptr)
+      if (DROP && !PRE && a.maskbits != nullptr)
         a.maskbits[((int64_t)bh * a.N + q_in_head) * (a.N / 32) + j * (TK / 32) + g] = keepbits;
       {
         float s0, s1;
@@ -289,16 +301,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// The forward's dropout decisions as a stand-alone pass: word w = ((b*H + h)*N + q)*(N/32) + kw holds the keep
+// bits of keys [32 kw, 32 kw + 32) of query q - exactly what attn_fwd_kernel<true, false> would store.
+__global__ void __launch_bounds__(256)
+attn_keepbits_kernel(uint32_t* __restrict__ maskbits, int N, int H, int64_t total_words, uint32_t thresh, uint64_t seed,
+                     const uint64_t* __restrict__ seed_dev, uint32_t site, int group_batches, uint32_t group_site_stride) {
+  if (seed_dev != nullptr) seed += *seed_dev;
+  const int words = N / 32;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total_words; w += (int64_t)gridDim.x * blockDim.x) {
+    const int kw = (int)(w % words);
+    const int64_t rowidx = w / words;
+    const int q = (int)(rowidx % N), bh = (int)(rowidx / N);
+    const int b = bh / H, h = bh % H;
+    const int grp = group_batches > 0 ? b / group_batches : 0;
+    const int bh_rng = group_batches > 0 ? (b - grp * group_batches) * H + h : bh;
+    const DropRoundKeys rk = dropout_round_keys(dropout_key(seed, site + (uint32_t)grp * group_site_stride));
+    const uint64_t q0 = ((((uint64_t)bh_rng * N + q) * (uint64_t)N) + (uint64_t)kw * 32u) >> 2;
+    uint32_t bits = 0u;
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) bits |= dropout_keepmask4(rk, q0 + q4, thresh) << (4 * q4);
+    maskbits[w] = bits;
+  }
+}
+
 }  // namespace attn
 }  // namespace corrif
 
 using namespace corrif;
 
-extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint32_t* maskbits,
-                                    int32_t B, int32_t N, int32_t H, int32_t D, float scale,
-                                    float p_drop, uint64_t seed,
-                                    const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
-                                    uint32_t group_site_stride, int32_t round_tf32, void* stream) {
+extern "C" int corrif_attention_keepbits(uint32_t* maskbits, int32_t B, int32_t N, int32_t H, float p_drop, uint64_t seed,
+                                         const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
+                                         uint32_t group_site_stride, void* stream) {
+  using namespace corrif::attn;
+  CORRIF_REQUIRE(maskbits && B > 0 && H > 0 && N > 0 && N % 32 == 0, "attention_keepbits: null/empty or N % 32 != 0");
+  CORRIF_REQUIRE(p_drop > 0.f && p_drop < 1.f, "attention_keepbits: 0 < p_drop < 1");
+  CORRIF_REQUIRE(group_batches >= 0 && (group_batches == 0 || B % group_batches == 0),
+                 "attention_keepbits: group_batches must divide B");
+  const int64_t total = (int64_t)B * H * N * (N / 32);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  attn_keepbits_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(maskbits, N, H, total, dropout_threshold(p_drop), seed,
+                                                                         seed_dev, site, group_batches, group_site_stride);
+  return launch_status("attention_keepbits");
+}
+
+static int attention_fwd_launch(const float* qkv, float* O, float* lse, uint32_t* maskbits,
+                                int32_t B, int32_t N, int32_t H, int32_t D, float scale,
+                                float p_drop, uint64_t seed,
+                                const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
+                                uint32_t group_site_stride, int32_t round_tf32, bool premasked, void* stream) {
   using namespace corrif::attn;
   CORRIF_REQUIRE(qkv && O && lse && B > 0, "attention_fwd: null/empty");
   CORRIF_REQUIRE(D == HD, "attention_fwd: head_dim must be 64 (got %d)", D);
@@ -319,9 +371,11 @@ extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint
   if (st) return st;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      e = cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { set_last_error("attention_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
@@ -333,7 +387,25 @@ extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint
   a.seed = seed; a.seed_dev = seed_dev; a.site = site; a.round_out = round_tf32;
   a.group_batches = group_batches; a.group_site_stride = group_site_stride;
   dim3 grid(N / TQ, B * H);
-  if (a.thresh != 0u) attn_fwd_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
-  else attn_fwd_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  if (a.thresh != 0u && premasked) attn_fwd_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  else if (a.thresh != 0u) attn_fwd_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
+  else attn_fwd_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, a);
   return launch_status("attention_fwd");
+}
+
+extern "C" int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint32_t* maskbits,
+                                    int32_t B, int32_t N, int32_t H, int32_t D, float scale,
+                                    float p_drop, uint64_t seed,
+                                    const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
+                                    uint32_t group_site_stride, int32_t round_tf32, void* stream) {
+  return attention_fwd_launch(qkv, O, lse, maskbits, B, N, H, D, scale, p_drop, seed, seed_dev, site, group_batches,
+                              group_site_stride, round_tf32, false, stream);
+}
+
+extern "C" int corrif_attention_fwd_premasked(const float* qkv, float* O, float* lse, const uint32_t* maskbits,
+                                              int32_t B, int32_t N, int32_t H, int32_t D, float scale,
+                                              float p_drop, int32_t round_tf32, void* stream) {
+  CORRIF_REQUIRE(p_drop > 0.f && maskbits != nullptr, "attention_fwd_premasked: needs p_drop > 0 and the keep bits");
+  return attention_fwd_launch(qkv, O, lse, const_cast<uint32_t*>(maskbits), B, N, H, D, scale, p_drop, 0, nullptr, 0, 0, 0,
+                              round_tf32, true, stream);
 }

@@ -227,6 +227,22 @@ def attention_fwd(qkv, O, lse, maskbits, B, N, H=8, D=64, scale=0.125, p=0.0, se
     _count()
 
 
+def attention_keepbits(maskbits, B, N, H, p, seed, site, seed_dev=None, group_batches=0, group_site_stride=0):
+    """The dropout keep bits attention_fwd would store, as a stand-alone pass (data-independent)."""
+    with _rec("attn_keepbits", 0.125 * B * H * N * N, "B%d N%d" % (B, N)):
+        L.check(lib().corrif_attention_keepbits(_ptr(maskbits, torch.int32), B, N, H, p, seed, _seed_dev(seed_dev), site,
+                                                group_batches, group_site_stride, _stream()), "corrif_attention_keepbits")
+    _count()
+
+
+def attention_fwd_premasked(qkv, O, lse, maskbits, B, N, H=8, D=64, scale=0.125, p=0.1, round_out=False):
+    with _rec("attn_fwd", 4.0 * B * H * N * N * D, "B%d N%d premasked" % (B, N)):
+        L.check(lib().corrif_attention_fwd_premasked(_ptr(qkv), _ptr(O), _ptr(lse), _ptr(maskbits, torch.int32), B, N,
+                                                     H, D, scale, p, int(round_out), _stream()),
+                "corrif_attention_fwd_premasked")
+    _count()
+
+
 def attention_bwd(qkv, O, dO, lse, maskbits, delta, dqkv, B, N, H=8, D=64, scale=0.125, p=0.0):
     # algorithmic FLOPs of the backward: dV, dP, dQ, dK = 4 products (recomputing S is not counted)
     with _rec("attn_bwd", 8.0 * B * H * N * N * D, "B%d N%d" % (B, N)):

@@ -170,6 +170,17 @@ int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint32_t* maskb
                          int32_t N, int32_t H, int32_t D, float scale, float p_drop, uint64_t seed,
                          const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
                          uint32_t group_site_stride, int32_t round_tf32, void* stream);
+/* The forward's dropout decisions as a stand-alone pass, and the forward that consumes them: the keep bits
+ * depend on (seed, site, element) only, so a host can produce them on a second stream while the GEMMs that
+ * precede the attention run, and keep the counter hash out of the forward's issue-bound softmax loop.
+ * corrif_attention_keepbits writes exactly the words corrif_attention_fwd would store for the same arguments;
+ * corrif_attention_fwd_premasked == corrif_attention_fwd with those words read instead of regenerated. */
+int corrif_attention_keepbits(uint32_t* maskbits, int32_t B, int32_t N, int32_t H, float p_drop, uint64_t seed,
+                              const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
+                              uint32_t group_site_stride, void* stream);
+int corrif_attention_fwd_premasked(const float* qkv, float* O, float* lse, const uint32_t* maskbits,
+                                   int32_t B, int32_t N, int32_t H, int32_t D, float scale,
+                                   float p_drop, int32_t round_tf32, void* stream);
 int corrif_attention_bwd(const float* qkv, const float* O, const float* dO, const float* lse,
                          const uint32_t* maskbits, float* delta, float* dqkv, int32_t B, int32_t N,
                          int32_t H, int32_t D, float scale, float p_drop, void* stream);

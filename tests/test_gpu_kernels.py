@@ -424,6 +424,24 @@ def test_fused_attention_fwd_bwd(B, N, p):
         assert e < 3e-3, f"d{nm}: {e:.3e}"
 
 
+@pytest.mark.parametrize("B,N,G", [(2, 256, 0), (6, 512, 2), (1, 2048, 0)])
+def test_attention_keepbits_and_premasked_forward(B, N, G):
+    """Stand-alone keep-bit pass == the bits the fused forward stores; the forward that READS them gives the
+    same O and lse bit for bit (also with several modules per launch: group_batches / group_site_stride)."""
+    H, d, Cc, p = 8, 64, 512, 0.1
+    qkv = _rand(B * N, 3 * Cc, seed=N + 7)
+    O1, O2 = torch.empty(B * N, Cc, device=dev()), torch.empty(B * N, Cc, device=dev())
+    l1, l2 = torch.empty(B * H, N, device=dev()), torch.empty(B * H, N, device=dev())
+    b1 = torch.zeros(B * H, N, N // 32, dtype=torch.int32, device=dev())
+    b2 = torch.zeros_like(b1)
+    sd = torch.tensor([3], dtype=torch.int64, device=dev())
+    ops.attention_fwd(qkv, O1, l1, b1, B, N, H, d, 0.125, p, seed=40, seed_dev=sd, site=5, group_batches=G, group_site_stride=8)
+    ops.attention_keepbits(b2, B, N, H, p, 40, 5, seed_dev=sd, group_batches=G, group_site_stride=8)
+    assert torch.equal(b1, b2)
+    ops.attention_fwd_premasked(qkv, O2, l2, b2, B, N, H, d, 0.125, p)
+    assert torch.equal(O1, O2) and torch.equal(l1, l2)
+
+
 def test_fused_loss_and_jaccard_tail():
     """F4_TRAIN.py:58-71 in one pass: BCEWithLogits over all elements (+ gradient) and Jaccard2 of
     channel 0, against torch and against the stand-alone Jaccard2 kernel (bit-exact on {0,1} masks and
