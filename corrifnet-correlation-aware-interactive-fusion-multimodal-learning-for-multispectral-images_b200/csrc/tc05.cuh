@@ -222,21 +222,6 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// ---- multicast variants for plain (cta_group::1) kernels launched as clusters: CTAs that walk the same
-// loop tiles each fetch a share of every tile and multicast it to all CTAs of `mask` (data and the
-// mbarrier complete_tx land at the same CTA-relative offsets), halving the L2 -> SM traffic per CTA.
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      :: "r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-// arrive (once the MMAs issued so far retire) on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               :: "r"(smem_u32(bar)), "h"(mask) : "memory");
-}
 // shared memory -> global through a tensor map (bulk async group); the issuing thread must wait for the
 // group's smem reads before the CTA exits or re-uses the buffer
 __device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, uint32_t src, int c0, int c1) {
