@@ -58,7 +58,7 @@ PROTOTYPES = {
     "corrif_softmax_fwd": (C.c_int, [f32p, f32p, i64, i32, f32, u64, u64p, u32, i32, stream_t]),
     "corrif_softmax_bwd": (C.c_int, [f32p, f32p, i64, i32, f32, f32, u64, u64p, u32, stream_t]),
     "corrif_attention_fwd": (C.c_int, [f32p, f32p, f32p, C.c_void_p, i32, i32, i32, i32, f32, f32, u64, u64p, u32, i32, u32, i32, stream_t]),
-    "corrif_attention_keepbits": (C.c_int, [C.c_void_p, i32, i32, i32, f32, u64, u64p, u32, i32, u32, stream_t]),
+    "corrif_attention_keepbits": (C.c_int, [C.c_void_p, i32, i32, i32, f32, u64, u64p, u32, i32, u32, i32, stream_t]),
     "corrif_attention_fwd_premasked": (C.c_int, [f32p, f32p, f32p, C.c_void_p, i32, i32, i32, i32, f32, f32, i32, stream_t]),
     "corrif_attention_bwd": (C.c_int, [f32p, f32p, f32p, f32p, C.c_void_p, f32p, f32p, i32, i32, i32, i32, f32, f32, stream_t]),
     "corrif_dropout": (C.c_int, [f32p, f32p, i64, f32, u64, u64p, u32, stream_t]),

@@ -308,19 +308,30 @@ attn_keepbits_kernel(uint32_t* __restrict__ maskbits, int N, int H, int64_t tota
                      const uint64_t* __restrict__ seed_dev, uint32_t site, int group_batches, uint32_t group_site_stride) {
   if (seed_dev != nullptr) seed += *seed_dev;
   const int words = N / 32;
-  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total_words; w += (int64_t)gridDim.x * blockDim.x) {
-    const int kw = (int)(w % words);
-    const int64_t rowidx = w / words;
-    const int q = (int)(rowidx % N), bh = (int)(rowidx / N);
-    const int b = bh / H, h = bh % H;
-    const int grp = group_batches > 0 ? b / group_batches : 0;
-    const int bh_rng = group_batches > 0 ? (b - grp * group_batches) * H + h : bh;
-    const DropRoundKeys rk = dropout_round_keys(dropout_key(seed, site + (uint32_t)grp * group_site_stride));
-    const uint64_t q0 = ((((uint64_t)bh_rng * N + q) * (uint64_t)N) + (uint64_t)kw * 32u) >> 2;
-    uint32_t bits = 0u;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // two words (16 independent hash chains) per thread and sweep: when the pass runs beside a GEMM it gets one
+  // block per SM, and 8 warps only fill the ALU pipe if each of them carries enough independent work
+  for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < total_words; w0 += 2 * stride) {
+    uint32_t bits[2] = {0u, 0u};
 #pragma unroll
-    for (int q4 = 0; q4 < 8; ++q4) bits |= dropout_keepmask4(rk, q0 + q4, thresh) << (4 * q4);
-    maskbits[w] = bits;
+    for (int u = 0; u < 2; ++u) {
+      const int64_t w = w0 + u * stride;
+      if (w < total_words) {
+        const int kw = (int)(w % words);
+        const int64_t rowidx = w / words;
+        const int q = (int)(rowidx % N), bh = (int)(rowidx / N);
+        const int b = bh / H, h = bh % H;
+        const int grp = group_batches > 0 ? b / group_batches : 0;
+        const int bh_rng = group_batches > 0 ? (b - grp * group_batches) * H + h : bh;
+        const DropRoundKeys rk = dropout_round_keys(dropout_key(seed, site + (uint32_t)grp * group_site_stride));
+        const uint64_t q0 = ((((uint64_t)bh_rng * N + q) * (uint64_t)N) + (uint64_t)kw * 32u) >> 2;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) bits[u] |= dropout_keepmask4(rk, q0 + q4, thresh) << (4 * q4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (w0 + u * stride < total_words) maskbits[w0 + u * stride] = bits[u];
   }
 }
 
@@ -331,7 +342,7 @@ using namespace corrif;
 
 extern "C" int corrif_attention_keepbits(uint32_t* maskbits, int32_t B, int32_t N, int32_t H, float p_drop, uint64_t seed,
                                          const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
-                                         uint32_t group_site_stride, void* stream) {
+                                         uint32_t group_site_stride, int32_t max_blocks, void* stream) {
   using namespace corrif::attn;
   CORRIF_REQUIRE(maskbits && B > 0 && H > 0 && N > 0 && N % 32 == 0, "attention_keepbits: null/empty or N % 32 != 0");
   CORRIF_REQUIRE(p_drop > 0.f && p_drop < 1.f, "attention_keepbits: 0 < p_drop < 1");
@@ -339,7 +350,7 @@ extern "C" int corrif_attention_keepbits(uint32_t* maskbits, int32_t B, int32_t 
                  "attention_keepbits: group_batches must divide B");
   const int64_t total = (int64_t)B * H * N * (N / 32);
   int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 8;
+  const int64_t cap = max_blocks > 0 ? max_blocks : (int64_t)num_sms() * 8;   // e.g. one block per SM beside a GEMM
   if (blocks > cap) blocks = cap;
   attn_keepbits_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(maskbits, N, H, total, dropout_threshold(p_drop), seed,
                                                                          seed_dev, site, group_batches, group_site_stride);

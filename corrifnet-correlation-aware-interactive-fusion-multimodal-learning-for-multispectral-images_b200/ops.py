@@ -227,11 +227,13 @@ def attention_fwd(qkv, O, lse, maskbits, B, N, H=8, D=64, scale=0.125, p=0.0, se
     _count()
 
 
-def attention_keepbits(maskbits, B, N, H, p, seed, site, seed_dev=None, group_batches=0, group_site_stride=0):
+def attention_keepbits(maskbits, B, N, H, p, seed, site, seed_dev=None, group_batches=0, group_site_stride=0,
+                       max_blocks=0):
     """The dropout keep bits attention_fwd would store, as a stand-alone pass (data-independent)."""
     with _rec("attn_keepbits", 0.125 * B * H * N * N, "B%d N%d" % (B, N)):
         L.check(lib().corrif_attention_keepbits(_ptr(maskbits, torch.int32), B, N, H, p, seed, _seed_dev(seed_dev), site,
-                                                group_batches, group_site_stride, _stream()), "corrif_attention_keepbits")
+                                                group_batches, group_site_stride, max_blocks, _stream()),
+                "corrif_attention_keepbits")
     _count()
 
 

@@ -177,7 +177,7 @@ int corrif_attention_fwd(const float* qkv, float* O, float* lse, uint32_t* maskb
  * corrif_attention_fwd_premasked == corrif_attention_fwd with those words read instead of regenerated. */
 int corrif_attention_keepbits(uint32_t* maskbits, int32_t B, int32_t N, int32_t H, float p_drop, uint64_t seed,
                               const uint64_t* seed_dev, uint32_t site, int32_t group_batches,
-                              uint32_t group_site_stride, void* stream);
+                              uint32_t group_site_stride, int32_t max_blocks /* 0 = fill the GPU */, void* stream);
 int corrif_attention_fwd_premasked(const float* qkv, float* O, float* lse, const uint32_t* maskbits,
                                    int32_t B, int32_t N, int32_t H, int32_t D, float scale,
                                    float p_drop, int32_t round_tf32, void* stream);
