@@ -55,6 +55,8 @@ PROTOTYPES = {
     "corrif_layernorm_bwd_scratch_floats": (i64, [i64, i32]),
     "corrif_layernorm_bwd": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, i32,
                                        f32p, f32, u64, u64p, u32, u32, stream_t]),
+    "corrif_layernorm_bwd_regroup": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, i32,
+                                               f32p, f32, u64, u64p, u32, u32, i32, i32, stream_t]),
     "corrif_softmax_fwd": (C.c_int, [f32p, f32p, i64, i32, f32, u64, u64p, u32, i32, stream_t]),
     "corrif_softmax_bwd": (C.c_int, [f32p, f32p, i64, i32, f32, f32, u64, u64p, u32, stream_t]),
     "corrif_attention_fwd": (C.c_int, [f32p, f32p, f32p, C.c_void_p, i32, i32, i32, i32, f32, f32, u64, u64p, u32, i32, u32, i32, stream_t]),
@@ -72,6 +74,7 @@ PROTOTYPES = {
     "corrif_add_rows": (C.c_int, [f32p, i64, f32p, i64, f32p, i64, i64, i32, stream_t]),
     "corrif_inter_corr_fwd": (C.c_int, [f32p, f32p, f32p, i32, i32, i32, i32, stream_t]),
     "corrif_inter_corr_bwd": (C.c_int, [f32p, f32p, f32p, i32, i32, i32, i32, stream_t]),
+    "corrif_inter_corr_bwd_layout": (C.c_int, [f32p, f32p, f32p, i32, i32, i32, i32, i32, stream_t]),
     "corrif_jaccard_sums": (C.c_int, [f32p, f32p, i64, f64p, stream_t]),
     "corrif_loss_jaccard_fused": (C.c_int, [f32p, f32p, i64, i32, i64, f32, f64p, f32p, f64p, stream_t]),
     "corrif_jaccard_finish": (C.c_int, [f64p, f32, f32p, stream_t]),

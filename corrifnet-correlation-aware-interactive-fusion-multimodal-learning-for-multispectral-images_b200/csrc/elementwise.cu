@@ -97,7 +97,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
                      const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
                      float* __restrict__ dx_drop, uint32_t thresh, float keep_scale, uint64_t seed,
-                     const uint64_t* seed_dev, uint32_t site_a, uint32_t site_b) {
+                     const uint64_t* seed_dev, uint32_t site_a, uint32_t site_b, int groups, int group_rows) {
   __shared__ __align__(16) float red[8][2][LN_C];
   uint64_t key_a = 0, key_b = 0;
   if (dx_drop != nullptr) {      // fused dropout of the outgoing gradient (backward of the next block's
@@ -115,6 +115,14 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
   }
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
     const float mu = mean[row], rs = rstd[row];
+    // groups > 0: rows are [batch][group][group_rows]; dx is written group-major, [group][batch][group_rows]
+    // (the multimodal token gradient leaves in the layout its consumers want: no strided copy afterwards)
+    int64_t orow = row;
+    if (groups > 0) {
+      const int64_t per_b = (int64_t)groups * group_rows, bb = row / per_b, rem = row - bb * per_b;
+      const int64_t X = rem / group_rows, sidx = rem - X * group_rows;
+      orow = (X * (rows / per_b) + bb) * group_rows + sidx;
+    }
     float4 xh[LN_V], d[LN_V], rres[LN_V];
     float c1 = 0.f, c2 = 0.f;
     // all 12 loads of the row are issued before the first use (the residual gradient used to be fetched
@@ -152,7 +160,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
         const float4 r = rres[j];
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
-      st4(dx + row * LN_C + lane * 4 + j * 128, o);
+      st4(dx + orow * LN_C + lane * 4 + j * 128, o);
       if (dx_drop != nullptr) {
         const uint64_t quad = (uint64_t)(row * LN_C + lane * 4 + j * 128) >> 2;
         uint32_t km = dropout_keepmask4(key_a, quad, thresh);
@@ -548,7 +556,18 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
                          float* dbeta, float* scratch, int64_t rows, int32_t C, int32_t accumulate,
                          float* dx_drop, float p_drop, uint64_t seed, const uint64_t* seed_dev,
                          uint32_t site_a, uint32_t site_b, void* stream) {
+  return corrif_layernorm_bwd_regroup(dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, scratch, rows, C, accumulate,
+                                      dx_drop, p_drop, seed, seed_dev, site_a, site_b, 0, 0, stream);
+}
+
+int corrif_layernorm_bwd_regroup(const float* dy, const float* x1, const float* gamma, const float* mean,
+                                 const float* rstd, const float* dres, float* dx, float* dgamma,
+                                 float* dbeta, float* scratch, int64_t rows, int32_t C, int32_t accumulate,
+                                 float* dx_drop, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                                 uint32_t site_a, uint32_t site_b, int32_t groups, int32_t group_rows, void* stream) {
   (void)scratch;
+  CORRIF_REQUIRE(groups >= 0 && (groups == 0 || (group_rows > 0 && rows % ((int64_t)groups * group_rows) == 0 && dx_drop == nullptr && dx != dy && dx != dres)),
+                 "layernorm_bwd: regrouping needs rows %% (groups * group_rows) == 0, no dx_drop and an out-of-place dx");
   CORRIF_REQUIRE(C == LN_C, "layernorm: C must be 512, got %d", C);
   CORRIF_REQUIRE(dy && x1 && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0,
                  "layernorm_bwd: null/empty");
@@ -565,7 +584,7 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
   if (dx_drop) { ks = 1.0f / (1.0f - p_drop); if (site_b != CORRIF_NO_SITE) ks *= ks; }
   layernorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, dx_drop, dx_drop ? dropout_threshold(p_drop) : 0u,
-      ks, seed, seed_dev, site_a, site_b);
+      ks, seed, seed_dev, site_a, site_b, groups, group_rows);
   return launch_status("layernorm_bwd");
 }
 

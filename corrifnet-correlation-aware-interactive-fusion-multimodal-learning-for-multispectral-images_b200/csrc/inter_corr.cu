@@ -77,7 +77,7 @@ inter_corr_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ s
 // g = dL/dtokens [B][(M+1)S][C]; dqkv [M][B][S][3C]
 __global__ void __launch_bounds__(128)
 inter_corr_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g,
-                      float* __restrict__ dqkv, int B, int S, int C) {
+                      float* __restrict__ dqkv, int B, int S, int C, int g_group_major) {
   const int cq = C / 4;
   const int64_t total = (int64_t)B * S * cq;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -120,7 +120,10 @@ inter_corr_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g
     f4 dv = {{0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
     for (int X = 0; X < IC_M; ++X) {
-      const f4 gx = ldf4(g + ((int64_t)bp * (IC_M + 1) * S + (int64_t)X * S + s) * C + c);
+      // g is [B][(M+1)S][C] (the token layout) or, group-major, [M+1][B][S][C] (as LayerNorm-backward can
+      // write it, see corrif_layernorm_bwd_regroup)
+      const f4 gx = ldf4(g + (g_group_major ? (((int64_t)X * B + bp) * S + s)
+                                            : ((int64_t)bp * (IC_M + 1) * S + (int64_t)X * S + s)) * C + c);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         dA[X][m].v[e] = gx.v[e] * v.v[e];
@@ -170,15 +173,20 @@ int corrif_inter_corr_fwd(const float* qkv, const float* skip, float* tokens, in
   return launch_status("inter_corr_fwd");
 }
 
-int corrif_inter_corr_bwd(const float* qkv, const float* g_tokens, float* dqkv, int32_t M,
-                          int32_t B, int32_t S, int32_t C, void* stream) {
+int corrif_inter_corr_bwd_layout(const float* qkv, const float* g_tokens, float* dqkv, int32_t M,
+                                 int32_t B, int32_t S, int32_t C, int32_t g_group_major, void* stream) {
   CORRIF_REQUIRE(M == IC_M, "inter_corr: M must be 3 (got %d)", M);
   CORRIF_REQUIRE(qkv && g_tokens && dqkv && B > 0 && S > 0 && C > 0 && C % 4 == 0,
                  "inter_corr_bwd: bad arguments");
   const int64_t total = (int64_t)B * S * (C / 4);
   inter_corr_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      qkv, g_tokens, dqkv, B, S, C);
+      qkv, g_tokens, dqkv, B, S, C, g_group_major);
   return launch_status("inter_corr_bwd");
+}
+
+int corrif_inter_corr_bwd(const float* qkv, const float* g_tokens, float* dqkv, int32_t M,
+                          int32_t B, int32_t S, int32_t C, void* stream) {
+  return corrif_inter_corr_bwd_layout(qkv, g_tokens, dqkv, M, B, S, C, 0, stream);
 }
 
 }  // extern "C"

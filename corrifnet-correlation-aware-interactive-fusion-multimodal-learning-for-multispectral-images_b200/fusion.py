@@ -356,7 +356,7 @@ class FusionBlockEngine:
                      **self._drop(t, SITE_FFN2))
         return tb.x3
 
-    def _transformer_bwd(self, t: int, dx3, tb: _TBuf, g: Dict[str, torch.Tensor], scratch):
+    def _transformer_bwd(self, t: int, dx3, tb: _TBuf, g: Dict[str, torch.Tensor], scratch, regroup=None):
         """Backward of _transformer_fwd.  ``dx3`` must not alias tb.t0/t1/t2 (callers pass tb.din).
         Returns d(x_in) == d(x1) in tb.t0 (also the pos gradient before the batch reduction).
         All parameter gradients are ACCUMULATED into ``g`` (which the caller zero-initialises)."""
@@ -398,6 +398,12 @@ class FusionBlockEngine:
             self._wgrad(tb.dqkv, tb.h, g[k["qkv_w"]], R, 3 * C, C)
         self._dgrad(tb.dqkv, self.pw[k["qkv_w"]], tb.t2, R, 3 * C, C)              # d(h)
         self._join()                                     # t0 (dy) is about to be overwritten
+        if regroup is not None:      # (out, groups, group_rows): d(x1) leaves group-major, [group][batch][rows]
+            out, groups, group_rows = regroup
+            ops.layernorm_bwd(tb.t2, tb.x1, P_[k["ln1_w"]], tb.mean1, tb.rstd1, dx2, out,
+                              g[k["ln1_w"]], g[k["ln1_b"]], scratch, R, accumulate=True, groups=groups,
+                              group_rows=group_rows)
+            return out
         ops.layernorm_bwd(tb.t2, tb.x1, P_[k["ln1_w"]], tb.mean1, tb.rstd1, dx2, tb.t0,
                           g[k["ln1_w"]], g[k["ln1_b"]], scratch, R, accumulate=True)   # t0 = d(x1)
         return tb.t0
@@ -681,21 +687,21 @@ class FusionBlockEngine:
             ops.colsum(ws["dytok"], ENC * NM, R, ENC * NM, g["multimodal_decode_conv.bias"], sc, accumulate=True)
         self._dgrad(ws["dytok"], self.pw["multimodal_decode_conv.weight"], tbm.din, R, ENC * NM, (NM + 1) * C)
         # ---- multimodal transformer
-        dtokens = self._transformer_bwd(NM, tbm.din, tbm, g, sc)                  # [B,2048,512]
-        # contiguous per-group copies of the token gradient: [4][B*S][512]
-        ws["dtokc"].view(NM + 1, B, S, C).copy_(dtokens.view(B, NM + 1, S, C).transpose(0, 1))
+        # the token gradient [B,2048,512] leaves the last LayerNorm-backward group-major, [4][B*S][512]: per-group
+        # contiguous for the fused6 conv, the skip paths and the pos sums (it used to be a 134 MB strided copy)
+        self._transformer_bwd(NM, tbm.din, tbm, g, sc, regroup=(ws["dtokc"], NM + 1, S))
         # ---- fused6 encode conv; pos grads of the concatenated [2048,512] beside it
         df6 = ws["dtokc"][NM]
         self._fork()
         with self._side_ctx():
             for X, m in enumerate(MODALITIES + ("fused6",)):
-                ops.batchsum((dtokens, X * S * C), B, (NM + 1) * S * C, S * C, g[f"{m}_pos"], accumulate=True)
+                ops.batchsum(ws["dtokc"][X], B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
             self._wgrad(df6, ws["fx6tok"], g["fused6_encode_conv.weight"], R, C, ENC * NM)
             ops.colsum(df6, C, R, C, g["fused6_encode_conv.bias"], sc, accumulate=True)
         self._dgrad(df6, self.pw["fused6_encode_conv.weight"], ws["dfx6tok"], R, C, ENC * NM)
         ops.transpose(ws["dfx6tok"], ws["dfused"], B, S, ENC * NM)
         # ---- inter-modal correlation
-        ops.inter_corr_bwd(ws["qkvi"], dtokens, ws["dqkvi"], NM, B, S, C)
+        ops.inter_corr_bwd(ws["qkvi"], ws["dtokc"], ws["dqkvi"], NM, B, S, C, g_group_major=True)
         if self.batched:
             self._intra_bwd_batched(ws, g, sc)          # joins the side stream at its end
             return (ws["dx6"].view(NM, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * NM, 8, 8, 8), grads)

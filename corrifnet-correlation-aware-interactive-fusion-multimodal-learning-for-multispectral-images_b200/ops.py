@@ -189,14 +189,16 @@ def layernorm_bwd_scratch_floats(rows, C_=512) -> int:
 
 
 def layernorm_bwd(dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, scratch, rows, C_=512,
-                  accumulate=False, dx_drop=None, p=0.0, seed=0, seed_dev=None, site_a=NO_SITE, site_b=NO_SITE):
+                  accumulate=False, dx_drop=None, p=0.0, seed=0, seed_dev=None, site_a=NO_SITE, site_b=NO_SITE,
+                  groups=0, group_rows=0):
+    """groups > 0: rows are [batch][group][group_rows] and dx is written [group][batch][group_rows]."""
     nbytes = (16.0 if dres is not None else 12.0) + (4.0 if dx_drop is not None else 0.0)
     with _rec('layernorm_bwd', nbytes * rows * C_):
-        L.check(lib().corrif_layernorm_bwd(_ptr(dy), _ptr(x1), _ptr(gamma), _ptr(mean), _ptr(rstd),
-                                           _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                                           _ptr(scratch), rows, C_, int(accumulate), _ptr(dx_drop), p, seed,
-                                           _seed_dev(seed_dev), site_a, site_b, _stream()),
-                    "corrif_layernorm_bwd")
+        L.check(lib().corrif_layernorm_bwd_regroup(_ptr(dy), _ptr(x1), _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                                   _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                                                   _ptr(scratch), rows, C_, int(accumulate), _ptr(dx_drop), p, seed,
+                                                   _seed_dev(seed_dev), site_a, site_b, groups, group_rows, _stream()),
+                    "corrif_layernorm_bwd_regroup")
     _count(1)
 
 
@@ -322,10 +324,11 @@ def inter_corr_fwd(qkv, skip, tokens, M, B, S, C_):
     _count()
 
 
-def inter_corr_bwd(qkv, g_tokens, dqkv, M, B, S, C_):
+def inter_corr_bwd(qkv, g_tokens, dqkv, M, B, S, C_, g_group_major=False):
+    """g_tokens [B][(M+1)S][C], or [M+1][B][S][C] with g_group_major."""
     with _rec('inter_corr_bwd', 4.0 * (3 * M + M + 3 * M) * B * S * C_):
-        L.check(lib().corrif_inter_corr_bwd(_ptr(qkv), _ptr(g_tokens), _ptr(dqkv), M, B, S, C_, _stream()),
-                "corrif_inter_corr_bwd")
+        L.check(lib().corrif_inter_corr_bwd_layout(_ptr(qkv), _ptr(g_tokens), _ptr(dqkv), M, B, S, C_,
+                                                   int(g_group_major), _stream()), "corrif_inter_corr_bwd_layout")
     _count()
 
 

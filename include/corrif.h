@@ -135,6 +135,17 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
                          float* dx_drop, float p_drop, uint64_t seed, const uint64_t* seed_dev,
                          uint32_t site_a, uint32_t site_b, void* stream);
 
+/* Same, with the rows of dx regrouped: the input rows are [batch][group][group_rows] (the multimodal token
+ * set: group = modality / fused token set, mmvit4.py:515-522) and dx is written [group][batch][group_rows],
+ * the layout the consumers of the token gradient use - the strided copy the host did before disappears.
+ * groups == 0: plain corrif_layernorm_bwd.  Needs dx_drop == NULL and dx distinct from dy / dres. */
+int corrif_layernorm_bwd_regroup(const float* dy, const float* x1, const float* gamma, const float* mean,
+                                 const float* rstd, const float* dres, float* dx, float* dgamma,
+                                 float* dbeta, float* scratch, int64_t rows, int32_t C, int32_t accumulate,
+                                 float* dx_drop, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                                 uint32_t site_a, uint32_t site_b, int32_t groups, int32_t group_rows,
+                                 void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Row softmax in place, for the materialised attention path: P = softmax(S) over `cols`
  * (mmvit4.py:310; the 0.125 scale of :309 is folded into the producing GEMM's alpha), with the
@@ -247,6 +258,9 @@ int corrif_inter_corr_fwd(const float* qkv, const float* skip, float* tokens, in
                           int32_t B, int32_t S, int32_t C, void* stream);
 int corrif_inter_corr_bwd(const float* qkv, const float* g_tokens, float* dqkv, int32_t M,
                           int32_t B, int32_t S, int32_t C, void* stream);
+/* g_group_major != 0: g_tokens is [M+1][B][S][C] (see corrif_layernorm_bwd_regroup) instead of [B][(M+1)S][C] */
+int corrif_inter_corr_bwd_layout(const float* qkv, const float* g_tokens, float* dqkv, int32_t M,
+                                 int32_t B, int32_t S, int32_t C, int32_t g_group_major, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Jaccard family, F5_JACCARD2.py:4-36 / F5_JACCARD.py:4-9.

@@ -183,6 +183,32 @@ def test_layernorm_fwd_bwd(rows, with_pos):
     assert rel_l2(db.cpu().numpy(), bd.grad.cpu().numpy()) < 1e-5
 
 
+def test_layernorm_bwd_regrouped_output_and_inter_corr_layout():
+    """LayerNorm-backward writing dx group-major ([batch][group][rows] -> [group][batch][rows]) equals the
+    plain kernel followed by the permutation, bit for bit; inter_corr_bwd reads either layout."""
+    Cc, B, G, S = 512, 3, 4, 64
+    rows = B * G * S
+    x, dy, dres = _rand(rows, Cc, seed=1), _rand(rows, Cc, seed=2), _rand(rows, Cc, seed=3)
+    g, b = 1 + 0.1 * _rand(Cc, seed=4), 0.1 * _rand(Cc, seed=5)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(rows, device=dev()), torch.empty(rows, device=dev())
+    ops.layernorm_fwd(x, None, 1, g, b, None, y, mean, rstd, rows)
+    scratch = torch.empty(ops.layernorm_bwd_scratch_floats(rows), device=dev())
+    dx0, dx1 = torch.empty_like(x), torch.empty_like(x)
+    dg, db = torch.empty(Cc, device=dev()), torch.empty(Cc, device=dev())
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dres, dx0, dg, db, scratch, rows)
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dres, dx1, dg, db, scratch, rows, groups=G, group_rows=S)
+    assert torch.equal(dx1.view(G, B, S, Cc), dx0.view(B, G, S, Cc).transpose(0, 1))
+    # inter_corr_bwd: [B][(M+1)S][C] vs [M+1][B][S][C] gradient layouts
+    M, S2, C2 = 3, 16, 64
+    qkv = _rand(M, B, S2, 3 * C2, seed=6)
+    gt = _rand(B, (M + 1) * S2, C2, seed=7)
+    d0, d1 = torch.empty_like(qkv), torch.empty_like(qkv)
+    ops.inter_corr_bwd(qkv, gt, d0, M, B, S2, C2)
+    ops.inter_corr_bwd(qkv, gt.view(B, M + 1, S2, C2).transpose(0, 1).contiguous(), d1, M, B, S2, C2, g_group_major=True)
+    assert torch.equal(d0, d1)
+
+
 @pytest.mark.parametrize("cols", [512, 2048, 3584])
 def test_softmax_fwd_bwd(cols):
     rows = 300
