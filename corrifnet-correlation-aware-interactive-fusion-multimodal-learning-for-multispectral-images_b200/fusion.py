@@ -198,6 +198,13 @@ class FusionBlockEngine:
             src = [self.p[k].data_ptr() for k in self.wnames] + [self.p[n].data_ptr() for n, _ in self._bias_copies]
             dst = [self.pw[k].data_ptr() for k in self.wnames] + [d.data_ptr() for _, d in self._bias_copies]
             cnt = [self.p[k].numel() for k in self.wnames] + [-self.p[n].numel() for n, _ in self._bias_copies]
+            # the concatenated positional table of the multimodal transformer (mmvit4.py:516,521): four plain
+            # copies ride in the same launch instead of four torch copy kernels per forward
+            self._posmm = torch.empty((NM + 1) * S, C, device=self.dev, dtype=torch.float32)
+            for X, m in enumerate(MODALITIES + ("fused6",)):
+                src.append(self.p[f"{m}_pos"].data_ptr())
+                dst.append(self._posmm[X * S:(X + 1) * S].data_ptr())
+                cnt.append(-S * C)
             self._rt = (torch.tensor(src, **i64), torch.tensor(dst, **i64), torch.tensor(cnt, **i64),
                         len(src), sum(abs(c) for c in cnt))
         src, dst, cnt, count, total = self._rt
@@ -662,10 +669,14 @@ class FusionBlockEngine:
                    M=S, N=C, K=ENC * NM, lda=ENC * NM, ldb=ENC * NM, ldd=C,
                    bias=P_["fused6_encode_conv.bias"], epilogue=EPI_BIAS, batch=(B, 1), tag="linear",
                    a_step=(S * ENC * NM, 0), d_step=((NM + 1) * S * C, 0))                 # :510-513
-        for X, m in enumerate(MODALITIES + ("fused6",)):
-            ws["posmm"][X * S:(X + 1) * S].copy_(P_[f"{m}_pos"][0])                        # :516,521
+        if self.rnd:
+            posmm = self._posmm                          # filled by refresh_weights()
+        else:
+            posmm = ws["posmm"]
+            for X, m in enumerate(MODALITIES + ("fused6",)):
+                posmm[X * S:(X + 1) * S].copy_(P_[f"{m}_pos"][0])                          # :516,521
         tbm = ws["tb"][NM]
-        x3 = self._transformer_fwd(NM, ws["tokens"], ws["posmm"], (NM + 1) * S, tbm)       # :519-522
+        x3 = self._transformer_fwd(NM, ws["tokens"], posmm, (NM + 1) * S, tbm)             # :519-522
         self._linear(x3, W["multimodal_decode_conv.weight"], ws["ytok"], B * S, ENC * NM,
                      (NM + 1) * C, bias=P_["multimodal_decode_conv.bias"], epilogue=EPI_BIAS)  # :525
         ops.transpose(ws["ytok"], ws["out"], B, S, ENC * NM)                               # :527-528
