@@ -56,7 +56,7 @@ PROTOTYPES = {
     "corrif_layernorm_bwd": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, i32,
                                        f32p, f32, u64, u64p, u32, u32, stream_t]),
     "corrif_layernorm_bwd_regroup": (C.c_int, [f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, i64, i32, i32,
-                                               f32p, f32, u64, u64p, u32, u32, i32, i32, stream_t]),
+                                               f32p, f32, u64, u64p, u32, u32, i32, i32, f32p, stream_t]),
     "corrif_softmax_fwd": (C.c_int, [f32p, f32p, i64, i32, f32, u64, u64p, u32, i32, stream_t]),
     "corrif_softmax_bwd": (C.c_int, [f32p, f32p, i64, i32, f32, f32, u64, u64p, u32, stream_t]),
     "corrif_attention_fwd": (C.c_int, [f32p, f32p, f32p, C.c_void_p, i32, i32, i32, i32, f32, f32, u64, u64p, u32, i32, u32, i32, stream_t]),

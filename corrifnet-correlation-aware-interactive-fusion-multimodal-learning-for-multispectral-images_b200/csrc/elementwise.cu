@@ -97,7 +97,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
                      const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
                      float* __restrict__ dx_drop, uint32_t thresh, float keep_scale, uint64_t seed,
-                     const uint64_t* seed_dev, uint32_t site_a, uint32_t site_b, int groups, int group_rows) {
+                     const uint64_t* seed_dev, uint32_t site_a, uint32_t site_b, int groups, int group_rows,
+                     const float* __restrict__ dres2) {
   __shared__ __align__(16) float red[8][2][LN_C];
   uint64_t key_a = 0, key_b = 0;
   if (dx_drop != nullptr) {      // fused dropout of the outgoing gradient (backward of the next block's
@@ -158,6 +159,10 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
       o.w = rs * (d[j].w - c1 - xh[j].w * c2);
       if (dres != nullptr) {
         const float4 r = rres[j];
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      if (dres2 != nullptr) {      // a second incoming gradient of the same tensor (the skip path, mmvit4.py:505)
+        const float4 r = ld4_stream(dres2 + row * LN_C + lane * 4 + j * 128);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       st4(dx + orow * LN_C + lane * 4 + j * 128, o);
@@ -557,14 +562,15 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
                          float* dx_drop, float p_drop, uint64_t seed, const uint64_t* seed_dev,
                          uint32_t site_a, uint32_t site_b, void* stream) {
   return corrif_layernorm_bwd_regroup(dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, scratch, rows, C, accumulate,
-                                      dx_drop, p_drop, seed, seed_dev, site_a, site_b, 0, 0, stream);
+                                      dx_drop, p_drop, seed, seed_dev, site_a, site_b, 0, 0, nullptr, stream);
 }
 
 int corrif_layernorm_bwd_regroup(const float* dy, const float* x1, const float* gamma, const float* mean,
                                  const float* rstd, const float* dres, float* dx, float* dgamma,
                                  float* dbeta, float* scratch, int64_t rows, int32_t C, int32_t accumulate,
                                  float* dx_drop, float p_drop, uint64_t seed, const uint64_t* seed_dev,
-                                 uint32_t site_a, uint32_t site_b, int32_t groups, int32_t group_rows, void* stream) {
+                                 uint32_t site_a, uint32_t site_b, int32_t groups, int32_t group_rows,
+                                 const float* dres2, void* stream) {
   (void)scratch;
   CORRIF_REQUIRE(groups >= 0 && (groups == 0 || (group_rows > 0 && rows % ((int64_t)groups * group_rows) == 0 && dx_drop == nullptr && dx != dy && dx != dres)),
                  "layernorm_bwd: regrouping needs rows %% (groups * group_rows) == 0, no dx_drop and an out-of-place dx");
@@ -584,7 +590,7 @@ int corrif_layernorm_bwd_regroup(const float* dy, const float* x1, const float* 
   if (dx_drop) { ks = 1.0f / (1.0f - p_drop); if (site_b != CORRIF_NO_SITE) ks *= ks; }
   layernorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, dx_drop, dx_drop ? dropout_threshold(p_drop) : 0u,
-      ks, seed, seed_dev, site_a, site_b, groups, group_rows);
+      ks, seed, seed_dev, site_a, site_b, groups, group_rows, dres2);
   return launch_status("layernorm_bwd");
 }
 

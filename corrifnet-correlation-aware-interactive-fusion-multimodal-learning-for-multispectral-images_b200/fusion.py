@@ -545,14 +545,17 @@ class FusionBlockEngine:
         self._bdgrad(tb.dqkv, W["qkv_w"], tb.t2, R, 3 * C, C)                      # d(h)
         self._join()                                     # t0 (dy) is about to be overwritten
         for X, m in enumerate(MODALITIES):
-            ops.layernorm_bwd(tb.t2[X], tb.x1[X], P_[tk[X]["ln1_w"]], tb.mean1[X], tb.rstd1[X], dx2[X], tb.t0[X],
-                              g[tk[X]["ln1_w"]], g[tk[X]["ln1_b"]], sc, R, accumulate=True)   # t0 = d(x1)
-            ops.add_rows(tb.t0[X], C, ws["dtokc"][X], C, ws["dtok3"][X], C, R, C)       # + skip path (:505)
+            # d(token) = d(x1) + skip-path gradient (:505) in the same pass: dres2.  The pos gradient of modality m
+            # is the batch sum of d(x1) here PLUS that of the multimodal token gradient dtokc[X] - i.e. the batch
+            # sum of dtok3[X] - so _backward leaves the first three groups to the one batchsum below.
+            ops.layernorm_bwd(tb.t2[X], tb.x1[X], P_[tk[X]["ln1_w"]], tb.mean1[X], tb.rstd1[X], dx2[X],
+                              ws["dtok3"][X], g[tk[X]["ln1_w"]], g[tk[X]["ln1_b"]], sc, R, accumulate=True,
+                              dres2=ws["dtokc"][X])
         # ---- encode convs (weight / bias / pos gradients beside the last dgrad)
         self._fork()
         with self._side_ctx():
             for X, m in enumerate(MODALITIES):
-                ops.batchsum(tb.t0[X], B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
+                ops.batchsum(ws["dtok3"][X], B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
             self._bwgrad(ws["dtok3"], ws["x6tok"], [g[f"{m}_encode_conv.weight"] for m in MODALITIES], R, C, ENC)
             self._bcolsum(ws["dtok3"], C, R, [g[f"{m}_encode_conv.bias"] for m in MODALITIES], sc)
         self._bdgrad(ws["dtok3"], W["enc_w"], ws["dx6tok3"], R, C, ENC)
@@ -706,6 +709,8 @@ class FusionBlockEngine:
         self._fork()
         with self._side_ctx():
             for X, m in enumerate(MODALITIES + ("fused6",)):
+                if self.batched and X < NM:
+                    continue                       # folded into the batch sum of dtok3[X] (_intra_bwd_batched)
                 ops.batchsum(ws["dtokc"][X], B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
             self._wgrad(df6, ws["fx6tok"], g["fused6_encode_conv.weight"], R, C, ENC * NM)
             ops.colsum(df6, C, R, C, g["fused6_encode_conv.bias"], sc, accumulate=True)

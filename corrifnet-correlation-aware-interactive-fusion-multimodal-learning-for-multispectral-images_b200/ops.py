@@ -190,14 +190,16 @@ def layernorm_bwd_scratch_floats(rows, C_=512) -> int:
 
 def layernorm_bwd(dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, scratch, rows, C_=512,
                   accumulate=False, dx_drop=None, p=0.0, seed=0, seed_dev=None, site_a=NO_SITE, site_b=NO_SITE,
-                  groups=0, group_rows=0):
-    """groups > 0: rows are [batch][group][group_rows] and dx is written [group][batch][group_rows]."""
-    nbytes = (16.0 if dres is not None else 12.0) + (4.0 if dx_drop is not None else 0.0)
+                  groups=0, group_rows=0, dres2=None):
+    """groups > 0: rows are [batch][group][group_rows] and dx is written [group][batch][group_rows];
+    dres2: a second incoming gradient added like dres."""
+    nbytes = (16.0 if dres is not None else 12.0) + (4.0 if dx_drop is not None else 0.0) + (4.0 if dres2 is not None else 0.0)
     with _rec('layernorm_bwd', nbytes * rows * C_):
         L.check(lib().corrif_layernorm_bwd_regroup(_ptr(dy), _ptr(x1), _ptr(gamma), _ptr(mean), _ptr(rstd),
                                                    _ptr(dres), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
                                                    _ptr(scratch), rows, C_, int(accumulate), _ptr(dx_drop), p, seed,
-                                                   _seed_dev(seed_dev), site_a, site_b, groups, group_rows, _stream()),
+                                                   _seed_dev(seed_dev), site_a, site_b, groups, group_rows, _ptr(dres2),
+                                                   _stream()),
                     "corrif_layernorm_bwd_regroup")
     _count(1)
 

@@ -138,13 +138,15 @@ int corrif_layernorm_bwd(const float* dy, const float* x1, const float* gamma, c
 /* Same, with the rows of dx regrouped: the input rows are [batch][group][group_rows] (the multimodal token
  * set: group = modality / fused token set, mmvit4.py:515-522) and dx is written [group][batch][group_rows],
  * the layout the consumers of the token gradient use - the strided copy the host did before disappears.
- * groups == 0: plain corrif_layernorm_bwd.  Needs dx_drop == NULL and dx distinct from dy / dres. */
+ * groups == 0: no regrouping; regrouping needs dx_drop == NULL and dx distinct from dy / dres.
+ * dres2 (may be NULL): a second incoming gradient of the same tensor, added like dres (the skip path of
+ * mmvit4.py:505 - the host's separate add pass disappears). */
 int corrif_layernorm_bwd_regroup(const float* dy, const float* x1, const float* gamma, const float* mean,
                                  const float* rstd, const float* dres, float* dx, float* dgamma,
                                  float* dbeta, float* scratch, int64_t rows, int32_t C, int32_t accumulate,
                                  float* dx_drop, float p_drop, uint64_t seed, const uint64_t* seed_dev,
                                  uint32_t site_a, uint32_t site_b, int32_t groups, int32_t group_rows,
-                                 void* stream);
+                                 const float* dres2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row softmax in place, for the materialised attention path: P = softmax(S) over `cols`
