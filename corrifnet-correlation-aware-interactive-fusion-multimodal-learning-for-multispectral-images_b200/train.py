@@ -140,7 +140,8 @@ class FlatAdam:
     into flat buffers laid out like the gradient buckets, with flat exp_avg / exp_avg_sq beside them, and
     ``corrif_adam_step`` walks each bucket once.  The wrapped optimizer stays the owner of the hyper-parameters
     (LR schedulers keep working on its ``param_groups``) and its ``state`` is filled with views of the flat
-    moments, so ``state_dict()`` is what stock Adam would hold."""
+    moments, so ``state_dict()`` is what stock Adam would hold.  Once FlatAdam has stepped, stepping the
+    wrapped optimizer directly is not supported (its per-parameter ``step`` entries are one shared tensor)."""
 
     @staticmethod
     def eligible(optim) -> bool:

@@ -81,3 +81,17 @@ def test_jaccard_dropins_export_reference_names():
         sys.path.remove(DROPIN)
         for name in ("F5_JACCARD2", "F5_JACCARD", "F3_DATASET"):
             sys.modules.pop(name, None)
+
+
+def test_flat_adam_only_takes_over_a_stock_reference_style_adam():
+    """TrainStep swaps optim.step() for the one-kernel FlatAdam only for torch.optim.Adam with the reference's
+    settings (F2_MAIN.py:168-169) on CUDA fp32 parameters; anything else keeps its own step()."""
+    import torch
+    from corrif_b200 import train
+    w = [torch.nn.Parameter(torch.zeros(4, 4))]
+    assert not train.FlatAdam.eligible(torch.optim.Adam(w, 1e-3))                       # CPU parameters
+    assert not train.FlatAdam.eligible(torch.optim.SGD(w, 1e-3))
+    assert not train.FlatAdam.eligible(torch.optim.AdamW(w, 1e-3))
+    step = train.TrainStep(torch.nn.Linear(2, 2), torch.optim.Adam(w, 1e-3, weight_decay=0.1))
+    assert step.flat_adam is None
+
