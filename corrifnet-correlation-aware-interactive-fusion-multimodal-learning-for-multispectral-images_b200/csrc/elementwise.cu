@@ -119,6 +119,9 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pos,
 // scratch and a second kernel folds the partials (deterministic, no atomics).
 constexpr int LN_BWD_MAX_BLOCKS = 592;  // 4 per SM
 
+// RES2 (a second residual input) is a template parameter: as a run-time pointer it cost the common
+// instantiation its last free registers (127 + a 16-byte spill; ncu 177 -> 213 us over the step's 8 launches).
+template <bool RES2>
 __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
                      const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -189,7 +192,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x1,
         const float4 r = rres[j];
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
-      if (dres2 != nullptr) {      // a second incoming gradient of the same tensor (the skip path, mmvit4.py:505)
+      if (RES2) {                  // a second incoming gradient of the same tensor (the skip path, mmvit4.py:505)
         const float4 r = ld4_stream(dres2 + row * LN_C + lane * 4 + j * 128);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
@@ -621,7 +624,8 @@ int corrif_layernorm_bwd_regroup(const float* dy, const float* x1, const float* 
   if (blocks > cap) blocks = cap;
   float ks = 1.0f;
   if (dx_drop) { ks = 1.0f / (1.0f - p_drop); if (site_b != CORRIF_NO_SITE) ks *= ks; }
-  layernorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  auto kern = dres2 != nullptr ? layernorm_bwd_kernel<true> : layernorm_bwd_kernel<false>;
+  kern<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       dy, x1, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, dx_drop, dx_drop ? dropout_threshold(p_drop) : 0u,
       ks, seed, seed_dev, site_a, site_b, groups, group_rows, dres2);
   return launch_status("layernorm_bwd");
