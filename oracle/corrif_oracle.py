@@ -381,3 +381,34 @@ def adam_step_np(p, g, m, v, step, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
     mhat = m / (1 - b1 ** step)
     vhat = v / (1 - b2 ** step)
     return p - lr * mhat / (np.sqrt(vhat) + eps), m, v
+
+
+# --------------------------------------------------------------------------------------------------
+# Next rows of the scope table: restatements pinned by tests/golden/next_rows.npz,
+# which tests/golden/make_golden.py generates from the UNMODIFIED reference classes.  No kernels yet.
+# --------------------------------------------------------------------------------------------------
+def instance_norm3d(x, eps: float = 1e-5):
+    """nn.InstanceNorm3d defaults (affine=False, no running stats), mmvit4.py:24: per (sample, channel)
+    normalisation over the spatial volume with the biased variance."""
+    dims = tuple(range(2, x.dim()))
+    mu = x.mean(dim=dims, keepdim=True)
+    var = x.var(dim=dims, unbiased=False, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps)
+
+
+def early_fusion_block(xs, weight, bias):
+    """EarlyFusionBlock.forward (mmvit4.py:76-81): cat over channels -> 1x1x1 Conv3d -> ReLU -> InstanceNorm3d.
+    xs: three [B, c, D, H, W]; weight [3c, 3c, 1, 1, 1]; bias [3c]."""
+    x = torch.cat(list(xs), dim=1)
+    y = torch.einsum("bkdhw,nk->bndhw", x, weight.reshape(weight.shape[0], weight.shape[1])) + bias.view(1, -1, 1, 1, 1)
+    return instance_norm3d(torch.relu(y))
+
+
+def general_conv3d_prenorm(x, weight, bias, k_size: int = 3, pad_type: str = "replicate"):
+    """general_conv3d_prenorm.forward (mmvit4.py:29-45) as the decoder uses it (mmvit4.py:225-237): Conv3d with
+    stride 1, padding k//2 of `pad_type`, bias -> ReLU -> InstanceNorm3d."""
+    pad = k_size // 2
+    if pad:
+        x = torch.nn.functional.pad(x, (pad,) * 6, mode=pad_type if pad_type != "zeros" else "constant")
+    return instance_norm3d(torch.relu(torch.nn.functional.conv3d(x, weight, bias)))
+

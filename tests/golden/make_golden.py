@@ -211,8 +211,49 @@ def make_loss_golden():
     print("bce golden loss=%.6f" % loss.item())
 
 
+def make_next_rows_golden():
+    """SURVEY.md 8f rows N2 / N1, straight from the reference classes (fp64 run, stored as fp32):
+    EarlyFusionBlock at the fusion6 shape (mmvit4.py:64-81, 449-454) and the decoder's
+    general_conv3d_prenorm blocks, 3x3x3 replicate-padded and 1x1x1 (mmvit4.py:29-45, 225-237), forward and
+    backward.  Parity anchors for the kernels of the next round."""
+    g = torch.Generator().manual_seed(77)
+    rec = {}
+    # ---- N2: EarlyFusionBlock(in_channels=64) on three [B,64,8,8,8] bottlenecks
+    blk = ref_mmvit4.EarlyFusionBlock(64).double()
+    with torch.no_grad():
+        blk.conv.weight.copy_(torch.randn(blk.conv.weight.shape, generator=g, dtype=torch.float64) * 0.05)
+        blk.conv.bias.copy_(torch.randn(blk.conv.bias.shape, generator=g, dtype=torch.float64) * 0.1)
+    xs = [torch.randn(2, 64, 8, 8, 8, generator=g, dtype=torch.float64).requires_grad_(True) for _ in range(3)]
+    gout = torch.randn(2, 192, 8, 8, 8, generator=g, dtype=torch.float64)
+    y = blk(*xs)
+    y.backward(gout)
+    rec["ef/w"], rec["ef/b"] = blk.conv.weight.detach().numpy(), blk.conv.bias.detach().numpy()
+    for i, x in enumerate(xs):
+        rec[f"ef/x{i}"], rec[f"ef/dx{i}"] = x.detach().numpy(), x.grad.numpy()
+    rec["ef/gout"], rec["ef/y"] = gout.numpy(), y.detach().numpy()
+    rec["ef/dw"], rec["ef/db"] = blk.conv.weight.grad.numpy(), blk.conv.bias.grad.numpy()
+    # ---- N1: decoder blocks, small volumes with the decoder's channel counts (d1_c2: 32 -> 8, d1_out: 8 -> 8 1x1x1)
+    for tag, cin, cout, k, vol in (("c3", 32, 8, 3, 12), ("c1", 8, 8, 1, 12), ("c3b", 16, 16, 3, 6)):
+        m = ref_mmvit4.general_conv3d_prenorm(cin, cout, k_size=k, padding=k // 2, pad_type="replicate").double()
+        with torch.no_grad():
+            m.conv.weight.copy_(torch.randn(m.conv.weight.shape, generator=g, dtype=torch.float64) * 0.1)
+            m.conv.bias.copy_(torch.randn(m.conv.bias.shape, generator=g, dtype=torch.float64) * 0.1)
+        x = torch.randn(2, cin, vol, vol, vol, generator=g, dtype=torch.float64).requires_grad_(True)
+        go = torch.randn(2, cout, vol, vol, vol, generator=g, dtype=torch.float64)
+        y = m(x)
+        y.backward(go)
+        rec[f"{tag}/w"], rec[f"{tag}/b"] = m.conv.weight.detach().numpy(), m.conv.bias.detach().numpy()
+        rec[f"{tag}/x"], rec[f"{tag}/gout"], rec[f"{tag}/y"] = x.detach().numpy(), go.numpy(), y.detach().numpy()
+        rec[f"{tag}/dx"], rec[f"{tag}/dw"], rec[f"{tag}/db"] = x.grad.numpy(), m.conv.weight.grad.numpy(), m.conv.bias.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "next_rows.npz"), **{k: v.astype(np.float32) for k, v in rec.items()})
+    print("next-rows golden: %d arrays" % len(rec))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
+    if "--next-rows" in sys.argv:
+        make_next_rows_golden()
+        sys.exit(0)
     make_jaccard_golden()
     make_loss_golden()
     make_inter_attn_golden()

@@ -105,3 +105,28 @@ def test_bce_on_probs_matches_reference():
     loss.backward()
     assert abs(loss.item() - float(g["loss"])) < 1e-6
     assert np.abs(p.grad.numpy() - g["grad"]).max() < 1e-9
+
+
+def test_next_rows_restatements_match_reference():
+    """SURVEY.md 8f rows N2 (EarlyFusionBlock) and N1 (decoder conv -> ReLU -> InstanceNorm blocks): the oracle
+    restatements against fixtures produced by the unmodified reference classes, forward and autograd backward
+    (fp64 oracle vs the fp32-stored fp64 reference run)."""
+    g = np.load(os.path.join(GOLDEN, "next_rows.npz"))
+    t = lambda k: torch.from_numpy(g[k]).double()  # noqa: E731
+    xs = [t(f"ef/x{i}").requires_grad_(True) for i in range(3)]
+    w, b = t("ef/w").requires_grad_(True), t("ef/b").requires_grad_(True)
+    y = O.early_fusion_block(xs, w, b)
+    y.backward(t("ef/gout"))
+    assert rel_l2(y.detach().numpy(), g["ef/y"]) < 1e-6
+    for i in range(3):
+        assert rel_l2(xs[i].grad.numpy(), g[f"ef/dx{i}"]) < 1e-5
+    assert rel_l2(w.grad.numpy(), g["ef/dw"]) < 1e-5 and rel_l2(b.grad.numpy(), g["ef/db"]) < 1e-5
+    for tag, k in (("c3", 3), ("c1", 1), ("c3b", 3)):
+        x = t(f"{tag}/x").requires_grad_(True)
+        w, b = t(f"{tag}/w").requires_grad_(True), t(f"{tag}/b").requires_grad_(True)
+        y = O.general_conv3d_prenorm(x, w, b, k_size=k)
+        y.backward(t(f"{tag}/gout"))
+        assert rel_l2(y.detach().numpy(), g[f"{tag}/y"]) < 1e-6, tag
+        assert rel_l2(x.grad.numpy(), g[f"{tag}/dx"]) < 1e-5, tag
+        assert rel_l2(w.grad.numpy(), g[f"{tag}/dw"]) < 1e-5 and rel_l2(b.grad.numpy(), g[f"{tag}/db"]) < 1e-5, tag
+
