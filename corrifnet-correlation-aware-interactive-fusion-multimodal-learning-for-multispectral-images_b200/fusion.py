@@ -13,6 +13,12 @@ Data layout in HBM (all fp32, row-major "tokens": row = b*N + s, s = d*64 + h*8 
 
 The token re-grouping before multimodal_decode_conv (mmvit4.py:525-529) is a pure re-view:
 [B,2048,512] == [B*512, 2048] row-major, so the decode conv is one GEMM with K = 2048.
+
+Backward-only buffers: dtokc [4, B*S, 512] is the multimodal token gradient written GROUP-major by the last
+LayerNorm-backward (per-group contiguous for the fused6 conv, the skip paths and the pos sums); dtok3 / dtok
+add the skip-path gradient inside the intra LayerNorm-backward (dres2).  Weight-gradient GEMMs and bias / pos
+column sums run on a second stream (_fork / _join).  With use_graphs, forward and backward are each replayed
+as one CUDA graph, keyed by the callers' buffers or, when those keep moving, by engine-owned staging buffers.
 """
 from __future__ import annotations
 
