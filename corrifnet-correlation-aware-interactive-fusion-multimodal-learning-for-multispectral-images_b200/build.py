@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libcorrif_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I", INCLUDE,
-]
+] + os.environ.get("CORRIF_NVCC_EXTRA", "").split()
+# e.g. CORRIF_NVCC_EXTRA=-DCORRIF_ATTN_EVLOG python build.py --force   (attention event log, tools/attn_timing.py)
 
 
 def _nvcc() -> str:

@@ -1,4 +1,6 @@
-"""Event log of one mid-grid CTA of the attention backward (CORRIF_ATTN_TIMING=1) at a bench shape."""
+"""Event log of one mid-grid CTA of the attention backward (CORRIF_ATTN_TIMING=1) at a bench shape.
+Needs a library built with the log compiled in:
+  CORRIF_NVCC_EXTRA=-DCORRIF_ATTN_EVLOG python corrifnet-*_b200/build.py --force"""
 import os
 import sys
 
