@@ -62,7 +62,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(BUILD_DIR, os.path.basename(s)[:-3] + ".o") for s in sources()]
     if force or jobs or _stale(LIB_PATH, objs):
-        cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        # -cudart shared: the library binds to the libcudart.so.12 the process already holds (torch loads its own
+        # copy first) instead of embedding a second, static runtime in the shipped artefact
+        cmd = [nvcc, "-shared", "-cudart", "shared", "-o", LIB_PATH] + objs + [
+            "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -173,7 +173,7 @@ class MMVit4(nn.Module):
         super().__init__()
         C, E = transformer_basic_dims, basic_dims * 8
         self.dropout_rate, self.precision = dropout_rate, precision
-        self._step, self.base_seed = 0, 0x5EED
+        self._step, self.base_seed = 0, _module.default_base_seed()
         for m in _MODS:
             setattr(self, f"{m}_encoder", Encoder())
         for m in _MODS:

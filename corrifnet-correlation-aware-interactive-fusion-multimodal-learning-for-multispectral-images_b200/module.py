@@ -29,8 +29,20 @@ def _engine_for(params: Sequence[Tensor], dropout_p: float, precision: str) -> F
         named = {n: p.detach() for n, p in zip(param_names(), params)}
         eng = FusionBlockEngine(named, dropout_p=dropout_p, precision=precision, use_graphs=USE_GRAPHS)
         eng._flat_grads = eng.new_grad_buffers()          # persistent: graph replay needs fixed addresses
+        eng.generation = 0                                # forward counter: the workspace holds ONE forward
         _ENGINES[key] = eng
     return eng
+
+
+class StaleForwardError(RuntimeError):
+    """corrif::fusion_block_backward was asked for the backward of a forward whose saved activations are gone."""
+
+
+def default_base_seed() -> int:
+    """Base of the dropout seeds: follows ``torch.manual_seed`` and differs between data-parallel ranks (the
+    masks are a pure function of (seed, site, element), so equal seeds would mean equal masks on every rank)."""
+    rank = int(_os.environ.get("RANK", "0"))
+    return (torch.initial_seed() ^ (0x9E3779B97F4A7C15 * (rank + 1))) & 0x3FFFFFFFFFFFFFFF
 
 
 @torch.library.custom_op("corrif::fusion_block", mutates_args=(), device_types="cuda")
@@ -39,8 +51,10 @@ def fusion_block_op(x6_rgb: Tensor, x6_nir: Tensor, x6_swir: Tensor, fused_x6: T
     """x6_inter = CorrIFNet fusion block (mmvit4.py:456-529).  ``params`` in ``param_names()`` order."""
     eng = _engine_for(params, dropout_p, precision)
     eng.set_seed(seed)
+    eng.generation += 1
     out = eng.forward([x6_rgb.contiguous(), x6_nir.contiguous(), x6_swir.contiguous()],
                       fused_x6.contiguous())
+    # the output is saved by the decoder's autograd nodes and must survive the next forward: one 0.4 MB/sample copy
     return out.clone()
 
 
@@ -51,10 +65,24 @@ def _(x6_rgb, x6_nir, x6_swir, fused_x6, params, dropout_p, seed, precision):
 
 @torch.library.custom_op("corrif::fusion_block_backward", mutates_args=(), device_types="cuda")
 def fusion_block_backward_op(gout: Tensor, params: Sequence[Tensor], dropout_p: float, seed: int,
-                             precision: str) -> List[Tensor]:
-    """Backward of the most recent corrif::fusion_block call on the same parameter set.  Returns
-    [d x6_rgb, d x6_nir, d x6_swir, d fused_x6, flat parameter gradients (param_names() order)]."""
+                             precision: str, generation: int) -> List[Tensor]:
+    """Backward of the corrif::fusion_block call number ``generation`` on the same parameter set.  Returns
+    [d x6_rgb, d x6_nir, d x6_swir, d fused_x6, flat parameter gradients (param_names() order)].
+
+    The saved activations (and keep-bits) live in the engine's single workspace, so only the MOST RECENT forward
+    can be differentiated; anything else (two forwards then two backwards, activation checkpointing, a second
+    model call before ``.backward()``, a forward with another batch size in between) raises StaleForwardError
+    instead of silently returning gradients of the wrong forward.
+
+    The five results are fresh tensors (autograd may adopt a returned tensor as ``.grad`` without copying, which
+    must never alias the workspace the next backward overwrites): 4 x 0.1-0.4 MB/sample of input gradients and
+    the 41 MB flat parameter-gradient buffer - 13 us of copy at HBM speed per backward."""
     eng = _engine_for(params, dropout_p, precision)
+    if generation != eng.generation or gout.shape[0] != getattr(eng, "_B", gout.shape[0]):
+        raise StaleForwardError(
+            "corrif::fusion_block_backward: forward #%d is no longer in the workspace (the latest forward on this "
+            "parameter set is #%d, batch %s); run backward before the next forward of the same block"
+            % (generation, eng.generation, getattr(eng, "_B", "?")))
     eng.set_seed(seed)
     flat, views = eng._flat_grads
     flat.zero_()
@@ -63,7 +91,7 @@ def fusion_block_backward_op(gout: Tensor, params: Sequence[Tensor], dropout_p: 
 
 
 @fusion_block_backward_op.register_fake
-def _(gout, params, dropout_p, seed, precision):
+def _(gout, params, dropout_p, seed, precision, generation):
     b = gout.shape[0]
     x = gout.new_empty(b, 64, 8, 8, 8)
     return [x, x.clone(), x.clone(), torch.empty_like(gout),
@@ -74,10 +102,13 @@ def _setup_ctx(ctx, inputs, output):
     _, _, _, _, params, dropout_p, seed, precision = inputs
     ctx.params = list(params)
     ctx.dropout_p, ctx.seed, ctx.precision = dropout_p, seed, precision
+    # setup_context runs right after the forward op, on the same thread: the engine's counter is this forward's id
+    ctx.generation = _engine_for(params, dropout_p, precision).generation
 
 
 def _backward(ctx, gout):
-    res = torch.ops.corrif.fusion_block_backward(gout, ctx.params, ctx.dropout_p, ctx.seed, ctx.precision)
+    res = torch.ops.corrif.fusion_block_backward(gout, ctx.params, ctx.dropout_p, ctx.seed, ctx.precision,
+                                                 ctx.generation)
     pgrads, off = [], 0
     for p in ctx.params:          # slice the flat buffer: one memset + one kernel set wrote all of it
         pgrads.append(res[4][off:off + p.numel()].view_as(p))
@@ -136,7 +167,7 @@ class CorrIFusionBlock(nn.Module):
         self.dropout_rate = dropout_rate
         self.precision = precision
         self._step = 0
-        self.base_seed = 0x5EED
+        self.base_seed = default_base_seed()
         for name, shape in fusion_param_shapes().items():
             p = nn.Parameter(torch.zeros(shape))
             if name.endswith("norm.weight"):

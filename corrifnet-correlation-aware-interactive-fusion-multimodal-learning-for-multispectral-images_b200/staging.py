@@ -19,7 +19,8 @@ class PinnedPipeline:
         self.dev = device
         self.depth = depth
         self.copy_stream = torch.cuda.Stream(device=device)
-        self._slots: List[dict] = [dict(bufs=None, ready=None, done=None) for _ in range(depth)]
+        self._slots: List[dict] = [dict(bufs=None, ready=None, done=None, busy=False) for _ in range(depth)]
+        self._cur = None
         self._next_fill = 0
         self._next_take = 0
         self._pending = 0
@@ -30,7 +31,14 @@ class PinnedPipeline:
         if self._pending >= self.depth:
             raise RuntimeError("PinnedPipeline: all staging slots are in flight")
         slot = self._slots[self._next_fill]
-        if slot["bufs"] is None:
+        if slot["busy"]:
+            raise RuntimeError("PinnedPipeline: the step that took this slot has not called release() yet")
+        # a ragged last batch (or any change of shape / dtype) gets buffers of its own shape: copy_() into the
+        # first batch's buffers would raise for a smaller batch and silently BROADCAST a batch of one
+        if slot["bufs"] is None or len(slot["bufs"]) != len(host_tensors) or any(
+                d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slot["bufs"], host_tensors)):
+            if slot["done"] is not None:
+                slot["done"].synchronize()               # the old buffers may still be read by a running step
             slot["bufs"] = [torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in host_tensors]
         with torch.cuda.stream(self.copy_stream):
             if slot["done"] is not None:                 # the step that last used this slot has finished
@@ -48,6 +56,9 @@ class PinnedPipeline:
             raise RuntimeError("PinnedPipeline.get() without a prefetch")
         slot = self._slots[self._next_take]
         torch.cuda.current_stream(self.dev).wait_event(slot["ready"])
+        if self._cur is not None and self._cur["busy"]:
+            self.release()                               # the previous step forgot: its kernels are all enqueued by now
+        slot["busy"] = True
         self._cur = slot
         self._next_take = (self._next_take + 1) % self.depth
         self._pending -= 1
@@ -58,6 +69,7 @@ class PinnedPipeline:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
         self._cur["done"] = ev
+        self._cur["busy"] = False
 
     def put(self, dev_tensor: torch.Tensor, host_out: torch.Tensor) -> None:
         """Read a result back into pinned memory on the copy stream."""

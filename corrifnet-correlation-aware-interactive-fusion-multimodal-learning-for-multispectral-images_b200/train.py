@@ -71,7 +71,7 @@ class GradBuckets:
                 view = flat[off:off + p.numel()].view_as(p)
                 view.copy_(p.grad)
                 p.grad = view                               # autograd accumulates in place from now on
-            b = {"flat": flat, "params": grp, "offsets": offs, "pending": len(grp), "index": gi}
+            b = {"flat": flat, "params": grp, "offsets": offs, "pending": len(grp), "index": gi, "launched": False}
             self.buckets.append(b)
             for p in grp:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
@@ -87,6 +87,7 @@ class GradBuckets:
         return hook
 
     def _launch(self, bucket):
+        bucket["launched"] = True
         if self.world > 1:
             self._handles.append(dist.all_reduce(bucket["flat"], group=self.group, async_op=True))
 
@@ -96,6 +97,7 @@ class GradBuckets:
             for b in self.buckets:
                 b["flat"].zero_()
                 b["pending"] = len(b["params"])
+                b["launched"] = False
             for p in self.skipped:
                 p.grad = None
         else:
@@ -106,25 +108,36 @@ class GradBuckets:
         """False while accumulating micro-batches; True on the last one (hooks then all-reduce)."""
         self._sync_now = sync
 
-    def finish(self, divisor: float = 1.0):
-        """Wait for the in-flight all-reduces and average.  On the first step (buckets not built yet)
-        do one blocking all-reduce per gradient, then build the buckets."""
+    def finish(self, divisor: float = 1.0, total: Optional[float] = None):
+        """Wait for the in-flight all-reduces and average.  ``divisor`` = local micro-batches of this step
+        (gradients are then divided by world * divisor); ``total`` overrides that product with the number of
+        micro-batches ALL ranks ran in this step (ragged last group of an epoch, where some ranks ran fewer or
+        none).  Buckets whose hooks did not all fire on this rank (no local micro-batch, or a parameter without
+        a gradient this step) are launched here, so every rank issues the same collectives in the same order.
+        On the first step (buckets not built yet) do one blocking all-reduce per gradient, then build the
+        buckets."""
+        denom = float(total) if total is not None else self.world * divisor
         if not self._built:
+            if any(p.grad is None for p in self.params) and all(p.grad is None for p in self.params):
+                raise RuntimeError("GradBuckets: the first step needs at least one micro-batch on every rank")
             if self.world > 1:
                 for p in self.params:
                     if p.grad is not None:
                         dist.all_reduce(p.grad, group=self.group)
-            scale = 1.0 / (self.world * divisor)
+            scale = 1.0 / denom
             if scale != 1.0:
                 for p in self.params:
                     if p.grad is not None:
                         p.grad.mul_(scale)
             self.build()
             return
+        for b in self.buckets:
+            if not b["launched"]:
+                self._launch(b)
         for h in self._handles:
             h.wait()
         self._handles.clear()
-        scale = 1.0 / (self.world * divisor)
+        scale = 1.0 / denom
         if scale != 1.0:
             for b in self.buckets:
                 b["flat"].mul_(scale)
@@ -184,12 +197,30 @@ class FlatAdam:
                           float(g["betas"][1]), float(g["eps"]), 1.0, self.t)
 
 
-def broadcast_module(model: nn.Module, src: int = 0, process_group=None):
-    """Make every rank start from rank ``src``'s parameters and buffers (as DDP does at construction)."""
+def broadcast_module(model: nn.Module, src: int = 0, process_group=None, buffers_only: bool = False):
+    """Make every rank hold rank ``src``'s parameters and buffers (as DDP does at construction);
+    ``buffers_only`` re-synchronises just the buffers (BatchNorm running statistics are rank-local during
+    training; evaluation and checkpoints use rank 0's)."""
     if not dist.is_initialized() or dist.get_world_size(process_group) == 1:
         return
-    for t in list(model.parameters()) + list(model.buffers()):
+    tensors = list(model.buffers()) if buffers_only else list(model.parameters()) + list(model.buffers())
+    for t in tensors:
         dist.broadcast(t.data, src=src, group=process_group)
+
+
+def shard_micro_batches(n_batches: int, group: int, rank: int, world: int):
+    """SURVEY.md section 8e partition.  The ``n_batches`` micro-batches of an epoch are consumed ``group`` at a
+    time (one optimizer step per group, ``group`` a multiple of ``world``); inside a group rank r takes
+    micro-batches r, r + world, ...  A micro-batch is never split (train-mode BatchNorm and the inter_attn
+    batch-mixing view couple its samples).  Returns one entry per optimizer step:
+    ``(indices of this rank, micro-batches of ALL ranks in the step)``; the last group may be ragged."""
+    if group % world != 0:
+        raise ValueError("micro-batches per step (%d) must be a multiple of the world size (%d)" % (group, world))
+    steps = []
+    for start in range(0, n_batches, group):
+        members = list(range(start, min(start + group, n_batches)))
+        steps.append((members[rank::world], len(members)))
+    return steps
 
 
 class TrainStep:
@@ -211,11 +242,18 @@ class TrainStep:
             from .metrics import Jaccard2 as jaccard_fn
         self.jaccard_fn = jaccard_fn
 
-    def __call__(self, micro_batches) -> Dict[str, torch.Tensor]:
+    def __call__(self, micro_batches, total_micro_batches: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        """``micro_batches``: this rank's (images, masks) pairs for the step (a tuple = one micro-batch; may be
+        empty on a rank that has no data in a ragged last group).  ``total_micro_batches``: how many micro-batches
+        all ranks run in this step together (default world * len(micro_batches))."""
         if isinstance(micro_batches, tuple):
             micro_batches = [micro_batches]
         self.buckets.zero()
         n = len(micro_batches)
+        if n == 0:
+            self.buckets.finish(total=float(total_micro_batches))
+            (self.flat_adam or self.optim).step()
+            return {"loss": None, "jaccard_sum": None, "pixels": 0}
         loss_acc, jac_acc, pixels = None, None, 0
         for k, (images, masks) in enumerate(micro_batches):
             self.buckets.set_sync(k == n - 1)
@@ -235,9 +273,9 @@ class TrainStep:
                 loss_acc = loss.detach() if loss_acc is None else loss_acc + loss.detach()
                 jac_acc = jac if jac_acc is None else jac_acc + jac
                 pixels += load
-        self.buckets.finish(divisor=float(n))
+        self.buckets.finish(divisor=float(n), total=total_micro_batches)
         if self.flat_adam is not None:
             self.flat_adam.step()                                            # :62
         else:
             self.optim.step()                                                # :62
-        return {"loss": loss_acc / n, "jaccard_sum": jac_acc, "pixels": pixels}
+        return {"loss": loss_acc / n, "loss_sum": loss_acc, "micro_batches": n, "jaccard_sum": jac_acc, "pixels": pixels}

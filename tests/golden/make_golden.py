@@ -249,17 +249,6 @@ def make_next_rows_golden():
     print("next-rows golden: %d arrays" % len(rec))
 
 
-if __name__ == "__main__":
-    torch.set_num_threads(os.cpu_count())
-    if "--next-rows" in sys.argv:
-        make_next_rows_golden()
-        sys.exit(0)
-    make_jaccard_golden()
-    make_loss_golden()
-    make_inter_attn_golden()
-    make_block_golden()
-
-
 def make_state_dict_inventory():
     """Key -> shape of the reference MMVit4.state_dict() (1140 entries): the drop-in must match it."""
     import json
@@ -271,6 +260,8 @@ def make_state_dict_inventory():
     n_param = sum(p.numel() for p in m.parameters())
     print("state_dict inventory: %d entries, %d parameters" % (len(inv), n_param))
 
+
+ADAM_LR = 1e-4          # lrFile.txt:1 of the reference's logged run
 
 FULL_GRAD_KEYS = (
     "RGB_encoder.e1_c1.weight", "NIR_encoder.e3.1.conv2.weight", "SWIR_encoder.conv6.weight",
@@ -301,7 +292,11 @@ def _full_model_run(dtype):
     named = dict(m.named_parameters())
     grads = {k: named[k].grad.reshape(-1).double().numpy() for k in FULL_GRAD_KEYS}
     nograd = sorted(k for k, p in named.items() if p.grad is None)
-    return x, masks, y.detach(), loss.item(), grads, nograd
+    # optim.step() of F4_TRAIN.py:62 with the optimizer F2_MAIN.py:168-169 builds (Adam, default betas / eps)
+    before = {k: named[k].detach().clone() for k in FULL_GRAD_KEYS}
+    torch.optim.Adam(m.parameters(), ADAM_LR).step()
+    deltas = {k: (named[k].detach() - before[k]).reshape(-1).double().numpy() for k in FULL_GRAD_KEYS}
+    return x, masks, y.detach(), loss.item(), grads, nograd, deltas
 
 
 def make_full_model_golden():
@@ -310,8 +305,8 @@ def make_full_model_golden():
     the per-tensor spread stored, because this decoder is ill-conditioned in fp32 (its gradients move
     by 1-4e-2 between fp32 and fp64) and a kernel cannot be held to more than the reference itself
     delivers.  Weights/inputs come from seeds (oracle.make_full_model_state); nothing large is stored."""
-    x, masks, y64, loss64, g64, nograd = _full_model_run(torch.float64)
-    _, _, y32, loss32, g32, _ = _full_model_run(torch.float32)
+    x, masks, y64, loss64, g64, nograd, d64 = _full_model_run(torch.float64)
+    _, _, y32, loss32, g32, _, d32 = _full_model_run(torch.float32)
     rec = {"x": x.numpy(), "masks": masks[:, :1].numpy(), "y": y64.float().numpy(), "loss": np.array(loss64),
            "ref_fp32_relerr/y": np.array(float((y32.double() - y64).norm() / y64.norm())),
            "ref_fp32_loss": np.array(loss32)}
@@ -319,6 +314,10 @@ def make_full_model_golden():
         rec[f"gnorm/{k}"] = np.array(np.linalg.norm(g64[k]))
         rec[f"gsample/{k}"] = g64[k][sample_idx(g64[k].size)].astype(np.float32)
         rec[f"ref_fp32_relerr/{k}"] = np.array(np.linalg.norm(g32[k] - g64[k]) / np.linalg.norm(g64[k]))
+        # Adam-updated weights: the first step moves every weight by ~lr * sign(g); stored as the update itself
+        rec[f"adam_delta_sample/{k}"] = d64[k][sample_idx(d64[k].size)].astype(np.float32)
+        rec[f"adam_delta_ref_fp32_relerr/{k}"] = np.array(np.linalg.norm(d32[k] - d64[k]) / np.linalg.norm(d64[k]))
+    rec["adam_lr"] = np.array(ADAM_LR)
     rec["nograd"] = np.array(nograd)
     jac = ref_jac.Jaccard2(masks[:, 0].reshape(-1, 1), y64.float()[:, 0].reshape(-1, 1))
     rec["jaccard2"] = jac.numpy()
@@ -327,6 +326,61 @@ def make_full_model_golden():
         loss64, len(nograd), jac.item(), max(float(rec[f"ref_fp32_relerr/{k}"]) for k in FULL_GRAD_KEYS)))
 
 
-if __name__ == "__main__" and os.environ.get("GOLDEN_EXTRA", "1") == "1":
-    make_state_dict_inventory()
-    make_full_model_golden()
+def make_input_pipeline_golden():
+    """the reference's get_images4 (F8_IMAGES4.py:11-95) and CrossVal (F6_CROSSVAL.py:5-37) run
+    unmodified.  get_images4 hard-codes a Windows path; on Linux that is just a relative directory name, so the
+    synthetic .mat tree is written under a scratch working directory.  os.listdir is pinned to sorted order for
+    the call (the reference takes whatever order the file system returns)."""
+    import tempfile
+    import F6_CROSSVAL as ref_cv
+    import F8_IMAGES4 as ref_im
+    from synth_dstl import write_synthetic_dstl, TRIND, N_TILES
+    rec = {}
+    cwd = os.getcwd()
+    real_listdir = os.listdir
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            write_synthetic_dstl(os.path.join(tmp, "C:/Users/Public/Server/data/DSTL"))
+            os.listdir = lambda p=".": sorted(real_listdir(p))
+            images, masks, r, g, b = ref_im.get_images4(N_TILES, 1, 5, None, TRIND, None, "x")
+        finally:
+            os.listdir = real_listdir
+            os.chdir(cwd)
+    rec["im/means_rgb"] = np.array([r, g, b], np.float32)
+    rec["im/shape"], rec["im/mask_shape"] = np.array(images.shape), np.array(masks.shape)
+    rec["im/sum64"] = np.array(images.double().sum().item())
+    rec["im/sample"] = images.reshape(-1)[::9973].numpy()
+    rec["im/band_means"] = images.double().mean(dim=(0, 3, 4)).numpy()
+    rec["im/mask_sum"] = np.array(masks.sum().item())
+    rec["im/mask_sample"] = masks.reshape(-1)[::9973].numpy()
+    os.chdir("/root/reference")                    # randInd5985.txt lives beside the scripts
+    try:
+        for fno in (1, 2, 5):
+            ts, tr, vl = ref_cv.CrossVal(5985, fno, 5)
+            rec[f"cv/f{fno}/ts"], rec[f"cv/f{fno}/tr"], rec[f"cv/f{fno}/vl"] = (np.asarray(a, np.int32) for a in (ts, tr, vl))
+        rec["cv/perm"] = np.asarray([int(x) for x in open("randInd5985.txt")], np.int32)
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "input_pipeline.npz"), **rec)
+    print("input pipeline golden: images", tuple(images.shape), "means", r, g, b)
+
+
+if __name__ == "__main__":
+    # python tests/golden/make_golden.py [--block] [--next-rows] [--input-pipeline] [--full-model]   (no flag: all)
+    torch.set_num_threads(os.cpu_count())
+    sys.path.insert(0, HERE)
+    want = set(a for a in sys.argv[1:] if a.startswith("--"))
+    every = not want
+    if every or "--block" in want:
+        make_jaccard_golden()
+        make_loss_golden()
+        make_inter_attn_golden()
+        make_block_golden()
+    if every or "--next-rows" in want:
+        make_next_rows_golden()
+    if every or "--input-pipeline" in want:
+        make_input_pipeline_golden()
+    if every or "--full-model" in want:
+        make_state_dict_inventory()
+        make_full_model_golden()

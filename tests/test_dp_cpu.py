@@ -86,3 +86,42 @@ def test_dp_world2_matches_single_process_reference():
         optim.step()
     for p, w in zip(model.parameters(), r0["w"]):
         assert torch.allclose(p.detach(), w, atol=1e-6), (p - w).abs().max()
+
+
+def _ragged_worker(rank, world, port, ret):
+    """5 micro-batches, groups of 2 on 2 ranks: the last optimizer step has ONE micro-batch, on rank 0 only."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from corrif_b200.train import TrainStep, broadcast_module, shard_micro_batches
+    torch.manual_seed(5)
+    model = Tiny()
+    broadcast_module(model)
+    w0 = [p.detach().clone() for p in model.parameters()]
+    step = TrainStep(model, torch.optim.SGD(model.parameters(), lr=0.1), lim=2, jaccard_fn=_soft_jaccard, bucket_bytes=256)
+    g = torch.Generator().manual_seed(9)
+    data = [(torch.randn(4, 6, generator=g), (torch.rand(4, 3, 1, 2, 2, generator=g) < 0.4).float()) for _ in range(5)]
+    for mine, total in shard_micro_batches(len(data), world, rank, world):
+        step([data[j] for j in mine], total_micro_batches=total)
+    ret[rank] = {"w0": w0, "w": [p.detach().clone() for p in model.parameters()], "data": data}
+    dist.destroy_process_group()
+
+
+def test_ragged_last_group_keeps_ranks_in_lock_step():
+    world, port = 2, _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_ragged_worker, args=(world, port, ret), nprocs=world, join=True)
+    for a, b in zip(ret[0]["w"], ret[1]["w"]):
+        assert torch.allclose(a, b, atol=1e-7)
+    model = Tiny()
+    with torch.no_grad():
+        for p, w in zip(model.parameters(), ret[0]["w0"]):
+            p.copy_(w)
+    optim = torch.optim.SGD(model.parameters(), lr=0.1)
+    data = ret[0]["data"]
+    for group in ([0, 1], [2, 3], [4]):                 # single-process reference: mean gradient over each group
+        optim.zero_grad()
+        for j in group:
+            (nn.functional.binary_cross_entropy_with_logits(model(data[j][0]), data[j][1]) / len(group)).backward()
+        optim.step()
+    for p, w in zip(model.parameters(), ret[0]["w"]):
+        assert torch.allclose(p.detach(), w, atol=1e-6), (p - w).abs().max()
