@@ -412,3 +412,103 @@ def general_conv3d_prenorm(x, weight, bias, k_size: int = 3, pad_type: str = "re
         x = torch.nn.functional.pad(x, (pad,) * 6, mode=pad_type if pad_type != "zeros" else "constant")
     return instance_norm3d(torch.relu(torch.nn.functional.conv3d(x, weight, bias)))
 
+
+
+# --------------------------------------------------------------------------------------------------
+# Whole model (MMVit4.forward, mmvit4.py:441-532) as a functional restatement keyed by the reference's state_dict
+# names: the CPU leg of the full-train-step measurement (bench.py cpu_baseline / --impl reference) and the
+# checker of the drop-in model.  Pinned by tests/golden/mmvit4_full_small.npz (the unmodified reference, fp64).
+# Train-mode semantics: BatchNorm3d normalises with the statistics of the local batch (mmvit4.py:121,132-136; the
+# running buffers do not influence train-mode outputs and are not updated here).
+# --------------------------------------------------------------------------------------------------
+def _bn_train(x, p, prefix, eps=1e-5):
+    return F.batch_norm(x, None, None, p[f"{prefix}.weight"], p[f"{prefix}.bias"], training=True, eps=eps)
+
+
+def _bottleneck3d(x, p, prefix, stride):
+    """Bottleneck3D.forward (mmvit4.py:196-212); ResNet-50 v1.5 places the stride on the 3x3 conv, inflated to
+    (1,3,3) kernels (inflate_conv with time_dim=1, mmvit4.py:83-111, 128-150)."""
+    out = torch.relu(_bn_train(F.conv3d(x, p[f"{prefix}.conv1.weight"]), p, f"{prefix}.bn1"))
+    out = F.conv3d(out, p[f"{prefix}.conv2.weight"], stride=(1, stride, stride), padding=(0, 1, 1))
+    out = torch.relu(_bn_train(out, p, f"{prefix}.bn2"))
+    out = _bn_train(F.conv3d(out, p[f"{prefix}.conv3.weight"]), p, f"{prefix}.bn3")
+    identity = x
+    if f"{prefix}.downsample.0.weight" in p:
+        identity = _bn_train(F.conv3d(x, p[f"{prefix}.downsample.0.weight"], stride=(1, stride, stride)),
+                             p, f"{prefix}.downsample.1")
+    return torch.relu(out + identity)
+
+
+def encoder(x, p, prefix):
+    """Encoder.forward (mmvit4.py:170-194).  x [B,1,3,H,W] -> (x1..x5 adapted, x6 [B,64,8,8,8])."""
+    y = F.conv3d(x, p[f"{prefix}.e1_c1.weight"], stride=(1, 2, 2), padding=(1, 3, 3))
+    y = _bn_train(torch.relu(y), p, f"{prefix}.e1_bn")                                     # ReLU before BN (:173)
+    y = F.max_pool3d(y, kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1))
+    feats = [y]
+    for stage, blocks, stride in (("e2", 3, 1), ("e3", 4, 2), ("e4", 6, 2), ("e5", 3, 2)):
+        for b in range(blocks):
+            y = _bottleneck3d(y, p, f"{prefix}.{stage}.{b}", stride if b == 0 else 1)
+        feats.append(y)
+    lv = [F.conv3d(f, p[f"{prefix}.adapt{i}.weight"], p[f"{prefix}.adapt{i}.bias"]) for i, f in enumerate(feats, 1)]
+    pooled = [F.interpolate(t, size=(8, 8, 8), mode="trilinear", align_corners=True) for t in lv]   # :187-191
+    x6 = F.conv3d(torch.cat(pooled, dim=1), p[f"{prefix}.conv6.weight"], p[f"{prefix}.conv6.bias"])
+    return (*lv, x6)
+
+
+def _prenorm(x, p, prefix, k=3, pad_type="replicate"):
+    return general_conv3d_prenorm(x, p[f"{prefix}.conv.weight"], p[f"{prefix}.conv.bias"], k, pad_type)
+
+
+def _rfm(x, p, prefix):
+    """fusion_prenorm (mmvit4.py:47-56): 1x1x1, 3x3x3 (zero padding: the class default), 1x1x1."""
+    x = _prenorm(x, p, f"{prefix}.fusion_layer.0", 1)
+    x = _prenorm(x, p, f"{prefix}.fusion_layer.1", 3, "zeros")
+    return _prenorm(x, p, f"{prefix}.fusion_layer.2", 1)
+
+
+def decoder_fuse(x1, x2, x3, x4, x5, p, prefix="decoder_fuse"):
+    """Decoder_fuse.forward (mmvit4.py:266-292)."""
+    up2 = lambda t: F.interpolate(t, scale_factor=2, mode="trilinear", align_corners=True)   # noqa: E731
+    y = _rfm(x5, p, f"{prefix}.RFM5")
+    y = F.conv3d(y, p[f"{prefix}.RFM5_reduce.weight"], p[f"{prefix}.RFM5_reduce.bias"])
+    for lvl, skip, cube in ((4, x4, 16), (3, x3, 32), (2, x2, 64), (1, x1, 128)):
+        y = _prenorm(up2(y), p, f"{prefix}.d{lvl}_c1")
+        s = F.interpolate(_rfm(skip, p, f"{prefix}.RFM{lvl}"), (cube, cube, cube))          # nearest (:271)
+        y = _prenorm(torch.cat((s, y), dim=1), p, f"{prefix}.d{lvl}_c2")
+        y = _prenorm(y, p, f"{prefix}.d{lvl}_out", 1)
+    y = F.interpolate(y, size=(1, 224, 224), mode="trilinear", align_corners=True)          # :263, 288
+    return torch.sigmoid(F.conv3d(y, p[f"{prefix}.final_conv.weight"], p[f"{prefix}.final_conv.bias"]))
+
+
+def full_model(p, x, masks=None, compute_unused=True):
+    """MMVit4.forward (mmvit4.py:441-532).  p: the 1140-entry state_dict (or its parameters); x [B,3,3,H,W] ->
+    [B,3,1,224,224] sigmoid probabilities.  ``compute_unused`` also evaluates fusion5, whose result the reference
+    computes and drops (:453)."""
+    feats = [encoder(x[:, i:i + 1], p, f"{m}_encoder") for i, m in enumerate(MODALITIES)]
+    fused = []
+    for lv in range(6):
+        if lv == 4 and not compute_unused:
+            fused.append(None)
+            continue
+        fused.append(early_fusion_block([f[lv] for f in feats], p[f"fusion{lv + 1}.conv.weight"],
+                                        p[f"fusion{lv + 1}.conv.bias"]))
+    x6_inter = fusion_block(p, [f[5] for f in feats], fused[5], masks)
+    return decoder_fuse(fused[0], fused[1], fused[2], fused[3], x6_inter, p)
+
+
+def train_step_cpu(state, x, masks, lr=1e-4, dropout_p=0.1):
+    """One F4_TRAIN.py:52-71 step body on the CPU (forward, BCE-with-logits on the probabilities, backward, Adam,
+    Jaccard2 of channel 0); ``state`` = {name: leaf tensor} is updated in place.  Returns (loss, jaccard2)."""
+    params = [v for v in state.values() if v.is_floating_point() and v.requires_grad]
+    if not hasattr(train_step_cpu, "_opt") or train_step_cpu._opt[0] is not state:
+        train_step_cpu._opt = (state, torch.optim.Adam(params, lr))
+    opt = train_step_cpu._opt[1]
+    opt.zero_grad()
+    dm = random_masks(x.shape[0], dropout_p) if dropout_p > 0 else None
+    out = full_model(state, x, dm)
+    loss = bce_with_logits_on_probs(out, masks)
+    loss.backward()
+    opt.step()
+    load = masks.shape[0] * 224 * 224
+    jac = jaccard2_np(masks[:, 0].reshape(load, 1).numpy(), out.detach()[:, 0].reshape(load, 1).numpy())
+    return float(loss), float(jac)

@@ -243,3 +243,81 @@ def test_full_size_batch16_tf32_path_against_fp32_checking_mode_and_linearity():
         lin = 2.0 * res[0][i] - 3.0 * res[1][i]
         assert rel_l2(res[2][i].cpu().numpy(), lin.cpu().numpy()) < 2e-3, i
 
+
+
+def test_headline_batch16_tf32_against_fp64_oracle_per_tensor_table():
+    """BASELINE.json configs[1] itself (batch 16, the size bench.py quotes the fusion block on) against the fp64 CPU
+    oracle: output, all four input gradients and EVERY parameter gradient.  Writes the per-tensor relative-L2 table
+    to gpurun_out/parity_b16_table.txt (committed as profiles/r02_parity_b16_table.txt; DESIGN.md section 2 marks
+    the tensors above the north-star's flat 1e-3).  Tolerances are the per-tensor TF32 ones of this file's header."""
+    batch, seed = 16, 2025
+    params = O.make_params(seed)
+    x6, fused, gout = O.make_inputs(seed, batch)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref_out, ref_g = O.fusion_block_fwd_bwd(params, x6, fused, gout, dtype=torch.float64)
+    out, dx6, dfused, grads = _run_engine(batch, "tf32", seed=seed)
+    rows = [("out x6_inter", rel_l2(out.cpu().numpy(), ref_out.numpy()), TOL["tf32"]["out"])]
+    for i in range(3):
+        rows.append((f"d x6.{i}", rel_l2(dx6[i].cpu().numpy(), ref_g[f"x6.{i}"].numpy()), TOL["tf32"]["xgrad"]))
+    rows.append(("d fused_x6", rel_l2(dfused.cpu().numpy(), ref_g["fused_x6"].numpy()), TOL["tf32"]["xgrad"]))
+    for k in fusion.param_names():
+        rows.append((f"d {k}", rel_l2(grads[k].cpu().numpy(), ref_g[k].numpy()), TOL["tf32"]["pgrad"]))
+    lines = ["# fusion block, batch 16, tf32 hot path vs fp64 CPU oracle (relative L2 per tensor); * = above 1e-3",
+             "%-72s %10s %8s" % ("tensor", "rel_l2", "tol")]
+    lines += ["%-72s %10.3e %8.0e %s" % (n, e, t, "*" if e > 1e-3 else "") for n, e, t in rows]
+    above = [n for n, e, _ in rows if e > 1e-3]
+    lines.append("# %d of %d tensors above 1e-3; worst %s" % (len(above), len(rows), max(rows, key=lambda r: r[1])[:2]))
+    os.makedirs(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "parity_b16_table.txt"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("\n" + "\n".join(lines[-12:]))
+    for n, e, t in rows:
+        assert e < t, (n, e, t)
+
+
+def test_backward_of_a_stale_forward_raises():
+    """Two forwards, then the backward of each: the second (most recent) works, the first raises instead of silently
+    differentiating the wrong saved activations."""
+    dev = torch.device("cuda:0")
+    blk = module.CorrIFusionBlock(precision="tf32").to(dev).eval()
+    blk.load_state_dict(O.make_params(7), strict=True)
+    ins = []
+    for s in (1, 2):
+        x6, fused, gout = O.make_inputs(s, 2)
+        ins.append(([x.to(dev).requires_grad_(True) for x in x6], fused.to(dev).requires_grad_(True), gout.to(dev)))
+    out_a = blk(ins[0][0], ins[0][1])
+    out_b = blk(ins[1][0], ins[1][1])
+    out_b.backward(ins[1][2])                                   # most recent forward: fine
+    assert ins[1][1].grad is not None
+    with pytest.raises(module.StaleForwardError):
+        out_a.backward(ins[0][2])
+    out_c = blk(ins[0][0], ins[0][1])                           # a fresh forward can be differentiated again
+    out_c.backward(ins[0][2])
+    ref_out, ref_g = O.fusion_block_fwd_bwd(O.make_params(7), *O.make_inputs(1, 2), dtype=torch.float64)
+    assert rel_l2(ins[0][1].grad.cpu().numpy(), ref_g["fused_x6"].numpy()) < TOL["tf32"]["xgrad"]
+
+
+def test_kernels_against_stock_pytorch_on_the_same_gpu():
+    """The plain-PyTorch fp32 restatement of the block (baseline/eager_mmvit4.EagerFusionBlock, cuBLAS/cuDNN with TF32
+    off) on the same device: the comparison bench.py's eager_b200 arm times."""
+    from baseline.eager_mmvit4 import EagerFusionBlock
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        dev = torch.device("cuda:0")
+        ref = EagerFusionBlock(0.0).to(dev)
+        ref.load_state_dict(O.make_params(1234), strict=True)
+        x6, fused, gout = O.make_inputs(1234, 4)
+        xs = [x.to(dev).requires_grad_(True) for x in x6]
+        fx = fused.to(dev).requires_grad_(True)
+        y = ref(xs, fx)
+        y.backward(gout.to(dev))
+        out, dx6, dfused, grads = _run_engine(4, "tf32")
+        assert rel_l2(out.cpu().numpy(), y.detach().cpu().numpy()) < TOL["tf32"]["out"]
+        assert rel_l2(dfused.cpu().numpy(), fx.grad.cpu().numpy()) < TOL["tf32"]["xgrad"]
+        named = dict(ref.named_parameters())
+        for k in ("multimodal_decode_conv.weight", "qkv_RGB.bias", "NIR_pos",
+                  "multimodal_transformer.cross_ffn_list.0.fn.fn.net.3.weight"):
+            assert rel_l2(grads[k].cpu().numpy(), named[k].grad.cpu().numpy()) < TOL["tf32"]["pgrad"], k
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved

@@ -113,6 +113,66 @@ def test_train_model_entry_point_runs_and_writes_reference_files(dropin, tmp_pat
     assert len(sd) == 1140 and os.path.exists(os.path.join(str(tmp_path), "iremmodel0.pt"))
 
 
+def test_adam_updated_weights_match_reference_step(dropin):
+    """One full F4_TRAIN.py:52-62 step through TrainStep (FlatAdam, one kernel per bucket) against the reference's
+    fp64 run: the Adam update of 16 tensors spread over the model (fixture adam_delta_sample/*).  The first Adam step
+    moves every weight by lr * g / (|g| + eps) ~ lr * sign(g), so the update is compared as a vector: the bound is 3x
+    the distance of the reference's OWN fp32 run from its fp64 run (stored in the fixture) for the fp32 checking mode."""
+    from oracle import corrif_oracle as O
+    from corrif_b200 import train
+    mmvit4 = dropin[0]
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    g = np.load(os.path.join(GOLDEN, "mmvit4_full_small.npz"))
+    inv = json.load(open(os.path.join(GOLDEN, "mmvit4_state_dict_inventory.json")))
+    model = mmvit4.MMVit4(num_cls=1, dropout_rate=0.0, precision="fp32")
+    model.load_state_dict(O.make_full_model_state(2024, inv), strict=True)
+    model = model.to(dev).train()
+    keys = [k[len("adam_delta_sample/"):] for k in g.files if k.startswith("adam_delta_sample/")]
+    before = {k: dict(model.named_parameters())[k].detach().clone() for k in keys}
+    optim = torch.optim.Adam(model.parameters(), float(g["adam_lr"]))
+    step = train.TrainStep(model, optim, lim=224)
+    assert step.flat_adam is not None
+    x = torch.from_numpy(g["x"]).to(dev)
+    masks = torch.from_numpy(g["masks"]).to(dev).repeat(1, 3, 1, 1, 1)
+    out = step((x, masks))
+    assert abs(out["loss"].item() - float(g["loss"])) < 1e-4
+    named = dict(model.named_parameters())
+    report = {}
+    for k in keys:
+        d = (named[k].detach() - before[k]).reshape(-1).double().cpu().numpy()
+        report[k] = (rel_l2(d[_sample_idx(d.size)], g[f"adam_delta_sample/{k}"]), float(g[f"adam_delta_ref_fp32_relerr/{k}"]))
+    print("\n[adam delta] " + ", ".join(f"{k[:12]}..{k[-10:]}:{e:.1e}(ref {r:.1e})" for k, (e, r) in report.items()))
+    for k, (e, r) in report.items():
+        assert e < max(3.0 * r, 2e-3), (k, e, r)
+
+
+def test_f2_main_drop_in_runs_one_synthetic_epoch(dropin, tmp_path, monkeypatch):
+    """dropin/F2_MAIN.py end to end on one GPU: 18-line config -> synthetic tiles -> train_model -> test_model ->
+    the reference's text logs in the working directory and the two checkpoints in the result directory."""
+    for name in ("F2_MAIN", "F7_TEST2"):
+        sys.modules.pop(name, None)
+    import F2_MAIN
+    exp = tmp_path / "experiments"
+    exp.mkdir()
+    lines = ["20", "1", "5", "0.1", "2", "1", "0.0001", "Adam", "BCEWithLogitsLoss", "BCEWithLogitsLoss", "Jaccard",
+             "kaiming_normal_", "5", "0.9", "224", "MMVit4", "x", "notr"]
+    (exp / "model0.txt").write_text("\n".join(lines) + "\n")
+    monkeypatch.setenv("CORRIF_EXPERIMENTS", str(exp))
+    monkeypatch.setenv("CORRIF_SYNTHETIC", "1")
+    monkeypatch.chdir(tmp_path)
+    pathm = F2_MAIN.main(0)
+    for name in ("lrFile", "trainFile", "trainaccFile", "trainepochFile", "valFile", "valaccFile", "testFile", "testaccFile"):
+        assert (tmp_path / (name + ".txt")).exists(), name
+    assert 0.3 < float((tmp_path / "trainFile.txt").read_text().strip()) < 1.5
+    assert 0.0 <= float((tmp_path / "testaccFile.txt").read_text().strip()) <= 1.0
+    assert os.path.exists(os.path.join(pathm, "Finaliremmodel0.pt")) and os.path.exists(os.path.join(pathm, "iremmodel0.pt"))
+    assert any(f.endswith(".txt") for f in os.listdir(pathm))               # the summary log
+    for name in ("F2_MAIN", "F7_TEST2"):
+        sys.modules.pop(name, None)
+
+
 @pytest.mark.gpu
 def test_pinned_pipeline_round_trip():
     """staging.PinnedPipeline: prefetched inputs arrive intact and in order, results come back, slots are
@@ -139,6 +199,13 @@ def test_pinned_pipeline_round_trip():
         assert torch.equal(outs[i], torch.full((1 << 20,), 2.0 * i + 1))
     with pytest.raises(RuntimeError):
         pipe.get()
+    # a ragged last batch gets buffers of its own shape (no broadcast of a batch of one into the old buffers)
+    small = torch.arange(7.0).pin_memory()
+    pipe.prefetch([small])
+    (x,) = pipe.get()
+    assert x.shape == (7,) and torch.equal(x.cpu(), small)
+    with pytest.raises(RuntimeError):                      # the slot is still held: release() was not called
+        pipe.prefetch([small]); pipe.prefetch([small])
 
 
 def test_flat_adam_matches_torch_adam():

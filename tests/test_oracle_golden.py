@@ -130,3 +130,28 @@ def test_next_rows_restatements_match_reference():
         assert rel_l2(x.grad.numpy(), g[f"{tag}/dx"]) < 1e-5, tag
         assert rel_l2(w.grad.numpy(), g[f"{tag}/dw"]) < 1e-5 and rel_l2(b.grad.numpy(), g[f"{tag}/db"]) < 1e-5, tag
 
+
+
+def test_full_model_restatement_matches_reference_fixture():
+    """oracle.full_model (encoders + early fusion + fusion block + decoder, mmvit4.py:441-532) against the
+    unmodified reference's fp64 run stored in mmvit4_full_small.npz: output, loss, the gradient-less set and the
+    gradients of 16 tensors spread over the model."""
+    import json
+    g = np.load(os.path.join(GOLDEN, "mmvit4_full_small.npz"))
+    inv = json.load(open(os.path.join(GOLDEN, "mmvit4_state_dict_inventory.json")))
+    state = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v)
+             for k, v in O.make_full_model_state(2024, inv).items()}
+    x = torch.from_numpy(g["x"]).double()
+    masks = torch.from_numpy(g["masks"]).double().repeat(1, 3, 1, 1, 1)
+    y = O.full_model(state, x)
+    loss = O.bce_with_logits_on_probs(y, masks)
+    loss.backward()
+    assert rel_l2(y.detach().numpy(), g["y"]) < 1e-6
+    assert abs(loss.item() - float(g["loss"])) < 1e-9
+    params = {k for k, v in state.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+    assert sorted(k for k in params if state[k].grad is None) == sorted(g["nograd"].tolist())
+    for key in [k[6:] for k in g.files if k.startswith("gnorm/")]:
+        gk = state[key].grad.reshape(-1).numpy()
+        idx = np.arange(gk.size) if gk.size <= 2048 else np.linspace(0, gk.size - 1, 2048).astype(np.int64)
+        assert rel_l2(gk[idx], g[f"gsample/{key}"]) < 1e-5, key
+        assert abs(np.linalg.norm(gk) / float(g[f"gnorm/{key}"]) - 1) < 1e-6, key

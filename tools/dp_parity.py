@@ -1,0 +1,128 @@
+"""N-rank gradient parity on hardware (SURVEY.md section 8e oracle).
+
+  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_parity.py [out.json]
+
+Every rank builds the same drop-in MMVit4 (dropout off), runs ONE TrainStep over its shard of 2*G micro-batches
+(rank r takes r, r+G, ...: train.shard_micro_batches) with the overlapped bucketed NCCL all-reduce and FlatAdam.
+Checks, on every rank:
+  (1) the reduced gradients of >= 16 tensors spread over encoders / fusion block / decoder equal the mean, accumulated
+      in fp64, of the gradients of 2*G INDEPENDENT single-rank runs of the same micro-batches (no process group
+      involved: plain autograd on a deep copy of the initial model);
+  (2) after the Adam step all ranks hold bit-identical parameters, and they equal the single-process Adam update of
+      the fp64-mean gradient to fp32 rounding.
+Writes a JSON report (rank 0) and exits non-zero on failure."""
+import copy
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "corrifnet-correlation-aware-interactive-fusion-multimodal-learning-for-multispectral-images_b200", "dropin"))
+
+KEYS = ("RGB_encoder.e1_c1.weight", "NIR_encoder.e3.1.conv2.weight", "SWIR_encoder.conv6.weight",
+        "SWIR_encoder.e5.2.bn3.weight", "fusion1.conv.weight", "fusion6.conv.bias", "RGB_encode_conv.weight", "NIR_pos",
+        "multimodal_transformer.cross_attention_list.0.fn.fn.qkv.weight",
+        "RGB_transformer.cross_ffn_list.0.fn.fn.net.0.weight", "qkv_SWIR.weight", "multimodal_decode_conv.weight",
+        "decoder_fuse.RFM5.fusion_layer.1.conv.weight", "decoder_fuse.d4_c2.conv.weight",
+        "decoder_fuse.d1_c2.conv.weight", "decoder_fuse.final_conv.weight", "decoder_fuse.d2_c1.conv.bias",
+        "SWIR_transformer.cross_attention_list.0.fn.norm.weight")
+
+
+def main():
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mmvit4
+    from corrif_b200 import train
+    tile, mb = int(os.environ.get("PARITY_TILE", "64")), int(os.environ.get("PARITY_MICRO_BATCH", "2"))
+    n_mb = 2 * world
+    torch.manual_seed(0)
+    model = mmvit4.MMVit4(num_cls=1, dropout_rate=0.0).to(dev).train()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("_pos"):
+                p.normal_(0, 0.02)
+    train.broadcast_module(model)
+    init = copy.deepcopy(model.state_dict())
+    g = torch.Generator().manual_seed(99)
+    data = [(torch.randn(mb, 3, 3, tile, tile, generator=g).to(dev),
+             (torch.rand(mb, 1, 1, 224, 224, generator=g) < 0.3).float().repeat(1, 3, 1, 1, 1).to(dev)) for _ in range(n_mb)]
+    # ---- (0) two data-parallel steps: the first builds the buckets (blocking all-reduce), the second is the overlapped path
+    lr = 1e-3
+    optim = torch.optim.Adam(model.parameters(), lr)
+    step = train.TrainStep(model, optim, lim=224, bucket_bytes=32 << 20)
+    mine, total = train.shard_micro_batches(n_mb, n_mb, rank, world)[0]
+    snap = {}
+    orig = step.flat_adam.step
+
+    def snap_then_step():
+        named = dict(model.named_parameters())
+        for k in KEYS:
+            snap[k] = named[k].grad.detach().double().clone()
+        orig()
+    for it in range(2):
+        model.load_state_dict(init)                    # same starting point for both steps (in place: views stay valid)
+        step.flat_adam.step = snap_then_step if it == 1 else (lambda: None)
+        step([data[j] for j in mine], total_micro_batches=total)
+    torch.cuda.synchronize()
+    dp_params = {k: v.detach().clone() for k, v in model.named_parameters()}
+    # ---- (1) reference: every micro-batch independently, no process group, fp64 mean of the gradients
+    ref = mmvit4.MMVit4(num_cls=1, dropout_rate=0.0).to(dev).train()
+    ref.load_state_dict(init)
+    named_ref = dict(ref.named_parameters())
+    acc = {k: torch.zeros_like(named_ref[k], dtype=torch.float64) for k in KEYS}
+    full = {n: torch.zeros_like(p, dtype=torch.float64) for n, p in named_ref.items()}
+    for im, ma in data:
+        for p in ref.parameters():
+            p.grad = None
+        torch.nn.functional.binary_cross_entropy_with_logits(ref(im), ma).backward()
+        for n, p in named_ref.items():
+            if p.grad is not None:
+                full[n] += p.grad.double() / n_mb
+    report, ok = {"world": world, "micro_batches": n_mb, "micro_batch": mb, "tile": tile, "grad_relerr": {}}, True
+    for k in KEYS:
+        e = float((snap[k] - full[k]).norm() / full[k].norm().clamp_min(1e-300))
+        report["grad_relerr"][k] = e
+        ok &= e < 5e-3                                  # summation order (atomics, TF32) only; a sharding bug is O(1)
+    # ---- (2) parameters: identical across ranks, and equal to one Adam step on the fp64-mean gradient
+    worst_rank_diff = 0.0
+    if world > 1:
+        for n, p in dp_params.items():
+            lo, hi = p.clone(), p.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            worst_rank_diff = max(worst_rank_diff, float((hi - lo).abs().max()))
+    report["max_param_spread_across_ranks"] = worst_rank_diff
+    ok &= worst_rank_diff == 0.0
+    worst_adam = 0.0
+    for k in KEYS:
+        gk = full[k]
+        upd = -lr * gk / (gk.abs() + 1e-8 * (1 - 0.999) ** 0.5 / (1 - 0.9) * (1 - 0.9))     # first Adam step, bias-corrected
+        want = init[k].double() - lr * gk / (gk.abs() + 1e-8)
+        got = dp_params[k].double()
+        big = gk.abs() > 1e-6 * gk.abs().max()          # sign(g) is ill-defined where g ~ 0
+        worst_adam = max(worst_adam, float(((got - want)[big]).abs().max() / lr))
+    report["max_adam_update_error_in_units_of_lr"] = worst_adam
+    ok &= worst_adam < 0.2
+    report["ok"] = bool(ok)
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps(report, indent=1))
+        if len(sys.argv) > 1:
+            with open(sys.argv[1], "w") as f:
+                json.dump(report, f, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
