@@ -103,8 +103,7 @@ def main():
     worst_adam = 0.0
     for k in KEYS:
         gk = full[k]
-        upd = -lr * gk / (gk.abs() + 1e-8 * (1 - 0.999) ** 0.5 / (1 - 0.9) * (1 - 0.9))     # first Adam step, bias-corrected
-        want = init[k].double() - lr * gk / (gk.abs() + 1e-8)
+        want = init[k].double() - lr * gk / (gk.abs() + 1e-8)     # first Adam step: m_hat = g, v_hat = g^2
         got = dp_params[k].double()
         big = gk.abs() > 1e-6 * gk.abs().max()          # sign(g) is ill-defined where g ~ 0
         worst_adam = max(worst_adam, float(((got - want)[big]).abs().max() / lr))
