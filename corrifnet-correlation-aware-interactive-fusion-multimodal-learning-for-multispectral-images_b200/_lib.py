@@ -36,6 +36,21 @@ class GemmDesc(C.Structure):
     ]
 
 
+class VolSrc(C.Structure):
+    """Mirror of ``corrif_vol_src``."""
+    _fields_ = [("p", C.c_void_p), ("C", i32), ("reserved", i32), ("ld", i64)]
+
+
+class Conv3dDesc(C.Structure):
+    """Mirror of ``corrif_conv3d_desc`` (include/corrif.h)."""
+    _fields_ = [
+        ("src", VolSrc * 3), ("nsrc", i32), ("B", i32), ("D", i32), ("H", i32), ("W", i32),
+        ("Cin", i32), ("Cout", i32), ("ksize", i32), ("pad_mode", i32), ("relu", i32),
+        ("wpk", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("ldo", i64), ("stats", C.c_void_p),
+    ]
+
+
+PAD_ZEROS, PAD_REPLICATE = 0, 1
 EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_MUL_DGELU, EPI_ATOMIC_ADD = range(6)
 GEMM_TF32, GEMM_FP32 = 0, 1
 GEMM_ROUND_TF32 = 1
@@ -81,6 +96,21 @@ PROTOTYPES = {
     "corrif_confusion_counts": (C.c_int, [u8p, u8p, i64, i32, u64p, stream_t]),
     "corrif_bce_probs_fwd_bwd": (C.c_int, [f32p, f32p, i64, f32, f64p, f32p, stream_t]),
     "corrif_adam_step": (C.c_int, [f32p, f32p, f32p, f32p, i64, f32, f32, f32, f32, f32, i32, stream_t]),
+    "corrif_sizeof_conv3d_desc": (C.c_int, []),
+    "corrif_conv3d_pack_floats": (i64, [i32, i32, i32]),
+    "corrif_conv3d_pack_weights": (C.c_int, [f32p, f32p, i32, i32, i32, i32, stream_t]),
+    "corrif_conv3d_fwd": (C.c_int, [C.POINTER(Conv3dDesc), stream_t]),
+    "corrif_conv3d_wgrad": (C.c_int, [C.POINTER(Conv3dDesc), f32p, i64, f32p, stream_t]),
+    "corrif_conv3d_dgrad_border": (C.c_int, [f32p, i64, f32p, f32p, i64, i32, i32, i32, i32, i32, i32, stream_t]),
+    "corrif_instnorm_apply": (C.c_int, [f32p, i64, f64p, f32p, f32p, i32, i64, i32, f32, stream_t]),
+    "corrif_instnorm_bwd_stats": (C.c_int, [f32p, i64, f32p, i64, f64p, i32, i64, i32, stream_t]),
+    "corrif_instnorm_relu_bwd_apply": (C.c_int, [f32p, i64, f32p, i64, f32p, f32p, f64p, f32p, i64, f32p, i32, i64, i32,
+                                                 i32, stream_t]),
+    "corrif_volume_colsum": (C.c_int, [f32p, i64, f32p, i64, i32, stream_t]),
+    "corrif_resize_trilinear_fwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),
+    "corrif_resize_trilinear_bwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),
+    "corrif_resize_nearest_fwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),
+    "corrif_resize_nearest_bwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),
 }
 
 _lib = None
@@ -104,10 +134,12 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.corrif_abi_version() != 2:
+    if lib.corrif_abi_version() != 3:
         raise CorrifError("libcorrif_b200.so ABI version mismatch")
     if lib.corrif_sizeof_gemm_desc() != C.sizeof(GemmDesc):
         raise CorrifError("corrif_gemm_desc layout mismatch between include/corrif.h and _lib.py")
+    if lib.corrif_sizeof_conv3d_desc() != C.sizeof(Conv3dDesc):
+        raise CorrifError("corrif_conv3d_desc layout mismatch between include/corrif.h and _lib.py")
     _lib = lib
     return lib
 

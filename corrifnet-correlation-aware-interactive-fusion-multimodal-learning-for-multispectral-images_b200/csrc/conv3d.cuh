@@ -1,0 +1,174 @@
+// Shared pieces of the channels-last 3-D convolution kernels (conv3d_fwd.cu, conv3d_wgrad.cu): tile geometry,
+// shared-memory layout of the staged input window, the multi-source channels-last loader and the warp-level
+// TF32 MMA.
+//
+// Why warp-level mma.sync here and tcgen05 in the GEMM / attention kernels.  The decoder's convolutions
+// (mmvit4.py:29-45, 222-292) have 8..64 output channels over up to 128^3 voxels: as implicit GEMMs they are
+// [16.8 M x 27*Cin] . [27*Cin x 8].  (1) The im2col operand is 27x the activation tensor; streaming it through
+// L2 (TMA im2col boxes) costs 58 GB for one 32 -> 8 channel layer, 10x the HBM floor, so the input window has to
+// be staged ONCE in shared memory and the 27 taps read as shifted views of it.  (2) tcgen05 shared-memory
+// descriptors address 8-row core matrices at fixed strides; a one-voxel shift is expressible only in the
+// un-swizzled K-major layout and not at all for the weight gradient (reduction over voxels with a per-tap shift of
+// one operand).  (3) With C_out = 8 a tcgen05 tile (M = 128, N >= 16) streams a 4 KB A operand from shared memory
+// for 8 cycles of math - it is shared-memory bound exactly like the warp-level path, but cannot reuse A fragments
+// across taps in registers, which the code below does (10 staged rows serve 3 dy-taps x 4 row pairs).
+// Measured mma.sync m16n8k8 TF32 rate on B200: 270 TFLOP/s (profiles/r02a_mma_sync_probe.txt); these layers need
+// ~90 FLOP per HBM byte, i.e. 270 TFLOP/s sits at the HBM ridge of 41 FLOP/B x 6.5 TB/s.
+#pragma once
+#include "common.cuh"
+
+namespace corrif {
+namespace conv {
+
+constexpr int TX = 8, TY = 8, TZ = 4;                 // output tile: one warp per z-slice, 8 x 8 voxels each
+constexpr int HX = TX + 2, HY = TY + 2, HZ = TZ + 2;  // staged input window (one-voxel halo)
+constexpr int TILE_VOX = TX * TY * TZ;                // 256
+constexpr int WIN_VOX = HX * HY * HZ;                 // 600
+constexpr int NTHREADS = 128;
+// shared-memory window: [channel group of 4][voxel][4 floats]; the group stride is padded by one voxel so that
+// (stride / 4) % 32 == 4: the 8 lanes of a quarter-warp that store the 8 groups of one voxel, and the 32 lanes of
+// a weight-gradient A-fragment load (two groups x four voxels), all hit distinct banks
+constexpr int CGS3 = (WIN_VOX + 1) * 16;              // bytes per channel group, 3x3x3 kernels
+constexpr int CGS1 = (TILE_VOX + 1) * 16;             // 1x1x1 kernels: the tile is 256 consecutive voxels
+constexpr int MAX_SRC = 3;
+
+struct Src {
+  const float* p;       // channels-last volume [B, D, H, W, C] with voxel stride ld (>= C)
+  int C;
+  long long ld;
+};
+
+struct Geom {
+  int B, D, H, W;
+  int tiles_x, tiles_y, tiles_z;
+};
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lds64(uint32_t addr, uint32_t& a, uint32_t& b) {
+  asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// 4 consecutive channels [c, c+4) of voxel `vox` of the channel-concatenation of the sources (c % 4 == 0;
+// every source has C % 4 == 0); zeros beyond the last source.  The caller rounds to TF32 (the MMA truncates).
+__device__ __forceinline__ float4 load_cat4_raw(const Src (&src)[MAX_SRC], int nsrc, long long vox, int c) {
+#pragma unroll
+  for (int s = 0; s < MAX_SRC; ++s) {
+    if (s < nsrc) {
+      if (c < src[s].C) return ld4(src[s].p + vox * src[s].ld + c);
+      c -= src[s].C;
+    }
+  }
+  return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Stage the input window of one tile for channels [c0, c0 + kc) into shared memory.
+//   KS == 3: window voxel (hz,hy,hx) = input voxel (z0+hz-1, y0+hy-1, x0+hx-1), out-of-volume coordinates are
+//            clamped (replicate padding, mmvit4.py:225-236 pad_type='replicate') or read as zeros (the RFM blocks'
+//            default zero padding, mmvit4.py:47-56)
+//   KS == 1: the tile is 256 consecutive voxels of sample b starting at v0
+// Loads are issued in batches of 8 per thread BEFORE any of them is stored: with a load -> store pair per
+// iteration every 16 bytes paid a full DRAM round trip (measured: 6.7 ms for the 32 -> 8 channel 128^3 layer, of
+// which the MMAs are ~1 ms).
+template <int KS>
+__device__ __forceinline__ void stage_window(uint32_t smem_in, const Src (&src)[MAX_SRC], int nsrc, const Geom& g,
+                                             int b, int z0, int y0, int x0, long long v0, long long nvox,
+                                             int c0, int kc, bool replicate) {
+  const int gshift = kc == 32 ? 3 : (kc == 16 ? 2 : 1);      // channel groups per voxel = kc / 4 (8, 4 or 2)
+  const int groups = 1 << gshift;
+  constexpr int NV = KS == 3 ? WIN_VOX : TILE_VOX;
+  constexpr int CGS = KS == 3 ? CGS3 : CGS1;
+  constexpr int U = 8;
+  const int total = NV << gshift;
+  for (int base = threadIdx.x; base < total; base += NTHREADS * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NTHREADS;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total) {
+        const int cg = i & (groups - 1), hv = i >> gshift;
+        if (KS == 3) {
+          const int hx = hv % HX, hy = (hv / HX) % HY, hz = hv / (HX * HY);
+          int z = z0 + hz - 1, y = y0 + hy - 1, x = x0 + hx - 1;
+          bool inside = z >= 0 && z < g.D && y >= 0 && y < g.H && x >= 0 && x < g.W;
+          if (replicate) {
+            z = min(max(z, 0), g.D - 1); y = min(max(y, 0), g.H - 1); x = min(max(x, 0), g.W - 1);
+            inside = true;
+          }
+          if (inside) v[u] = load_cat4_raw(src, nsrc, (((long long)b * g.D + z) * g.H + y) * g.W + x, c0 + cg * 4);
+        } else {
+          const long long vv = v0 + hv;
+          if (vv < nvox) v[u] = load_cat4_raw(src, nsrc, (long long)b * nvox + vv, c0 + cg * 4);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NTHREADS;
+      if (i < total) sts128(smem_in + (i & (groups - 1)) * CGS + (i >> gshift) * 16, round_tf32_4(v[u]));
+    }
+  }
+}
+
+// batched copy of n16 16-byte words global -> shared (packed weights), loads first, then stores
+__device__ __forceinline__ void stage_linear(uint32_t smem_dst, const float4* __restrict__ gsrc, int n16) {
+  constexpr int U = 8;
+  for (int base = threadIdx.x; base < n16; base += NTHREADS * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NTHREADS;
+      v[u] = i < n16 ? __ldg(gsrc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NTHREADS;
+      if (i < n16) sts128(smem_dst + i * 16, v[u]);
+    }
+  }
+}
+
+// Tiling plan shared by the packer and the kernels: NB = 8-channel output blocks per CTA, KC = input channels
+// staged per pass.  Sized for occupancy (the loader's DRAM latency is hidden by the OTHER resident CTAs' math):
+// NB = 1 -> 52 KB of shared memory and 112 registers = 4 CTAs per SM, NB = 2 -> 3, wider blocks -> 2.  KC never
+// exceeds the channel count rounded up to 8 / 16 / 32 (no passes over zero padding).
+struct Plan { int NB, KC; };
+inline Plan conv_plan(int Cin, int Cout, int ks) {
+  static const int cand[6] = {8, 6, 4, 3, 2, 1};
+  Plan p{1, 32};
+  for (int i = 0; i < 6; ++i)
+    if ((Cout / 8) % cand[i] == 0) { p.NB = cand[i]; break; }
+  if (ks == 3) p.KC = p.NB <= 4 ? 16 : 8;
+  else p.KC = 32;
+  const int need = Cin <= 8 ? 8 : (Cin <= 16 ? 16 : 32);
+  if (p.KC > need) p.KC = need;
+  return p;
+}
+inline int wgrad_nb(int Cout) {
+  static const int cand[4] = {4, 3, 2, 1};
+  for (int i = 0; i < 4; ++i)
+    if ((Cout / 8) % cand[i] == 0) return cand[i];
+  return 1;
+}
+
+}  // namespace conv
+}  // namespace corrif

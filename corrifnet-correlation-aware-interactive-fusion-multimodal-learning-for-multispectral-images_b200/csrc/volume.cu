@@ -1,0 +1,445 @@
+// Element-wise / resampling kernels on channels-last volumes [B, D, H, W, C] (voxel stride ld): InstanceNorm3d after
+// ReLU (apply, and the two-pass backward of ReLU -> InstanceNorm), bias-gradient column sums, trilinear
+// (align_corners=True) and nearest resize, forward and gather-form backward.  All accesses are 128-bit; a thread
+// always works on the same 4 channels, so per-channel statistics live in registers and leave through one block
+// reduction + one double atomic per (sample, channel quad element) and block.
+#include "common.cuh"
+
+namespace corrif {
+namespace vol {
+
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+
+// grid: (blocks over voxels, B).  Every thread owns channel quad q = tid % Q and voxels (tid / Q) + k * (THREADS / Q)...
+// requires THREADS % Q == 0 (Q = C / 4 in {2,4,6,8,12,16,24,32,48}: handled by using the largest multiple of Q <= THREADS).
+struct Lane { int q; long long v, vstep; bool active; };
+__device__ __forceinline__ Lane lane_of(int Q, long long blocks_x) {
+  const int usable = (THREADS / Q) * Q;
+  Lane l;
+  l.active = (int)threadIdx.x < usable;
+  l.q = threadIdx.x % Q;
+  const int rows = usable / Q;
+  l.v = (long long)blockIdx.x * rows + threadIdx.x / Q;
+  l.vstep = blocks_x * rows;
+  return l;
+}
+
+// block-reduce 4 + 4 doubles held per thread for channel quad q and add them to out[(b*C + 4q + e)*2 + {0,1}]
+__device__ __forceinline__ void reduce_pairs_to_global(double (&s)[4], double (&t)[4], int Q, int q, bool active,
+                                                       double* out, int b, int C) {
+  __shared__ double sh[THREADS][8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { sh[threadIdx.x][e] = active ? s[e] : 0.0; sh[threadIdx.x][4 + e] = active ? t[e] : 0.0; }
+  __syncthreads();
+  if ((int)threadIdx.x < Q) {
+    const int usable = (THREADS / Q) * Q;
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < usable; i += Q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += sh[i][e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      atomicAdd(out + ((long long)b * C + 4 * threadIdx.x + e) * 2, a[e]);
+      atomicAdd(out + ((long long)b * C + 4 * threadIdx.x + e) * 2 + 1, a[4 + e]);
+    }
+  }
+}
+
+// y = (r - mean) * rstd in place; statistics from the convolution's (sum, sum of squares)
+__global__ void __launch_bounds__(THREADS) instnorm_apply_kernel(float* x, long long ld, const double* __restrict__ stats,
+                                                                 float* mean_out, float* rstd_out, long long nvox, int C,
+                                                                 float eps) {
+  const int Q = C / 4, b = blockIdx.y;
+  const Lane l = lane_of(Q, gridDim.x);
+  if (!l.active) return;
+  float mu[4], rs[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const double s = stats[((long long)b * C + 4 * l.q + e) * 2], ss = stats[((long long)b * C + 4 * l.q + e) * 2 + 1];
+    const double m = s / (double)nvox;
+    double var = ss / (double)nvox - m * m;
+    var = var > 0.0 ? var : 0.0;
+    mu[e] = (float)m;
+    rs[e] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < Q) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      mean_out[(long long)b * C + 4 * l.q + e] = mu[e];
+      rstd_out[(long long)b * C + 4 * l.q + e] = rs[e];
+    }
+  }
+  float* base = x + (long long)b * nvox * ld + 4 * l.q;
+  for (long long v = l.v; v < nvox; v += l.vstep) {
+    float4 r = ld4(base + v * ld);
+    r.x = (r.x - mu[0]) * rs[0]; r.y = (r.y - mu[1]) * rs[1]; r.z = (r.z - mu[2]) * rs[2]; r.w = (r.w - mu[3]) * rs[3];
+    st4(base + v * ld, r);
+  }
+}
+
+// sums[b][c] += (sum dy, sum dy * y)
+__global__ void __launch_bounds__(THREADS) instnorm_bwd_stats_kernel(const float* __restrict__ dy, long long lddy,
+                                                                     const float* __restrict__ y, long long ldy,
+                                                                     double* sums, long long nvox, int C) {
+  const int Q = C / 4, b = blockIdx.y;
+  const Lane l = lane_of(Q, gridDim.x);
+  double s[4] = {0, 0, 0, 0}, t[4] = {0, 0, 0, 0};
+  if (l.active) {
+    const float* pd = dy + (long long)b * nvox * lddy + 4 * l.q;
+    const float* py = y + (long long)b * nvox * ldy + 4 * l.q;
+    float fs[4] = {0, 0, 0, 0}, ft[4] = {0, 0, 0, 0};
+    int n = 0;
+    for (long long v = l.v; v < nvox; v += l.vstep) {
+      const float4 d = ld4_stream(pd + v * lddy), yy = ld4_stream(py + v * ldy);
+      fs[0] += d.x; fs[1] += d.y; fs[2] += d.z; fs[3] += d.w;
+      ft[0] += d.x * yy.x; ft[1] += d.y * yy.y; ft[2] += d.z * yy.z; ft[3] += d.w * yy.w;
+      if (++n == 64) {                      // flush the fp32 partials into doubles every 64 voxels
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s[e] += fs[e]; t[e] += ft[e]; fs[e] = ft[e] = 0.f; }
+        n = 0;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s[e] += fs[e]; t[e] += ft[e]; }
+  }
+  reduce_pairs_to_global(s, t, Q, l.q, l.active, sums, b, C);
+}
+
+// g = [r > 0] * rstd * (dy - sum_dy/n - y * sum_dyy/n);  dbias[c] += sum g.   relu == 0: no mask.
+// mean == nullptr: no normalisation at all (plain ReLU backward is not needed by the model; rejected by the launcher)
+__global__ void __launch_bounds__(THREADS) instnorm_relu_bwd_apply_kernel(
+    const float* __restrict__ dy, long long lddy, const float* __restrict__ y, long long ldy,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const double* __restrict__ sums, float* g,
+    long long ldg, float* dbias, long long nvox, int C, int relu) {
+  const int Q = C / 4, b = blockIdx.y;
+  const Lane l = lane_of(Q, gridDim.x);
+  float acc[4] = {0, 0, 0, 0};
+  if (l.active) {
+    float rs[4], thr[4], m1[4], m2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long ch = (long long)b * C + 4 * l.q + e;
+      rs[e] = rstd[ch];
+      thr[e] = (0.f - mean[ch]) * rs[e];           // the forward's value of a clamped-to-zero activation
+      m1[e] = (float)(sums[ch * 2] / (double)nvox);
+      m2[e] = (float)(sums[ch * 2 + 1] / (double)nvox);
+    }
+    const float* pd = dy + (long long)b * nvox * lddy + 4 * l.q;
+    const float* py = y + (long long)b * nvox * ldy + 4 * l.q;
+    float* pg = g + (long long)b * nvox * ldg + 4 * l.q;
+    for (long long v = l.v; v < nvox; v += l.vstep) {
+      const float4 d = ld4(pd + v * lddy), yy = ld4_stream(py + v * ldy);
+      float4 o;
+      o.x = rs[0] * (d.x - m1[0] - yy.x * m2[0]); o.y = rs[1] * (d.y - m1[1] - yy.y * m2[1]);
+      o.z = rs[2] * (d.z - m1[2] - yy.z * m2[2]); o.w = rs[3] * (d.w - m1[3] - yy.w * m2[3]);
+      if (relu) {
+        o.x = yy.x > thr[0] ? o.x : 0.f; o.y = yy.y > thr[1] ? o.y : 0.f;
+        o.z = yy.z > thr[2] ? o.z : 0.f; o.w = yy.w > thr[3] ? o.w : 0.f;
+      }
+      st4(pg + v * ldg, o);
+      acc[0] += o.x; acc[1] += o.y; acc[2] += o.z; acc[3] += o.w;
+    }
+  }
+  if (dbias != nullptr) {
+    __shared__ float sh[THREADS][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sh[threadIdx.x][e] = l.active ? acc[e] : 0.f;
+    __syncthreads();
+    if ((int)threadIdx.x < Q) {
+      const int usable = (THREADS / Q) * Q;
+      float a[4] = {0, 0, 0, 0};
+      for (int i = threadIdx.x; i < usable; i += Q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[e] += sh[i][e];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(dbias + 4 * threadIdx.x + e, a[e]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) colsum_kernel(const float* __restrict__ g, long long ldg, float* dbias,
+                                                         long long rows, int C) {
+  const int Q = C / 4;
+  const Lane l = lane_of(Q, gridDim.x);
+  float acc[4] = {0, 0, 0, 0};
+  if (l.active)
+    for (long long v = l.v; v < rows; v += l.vstep) {
+      const float4 d = ld4_stream(g + v * ldg + 4 * l.q);
+      acc[0] += d.x; acc[1] += d.y; acc[2] += d.z; acc[3] += d.w;
+    }
+  __shared__ float sh[THREADS][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) sh[threadIdx.x][e] = l.active ? acc[e] : 0.f;
+  __syncthreads();
+  if ((int)threadIdx.x < Q) {
+    const int usable = (THREADS / Q) * Q;
+    float a[4] = {0, 0, 0, 0};
+    for (int i = threadIdx.x; i < usable; i += Q)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] += sh[i][e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) atomicAdd(dbias + 4 * threadIdx.x + e, a[e]);
+  }
+}
+
+// ---- resampling --------------------------------------------------------------------------------------------
+// torch's area_pixel_compute_source_index for align_corners=True: src = dst * (in - 1) / (out - 1) (0 if out == 1)
+__device__ __forceinline__ float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+__device__ __forceinline__ void ac_src(int dst, float scale, int in, int& i0, int& i1, float& w1) {
+  const float s = scale * (float)dst;
+  i0 = (int)s;
+  i0 = i0 > in - 1 ? in - 1 : i0;
+  i1 = i0 < in - 1 ? i0 + 1 : i0;
+  w1 = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(THREADS) trilinear_fwd_kernel(const float* __restrict__ x, long long ldx, float* y,
+                                                                long long ldy, int C, int Di, int Hi, int Wi, int Do,
+                                                                int Ho, int Wo, long long total) {
+  const int Q = C / 4;
+  const float sz = ac_scale(Di, Do), sy = ac_scale(Hi, Ho), sx = ac_scale(Wi, Wo);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Q);
+    long long v = i / Q;
+    const int xo = (int)(v % Wo); v /= Wo;
+    const int yo = (int)(v % Ho); v /= Ho;
+    const int zo = (int)(v % Do);
+    const long long b = v / Do;
+    int z0, z1, y0, y1, x0, x1;
+    float wz, wy, wx;
+    ac_src(zo, sz, Di, z0, z1, wz); ac_src(yo, sy, Hi, y0, y1, wy); ac_src(xo, sx, Wi, x0, x1, wx);
+    const float* base = x + 4 * q;
+    auto at = [&](int z, int yy, int xx) { return ld4(base + ((((long long)b * Di + z) * Hi + yy) * Wi + xx) * ldx); };
+    float4 o = f4(0.f);
+    auto fma4 = [&](float w, float4 a) { o.x += w * a.x; o.y += w * a.y; o.z += w * a.z; o.w += w * a.w; };
+    fma4((1 - wz) * (1 - wy) * (1 - wx), at(z0, y0, x0)); fma4((1 - wz) * (1 - wy) * wx, at(z0, y0, x1));
+    fma4((1 - wz) * wy * (1 - wx), at(z0, y1, x0));       fma4((1 - wz) * wy * wx, at(z0, y1, x1));
+    fma4(wz * (1 - wy) * (1 - wx), at(z1, y0, x0));       fma4(wz * (1 - wy) * wx, at(z1, y0, x1));
+    fma4(wz * wy * (1 - wx), at(z1, y1, x0));             fma4(wz * wy * wx, at(z1, y1, x1));
+    st4(y + ((((long long)b * Do + zo) * Ho + yo) * Wo + xo) * ldy + 4 * q, o);
+  }
+}
+
+// gather-form backward: input index i receives from outputs o with floor(scale*o) in {i-1, i}; the candidate range
+// is bracketed from the inverse map and every candidate re-evaluates the forward's own index / weight arithmetic
+__device__ __forceinline__ void ac_range(int i, float scale, int in, int out, int& lo, int& hi) {
+  if (scale <= 0.f) { lo = 0; hi = out - 1; return; }         // out == 1 or in == 1: everything reads index 0
+  const float inv = 1.f / scale;
+  lo = (int)floorf((float)(i - 1) * inv) - 1;
+  hi = (int)ceilf((float)(i + 1) * inv) + 1;
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > out - 1 ? out - 1 : hi;
+}
+__device__ __forceinline__ float ac_weight(int o, int i, float scale, int in) {
+  int i0, i1;
+  float w1;
+  ac_src(o, scale, in, i0, i1, w1);
+  float w = 0.f;
+  if (i0 == i) w += 1.f - w1;
+  if (i1 == i) w += w1;                                         // i0 == i1 at the last index: weights add to 1
+  return w;
+}
+
+__global__ void __launch_bounds__(THREADS) trilinear_bwd_kernel(const float* __restrict__ dy, long long lddy, float* dx,
+                                                                long long lddx, int C, int Di, int Hi, int Wi, int Do,
+                                                                int Ho, int Wo, long long total) {
+  const int Q = C / 4;
+  const float sz = ac_scale(Di, Do), sy = ac_scale(Hi, Ho), sx = ac_scale(Wi, Wo);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Q);
+    long long v = i / Q;
+    const int xi = (int)(v % Wi); v /= Wi;
+    const int yi = (int)(v % Hi); v /= Hi;
+    const int zi = (int)(v % Di);
+    const long long b = v / Di;
+    int zl, zh, yl, yh, xl, xh;
+    ac_range(zi, sz, Di, Do, zl, zh); ac_range(yi, sy, Hi, Ho, yl, yh); ac_range(xi, sx, Wi, Wo, xl, xh);
+    float4 o = f4(0.f);
+    for (int zo = zl; zo <= zh; ++zo) {
+      const float wz = ac_weight(zo, zi, sz, Di);
+      if (wz == 0.f) continue;
+      for (int yo = yl; yo <= yh; ++yo) {
+        const float wy = ac_weight(yo, yi, sy, Hi);
+        if (wy == 0.f) continue;
+        for (int xo = xl; xo <= xh; ++xo) {
+          const float wx = ac_weight(xo, xi, sx, Wi);
+          if (wx == 0.f) continue;
+          const float4 d = ld4(dy + ((((long long)b * Do + zo) * Ho + yo) * Wo + xo) * lddy + 4 * q);
+          const float w = wz * wy * wx;
+          o.x += w * d.x; o.y += w * d.y; o.z += w * d.z; o.w += w * d.w;
+        }
+      }
+    }
+    st4(dx + ((((long long)b * Di + zi) * Hi + yi) * Wi + xi) * lddx + 4 * q, o);
+  }
+}
+
+// torch 'nearest': src = min(floor(dst * (in / out)), in - 1) in float arithmetic
+__device__ __forceinline__ int nn_src(int dst, float scale, int in) {
+  const int s = (int)floorf((float)dst * scale);
+  return s < in - 1 ? s : in - 1;
+}
+__global__ void __launch_bounds__(THREADS) nearest_fwd_kernel(const float* __restrict__ x, long long ldx, float* y,
+                                                              long long ldy, int C, int Di, int Hi, int Wi, int Do,
+                                                              int Ho, int Wo, long long total) {
+  const int Q = C / 4;
+  const float sz = (float)Di / (float)Do, sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % Q);
+    long long v = i / Q;
+    const int xo = (int)(v % Wo); v /= Wo;
+    const int yo = (int)(v % Ho); v /= Ho;
+    const int zo = (int)(v % Do);
+    const long long b = v / Do;
+    const long long sv = (((long long)b * Di + nn_src(zo, sz, Di)) * Hi + nn_src(yo, sy, Hi)) * Wi + nn_src(xo, sx, Wi);
+    st4(y + ((((long long)b * Do + zo) * Ho + yo) * Wo + xo) * ldy + 4 * q, ld4(x + sv * ldx + 4 * q));
+  }
+}
+__device__ __forceinline__ void nn_range(int i, float scale, int in, int out, int& lo, int& hi) {
+  const float inv = 1.f / scale;
+  lo = (int)floorf((float)i * inv) - 1;
+  hi = (int)ceilf((float)(i + 1) * inv) + 1;
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > out - 1 ? out - 1 : hi;
+  while (lo <= hi && nn_src(lo, scale, in) != i) ++lo;
+  while (hi >= lo && nn_src(hi, scale, in) != i) --hi;
+}
+// one warp per (input voxel, channel quad group): lanes stride the contributing output voxels, then shuffle-reduce
+__global__ void __launch_bounds__(THREADS) nearest_bwd_kernel(const float* __restrict__ dy, long long lddy, float* dx,
+                                                              long long lddx, int C, int Di, int Hi, int Wi, int Do,
+                                                              int Ho, int Wo, long long total_warps) {
+  const int Q = C / 4, lane = threadIdx.x & 31;
+  const float sz = (float)Di / (float)Do, sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= total_warps) return;
+  const int q = (int)(wid % Q);
+  long long v = wid / Q;
+  const int xi = (int)(v % Wi); v /= Wi;
+  const int yi = (int)(v % Hi); v /= Hi;
+  const int zi = (int)(v % Di);
+  const long long b = v / Di;
+  int zl, zh, yl, yh, xl, xh;
+  nn_range(zi, sz, Di, Do, zl, zh); nn_range(yi, sy, Hi, Ho, yl, yh); nn_range(xi, sx, Wi, Wo, xl, xh);
+  const int nz = zh - zl + 1, ny = yh - yl + 1, nx = xh - xl + 1;
+  float4 o = f4(0.f);
+  if (nz > 0 && ny > 0 && nx > 0)
+    for (int j = lane; j < nz * ny * nx; j += 32) {
+      const int xo = xl + j % nx, yo = yl + (j / nx) % ny, zo = zl + j / (nx * ny);
+      const float4 d = ld4_stream(dy + ((((long long)b * Do + zo) * Ho + yo) * Wo + xo) * lddy + 4 * q);
+      o.x += d.x; o.y += d.y; o.z += d.z; o.w += d.w;
+    }
+  o.x = warp_sum(o.x); o.y = warp_sum(o.y); o.z = warp_sum(o.z); o.w = warp_sum(o.w);
+  if (lane == 0) st4(dx + ((((long long)b * Di + zi) * Hi + yi) * Wi + xi) * lddx + 4 * q, o);
+}
+
+static int grid_for(long long nvox, int Q) {
+  const int rows = ((THREADS / Q) * Q) / Q;
+  long long blocks = (nvox + (long long)rows * 8 - 1) / ((long long)rows * 8);      // ~8 voxels per thread
+  const long long cap = (long long)num_sms() * 16;
+  blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
+  return (int)blocks;
+}
+
+}  // namespace vol
+}  // namespace corrif
+
+using namespace corrif;
+using namespace corrif::vol;
+
+#define VOL_CHECK(p, ld, C, what)                                                                          \
+  CORRIF_REQUIRE((p) != nullptr && ((uintptr_t)(p) % 16) == 0 && (C) > 0 && (C) % 4 == 0 && (ld) % 4 == 0 && \
+                     (ld) >= (C) && (C) / 4 <= THREADS,                                                      \
+                 what ": volume must be 16-byte aligned with C %% 4 == 0, ld %% 4 == 0, ld >= C")
+
+extern "C" int corrif_instnorm_apply(float* x, int64_t ld, const double* stats, float* mean, float* rstd, int32_t B,
+                                     int64_t nvox, int32_t C, float eps, void* stream) {
+  VOL_CHECK(x, ld, C, "instnorm_apply");
+  CORRIF_REQUIRE(stats && mean && rstd && B > 0 && nvox > 0, "instnorm_apply: null statistics / empty volume");
+  dim3 grid(grid_for(nvox, C / 4), B);
+  instnorm_apply_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(x, ld, stats, mean, rstd, nvox, C, eps);
+  return launch_status("instnorm_apply");
+}
+
+extern "C" int corrif_instnorm_bwd_stats(const float* dy, int64_t lddy, const float* y, int64_t ldy, double* sums,
+                                         int32_t B, int64_t nvox, int32_t C, void* stream) {
+  VOL_CHECK(dy, lddy, C, "instnorm_bwd_stats(dy)");
+  VOL_CHECK(y, ldy, C, "instnorm_bwd_stats(y)");
+  CORRIF_REQUIRE(sums && B > 0 && nvox > 0, "instnorm_bwd_stats: null sums / empty volume");
+  dim3 grid(grid_for(nvox, C / 4), B);
+  instnorm_bwd_stats_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, sums, nvox, C);
+  return launch_status("instnorm_bwd_stats");
+}
+
+extern "C" int corrif_instnorm_relu_bwd_apply(const float* dy, int64_t lddy, const float* y, int64_t ldy,
+                                              const float* mean, const float* rstd, const double* sums, float* g,
+                                              int64_t ldg, float* dbias, int32_t B, int64_t nvox, int32_t C,
+                                              int32_t relu, void* stream) {
+  VOL_CHECK(dy, lddy, C, "instnorm_relu_bwd_apply(dy)");
+  VOL_CHECK(y, ldy, C, "instnorm_relu_bwd_apply(y)");
+  VOL_CHECK(g, ldg, C, "instnorm_relu_bwd_apply(g)");
+  CORRIF_REQUIRE(mean && rstd && sums && B > 0 && nvox > 0, "instnorm_relu_bwd_apply: null statistics / empty volume");
+  dim3 grid(grid_for(nvox, C / 4), B);
+  instnorm_relu_bwd_apply_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, mean, rstd, sums, g, ldg,
+                                                                             dbias, nvox, C, relu);
+  return launch_status("instnorm_relu_bwd_apply");
+}
+
+extern "C" int corrif_volume_colsum(const float* g, int64_t ldg, float* dbias, int64_t rows, int32_t C, void* stream) {
+  VOL_CHECK(g, ldg, C, "volume_colsum");
+  CORRIF_REQUIRE(dbias && rows > 0, "volume_colsum: null output / empty volume");
+  colsum_kernel<<<grid_for(rows, C / 4), THREADS, 0, (cudaStream_t)stream>>>(g, ldg, dbias, rows, C);
+  return launch_status("volume_colsum");
+}
+
+static int resize_check(const void* x, int64_t ldx, const void* y, int64_t ldy, int B, int C, int Di, int Hi, int Wi,
+                        int Do, int Ho, int Wo) {
+  VOL_CHECK(x, ldx, C, "resize(in)");
+  VOL_CHECK(y, ldy, C, "resize(out)");
+  CORRIF_REQUIRE(B > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "resize: empty volume");
+  return 0;
+}
+static unsigned flat_grid(long long total) {
+  long long blocks = (total + THREADS - 1) / THREADS;
+  const long long cap = (long long)num_sms() * 32;
+  return (unsigned)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+}
+
+extern "C" int corrif_resize_trilinear_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int32_t B, int32_t C,
+                                           int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo,
+                                           void* stream) {
+  int rc = resize_check(x, ldx, y, ldy, B, C, Di, Hi, Wi, Do, Ho, Wo);
+  if (rc) return rc;
+  const long long total = (long long)B * Do * Ho * Wo * (C / 4);
+  trilinear_fwd_kernel<<<flat_grid(total), THREADS, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, C, Di, Hi, Wi, Do, Ho, Wo, total);
+  return launch_status("resize_trilinear_fwd");
+}
+extern "C" int corrif_resize_trilinear_bwd(const float* dy, int64_t lddy, float* dx, int64_t lddx, int32_t B, int32_t C,
+                                           int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo,
+                                           void* stream) {
+  int rc = resize_check(dx, lddx, dy, lddy, B, C, Di, Hi, Wi, Do, Ho, Wo);
+  if (rc) return rc;
+  const long long total = (long long)B * Di * Hi * Wi * (C / 4);
+  trilinear_bwd_kernel<<<flat_grid(total), THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, lddx, C, Di, Hi, Wi, Do, Ho, Wo, total);
+  return launch_status("resize_trilinear_bwd");
+}
+extern "C" int corrif_resize_nearest_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int32_t B, int32_t C,
+                                         int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo,
+                                         void* stream) {
+  int rc = resize_check(x, ldx, y, ldy, B, C, Di, Hi, Wi, Do, Ho, Wo);
+  if (rc) return rc;
+  const long long total = (long long)B * Do * Ho * Wo * (C / 4);
+  nearest_fwd_kernel<<<flat_grid(total), THREADS, 0, (cudaStream_t)stream>>>(x, ldx, y, ldy, C, Di, Hi, Wi, Do, Ho, Wo, total);
+  return launch_status("resize_nearest_fwd");
+}
+extern "C" int corrif_resize_nearest_bwd(const float* dy, int64_t lddy, float* dx, int64_t lddx, int32_t B, int32_t C,
+                                         int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo,
+                                         void* stream) {
+  int rc = resize_check(dx, lddx, dy, lddy, B, C, Di, Hi, Wi, Do, Ho, Wo);
+  if (rc) return rc;
+  const long long warps = (long long)B * Di * Hi * Wi * (C / 4);
+  const long long blocks = (warps * 32 + THREADS - 1) / THREADS;
+  nearest_bwd_kernel<<<(unsigned)blocks, THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, lddx, C, Di, Hi, Wi, Do, Ho, Wo, warps);
+  return launch_status("resize_nearest_bwd");
+}

@@ -3,12 +3,15 @@ contract ([B,3,3,H,W] -> [B,3,1,224,224] sigmoid probabilities) and the SAME 114
 and shapes, so ``iremmodel{i}.pt`` / ``Finaliremmodel{i}.pt`` checkpoints load strictly in both
 directions (reference F4_TRAIN.py:84-86,180).
 
-What differs is only where the fusion hot path (reference mmvit4.py:456-529) runs: here it is one
-call to ``torch.ops.corrif.fusion_block`` (hand-written sm_100a kernels behind the C ABI, see
-include/corrif.h), forward and backward.  The modality encoders, the early-fusion blocks and the
-decoder are outside the hot path (SURVEY.md section 8f ranks them "next") and run on stock PyTorch /
-cuDNN; they are re-stated here from the architecture description, table-driven, because the class
-has to own their parameters under the reference's names.
+What differs is where the work runs.  The fusion hot path (reference mmvit4.py:456-529) is one call to
+``torch.ops.corrif.fusion_block``; the six EarlyFusionBlocks (:64-81, 449-454) and the whole decoder
+(:29-56, 222-292) run on the channels-last volume kernels of corrif_b200.volume (conv -> ReLU ->
+InstanceNorm as one fused block with a hand-written backward, trilinear / nearest resizes) - all
+hand-written sm_100a kernels behind the C ABI (include/corrif.h).  Only the modality encoders'
+ResNet-50 trunks (carried on stock PyTorch / cuDNN) and the final 8 -> 3
+channel 1x1x1 convolution + sigmoid on the 224^2 output remain ATen calls.  The sub-modules are
+re-stated here from the architecture description, table-driven, because the class has to own their
+parameters under the reference's names.
 """
 from __future__ import annotations
 
@@ -24,6 +27,7 @@ if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 from corrif_b200 import fusion as _fusion  # noqa: E402
 from corrif_b200 import module as _module  # noqa: E402  (registers torch.ops.corrif.*)
+from corrif_b200 import volume as _V  # noqa: E402
 
 basic_dims = 8
 transformer_basic_dims = 512
@@ -99,30 +103,40 @@ class Encoder(nn.Module):
 
 
 class EarlyFusionBlock(nn.Module):
+    """cat(3 modalities) -> 1x1x1 conv -> ReLU -> InstanceNorm3d (reference mmvit4.py:64-81) as ONE fused block on
+    channels-last volumes: the three sources are concatenated by the convolution's loader.  Takes the encoders'
+    [B,c,D,H,W] maps, returns a volume [B,D,H,W,3c]."""
+
     def __init__(self, in_channels):
         super().__init__()
         c = num_modals * in_channels
-        self.conv = nn.Conv3d(c, c, kernel_size=1)
-        self.act = nn.ReLU(inplace=True)
-        self.norm = nn.InstanceNorm3d(c)
+        self.conv = nn.Conv3d(c, c, kernel_size=1)          # parameter holder: keys conv.weight / conv.bias
+        self.norm = nn.InstanceNorm3d(c)                    # no parameters, no buffers (affine=False)
 
     def forward(self, a, b, c):
-        return self.norm(self.act(self.conv(torch.cat([a, b, c], dim=1))))
+        srcs = [_V.to_channels_last(t) for t in (a, b, c)]
+        return _V.conv_block(srcs, self.conv.weight, self.conv.bias, 1, _V.PAD_ZEROS)
 
 
 # ----------------------------------------------------------------------------------------------
-# decoder (reference mmvit4.py:29-56, 222-292)
+# decoder (reference mmvit4.py:29-56, 222-292) on channels-last volumes [B,D,H,W,C]
 # ----------------------------------------------------------------------------------------------
 class general_conv3d_prenorm(nn.Module):
+    """Conv3d (k=1 or 3, stride 1, 'same' padding of pad_type) -> ReLU -> InstanceNorm3d (reference mmvit4.py:29-45)
+    as one fused block: padding resolved by the convolution's loader, norm statistics from its epilogue.
+    ``forward(*sources)`` convolves the channel concatenation of its sources (the reference's torch.cat, :272)."""
+
     def __init__(self, in_ch, out_ch, k_size=3, stride=1, padding=1, pad_type="zeros"):
         super().__init__()
+        if stride != 1 or padding != k_size // 2 or k_size not in (1, 3):
+            raise ValueError("general_conv3d_prenorm: the model only uses stride 1, 'same' padding, k in {1,3}")
         self.conv = nn.Conv3d(in_ch, out_ch, k_size, stride=stride, padding=padding,
                               padding_mode=pad_type, bias=True)
         self.norm = nn.InstanceNorm3d(out_ch)
-        self.activation = nn.ReLU(inplace=True)
+        self.k, self.pad_mode = k_size, (_V.PAD_REPLICATE if pad_type == "replicate" else _V.PAD_ZEROS)
 
-    def forward(self, x):
-        return self.norm(self.activation(self.conv(x)))
+    def forward(self, *xs):
+        return _V.conv_block(xs, self.conv.weight, self.conv.bias, self.k, self.pad_mode)
 
 
 class fusion_prenorm(nn.Module):
@@ -155,16 +169,20 @@ class Decoder_fuse(nn.Module):
         self.RFM5 = fusion_prenorm(192)
         self.RFM5_reduce = nn.Conv3d(192, 128, kernel_size=1)
         self.final_conv = nn.Conv3d(8, 3, kernel_size=1)
-        self.up2 = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)
-        self.up_to_224 = nn.Upsample(size=(1, 224, 224), mode="trilinear", align_corners=True)
 
     def forward(self, x1, x2, x3, x4, x5):
-        y = self.RFM5_reduce(self.RFM5(x5))
+        """x1..x4: early-fusion volumes [B,D,H,W,C]; x5: x6_inter [B,8,8,8,192] -> sigmoid probs [B,3,1,224,224]."""
+        y = self.RFM5(x5)
+        y = _V.conv_block([y], self.RFM5_reduce.weight, self.RFM5_reduce.bias, 1, relu=False, norm=False)
         for (lvl, _, _, _, cube), skip in zip(self._LEVELS, (x4, x3, x2, x1)):
-            y = getattr(self, f"d{lvl}_c1")(self.up2(y))
-            s = F.interpolate(getattr(self, f"RFM{lvl}")(skip), (cube, cube, cube))
-            y = getattr(self, f"d{lvl}_out")(getattr(self, f"d{lvl}_c2")(torch.cat((s, y), dim=1)))
-        return torch.sigmoid(self.final_conv(self.up_to_224(y)))
+            up = _V.resize_trilinear(y, tuple(2 * d for d in y.shape[1:4]))                 # self.up2 (:269)
+            y = getattr(self, f"d{lvl}_c1")(up)
+            s = _V.resize_nearest(getattr(self, f"RFM{lvl}")(skip), (cube, cube, cube))     # F.interpolate (:271)
+            y = getattr(self, f"d{lvl}_out")(getattr(self, f"d{lvl}_c2")(s, y))             # cat((s, y)) (:272)
+        # nn.Upsample(size=(1,224,224), trilinear, align_corners=True) (:263, 288): with ONE output slice along
+        # depth the source index is 0 for every output voxel, i.e. only depth slice 0 of the 128^3 volume is read
+        top = _V.resize_trilinear(y[:, 0:1], (1, 224, 224))
+        return torch.sigmoid(self.final_conv(_V.to_channels_first(top)))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -216,7 +234,7 @@ class MMVit4(nn.Module):
         fused_x1, fused_x2, fused_x3, fused_x4, fused_x6 = fused          # fusion5's output is unused
         p = self.dropout_rate if self.training else 0.0
         self._step += 1
-        x6_inter = torch.ops.corrif.fusion_block(feats[0][5], feats[1][5], feats[2][5], fused_x6,
+        x6_inter = torch.ops.corrif.fusion_block(feats[0][5], feats[1][5], feats[2][5], _V.to_channels_first(fused_x6),
                                                  self.fusion_parameters(), p,
                                                  self.base_seed + self._step, self.precision)
-        return self.decoder_fuse(fused_x1, fused_x2, fused_x3, fused_x4, x6_inter)
+        return self.decoder_fuse(fused_x1, fused_x2, fused_x3, fused_x4, _V.to_channels_last(x6_inter))

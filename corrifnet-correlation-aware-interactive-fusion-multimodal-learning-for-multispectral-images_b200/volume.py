@@ -1,0 +1,264 @@
+"""Channels-last 3-D volume operators of the blocks either side of the fusion hot path (SURVEY.md section 8f rows
+N1 / N2): ``conv_block`` = Conv3d (1x1x1 or 3x3x3, replicate / zero padding) -> ReLU -> InstanceNorm3d, i.e. the
+reference's ``general_conv3d_prenorm`` (mmvit4.py:29-45) and ``EarlyFusionBlock`` (:64-81, with three sources), the
+bias-only 1x1x1 convolutions, and the trilinear / nearest resizes of the decoder (:260-288), each with a hand-written
+backward, as torch.autograd Functions over libcorrif_b200 kernels (include/corrif.h, "volume operators").
+
+A volume is a tensor [B, D, H, W, C] whose channel stride is 1 and whose voxel stride ``ld`` is uniform - a
+contiguous tensor or a channel slice of one.  ``torch.cat`` along channels never happens: a convolution takes up to
+three sources and concatenates them inside its loader, and its data gradient is one buffer whose channel slices are
+returned as the sources' gradients.
+
+What is saved for the backward of a block: its sources (alive anyway: they are the previous blocks' outputs), its
+OUTPUT y (alive anyway: the next block's source) and 2 x B x C statistics.  The ReLU mask is recovered from y
+(r > 0 <=> y > (0 - mean) * rstd, the forward's own arithmetic), so no pre-activation or post-ReLU tensor is kept:
+stock PyTorch keeps the padded input, the conv output and the ReLU output of every block.
+
+No CPU path: CUDA fp32 tensors only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+from ._lib import PAD_REPLICATE, PAD_ZEROS  # noqa: F401
+
+EPS = 1e-5          # nn.InstanceNorm3d default (mmvit4.py:24)
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Voxel stride of a channels-last volume view, or raise."""
+    if t.dim() != 5 or not t.is_cuda or t.dtype != torch.float32:
+        raise ValueError("volume ops need CUDA fp32 tensors of shape [B, D, H, W, C] (no CPU fallback)")
+    B, D, H, W, Cc = t.shape
+    st = t.stride()
+    inner = {3: 1, 2: W, 1: H * W, 0: D * H * W}              # voxels spanned by one step along each axis
+    ld = Cc
+    for ax in (3, 2, 1, 0):
+        if t.shape[ax] > 1:
+            ld = st[ax] // inner[ax]
+            break
+    ok = (st[4] == 1 or Cc == 1) and all(t.shape[ax] == 1 or st[ax] == inner[ax] * ld for ax in (3, 2, 1, 0))
+    if not ok or ld < Cc or ld % 4 or Cc % 4 or t.data_ptr() % 16:
+        raise ValueError("not a channels-last volume view: shape %s strides %s" % (tuple(t.shape), st))
+    return ld
+
+
+def as_volume(t: torch.Tensor) -> torch.Tensor:
+    """Return ``t`` if it already is a valid volume view, else a contiguous copy."""
+    try:
+        _ld(t)
+        return t
+    except ValueError:
+        return t.contiguous()
+
+
+def to_channels_last(x: torch.Tensor) -> torch.Tensor:
+    """[B, C, D, H, W] (any strides) -> volume [B, D, H, W, C]; free when x is in channels_last_3d memory format."""
+    return as_volume(x.permute(0, 2, 3, 4, 1))
+
+
+def to_channels_first(v: torch.Tensor) -> torch.Tensor:
+    """volume [B, D, H, W, C] -> logical [B, C, D, H, W] view (channels_last_3d strides; no copy)."""
+    return v.permute(0, 4, 1, 2, 3)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _desc(srcs: Sequence[torch.Tensor], Cout: int, ksize: int, pad_mode: int) -> L.Conv3dDesc:
+    d = L.Conv3dDesc()
+    B, D, H, W = srcs[0].shape[:4]
+    cin = 0
+    for i, s in enumerate(srcs):
+        if tuple(s.shape[:4]) != (B, D, H, W):
+            raise ValueError("sources of a convolution must share [B, D, H, W]")
+        d.src[i].p, d.src[i].C, d.src[i].ld = s.data_ptr(), s.shape[4], _ld(s)
+        cin += s.shape[4]
+    d.nsrc, d.B, d.D, d.H, d.W, d.Cin, d.Cout = len(srcs), B, D, H, W, cin, Cout
+    d.ksize, d.pad_mode = ksize, pad_mode
+    return d
+
+
+def pack_weights(weight: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
+    """[Cout, Cin, k, k, k] -> the kernels' fragment-ordered TF32 operand (forward, or data-gradient form)."""
+    Cout, Cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
+    n = ops.lib().corrif_conv3d_pack_floats(Cin, Cout, k)
+    if n <= 0:
+        raise ValueError("conv3d: Cin (%d) and Cout (%d) must be multiples of 8, kernel 1 or 3" % (Cin, Cout))
+    w = weight.detach().contiguous()
+    wpk = torch.zeros(n, device=weight.device, dtype=torch.float32)
+    with ops._rec("conv_pack", 8.0 * w.numel()):
+        L.check(ops.lib().corrif_conv3d_pack_weights(w.data_ptr(), wpk.data_ptr(), Cin, Cout, k, int(transpose_flip),
+                                                     _stream()), "conv3d_pack_weights")
+    ops._count()
+    return wpk
+
+
+def conv3d_forward(srcs, wpk, bias, Cout, ksize, pad_mode, relu, out, stats=None):
+    d = _desc(srcs, Cout, ksize, pad_mode)
+    d.relu, d.wpk, d.bias = int(relu), wpk.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    d.out, d.ldo, d.stats = out.data_ptr(), _ld(out), (stats.data_ptr() if stats is not None else None)
+    nvox = d.B * d.D * d.H * d.W
+    taps = 27 if ksize == 3 else 1
+    # algorithmic work: 2 * voxels * taps * Cin * Cout FLOP; bytes = read every source once + write the output once
+    with ops._rec("conv3d_fwd", 2.0 * nvox * taps * d.Cin * Cout, "k%d %dx%dx%dx%d %d->%d bytes=%d" % (
+            ksize, d.B, d.D, d.H, d.W, d.Cin, Cout, 4 * nvox * (d.Cin + Cout))):
+        L.check(ops.lib().corrif_conv3d_fwd(C.byref(d), _stream()), "conv3d_fwd")
+    ops._count()
+
+
+def conv3d_wgrad(srcs, g, dW, ksize, pad_mode):
+    Cout = g.shape[4]
+    d = _desc(srcs, Cout, ksize, pad_mode)
+    nvox = d.B * d.D * d.H * d.W
+    taps = 27 if ksize == 3 else 1
+    with ops._rec("conv3d_wgrad", 2.0 * nvox * taps * d.Cin * Cout, "k%d %dx%dx%dx%d %d->%d" % (
+            ksize, d.B, d.D, d.H, d.W, d.Cin, Cout)):
+        L.check(ops.lib().corrif_conv3d_wgrad(C.byref(d), g.data_ptr(), _ld(g), dW.data_ptr(), _stream()), "conv3d_wgrad")
+    ops._count()
+
+
+def conv3d_dgrad(g, weight, Cin, ksize, pad_mode, dx):
+    """dx [B,D,H,W,Cin] = d(cat of the sources) from g = d(pre-activation)."""
+    Cout = g.shape[4]
+    wpk_t = pack_weights(weight, transpose_flip=True)
+    d = _desc([g], Cin, ksize, PAD_ZEROS)
+    d.relu, d.wpk, d.bias, d.out, d.ldo, d.stats = 0, wpk_t.data_ptr(), None, dx.data_ptr(), _ld(dx), None
+    nvox = d.B * d.D * d.H * d.W
+    taps = 27 if ksize == 3 else 1
+    with ops._rec("conv3d_dgrad", 2.0 * nvox * taps * Cin * Cout, "k%d %dx%dx%dx%d %d->%d" % (
+            ksize, d.B, d.D, d.H, d.W, Cout, Cin)):
+        L.check(ops.lib().corrif_conv3d_fwd(C.byref(d), _stream()), "conv3d_dgrad")
+    ops._count()
+    if ksize == 3 and pad_mode == PAD_REPLICATE:
+        w = weight.detach().permute(2, 3, 4, 0, 1).contiguous()          # [27][Cout][Cin]: coalesced over ci
+        with ops._rec("conv3d_dgrad_border", 0.0):
+            L.check(ops.lib().corrif_conv3d_dgrad_border(g.data_ptr(), _ld(g), w.data_ptr(), dx.data_ptr(), _ld(dx),
+                                                         d.B, d.D, d.H, d.W, Cin, Cout, _stream()), "conv3d_dgrad_border")
+        ops._count()
+
+
+class _ConvBlock(torch.autograd.Function):
+    """conv (+bias) [-> ReLU] [-> InstanceNorm3d] over the channel concatenation of 1..3 volumes."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, ksize, pad_mode, relu, norm, *srcs):
+        if relu and not norm:
+            raise ValueError("conv_block: ReLU without InstanceNorm does not occur in the model and has no backward")
+        srcs = [as_volume(s) for s in srcs]
+        Cout = weight.shape[0]
+        B, D, H, W = srcs[0].shape[:4]
+        dev = weight.device
+        wpk = pack_weights(weight)
+        out = torch.empty(B, D, H, W, Cout, device=dev, dtype=torch.float32)
+        stats = torch.zeros(B, Cout, 2, device=dev, dtype=torch.float64) if norm else None
+        b = bias.detach().contiguous() if bias is not None else None
+        conv3d_forward(srcs, wpk, b, Cout, ksize, pad_mode, relu, out, stats)
+        mean = rstd = None
+        if norm:
+            mean = torch.empty(B, Cout, device=dev, dtype=torch.float32)
+            rstd = torch.empty(B, Cout, device=dev, dtype=torch.float32)
+            nvox = D * H * W
+            with ops._rec("instnorm_apply", 8.0 * B * nvox * Cout):
+                L.check(ops.lib().corrif_instnorm_apply(out.data_ptr(), Cout, stats.data_ptr(), mean.data_ptr(),
+                                                        rstd.data_ptr(), B, nvox, Cout, EPS, _stream()), "instnorm_apply")
+            ops._count()
+        ctx.cfg = (ksize, pad_mode, relu, norm, bias is not None, [s.shape[4] for s in srcs])
+        ctx.save_for_backward(weight, out if norm else None, mean, rstd, *srcs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        ksize, pad_mode, relu, norm, has_bias, chans = ctx.cfg
+        weight, y, mean, rstd, *srcs = ctx.saved_tensors
+        dy = as_volume(dy)
+        B, D, H, W, Cout = dy.shape
+        nvox = D * H * W
+        dev = dy.device
+        dbias = torch.zeros(Cout, device=dev, dtype=torch.float32) if has_bias else None
+        if norm:
+            sums = torch.zeros(B, Cout, 2, device=dev, dtype=torch.float64)
+            with ops._rec("instnorm_bwd_stats", 8.0 * B * nvox * Cout):
+                L.check(ops.lib().corrif_instnorm_bwd_stats(dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), sums.data_ptr(),
+                                                            B, nvox, Cout, _stream()), "instnorm_bwd_stats")
+            g = torch.empty(B, D, H, W, Cout, device=dev, dtype=torch.float32)
+            with ops._rec("instnorm_bwd_apply", 12.0 * B * nvox * Cout):
+                L.check(ops.lib().corrif_instnorm_relu_bwd_apply(
+                    dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(),
+                    g.data_ptr(), Cout, dbias.data_ptr() if has_bias else None, B, nvox, Cout, int(relu), _stream()),
+                    "instnorm_relu_bwd_apply")
+            ops._count(2)
+        else:
+            g = dy
+            if has_bias:
+                with ops._rec("volume_colsum", 4.0 * B * nvox * Cout):
+                    L.check(ops.lib().corrif_volume_colsum(g.data_ptr(), _ld(g), dbias.data_ptr(), B * nvox, Cout,
+                                                           _stream()), "volume_colsum")
+                ops._count()
+        dW = None
+        if ctx.needs_input_grad[0]:
+            dW = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+            conv3d_wgrad(srcs, g, dW, ksize, pad_mode)
+        dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
+        if any(ctx.needs_input_grad[6:]):
+            cin = sum(chans)
+            dx = torch.empty(B, D, H, W, cin, device=dev, dtype=torch.float32)
+            conv3d_dgrad(g, weight, cin, ksize, pad_mode, dx)
+            off = 0
+            for i, c in enumerate(chans):
+                if ctx.needs_input_grad[6 + i]:
+                    dsrcs[i] = dx[..., off:off + c]
+                off += c
+        return (dW, dbias, None, None, None, None, *dsrcs)
+
+
+def conv_block(srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor], ksize: int,
+               pad_mode: int = PAD_ZEROS, relu: bool = True, norm: bool = True) -> torch.Tensor:
+    """general_conv3d_prenorm / EarlyFusionBlock (relu=norm=True) or a plain biased convolution (relu=norm=False)
+    over cat(srcs, channels).  srcs and the result are channels-last volumes [B, D, H, W, C]."""
+    if not 1 <= len(srcs) <= 3:
+        raise ValueError("conv_block takes 1..3 sources")
+    return _ConvBlock.apply(weight, bias, ksize, pad_mode, relu, norm, *srcs)
+
+
+class _Resize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size, mode):
+        x = as_volume(x)
+        B, Di, Hi, Wi, Cc = x.shape
+        Do, Ho, Wo = size
+        y = torch.empty(B, Do, Ho, Wo, Cc, device=x.device, dtype=torch.float32)
+        fn = ops.lib().corrif_resize_trilinear_fwd if mode == "trilinear" else ops.lib().corrif_resize_nearest_fwd
+        with ops._rec("resize_" + mode + "_fwd", 4.0 * Cc * B * (Di * Hi * Wi + Do * Ho * Wo)):
+            L.check(fn(x.data_ptr(), _ld(x), y.data_ptr(), Cc, B, Cc, Di, Hi, Wi, Do, Ho, Wo, _stream()), "resize_fwd")
+        ops._count()
+        ctx.cfg = (mode, (Di, Hi, Wi), size)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        mode, (Di, Hi, Wi), (Do, Ho, Wo) = ctx.cfg
+        dy = as_volume(dy)
+        B, Cc = dy.shape[0], dy.shape[4]
+        dx = torch.empty(B, Di, Hi, Wi, Cc, device=dy.device, dtype=torch.float32)
+        fn = ops.lib().corrif_resize_trilinear_bwd if mode == "trilinear" else ops.lib().corrif_resize_nearest_bwd
+        with ops._rec("resize_" + mode + "_bwd", 4.0 * Cc * B * (Di * Hi * Wi + Do * Ho * Wo)):
+            L.check(fn(dy.data_ptr(), _ld(dy), dx.data_ptr(), Cc, B, Cc, Di, Hi, Wi, Do, Ho, Wo, _stream()), "resize_bwd")
+        ops._count()
+        return dx, None, None
+
+
+def resize_trilinear(x: torch.Tensor, size: Tuple[int, int, int]) -> torch.Tensor:
+    """F.interpolate(mode='trilinear', align_corners=True) / nn.Upsample on a channels-last volume."""
+    return _Resize.apply(x, tuple(int(s) for s in size), "trilinear")
+
+
+def resize_nearest(x: torch.Tensor, size: Tuple[int, int, int]) -> torch.Tensor:
+    """F.interpolate(x, size) (default nearest, mmvit4.py:271) on a channels-last volume."""
+    return _Resize.apply(x, tuple(int(s) for s in size), "nearest")

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CORRIF_ABI_VERSION 2
+#define CORRIF_ABI_VERSION 3
 
 #define CORRIF_EINVAL (-1)  /* bad argument (shape, alignment, null pointer) */
 #define CORRIF_EARCH  (-2)  /* device is not sm_100 */
@@ -299,6 +299,94 @@ int corrif_bce_probs_fwd_bwd(const float* x, const float* y, int64_t n, float gr
 int corrif_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                      float beta1, float beta2, float eps, float grad_scale, int32_t step,
                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Channels-last 3-D volume operators: the blocks either side of the fusion hot path (SURVEY.md section 8f rows
+ * N1 / N2).  A "volume" is [B, D, H, W, C] fp32 with channels contiguous and `ld` floats between consecutive
+ * voxels (ld >= C: a channel slice of a wider buffer is a valid volume, so the reference's torch.cat calls
+ * (mmvit4.py:77, 272-287) are just two producers writing into one buffer, or one consumer reading several
+ * sources).  C and ld are multiples of 4, pointers 16-byte aligned.
+ *
+ * corrif_conv3d_fwd: out = act(conv(cat(src...), W) + bias), stride 1, "same" padding, kernel 1x1x1 or 3x3x3,
+ *   as warp-level TF32 tensor-core MMAs over an input window staged once in shared memory.  Replaces nn.Conv3d
+ *   (+ F.pad replicate) + ReLU of general_conv3d_prenorm (mmvit4.py:29-45), EarlyFusionBlock (:64-81) and the
+ *   bias-only 1x1x1 convs (:231, :264, adapt1-5/conv6 :157-164).  If `stats` is given, sum and sum of squares of
+ *   the stored output are accumulated per (sample, channel): the InstanceNorm3d statistics (mmvit4.py:24) come
+ *   out of the convolution's epilogue instead of a second reduction pass.
+ *   The SAME kernel computes the data gradient: run it on d(pre-activation) with weights packed with
+ *   `transpose_flip` = 1 and zero padding; for replicate padding corrif_conv3d_dgrad_border then adds what the
+ *   clamped border taps contribute (replication_pad3d_backward without a padded tensor).
+ * corrif_conv3d_wgrad: dW[co][ci][tap] += sum_voxels x[voxel + tap][ci] * g[voxel][co]  (persistent CTAs keep the
+ *   partial weight gradient in registers across tiles; one atomic add per element and CTA at the end).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct corrif_vol_src {
+  const float* p;
+  int32_t C;
+  int32_t reserved;
+  int64_t ld;
+} corrif_vol_src;
+
+enum { CORRIF_PAD_ZEROS = 0, CORRIF_PAD_REPLICATE = 1 };
+
+typedef struct corrif_conv3d_desc {
+  corrif_vol_src src[3];      /* inputs, concatenated along channels in this order      */
+  int32_t nsrc;
+  int32_t B, D, H, W;
+  int32_t Cin, Cout;          /* Cin = sum of src[i].C; both multiples of 8             */
+  int32_t ksize;              /* 1 or 3                                                 */
+  int32_t pad_mode;           /* CORRIF_PAD_* (ignored for ksize 1)                     */
+  int32_t relu;               /* apply max(.,0) after the bias                          */
+  const float* wpk;           /* weights packed by corrif_conv3d_pack_weights           */
+  const float* bias;          /* [Cout] or NULL                                         */
+  float* out;                 /* [B,D,H,W,Cout] with voxel stride ldo                   */
+  int64_t ldo;
+  double* stats;              /* [B][Cout][2] += (sum, sum of squares) of out, or NULL  */
+} corrif_conv3d_desc;
+
+int corrif_sizeof_conv3d_desc(void);
+/* floats needed for the packed form of a [Cout, Cin, k, k, k] weight (0 on bad arguments) */
+int64_t corrif_conv3d_pack_floats(int32_t Cin, int32_t Cout, int32_t ksize);
+/* w: torch layout [Cout][Cin][k][k][k].  transpose_flip = 0: forward operand.  transpose_flip = 1: the operand of
+ * the data gradient (in/out channels swapped, taps mirrored); Cin / Cout are still those of the forward conv. */
+int corrif_conv3d_pack_weights(const float* w, float* wpk, int32_t Cin, int32_t Cout, int32_t ksize,
+                               int32_t transpose_flip, void* stream);
+int corrif_conv3d_fwd(const corrif_conv3d_desc* desc, void* stream);
+/* desc: src / geometry / ksize / pad_mode as in the forward (out, wpk, bias, stats ignored); g = d(pre-activation)
+ * [B,D,H,W,Cout] with stride ldg; dW: torch layout, accumulated. */
+int corrif_conv3d_wgrad(const corrif_conv3d_desc* desc, const float* g, int64_t ldg, float* dW, void* stream);
+/* dx[B,D,H,W,Cin] (stride ldx) += the replicate-padding part of the 3x3x3 data gradient; w_taps_major is the weight
+ * transposed to [27][Cout][Cin] (weight.permute(2,3,4,0,1)), so that threads of consecutive ci read consecutive words */
+int corrif_conv3d_dgrad_border(const float* g, int64_t ldg, const float* w_taps_major, float* dx, int64_t ldx, int32_t B,
+                               int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream);
+
+/* InstanceNorm3d (affine=False, eps, biased variance; mmvit4.py:24) after ReLU, in place on a volume:
+ * y = (r - mean) * rstd with the statistics the convolution accumulated; also writes mean / rstd [B][C] for the
+ * backward.  Backward of ReLU -> InstanceNorm given dy and the saved OUTPUT y (the ReLU mask is recovered from y:
+ * r > 0  <=>  y > (0 - mean) * rstd, evaluated with the forward's arithmetic):
+ *   sums[b][c] = (sum dy, sum dy*y)                                              (..._bwd_stats)
+ *   g = [r > 0] * rstd * (dy - sum_dy / n - y * sum_dyy / n);  dbias[c] += sum g   (..._bwd_apply) */
+int corrif_instnorm_apply(float* x, int64_t ld, const double* stats, float* mean, float* rstd, int32_t B,
+                          int64_t nvox, int32_t C, float eps, void* stream);
+int corrif_instnorm_bwd_stats(const float* dy, int64_t lddy, const float* y, int64_t ldy, double* sums, int32_t B,
+                              int64_t nvox, int32_t C, void* stream);
+int corrif_instnorm_relu_bwd_apply(const float* dy, int64_t lddy, const float* y, int64_t ldy, const float* mean,
+                                   const float* rstd, const double* sums, float* g, int64_t ldg, float* dbias,
+                                   int32_t B, int64_t nvox, int32_t C, int32_t relu, void* stream);
+/* dbias[c] += sum over voxels of g (bias gradient of a convolution without norm) */
+int corrif_volume_colsum(const float* g, int64_t ldg, float* dbias, int64_t rows, int32_t C, void* stream);
+
+/* Trilinear resize with align_corners=True (nn.Upsample / F.interpolate, mmvit4.py:187-191, 260, 269-285) and
+ * nearest resize (F.interpolate default, mmvit4.py:271-286) on channels-last volumes, forward and backward
+ * (backward in gather form: every input voxel sums its few contributing output voxels - no atomics; `dx` is
+ * overwritten). */
+int corrif_resize_trilinear_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int32_t B, int32_t C,
+                                int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo, void* stream);
+int corrif_resize_trilinear_bwd(const float* dy, int64_t lddy, float* dx, int64_t lddx, int32_t B, int32_t C,
+                                int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo, void* stream);
+int corrif_resize_nearest_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int32_t B, int32_t C,
+                              int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo, void* stream);
+int corrif_resize_nearest_bwd(const float* dy, int64_t lddy, float* dx, int64_t lddx, int32_t B, int32_t C,
+                              int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,7 @@ def test_library_exports_every_header_symbol(lib):
 def test_ctypes_prototypes_cover_header(lib):
     from corrif_b200 import _lib
     assert sorted(_lib.PROTOTYPES) == header_symbols()
-    assert lib.corrif_abi_version() == 2
+    assert lib.corrif_abi_version() == 3
 
 
 def test_gemm_desc_layout_matches_c_struct(lib):

@@ -27,3 +27,22 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step((images, masks))
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=35, max_name_column_width=60))
+
+# per-launch CUDA-event times of the library's own kernels in one step (volume ops with their shapes)
+from corrif_b200 import ops  # noqa: E402
+with ops.profile() as rec:
+    step((images, masks))
+rows = rec.details()
+agg = {}
+for cls, detail, ms, work in rows:
+    key = (cls, detail.split(" bytes=")[0])
+    a = agg.setdefault(key, [0, 0.0, 0.0])
+    a[0] += 1; a[1] += ms; a[2] += work
+print("\n# libcorrif_b200 launches of one micro-batch step (CUDA events per launch; serialised, so the sum exceeds the step)")
+print("%-22s %-34s %6s %10s %12s" % ("kernel", "shape", "n", "ms", "TFLOP/s|GB/s"))
+tot = 0.0
+for (cls, detail), (n, ms, work) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+    rate = work / (ms * 1e-3) / (1e12 if cls.startswith(("conv3d", "gemm", "attn")) else 1e9) if ms > 0 else 0
+    print("%-22s %-34s %6d %10.3f %12.1f" % (cls, detail[:34], n, ms, rate))
+    tot += ms
+print("total of listed: %.2f ms" % tot)
