@@ -80,51 +80,91 @@ __device__ __forceinline__ float4 load_cat4_raw(const Src (&src)[MAX_SRC], int n
   return make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Round-to-nearest TF32 for values on their way into an MMA operand: add half a TF32 ulp and let the tensor core
+// truncate the low 13 bits (ties away from zero, like cvt.rna; finite inputs only; the low bits stay dirty).
+// One integer add per element instead of the four instructions cvt.rna.tf32 expands to.
+__device__ __forceinline__ float4 rnd4(float4 v) {
+  v.x = __uint_as_float(__float_as_uint(v.x) + 0x1000u); v.y = __uint_as_float(__float_as_uint(v.y) + 0x1000u);
+  v.z = __uint_as_float(__float_as_uint(v.z) + 0x1000u); v.w = __uint_as_float(__float_as_uint(v.w) + 0x1000u);
+  return v;
+}
+
 // Stage the input window of one tile for channels [c0, c0 + kc) into shared memory.
 //   KS == 3: window voxel (hz,hy,hx) = input voxel (z0+hz-1, y0+hy-1, x0+hx-1), out-of-volume coordinates are
 //            clamped (replicate padding, mmvit4.py:225-236 pad_type='replicate') or read as zeros (the RFM blocks'
 //            default zero padding, mmvit4.py:47-56)
 //   KS == 1: the tile is 256 consecutive voxels of sample b starting at v0
-// Loads are issued in batches of 8 per thread BEFORE any of them is stored: with a load -> store pair per
-// iteration every 16 bytes paid a full DRAM round trip (measured: 6.7 ms for the 32 -> 8 channel 128^3 layer, of
-// which the MMAs are ~1 ms).
+// A thread keeps ONE (x, channel group) for the whole window and walks its 60 (z, y) lines, so the source tensor of
+// the concatenation, its stride and the clamped x are resolved once per pass instead of once per 16 bytes (the
+// first version spent 70 % of the kernel's instructions on per-item index arithmetic).  Loads are issued in batches
+// of 8-10 BEFORE any of them is stored (a load -> store pair per iteration pays a DRAM round trip per 16 bytes).
 template <int KS>
 __device__ __forceinline__ void stage_window(uint32_t smem_in, const Src (&src)[MAX_SRC], int nsrc, const Geom& g,
                                              int b, int z0, int y0, int x0, long long v0, long long nvox,
                                              int c0, int kc, bool replicate) {
   const int gshift = kc == 32 ? 3 : (kc == 16 ? 2 : 1);      // channel groups per voxel = kc / 4 (8, 4 or 2)
   const int groups = 1 << gshift;
-  constexpr int NV = KS == 3 ? WIN_VOX : TILE_VOX;
   constexpr int CGS = KS == 3 ? CGS3 : CGS1;
-  constexpr int U = 8;
-  const int total = NV << gshift;
-  for (int base = threadIdx.x; base < total; base += NTHREADS * U) {
-    float4 v[U];
+  // the thread's channel group -> source tensor (fixed for the pass)
+  const int cg = threadIdx.x & (groups - 1);
+  const float* sp = nullptr;
+  long long sld = 0;
+  {
+    int c = c0 + cg * 4;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * NTHREADS;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < total) {
-        const int cg = i & (groups - 1), hv = i >> gshift;
-        if (KS == 3) {
-          const int hx = hv % HX, hy = (hv / HX) % HY, hz = hv / (HX * HY);
-          int z = z0 + hz - 1, y = y0 + hy - 1, x = x0 + hx - 1;
-          bool inside = z >= 0 && z < g.D && y >= 0 && y < g.H && x >= 0 && x < g.W;
-          if (replicate) {
-            z = min(max(z, 0), g.D - 1); y = min(max(y, 0), g.H - 1); x = min(max(x, 0), g.W - 1);
-            inside = true;
-          }
-          if (inside) v[u] = load_cat4_raw(src, nsrc, (((long long)b * g.D + z) * g.H + y) * g.W + x, c0 + cg * 4);
-        } else {
-          const long long vv = v0 + hv;
-          if (vv < nvox) v[u] = load_cat4_raw(src, nsrc, (long long)b * nvox + vv, c0 + cg * 4);
+    for (int s = 0; s < MAX_SRC; ++s)
+      if (s < nsrc && sp == nullptr) {
+        if (c < src[s].C) { sp = src[s].p + c; sld = src[s].ld; }
+        else c -= src[s].C;
+      }
+  }
+  if constexpr (KS == 3) {
+    const int per = HX << gshift;                        // threads per window line
+    const int lines_per_iter = NTHREADS / per;           // 6 / 3 / 1
+    const int rl = threadIdx.x / per, hx = (threadIdx.x - rl * per) >> gshift;
+    const bool active = rl < lines_per_iter;
+    int x = x0 + hx - 1;
+    const bool xin = x >= 0 && x < g.W;
+    x = min(max(x, 0), g.W - 1);
+    const uint32_t sdst = smem_in + cg * CGS + hx * 16;
+    constexpr int U = 10, LINES = HZ * HY;
+    for (int r0 = rl; r0 < LINES; r0 += lines_per_iter * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * lines_per_iter;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && r < LINES && sp != nullptr) {
+          const int hz = r / HY, hy = r - hz * HY;
+          int z = z0 + hz - 1, y = y0 + hy - 1;
+          bool inside = xin && z >= 0 && z < g.D && y >= 0 && y < g.H;
+          if (replicate) { z = min(max(z, 0), g.D - 1); y = min(max(y, 0), g.H - 1); inside = true; }
+          if (inside) v[u] = ld4(sp + (long long)(((b * g.D + z) * g.H + y) * g.W + x) * sld);
         }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * NTHREADS;
-      if (i < total) sts128(smem_in + (i & (groups - 1)) * CGS + (i >> gshift) * 16, round_tf32_4(v[u]));
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * lines_per_iter;
+        if (active && r < LINES) sts128(sdst + r * (HX * 16), rnd4(v[u]));
+      }
+    }
+  } else {
+    constexpr int U = 8;
+    const int vl = threadIdx.x >> gshift, vstep = NTHREADS >> gshift;     // voxels advance by vstep per item
+    const uint32_t sdst = smem_in + cg * CGS;
+    for (int h0 = vl; h0 < TILE_VOX; h0 += vstep * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int hv = h0 + u * vstep;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hv < TILE_VOX && sp != nullptr && v0 + hv < nvox) v[u] = ld4(sp + ((long long)b * nvox + v0 + hv) * sld);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int hv = h0 + u * vstep;
+        if (hv < TILE_VOX) sts128(sdst + hv * 16, rnd4(v[u]));
+      }
     }
   }
 }

@@ -10,6 +10,7 @@
 // the voxel steps (1x1x1).  Fragment mapping (m16n8k8, A = x^T [16 ci x 8 voxels], B = g [8 voxels x 8 co]): the 8
 // voxels of a step are the 8 x-neighbours of one line; k = 0..3 are the even, k = 4..7 the odd ones, which makes
 // the 32 lanes of every A load hit 32 distinct banks of the [channel group][voxel][4] window.
+#include <stdlib.h>
 #include "conv3d.cuh"
 
 namespace corrif {
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(NTHREADS, NB <= 2 ? 3 : 2) conv3d_wgrad_kernel
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int i = base + u * NTHREADS;
-          if (i < TOTAL) sts128(s_g + ((i / (NB * 2)) * GLD + (i % (NB * 2)) * 4) * 4, round_tf32_4(val[u]));
+          if (i < TOTAL) sts128(s_g + ((i / (NB * 2)) * GLD + (i % (NB * 2)) * 4) * 4, rnd4(val[u]));
         }
       }
     }
@@ -157,6 +158,106 @@ __global__ void __launch_bounds__(NTHREADS, NB <= 2 ? 3 : 2) conv3d_wgrad_kernel
   }
 }
 
+// ---- 3x3x3, second version: input lines reused across the dy taps in registers -----------------------------
+// The kernel above loads one A fragment (x^T of one shifted line: 4 shared-memory loads) per MMA - 4.3 loads per
+// MMA, shared-memory bound at 43 TFLOP/s on the 128^3 layers.  Here warp w owns the 8 output lines of z-slice w
+// and keeps their gradient fragments in 16 registers; it walks the 3 x 10 x 3 (dz, window line, dx) A fragments
+// once, and each of them is multiplied with the gradient lines y = line - dy of all three dy taps: 360 + 16 loads
+// feed 216 MMAs (1.7 per MMA).  All 27 taps accumulate in registers (108); 8 output channels per CTA (grid.z).
+__global__ void __launch_bounds__(NTHREADS, 3) conv3d_wgrad3_kernel(const WgradArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int GLD = 12;                            // 8 channels + 4 padding floats per gradient voxel
+  const uint32_t s_in = smem_addr(smem);
+  const uint32_t s_g = s_in + (WKC / 4) * CGS3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int pass = blockIdx.y, nt = blockIdx.z;
+  const int per = a.g.tiles_x * a.g.tiles_y * a.g.tiles_z;
+
+  float acc[27][4];
+#pragma unroll
+  for (int i = 0; i < 27; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+    const int b = tile / per;
+    int rem = tile - b * per;
+    const int x0 = (rem % a.g.tiles_x) * TX; rem /= a.g.tiles_x;
+    const int y0 = (rem % a.g.tiles_y) * TY;
+    const int z0 = (rem / a.g.tiles_y) * TZ;
+    __syncthreads();
+    stage_window<3>(s_in, a.src, a.nsrc, a.g, b, z0, y0, x0, 0, 0, pass * WKC, WKC, a.replicate != 0);
+    {   // gradient tile: 256 voxels x 8 channels (2 float4 per voxel), zeros outside the volume
+      float4 val[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * NTHREADS;          // 512 items
+        const int q = i & 1, v = i >> 1;
+        const int x = x0 + (v & 7), y = y0 + ((v >> 3) & 7), z = z0 + (v >> 6);
+        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (z < a.g.D && y < a.g.H && x < a.g.W)
+          val[u] = ld4(a.grad + (long long)(((b * a.g.D + z) * a.g.H + y) * a.g.W + x) * a.ldg + nt * 8 + q * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * NTHREADS;
+        sts128(s_g + ((i >> 1) * GLD + (i & 1) * 4) * 4, rnd4(val[u]));
+      }
+    }
+    __syncthreads();
+    uint32_t Bf[8][2];
+#pragma unroll
+    for (int yy = 0; yy < 8; ++yy) {
+      const uint32_t gb = s_g + (((warp * 8 + yy) * 8 + 2 * t) * GLD + g) * 4;
+      Bf[yy][0] = lds32(gb);
+      Bf[yy][1] = lds32(gb + GLD * 4);
+    }
+    const uint32_t a_lane = s_in + (g >> 2) * CGS3 + (g & 3) * 4 + (2 * t) * 16;
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz) {
+#pragma unroll
+      for (int hy = 0; hy < HY; ++hy) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint32_t ad = a_lane + ((((warp + dz) * HY + hy) * HX) + dx) * 16;
+          const uint32_t a0 = lds32(ad), a1 = lds32(ad + 2 * CGS3), a2 = lds32(ad + 16), a3 = lds32(ad + 2 * CGS3 + 16);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int yy = hy - dy;
+            if (yy >= 0 && yy < 8) mma_tf32(acc[(dz * 3 + dy) * 3 + dx], a0, a1, a2, a3, Bf[yy][0], Bf[yy][1]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int tap = 0; tap < 27; ++tap)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = pass * WKC + g + (j >> 1) * 8;
+      const int co = nt * 8 + 2 * t + (j & 1);
+      if (ci < a.Cin) atomicAdd(a.dW + ((long long)co * a.Cin + ci) * 27 + tap, acc[tap][j]);
+    }
+}
+
+static int launch_wgrad3(const WgradArgs& a0, cudaStream_t stream) {
+  WgradArgs a = a0;
+  const int smem = (WKC / 4) * CGS3 + TILE_VOX * 12 * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_last_error("conv3d_wgrad: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  a.total_tiles = a.g.tiles_x * a.g.tiles_y * a.g.tiles_z * a.g.B;
+  const int passes = (a.Cin + WKC - 1) / WKC, ntiles = a.Cout / 8;
+  int px = (6 * num_sms() + passes * ntiles - 1) / (passes * ntiles);     // two rounds of the 3 resident CTAs per SM
+  px = px < 1 ? 1 : (px > a.total_tiles ? a.total_tiles : px);
+  dim3 grid((unsigned)px, (unsigned)passes, (unsigned)ntiles);
+  conv3d_wgrad3_kernel<<<grid, NTHREADS, smem, stream>>>(a);
+  return launch_status("conv3d_wgrad");
+}
+
 template <int KS, int NB>
 static int launch(const WgradArgs& a0, cudaStream_t stream) {
   WgradArgs a = a0;
@@ -199,69 +300,84 @@ static int launch_nb(int NB, const WgradArgs& a, cudaStream_t s) {
 // Per axis the v with clamp(v + t) == u are  u - t  (inside the volume: already counted unless another axis is
 // outside) and  u itself when (t == -1 and u == 0) or (t == +1 and u == n-1)  (outside: the clamped read).
 // One thread per (border voxel, input channel), channels fastest.
-__device__ __forceinline__ void border_voxel(long long r, int D, int H, int W, int& z, int& y, int& x) {
-  // z faces, then y faces of the remaining slab, then x faces of the remaining core
-  const long long zf = (long long)H * W, nz = D >= 2 ? 2 : 1, nyf = H >= 2 ? 2 : 1, nxf = W >= 2 ? 2 : 1;
-  const int Dm = D - (int)nz, Hm = H - (int)nyf;
+__device__ __forceinline__ void border_voxel(uint32_t r, int D, int H, int W, int& z, int& y, int& x) {
+  // z faces, then y faces of the remaining slab, then x faces of the remaining core (32-bit arithmetic throughout:
+  // the first version's 64-bit divisions cost more than the gradient itself)
+  const uint32_t zf = (uint32_t)H * W, nz = D >= 2 ? 2 : 1, nyf = H >= 2 ? 2 : 1, nxf = W >= 2 ? 2 : 1;
+  const uint32_t Dm = D - nz, Hm = H - nyf;
   if (r < nz * zf) {
-    z = r < zf ? 0 : D - 1; r %= zf; y = (int)(r / W); x = (int)(r % W);
+    z = r < zf ? 0 : D - 1; r -= r < zf ? 0 : zf; y = (int)(r / W); x = (int)(r - (uint32_t)y * W);
     return;
   }
   r -= nz * zf;
-  const long long yfaces = (long long)Dm * nyf * W;
+  const uint32_t yfaces = Dm * nyf * W;
   if (r < yfaces) {
-    z = 1 + (int)(r / (nyf * W)); r %= nyf * W; y = r < W ? 0 : H - 1; x = (int)(r % W);
+    const uint32_t zz = r / (nyf * W);
+    r -= zz * (nyf * W);
+    z = 1 + (int)zz; y = r < (uint32_t)W ? 0 : H - 1; x = (int)(r < (uint32_t)W ? r : r - W);
     return;
   }
   r -= yfaces;
-  z = 1 + (int)(r / (Hm * nxf)); r %= Hm * nxf; y = 1 + (int)(r / nxf); x = (r % nxf) == 0 ? 0 : W - 1;
+  const uint32_t zz = r / (Hm * nxf);
+  r -= zz * (Hm * nxf);
+  z = 1 + (int)zz; y = 1 + (int)(r / nxf); x = (r % nxf) == 0 ? 0 : W - 1;
 }
 
 __global__ void __launch_bounds__(256) dgrad_border_kernel(const float* __restrict__ grad, long long ldg,
                                                            const float* __restrict__ w, float* __restrict__ dx,
                                                            long long ldx, int B, int D, int H, int W, int Cin, int Cout,
-                                                           long long nborder) {
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= nborder * B * Cin) return;
-  const int ci = (int)(tid % Cin);
-  const long long bu = tid / Cin;
+                                                           uint32_t nborder, uint32_t total) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= total) return;
+  const uint32_t bu = tid / (uint32_t)Cin;
+  const int ci = (int)(tid - bu * (uint32_t)Cin);
   const int b = (int)(bu / nborder);
   int uz, uy, ux;
-  border_voxel(bu % nborder, D, H, W, uz, uy, ux);
+  border_voxel(bu - (uint32_t)b * nborder, D, H, W, uz, uy, ux);
   float sum = 0.f;
 #pragma unroll 1
-  for (int tap = 0; tap < 27; ++tap) {
-    const int tz = tap / 9 - 1, ty = (tap / 3) % 3 - 1, tx = tap % 3 - 1;
+  for (int tz = -1; tz <= 1; ++tz) {
     const bool oz = (tz == -1 && uz == 0) || (tz == 1 && uz == D - 1);
-    const bool oy = (ty == -1 && uy == 0) || (ty == 1 && uy == H - 1);
-    const bool ox = (tx == -1 && ux == 0) || (tx == 1 && ux == W - 1);
-    if (!(oz || oy || ox)) continue;                    // no clamped read reaches u through this tap
-    const int vz_in = uz - tz, vy_in = uy - ty, vx_in = ux - tx;
-    const bool iz = vz_in >= 0 && vz_in < D, iy = vy_in >= 0 && vy_in < H, ix = vx_in >= 0 && vx_in < W;
-    const float* wt = w + (long long)tap * Cout * Cin + ci;          // w is taps-major: [27][Cout][Cin]
-    // 2 x 2 x 2 choices (inside / clamped) per axis; at least one clamped
+    const int vz_in = uz - tz;
+    const bool iz = vz_in >= 0 && vz_in < D;
+#pragma unroll 1
+    for (int ty = -1; ty <= 1; ++ty) {
+      const bool oy = (ty == -1 && uy == 0) || (ty == 1 && uy == H - 1);
+      const int vy_in = uy - ty;
+      const bool iy = vy_in >= 0 && vy_in < H;
+#pragma unroll 1
+      for (int tx = -1; tx <= 1; ++tx) {
+        const bool ox = (tx == -1 && ux == 0) || (tx == 1 && ux == W - 1);
+        if (!(oz || oy || ox)) continue;                    // no clamped read reaches u through this tap
+        const int vx_in = ux - tx;
+        const bool ix = vx_in >= 0 && vx_in < W;
+        const int tap = ((tz + 1) * 3 + (ty + 1)) * 3 + (tx + 1);
+        const float* wt = w + (uint32_t)(tap * Cout) * (uint32_t)Cin + ci;          // w is taps-major: [27][Cout][Cin]
+        // 2 x 2 x 2 choices (inside / clamped) per axis; at least one clamped
 #pragma unroll
-    for (int cz = 0; cz < 2; ++cz) {
-      if (cz ? !oz : !iz) continue;
+        for (int cz = 0; cz < 2; ++cz) {
+          if (cz ? !oz : !iz) continue;
 #pragma unroll
-      for (int cy = 0; cy < 2; ++cy) {
-        if (cy ? !oy : !iy) continue;
+          for (int cy = 0; cy < 2; ++cy) {
+            if (cy ? !oy : !iy) continue;
 #pragma unroll
-        for (int cx = 0; cx < 2; ++cx) {
-          if (cx ? !ox : !ix) continue;
-          if (!(cz | cy | cx)) continue;                // fully inside: the zero-padded pass has it
-          const int vz = cz ? uz : vz_in, vy = cy ? uy : vy_in, vx = cx ? ux : vx_in;
-          const float* gp = grad + ((((long long)b * D + vz) * H + vy) * W + vx) * ldg;
-          for (int co = 0; co < Cout; co += 4) {
-            const float4 gv = ld4(gp + co);
-            sum += gv.x * __ldg(wt + (long long)co * Cin) + gv.y * __ldg(wt + (long long)(co + 1) * Cin) +
-                   gv.z * __ldg(wt + (long long)(co + 2) * Cin) + gv.w * __ldg(wt + (long long)(co + 3) * Cin);
+            for (int cx = 0; cx < 2; ++cx) {
+              if (cx ? !ox : !ix) continue;
+              if (!(cz | cy | cx)) continue;                // fully inside: the zero-padded pass has it
+              const int vz = cz ? uz : vz_in, vy = cy ? uy : vy_in, vx = cx ? ux : vx_in;
+              const float* gp = grad + (long long)(((b * D + vz) * H + vy) * W + vx) * ldg;
+              for (int co = 0; co < Cout; co += 4) {
+                const float4 gv = ld4(gp + co);
+                sum += gv.x * __ldg(wt + co * Cin) + gv.y * __ldg(wt + (co + 1) * Cin) +
+                       gv.z * __ldg(wt + (co + 2) * Cin) + gv.w * __ldg(wt + (co + 3) * Cin);
+              }
+            }
           }
         }
       }
     }
   }
-  dx[((((long long)b * D + uz) * H + uy) * W + ux) * ldx + ci] += sum;
+  dx[(long long)(((b * D + uz) * H + uy) * W + ux) * ldx + ci] += sum;
 }
 
 }  // namespace conv
@@ -289,6 +405,8 @@ extern "C" int corrif_conv3d_wgrad(const corrif_conv3d_desc* desc, const float* 
   a.Cin = d.Cin; a.Cout = d.Cout; a.replicate = d.pad_mode == CORRIF_PAD_REPLICATE;
   a.grad = g; a.ldg = ldg; a.dW = dW; a.total_tiles = 0;
   const int NB = wgrad_nb(d.Cout);
+  static const bool old3 = getenv("CORRIF_WGRAD_V1") != nullptr;      // A/B switch: first 3x3x3 kernel
+  if (d.ksize == 3 && !old3) return launch_wgrad3(a, (cudaStream_t)stream);
   if (d.ksize == 3) return launch_nb<3>(NB, a, (cudaStream_t)stream);
   return launch_nb<1>(NB, a, (cudaStream_t)stream);
 }
@@ -303,7 +421,9 @@ extern "C" int corrif_conv3d_dgrad_border(const float* g, int64_t ldg, const flo
   const long long nborder = nz * H * W + Dm * nyf * W + Dm * Hm * nxf;
   const long long threads_total = nborder * B * Cin;
   CORRIF_REQUIRE(Cout % 4 == 0 && ldg % 4 == 0 && ((uintptr_t)g % 16) == 0, "conv3d_dgrad_border: Cout / ldg must be multiples of 4");
+  CORRIF_REQUIRE(threads_total < (1ll << 31) && (long long)B * D * H * W < (1ll << 31), "conv3d_dgrad_border: problem too large");
   const long long blocks = (threads_total + 255) / 256;
-  dgrad_border_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, w, dx, ldx, B, D, H, W, Cin, Cout, nborder);
+  dgrad_border_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, w, dx, ldx, B, D, H, W, Cin, Cout,
+                                                                       (uint32_t)nborder, (uint32_t)threads_total);
   return launch_status("conv3d_dgrad_border");
 }
