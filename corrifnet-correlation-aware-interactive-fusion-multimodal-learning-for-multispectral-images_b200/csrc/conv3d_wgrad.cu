@@ -327,14 +327,16 @@ __global__ void __launch_bounds__(256) dgrad_border_kernel(const float* __restri
                                                            const float* __restrict__ w, float* __restrict__ dx,
                                                            long long ldx, int B, int D, int H, int W, int Cin, int Cout,
                                                            uint32_t nborder, uint32_t total) {
+  // one thread per (border voxel, 4 input channels)
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= total) return;
-  const uint32_t bu = tid / (uint32_t)Cin;
-  const int ci = (int)(tid - bu * (uint32_t)Cin);
+  const uint32_t Q = (uint32_t)Cin >> 2;
+  const uint32_t bu = tid / Q;
+  const int ci = (int)(tid - bu * Q) * 4;
   const int b = (int)(bu / nborder);
   int uz, uy, ux;
   border_voxel(bu - (uint32_t)b * nborder, D, H, W, uz, uy, ux);
-  float sum = 0.f;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int tz = -1; tz <= 1; ++tz) {
     const bool oz = (tz == -1 && uz == 0) || (tz == 1 && uz == D - 1);
@@ -368,8 +370,14 @@ __global__ void __launch_bounds__(256) dgrad_border_kernel(const float* __restri
               const float* gp = grad + (long long)(((b * D + vz) * H + vy) * W + vx) * ldg;
               for (int co = 0; co < Cout; co += 4) {
                 const float4 gv = ld4(gp + co);
-                sum += gv.x * __ldg(wt + co * Cin) + gv.y * __ldg(wt + (co + 1) * Cin) +
-                       gv.z * __ldg(wt + (co + 2) * Cin) + gv.w * __ldg(wt + (co + 3) * Cin);
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + co * Cin));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (co + 1) * Cin));
+                const float4 w2 = __ldg(reinterpret_cast<const float4*>(wt + (co + 2) * Cin));
+                const float4 w3 = __ldg(reinterpret_cast<const float4*>(wt + (co + 3) * Cin));
+                sum.x += gv.x * w0.x + gv.y * w1.x + gv.z * w2.x + gv.w * w3.x;
+                sum.y += gv.x * w0.y + gv.y * w1.y + gv.z * w2.y + gv.w * w3.y;
+                sum.z += gv.x * w0.z + gv.y * w1.z + gv.z * w2.z + gv.w * w3.z;
+                sum.w += gv.x * w0.w + gv.y * w1.w + gv.z * w2.w + gv.w * w3.w;
               }
             }
           }
@@ -377,7 +385,10 @@ __global__ void __launch_bounds__(256) dgrad_border_kernel(const float* __restri
       }
     }
   }
-  dx[(long long)(((b * D + uz) * H + uy) * W + ux) * ldx + ci] += sum;
+  float* o = dx + (long long)(((b * D + uz) * H + uy) * W + ux) * ldx + ci;
+  float4 cur = ld4(o);
+  cur.x += sum.x; cur.y += sum.y; cur.z += sum.z; cur.w += sum.w;
+  st4(o, cur);
 }
 
 }  // namespace conv
@@ -419,8 +430,9 @@ extern "C" int corrif_conv3d_dgrad_border(const float* g, int64_t ldg, const flo
   const long long nz = D >= 2 ? 2 : 1, nyf = H >= 2 ? 2 : 1, nxf = W >= 2 ? 2 : 1;
   const long long Dm = D - nz, Hm = H - nyf;
   const long long nborder = nz * H * W + Dm * nyf * W + Dm * Hm * nxf;
-  const long long threads_total = nborder * B * Cin;
+  const long long threads_total = nborder * B * (Cin / 4);
   CORRIF_REQUIRE(Cout % 4 == 0 && ldg % 4 == 0 && ((uintptr_t)g % 16) == 0, "conv3d_dgrad_border: Cout / ldg must be multiples of 4");
+  CORRIF_REQUIRE(Cin % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)dx % 16) == 0 && ((uintptr_t)w % 16) == 0, "conv3d_dgrad_border: Cin / ldx must be multiples of 4, pointers 16-byte aligned");
   CORRIF_REQUIRE(threads_total < (1ll << 31) && (long long)B * D * H * W < (1ll << 31), "conv3d_dgrad_border: problem too large");
   const long long blocks = (threads_total + 255) / 256;
   dgrad_border_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, w, dx, ldx, B, D, H, W, Cin, Cout,

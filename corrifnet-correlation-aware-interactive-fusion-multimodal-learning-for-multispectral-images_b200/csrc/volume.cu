@@ -242,9 +242,23 @@ __device__ __forceinline__ float ac_weight(int o, int i, float scale, int in) {
   return w;
 }
 
+// per-axis candidate list of one input index: first output index and up to MAXC weights (zero = no contribution)
+constexpr int MAXC = 8;
+__device__ __forceinline__ int ac_candidates(int i, float scale, int in, int out, float (&w)[MAXC]) {
+  int lo, hi;
+  ac_range(i, scale, in, out, lo, hi);
+  // trim leading non-contributors so that the window of MAXC candidates starts at the first real one
+  while (lo < hi && ac_weight(lo, i, scale, in) == 0.f) ++lo;
+#pragma unroll
+  for (int k = 0; k < MAXC; ++k) w[k] = (lo + k <= hi) ? ac_weight(lo + k, i, scale, in) : 0.f;
+  return lo;
+}
+
+// Gather-form backward.  With more than MAXC contributing outputs per axis (strong down-sampling, e.g. the
+// encoder's 64 -> 8 pooling has at most 2 / scale = 18) the generic loop below is used instead.
 __global__ void __launch_bounds__(THREADS) trilinear_bwd_kernel(const float* __restrict__ dy, long long lddy, float* dx,
                                                                 long long lddx, int C, int Di, int Hi, int Wi, int Do,
-                                                                int Ho, int Wo, long long total) {
+                                                                int Ho, int Wo, long long total, int small) {
   const int Q = C / 4;
   const float sz = ac_scale(Di, Do), sy = ac_scale(Hi, Ho), sx = ac_scale(Wi, Wo);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -254,21 +268,44 @@ __global__ void __launch_bounds__(THREADS) trilinear_bwd_kernel(const float* __r
     const int yi = (int)(v % Hi); v /= Hi;
     const int zi = (int)(v % Di);
     const long long b = v / Di;
-    int zl, zh, yl, yh, xl, xh;
-    ac_range(zi, sz, Di, Do, zl, zh); ac_range(yi, sy, Hi, Ho, yl, yh); ac_range(xi, sx, Wi, Wo, xl, xh);
     float4 o = f4(0.f);
-    for (int zo = zl; zo <= zh; ++zo) {
-      const float wz = ac_weight(zo, zi, sz, Di);
-      if (wz == 0.f) continue;
-      for (int yo = yl; yo <= yh; ++yo) {
-        const float wy = ac_weight(yo, yi, sy, Hi);
-        if (wy == 0.f) continue;
-        for (int xo = xl; xo <= xh; ++xo) {
-          const float wx = ac_weight(xo, xi, sx, Wi);
-          if (wx == 0.f) continue;
-          const float4 d = ld4(dy + ((((long long)b * Do + zo) * Ho + yo) * Wo + xo) * lddy + 4 * q);
-          const float w = wz * wy * wx;
-          o.x += w * d.x; o.y += w * d.y; o.z += w * d.z; o.w += w * d.w;
+    if (small) {
+      float wz[MAXC], wy[MAXC], wx[MAXC];
+      const int zl = ac_candidates(zi, sz, Di, Do, wz), yl = ac_candidates(yi, sy, Hi, Ho, wy),
+                xl = ac_candidates(xi, sx, Wi, Wo, wx);
+#pragma unroll
+      for (int a = 0; a < MAXC; ++a) {
+        if (wz[a] == 0.f) continue;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          if (wy[c] == 0.f) continue;
+          const float wzy = wz[a] * wy[c];
+          const float* row = dy + ((((long long)b * Do + zl + a) * Ho + yl + c) * Wo + xl) * lddy + 4 * q;
+#pragma unroll
+          for (int e = 0; e < MAXC; ++e) {
+            if (wx[e] == 0.f) continue;
+            const float4 d = ld4(row + (long long)e * lddy);
+            const float w = wzy * wx[e];
+            o.x += w * d.x; o.y += w * d.y; o.z += w * d.z; o.w += w * d.w;
+          }
+        }
+      }
+    } else {
+      int zl, zh, yl, yh, xl, xh;
+      ac_range(zi, sz, Di, Do, zl, zh); ac_range(yi, sy, Hi, Ho, yl, yh); ac_range(xi, sx, Wi, Wo, xl, xh);
+      for (int zo = zl; zo <= zh; ++zo) {
+        const float wz = ac_weight(zo, zi, sz, Di);
+        if (wz == 0.f) continue;
+        for (int yo = yl; yo <= yh; ++yo) {
+          const float wy = ac_weight(yo, yi, sy, Hi);
+          if (wy == 0.f) continue;
+          for (int xo = xl; xo <= xh; ++xo) {
+            const float wx = ac_weight(xo, xi, sx, Wi);
+            if (wx == 0.f) continue;
+            const float4 d = ld4(dy + ((((long long)b * Do + zo) * Ho + yo) * Wo + xo) * lddy + 4 * q);
+            const float w = wz * wy * wx;
+            o.x += w * d.x; o.y += w * d.y; o.z += w * d.z; o.w += w * d.w;
+          }
         }
       }
     }
@@ -421,7 +458,10 @@ extern "C" int corrif_resize_trilinear_bwd(const float* dy, int64_t lddy, float*
   int rc = resize_check(dx, lddx, dy, lddy, B, C, Di, Hi, Wi, Do, Ho, Wo);
   if (rc) return rc;
   const long long total = (long long)B * Di * Hi * Wi * (C / 4);
-  trilinear_bwd_kernel<<<flat_grid(total), THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, lddx, C, Di, Hi, Wi, Do, Ho, Wo, total);
+  // every input index has at most ceil(2 * (out-1)/(in-1)) + 1 contributing outputs per axis
+  auto fits = [](int in, int out) { return in <= 1 ? out <= 8 : (2.0 * (out - 1) / (in - 1) + 1.0) <= 7.0; };
+  const int small = fits(Di, Do) && fits(Hi, Ho) && fits(Wi, Wo);
+  trilinear_bwd_kernel<<<flat_grid(total), THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, lddx, C, Di, Hi, Wi, Do, Ho, Wo, total, small);
   return launch_status("resize_trilinear_bwd");
 }
 extern "C" int corrif_resize_nearest_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int32_t B, int32_t C,
