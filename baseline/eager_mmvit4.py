@@ -3,8 +3,8 @@ BASELINE.md): every op an ATen call into cuBLAS / cuDNN, no corrif_b200 kernel a
 
 ``EagerFusionBlock`` restates mmvit4.py:295-388, 398-426, 456-529 with nn.Linear / nn.Conv3d / nn.LayerNorm /
 nn.Dropout modules under the reference's attribute names, so a drop-in (or reference) ``state_dict`` loads into it
-strictly for the hot-path subset; ``EagerMMVit4`` is the drop-in model class with the fusion block, the early-fusion
-blocks and the decoder all on stock PyTorch (the drop-in's own encoders already are).  Baseline only: bench.py times
+strictly for the hot-path subset; ``EagerMMVit4`` is the whole model - encoders, early-fusion blocks, fusion block, decoder -
+on stock PyTorch under the same state_dict keys.  Baseline only: bench.py times
 it beside the kernels, tests use it as a same-device comparison; the product never imports it.
 """
 import math
@@ -112,6 +112,46 @@ class EagerFusionBlock(nn.Module):
             mm.view(B, PATCH, PATCH, PATCH, 4 * DIM).permute(0, 4, 1, 2, 3).contiguous())
 
 
+def _conv(cin, cout, k, stride, pad, depth_k=1):    # torchvision conv2d inflated to (depth_k, k, k) (mmvit4.py:83-111)
+    return nn.Conv3d(cin, cout, (depth_k, k, k), stride=(1, stride, stride), padding=(depth_k // 2, pad, pad), bias=False)
+
+
+class _Bottleneck(nn.Module):                      # Bottleneck3D (mmvit4.py:196-212), ResNet-50 v1.5 strides
+    def __init__(self, cin, planes, stride, project):
+        super().__init__()
+        self.conv1, self.bn1 = _conv(cin, planes, 1, 1, 0), nn.BatchNorm3d(planes)
+        self.conv2, self.bn2 = _conv(planes, planes, 3, stride, 1), nn.BatchNorm3d(planes)
+        self.conv3, self.bn3 = _conv(planes, 4 * planes, 1, 1, 0), nn.BatchNorm3d(4 * planes)
+        self.downsample = nn.Sequential(_conv(cin, 4 * planes, 1, stride, 0), nn.BatchNorm3d(4 * planes)) if project else None
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        y = F.relu(self.bn2(self.conv2(y)))
+        y = self.bn3(self.conv3(y))
+        return F.relu(y + (x if self.downsample is None else self.downsample(x)))
+
+
+class _Encoder(nn.Module):                         # Encoder (mmvit4.py:113-194), all stock PyTorch
+    def __init__(self):
+        super().__init__()
+        self.e1_c1, self.e1_bn = _conv(1, 64, 7, 2, 3, depth_k=3), nn.BatchNorm3d(64)
+        self.e1_mp = nn.MaxPool3d(kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1))
+        for name, cin, planes, blocks, stride in (("e2", 64, 64, 3, 1), ("e3", 256, 128, 4, 2), ("e4", 512, 256, 6, 2),
+                                                  ("e5", 1024, 512, 3, 2)):
+            setattr(self, name, nn.Sequential(_Bottleneck(cin, planes, stride, True),
+                                              *[_Bottleneck(4 * planes, planes, 1, False) for _ in range(blocks - 1)]))
+        self.conv6 = nn.Conv3d(184, 64, 1)
+        for i, (cin, cout) in enumerate(zip((64, 256, 512, 1024, 2048), (8, 16, 32, 64, 64)), start=1):
+            setattr(self, f"adapt{i}", nn.Conv3d(cin, cout, 1))
+
+    def forward(self, x):
+        f1 = self.e1_mp(self.e1_bn(F.relu(self.e1_c1(x))))
+        f2 = self.e2(f1); f3 = self.e3(f2); f4 = self.e4(f3); f5 = self.e5(f4)       # noqa: E702
+        lv = [getattr(self, f"adapt{i}")(f) for i, f in enumerate((f1, f2, f3, f4, f5), start=1)]
+        pooled = [F.interpolate(t, size=(8, 8, 8), mode="trilinear", align_corners=True) for t in lv]
+        return (*lv, self.conv6(torch.cat(pooled, dim=1)))
+
+
 class _ConvReluNorm(nn.Module):                    # general_conv3d_prenorm (mmvit4.py:29-45): conv -> ReLU -> IN
     def __init__(self, cin, cout, k=3, pad_type="zeros"):
         super().__init__()
@@ -166,14 +206,12 @@ class _Decoder(nn.Module):                         # Decoder_fuse (mmvit4.py:222
 
 
 class EagerMMVit4(EagerFusionBlock):
-    """Whole CorrIFNet on stock PyTorch with the reference's 1140 state_dict keys (the encoder class is shared with
-    the drop-in, where it is stock PyTorch as well)."""
+    """Whole CorrIFNet on stock PyTorch with the reference's 1140 state_dict keys."""
 
     def __init__(self, num_cls=1, dropout_rate=0.1):
         super().__init__(dropout_rate)
-        import mmvit4 as dropin
         for m in MODS:
-            setattr(self, f"{m}_encoder", dropin.Encoder())
+            setattr(self, f"{m}_encoder", _Encoder())
             setattr(self, f"{m}_decode_conv", nn.Conv3d(DIM, ENC, 1))                  # unused in forward
         for i, c in enumerate((1, 2, 4, 8, 8, 8), start=1):
             setattr(self, f"fusion{i}", _EarlyFusion(8 * c))

@@ -1,4 +1,6 @@
-// Inter-modal correlation (InterFormer) forward/backward, mmvit4.py:481-507, M = 3 modalities.
+// Inter-modal correlation (InterFormer) forward/backward, mmvit4.py:481-507.  The reference hard-wires M = 3
+// modalities (mmvit4.py:15, 394-396); the kernels are templates over M (2..6) so that the same code serves
+// BASELINE.json configs[4] (every 3-band group of the 20-band cube as its own modality: M = 6, 3584 tokens).
 //
 // Reference semantics: scores of query modality X are flattened to
 // [3, B*C*S], soft-maxed over the 3 key modalities and re-viewed as [B, 3C, S].  The view keeps the
@@ -13,8 +15,6 @@
 
 namespace corrif {
 
-constexpr int IC_M = 3;
-constexpr float IC_RSQRT_M = 0.57735026918962576451f;  // 1/sqrt(3), mmvit4.py:484
 
 struct f4 { float v[4]; };
 __device__ __forceinline__ f4 ldf4(const float* p) {
@@ -24,9 +24,11 @@ __device__ __forceinline__ f4 ldf4(const float* p) {
 __device__ __forceinline__ void stf4(float* p, const f4& a) { st4(p, make_float4(a.v[0], a.v[1], a.v[2], a.v[3])); }
 
 // qkv [M][B][S][3C]; skip [M][B][S][C]; tokens [B][(M+1)S][C]
+template <int IC_M>
 __global__ void __launch_bounds__(128)
 inter_corr_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ skip,
                       float* __restrict__ tokens, int B, int S, int C) {
+  const float IC_RSQRT_M = rsqrtf((float)IC_M);            // 1/sqrt(M), mmvit4.py:484 (correctly rounded for M = 3, 4)
   const int cq = C / 4;
   const int64_t total = (int64_t)B * S * cq;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,13 +61,17 @@ inter_corr_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ s
       const f4 q = ldf4(qkv + X * mod_stride + row_b);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float s0 = q.v[e] * k[0].v[e] * IC_RSQRT_M;
-        const float s1 = q.v[e] * k[1].v[e] * IC_RSQRT_M;
-        const float s2 = q.v[e] * k[2].v[e] * IC_RSQRT_M;
-        const float mx = fmaxf(s0, fmaxf(s1, s2));
-        const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
-        const float em = m == 0 ? e0 : (m == 1 ? e1 : e2);
-        acc[X].v[e] += em / (e0 + e1 + e2) * v.v[e];
+        float sc[IC_M], mx = -3.0e38f;
+#pragma unroll
+        for (int mm = 0; mm < IC_M; ++mm) { sc[mm] = q.v[e] * k[mm].v[e] * IC_RSQRT_M; mx = fmaxf(mx, sc[mm]); }
+        float sum = 0.f, em = 0.f;
+#pragma unroll
+        for (int mm = 0; mm < IC_M; ++mm) {
+          const float ex = __expf(sc[mm] - mx);
+          sum += ex;
+          em = mm == m ? ex : em;
+        }
+        acc[X].v[e] += em / sum * v.v[e];
       }
     }
   }
@@ -75,9 +81,11 @@ inter_corr_fwd_kernel(const float* __restrict__ qkv, const float* __restrict__ s
 }
 
 // g = dL/dtokens [B][(M+1)S][C]; dqkv [M][B][S][3C]
+template <int IC_M>
 __global__ void __launch_bounds__(128)
 inter_corr_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g,
                       float* __restrict__ dqkv, int B, int S, int C, int g_group_major) {
+  const float IC_RSQRT_M = rsqrtf((float)IC_M);
   const int cq = C / 4;
   const int64_t total = (int64_t)B * S * cq;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,13 +109,15 @@ inter_corr_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g
   for (int X = 0; X < IC_M; ++X)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float s0 = q[X].v[e] * k[0].v[e] * IC_RSQRT_M;
-      const float s1 = q[X].v[e] * k[1].v[e] * IC_RSQRT_M;
-      const float s2 = q[X].v[e] * k[2].v[e] * IC_RSQRT_M;
-      const float mx = fmaxf(s0, fmaxf(s1, s2));
-      const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
-      const float inv = 1.0f / (e0 + e1 + e2);
-      A[X][0].v[e] = e0 * inv; A[X][1].v[e] = e1 * inv; A[X][2].v[e] = e2 * inv;
+      float sc[IC_M], mx = -3.0e38f;
+#pragma unroll
+      for (int mm = 0; mm < IC_M; ++mm) { sc[mm] = q[X].v[e] * k[mm].v[e] * IC_RSQRT_M; mx = fmaxf(mx, sc[mm]); }
+      float sum = 0.f;
+#pragma unroll
+      for (int mm = 0; mm < IC_M; ++mm) { sc[mm] = __expf(sc[mm] - mx); sum += sc[mm]; }
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int mm = 0; mm < IC_M; ++mm) A[X][mm].v[e] = sc[mm] * inv;
     }
   // dA[X][m] = g_X[b'] * v_i[b'] with (b', i) = divmod(m*B + b, 3); dv_i[b'] = sum_X A[X][m]*g_X[b']
   f4 dA[IC_M][IC_M];
@@ -141,8 +151,9 @@ inter_corr_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g
     f4 dq = {{0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float dot = A[X][0].v[e] * dA[X][0].v[e] + A[X][1].v[e] * dA[X][1].v[e] +
-                        A[X][2].v[e] * dA[X][2].v[e];
+      float dot = 0.f;
+#pragma unroll
+      for (int mm = 0; mm < IC_M; ++mm) dot += A[X][mm].v[e] * dA[X][mm].v[e];
 #pragma unroll
       for (int m = 0; m < IC_M; ++m) {
         const float ds = A[X][m].v[e] * (dA[X][m].v[e] - dot) * IC_RSQRT_M;
@@ -160,27 +171,48 @@ inter_corr_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g
 
 using namespace corrif;
 
+template <int M>
+static void launch_fwd(const float* qkv, const float* skip, float* tokens, int B, int S, int C, cudaStream_t st) {
+  const int64_t total = (int64_t)B * S * (C / 4);
+  inter_corr_fwd_kernel<M><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(qkv, skip, tokens, B, S, C);
+}
+template <int M>
+static void launch_bwd(const float* qkv, const float* g, float* dqkv, int B, int S, int C, int gm, cudaStream_t st) {
+  const int64_t total = (int64_t)B * S * (C / 4);
+  inter_corr_bwd_kernel<M><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(qkv, g, dqkv, B, S, C, gm);
+}
+
 extern "C" {
 
 int corrif_inter_corr_fwd(const float* qkv, const float* skip, float* tokens, int32_t M, int32_t B,
                           int32_t S, int32_t C, void* stream) {
-  CORRIF_REQUIRE(M == IC_M, "inter_corr: M must be 3 (got %d)", M);
+  CORRIF_REQUIRE(M >= 2 && M <= 6, "inter_corr: M must be 2..6 (got %d)", M);
   CORRIF_REQUIRE(qkv && skip && tokens && B > 0 && S > 0 && C > 0 && C % 4 == 0,
                  "inter_corr_fwd: bad arguments");
-  const int64_t total = (int64_t)B * S * (C / 4);
-  inter_corr_fwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      qkv, skip, tokens, B, S, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (M) {
+    case 2: launch_fwd<2>(qkv, skip, tokens, B, S, C, st); break;
+    case 3: launch_fwd<3>(qkv, skip, tokens, B, S, C, st); break;
+    case 4: launch_fwd<4>(qkv, skip, tokens, B, S, C, st); break;
+    case 5: launch_fwd<5>(qkv, skip, tokens, B, S, C, st); break;
+    default: launch_fwd<6>(qkv, skip, tokens, B, S, C, st); break;
+  }
   return launch_status("inter_corr_fwd");
 }
 
 int corrif_inter_corr_bwd_layout(const float* qkv, const float* g_tokens, float* dqkv, int32_t M,
                                  int32_t B, int32_t S, int32_t C, int32_t g_group_major, void* stream) {
-  CORRIF_REQUIRE(M == IC_M, "inter_corr: M must be 3 (got %d)", M);
+  CORRIF_REQUIRE(M >= 2 && M <= 6, "inter_corr: M must be 2..6 (got %d)", M);
   CORRIF_REQUIRE(qkv && g_tokens && dqkv && B > 0 && S > 0 && C > 0 && C % 4 == 0,
                  "inter_corr_bwd: bad arguments");
-  const int64_t total = (int64_t)B * S * (C / 4);
-  inter_corr_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      qkv, g_tokens, dqkv, B, S, C, g_group_major);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (M) {
+    case 2: launch_bwd<2>(qkv, g_tokens, dqkv, B, S, C, g_group_major, st); break;
+    case 3: launch_bwd<3>(qkv, g_tokens, dqkv, B, S, C, g_group_major, st); break;
+    case 4: launch_bwd<4>(qkv, g_tokens, dqkv, B, S, C, g_group_major, st); break;
+    case 5: launch_bwd<5>(qkv, g_tokens, dqkv, B, S, C, g_group_major, st); break;
+    default: launch_bwd<6>(qkv, g_tokens, dqkv, B, S, C, g_group_major, st); break;
+  }
   return launch_status("inter_corr_bwd");
 }
 

@@ -74,7 +74,8 @@ def _stage(cin, planes, blocks, stride):
 
 
 class Encoder(nn.Module):
-    """One modality encoder.  Returns the five adapted pyramid levels and x6 [B,64,8,8,8]."""
+    """One modality encoder.  Returns the five adapted pyramid levels and x6 [B,64,8,8,8].  The ResNet-50 trunk is
+    stock PyTorch / cuDNN; the tail runs on corrif_b200.volume kernels."""
 
     def __init__(self, inflate_time=3):
         super().__init__()
@@ -97,9 +98,16 @@ class Encoder(nn.Module):
         f3 = self.e3(f2)
         f4 = self.e4(f3)
         f5 = self.e5(f4)
-        lv = [getattr(self, f"adapt{i}")(f) for i, f in enumerate((f1, f2, f3, f4, f5), start=1)]
-        pooled = [F.interpolate(t, size=(8, 8, 8), mode="trilinear", align_corners=True) for t in lv]
-        return (*lv, self.conv6(torch.cat(pooled, dim=1)))
+        # encoder tail (reference mmvit4.py:181-193) on the channels-last volume kernels: adapt1-5 are bias-only
+        # 1x1x1 convolutions, the five trilinear resizes to 8^3 and conv6 over their concatenation follow
+        lv = []
+        for i, f in enumerate((f1, f2, f3, f4, f5), start=1):
+            a = getattr(self, f"adapt{i}")
+            lv.append(_V.conv_block([_V.to_channels_last(f)], a.weight, a.bias, 1, relu=False, norm=False))
+        pooled = torch.cat([_V.resize_trilinear(t, (8, 8, 8)) for t in lv], dim=-1)       # [B,8,8,8,184]
+        x6 = _V.conv_block([pooled], self.conv6.weight, self.conv6.bias, 1, relu=False, norm=False)
+        # same shapes as the reference's outputs ([B,C,D,H,W]); the memory underneath stays channels-last
+        return tuple(_V.to_channels_first(t) for t in (*lv, x6))
 
 
 class EarlyFusionBlock(nn.Module):

@@ -56,15 +56,17 @@ def transformer_keys(prefix: str) -> Dict[str, str]:
     }
 
 
-def param_names() -> List[str]:
+def param_names(modalities=MODALITIES) -> List[str]:
+    """state_dict keys of the block in engine order.  ``modalities`` defaults to the reference's three
+    (mmvit4.py:394-396); BASELINE.json configs[4] runs the same block with more modality names."""
     names = []
-    for m in MODALITIES:
+    for m in modalities:
         names += [f"{m}_encode_conv.weight", f"{m}_encode_conv.bias"]
     names += ["fused6_encode_conv.weight", "fused6_encode_conv.bias"]
-    names += [f"{m}_pos" for m in MODALITIES] + ["fused6_pos"]
-    for m in MODALITIES:
+    names += [f"{m}_pos" for m in modalities] + ["fused6_pos"]
+    for m in modalities:
         names += list(transformer_keys(f"{m}_transformer").values())
-    for m in MODALITIES:
+    for m in modalities:
         names += [f"qkv_{m}.weight", f"qkv_{m}.bias"]
     names += list(transformer_keys("multimodal_transformer").values())
     names += ["multimodal_decode_conv.weight", "multimodal_decode_conv.bias"]
@@ -119,17 +121,21 @@ class FusionBlockEngine:
     CUDA fp32 tensors (conv weights may keep their [out,in,1,1,1] shape)."""
 
     def __init__(self, params: Dict[str, torch.Tensor], dropout_p: float = 0.0,
-                 precision: str = "tf32", use_graphs: bool = False):
+                 precision: str = "tf32", use_graphs: bool = False, modalities=MODALITIES):
         ops.check_device()
+        self.mods = tuple(modalities)
+        self.nm = len(self.mods)
+        if not 2 <= self.nm <= 6:
+            raise ValueError("the fusion block runs 2..6 modalities (the reference has 3)")
         self.p = params
-        for k in param_names():
+        for k in param_names(self.mods):
             t = params[k]
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise ValueError(f"parameter {k} must be a contiguous CUDA fp32 tensor")
         self.dev = params["RGB_pos"].device
         self.dropout_p = float(dropout_p)
         self.prec = {"tf32": GEMM_TF32, "fp32": GEMM_FP32}[precision]
-        self.tk = [transformer_keys(f"{m}_transformer") for m in MODALITIES]
+        self.tk = [transformer_keys(f"{m}_transformer") for m in self.mods]
         self.tk.append(transformer_keys("multimodal_transformer"))
         self._ws: Dict[int, dict] = {}
         self.seed = 0
@@ -155,7 +161,7 @@ class FusionBlockEngine:
         # forward, 41 MB).  In fp32 checking mode nothing is rounded.
         self.rnd = self.prec == GEMM_TF32
         self.fused_attn = self.prec == GEMM_TF32     # fused flash-style attention on the tcgen05 path
-        self.wnames = [k for k in param_names()
+        self.wnames = [k for k in param_names(self.mods)
                        if k.endswith(".weight") and "norm" not in k]
         # The three intra-modal branches have identical shapes: on the tensor-core path their rounded
         # weight copies (and plain bias copies) are STACKED [3, ...] so that each of their GEMMs is one
@@ -164,19 +170,19 @@ class FusionBlockEngine:
         self.pw, self.pws, self.pbs = {}, {}, {}
         self._bias_copies = []                      # (parameter name, stacked destination row)
         if self.batched:
-            wk = {kk: [self.tk[X][kk] for X in range(NM)] for kk in ("qkv_w", "proj_w", "fc1_w", "fc2_w")}
-            wk["enc_w"] = [f"{m}_encode_conv.weight" for m in MODALITIES]
-            wk["qkvc_w"] = [f"qkv_{m}.weight" for m in MODALITIES]
+            wk = {kk: [self.tk[X][kk] for X in range(self.nm)] for kk in ("qkv_w", "proj_w", "fc1_w", "fc2_w")}
+            wk["enc_w"] = [f"{m}_encode_conv.weight" for m in self.mods]
+            wk["qkvc_w"] = [f"qkv_{m}.weight" for m in self.mods]
             for kind, names in wk.items():
-                st = torch.empty(NM, *params[names[0]].shape, device=self.dev)
+                st = torch.empty(self.nm, *params[names[0]].shape, device=self.dev)
                 self.pws[kind] = st
                 for X, n in enumerate(names):
                     self.pw[n] = st[X]
-            bk = {kk: [self.tk[X][kk] for X in range(NM)] for kk in ("proj_b", "fc1_b", "fc2_b")}
-            bk["enc_b"] = [f"{m}_encode_conv.bias" for m in MODALITIES]
-            bk["qkvc_b"] = [f"qkv_{m}.bias" for m in MODALITIES]
+            bk = {kk: [self.tk[X][kk] for X in range(self.nm)] for kk in ("proj_b", "fc1_b", "fc2_b")}
+            bk["enc_b"] = [f"{m}_encode_conv.bias" for m in self.mods]
+            bk["qkvc_b"] = [f"qkv_{m}.bias" for m in self.mods]
             for kind, names in bk.items():
-                st = torch.empty(NM, params[names[0]].numel(), device=self.dev)
+                st = torch.empty(self.nm, params[names[0]].numel(), device=self.dev)
                 self.pbs[kind] = st
                 self._bias_copies += [(n, st[X]) for X, n in enumerate(names)]
         for k in self.wnames:
@@ -185,8 +191,8 @@ class FusionBlockEngine:
 
     def new_grad_buffers(self):
         """(flat, {name: view}): one zero-filled flat fp32 buffer holding every parameter gradient in
-        ``param_names()`` order - one memset per step, one all-reduce under data parallelism."""
-        names = param_names()
+        ``param_names(self.mods)`` order - one memset per step, one all-reduce under data parallelism."""
+        names = param_names(self.mods)
         flat = torch.zeros(sum(self.p[n].numel() for n in names), device=self.dev)
         views, off = {}, 0
         for n in names:
@@ -206,8 +212,8 @@ class FusionBlockEngine:
             cnt = [self.p[k].numel() for k in self.wnames] + [-self.p[n].numel() for n, _ in self._bias_copies]
             # the concatenated positional table of the multimodal transformer (mmvit4.py:516,521): four plain
             # copies ride in the same launch instead of four torch copy kernels per forward
-            self._posmm = torch.empty((NM + 1) * S, C, device=self.dev, dtype=torch.float32)
-            for X, m in enumerate(MODALITIES + ("fused6",)):
+            self._posmm = torch.empty((self.nm + 1) * S, C, device=self.dev, dtype=torch.float32)
+            for X, m in enumerate(self.mods + ("fused6",)):
                 src.append(self.p[f"{m}_pos"].data_ptr())
                 dst.append(self._posmm[X * S:(X + 1) * S].data_ptr())
                 cnt.append(-S * C)
@@ -224,23 +230,23 @@ class FusionBlockEngine:
         dev = self.dev
         f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         ws = {
-            "x6tok": f(NM, B * S, ENC), "skip": f(NM, B * S, C), "qkvi": f(NM, B * S, 3 * C),
-            "fx6tok": f(B * S, ENC * NM), "tokens": f(B, (NM + 1) * S, C), "posmm": f((NM + 1) * S, C),
-            "ytok": f(B * S, ENC * NM), "out": f(B, ENC * NM, S),
-            "tbm": _TBuf(B, (NM + 1) * S, dev, self.fused_attn, self.dropout_p > 0),
+            "x6tok": f(self.nm, B * S, ENC), "skip": f(self.nm, B * S, C), "qkvi": f(self.nm, B * S, 3 * C),
+            "fx6tok": f(B * S, ENC * self.nm), "tokens": f(B, (self.nm + 1) * S, C), "posmm": f((self.nm + 1) * S, C),
+            "ytok": f(B * S, ENC * self.nm), "out": f(B, ENC * self.nm, S),
+            "tbm": _TBuf(B, (self.nm + 1) * S, dev, self.fused_attn, self.dropout_p > 0),
             # backward
-            "dytok": f(B * S, ENC * NM), "dtokc": f(NM + 1, B * S, C), "dqkvi": f(NM, B * S, 3 * C),
-            "dtok": f(B * S, C), "dx6tok": f(B * S, ENC), "dfx6tok": f(B * S, ENC * NM),
-            "dx6": f(NM, B, ENC, S), "dfused": f(B, ENC * NM, S), "dposmm": f((NM + 1) * S, C),
+            "dytok": f(B * S, ENC * self.nm), "dtokc": f(self.nm + 1, B * S, C), "dqkvi": f(self.nm, B * S, 3 * C),
+            "dtok": f(B * S, C), "dx6tok": f(B * S, ENC), "dfx6tok": f(B * S, ENC * self.nm),
+            "dx6": f(self.nm, B, ENC, S), "dfused": f(B, ENC * self.nm, S), "dposmm": f((self.nm + 1) * S, C),
             "scratch": f(max(ops.layernorm_bwd_scratch_floats(B * 4 * S),
                              ops.colsum_scratch_floats(B * 4 * S, 3 * C))),
         }
         if self.batched:
-            ws["tbi"] = _TBuf(B, S, dev, self.fused_attn, self.dropout_p > 0, G=NM)
-            ws["tb"] = [ws["tbi"].sub(X) for X in range(NM)] + [ws["tbm"]]
-            ws["dtok3"], ws["dx6tok3"] = f(NM, B * S, C), f(NM, B * S, ENC)
+            ws["tbi"] = _TBuf(B, S, dev, self.fused_attn, self.dropout_p > 0, G=self.nm)
+            ws["tb"] = [ws["tbi"].sub(X) for X in range(self.nm)] + [ws["tbm"]]
+            ws["dtok3"], ws["dx6tok3"] = f(self.nm, B * S, C), f(self.nm, B * S, ENC)
         else:
-            ws["tb"] = [_TBuf(B, S, dev, self.fused_attn, self.dropout_p > 0) for _ in range(NM)] + [ws["tbm"]]
+            ws["tb"] = [_TBuf(B, S, dev, self.fused_attn, self.dropout_p > 0) for _ in range(self.nm)] + [ws["tbm"]]
         self._ws[B] = ws
         return ws
 
@@ -426,12 +432,12 @@ class FusionBlockEngine:
     # launch with batch_outer = 3 over stacked activations / weights / biases, their attention one
     # launch over 3B "batches" (per-module dropout sites), so 8192-row problems become 24576-row ones.
     def _blinear(self, x, w, out, R, N, K, bias=None, **k):
-        self._gemm(x, w, out, M=R, N=N, K=K, lda=K, ldb=K, ldd=N, bias=bias, batch=(NM, 1),
+        self._gemm(x, w, out, M=R, N=N, K=K, lda=K, ldb=K, ldd=N, bias=bias, batch=(self.nm, 1),
                    a_step=(R * K, 0), b_step=(N * K, 0), d_step=(R * N, 0),
                    bias_step=N if bias is not None else 0, tag="linear", **k)
 
     def _bdgrad(self, dy, w, dx, R, N_out, K_in, **k):
-        self._gemm(dy, w, dx, M=R, N=K_in, K=N_out, lda=N_out, ldb=K_in, ldd=K_in, b_mn=True, batch=(NM, 1),
+        self._gemm(dy, w, dx, M=R, N=K_in, K=N_out, lda=N_out, ldb=K_in, ldd=K_in, b_mn=True, batch=(self.nm, 1),
                    a_step=(R * N_out, 0), b_step=(N_out * K_in, 0), d_step=(R * K_in, 0), tag="dgrad", **k)
 
     def _bwgrad(self, dy, x, dws, R, N_out, K_in):
@@ -440,18 +446,18 @@ class FusionBlockEngine:
         d01 = (dws[1].data_ptr() - dws[0].data_ptr()) // 4
         d12 = (dws[2].data_ptr() - dws[1].data_ptr()) // 4
         if d01 != d12 or d01 <= 0 or d01 % K_in != 0:
-            for X in range(NM):
+            for X in range(self.nm):
                 self._wgrad(dy[X], x[X], dws[X], R, N_out, K_in)
             return
         kblocks = R // 32
         if N_out > 128 and K_in > 128:
-            tiles = NM * ((N_out + 255) // 256) * ((K_in + 255) // 256)
+            tiles = self.nm * ((N_out + 255) // 256) * ((K_in + 255) // 256)
             split = max(1, min((self.sms // 2) // tiles, max(1, kblocks // 4), 64))
         else:
-            tiles = NM * ((N_out + 127) // 128) * ((K_in + (63 if K_in <= 64 else 127)) // (64 if K_in <= 64 else 128))
+            tiles = self.nm * ((N_out + 127) // 128) * ((K_in + (63 if K_in <= 64 else 127)) // (64 if K_in <= 64 else 128))
             split = _split_for(tiles, kblocks, self.sms)
         self._gemm(dy, x, dws[0], M=N_out, N=K_in, K=R, lda=N_out, ldb=K_in, ldd=K_in, a_mn=True, b_mn=True,
-                   batch=(NM, 1), a_step=(R * N_out, 0), b_step=(R * K_in, 0), d_step=(d01, 0),
+                   batch=(self.nm, 1), a_step=(R * N_out, 0), b_step=(R * K_in, 0), d_step=(d01, 0),
                    split_k=split, epilogue=EPI_ATOMIC_ADD, tag="wgrad")
 
     def _bcolsum(self, x, cols, R, outs, sc):
@@ -460,9 +466,9 @@ class FusionBlockEngine:
         d01 = (outs[1].data_ptr() - outs[0].data_ptr()) // 4
         d12 = (outs[2].data_ptr() - outs[1].data_ptr()) // 4
         if d01 == d12 and d01 > 0 and d01 % 4 == 0:
-            ops.colsum_batched(x, cols, R, cols, outs[0], NM, R * cols, d01, accumulate=True)
+            ops.colsum_batched(x, cols, R, cols, outs[0], self.nm, R * cols, d01, accumulate=True)
         else:
-            for X in range(NM):
+            for X in range(self.nm):
                 ops.colsum(x[X], cols, R, cols, outs[X], sc, accumulate=True)
 
     def _bdrop(self, kind_a: int, kind_b: Optional[int] = None) -> dict:
@@ -476,19 +482,19 @@ class FusionBlockEngine:
         B, P_, p = self._B, self.p, self.dropout_p
         R = B * S
         tb, tk, W, Bs = ws["tbi"], self.tk, self.pws, self.pbs
-        for X in range(NM):
+        for X in range(self.nm):
             ops.transpose(x6[X], ws["x6tok"][X], B, ENC, S, round_out=self.rnd)
         self._blinear(ws["x6tok"], W["enc_w"], ws["skip"], R, C, ENC, bias=Bs["enc_b"], epilogue=EPI_BIAS)
-        for X, m in enumerate(MODALITIES):
+        for X, m in enumerate(self.mods):
             ops.layernorm_fwd(ws["skip"][X], P_[f"{m}_pos"], S, P_[tk[X]["ln1_w"]], P_[tk[X]["ln1_b"]], tb.x1[X],
                               tb.h[X], tb.mean1[X], tb.rstd1[X], R, round_out=self.rnd)
         self._blinear(tb.h, W["qkv_w"], tb.qkv, R, 3 * C, C, round_out=self.rnd)
-        ops.attention_fwd(tb.qkv, tb.O, tb.lse, tb.maskbits, NM * B, S, HEADS, HD, HD ** -0.5, p, self.seed,
+        ops.attention_fwd(tb.qkv, tb.O, tb.lse, tb.maskbits, self.nm * B, S, HEADS, HD, HD ** -0.5, p, self.seed,
                           self.seed_dev, self._site(0, SITE_ATTN), round_out=self.rnd, group_batches=B,
                           group_site_stride=8)
         self._blinear(tb.O, W["proj_w"], tb.x2, R, C, C, bias=Bs["proj_b"], epilogue=EPI_BIAS_RESIDUAL,
                       residual=tb.x1, ldr=C, **self._bdrop(SITE_PROJ, SITE_PRENORM))
-        for X in range(NM):
+        for X in range(self.nm):
             ops.layernorm_fwd(tb.x2[X], None, 1, P_[tk[X]["ln2_w"]], P_[tk[X]["ln2_b"]], None, tb.h2[X],
                               tb.mean2[X], tb.rstd2[X], R, round_out=self.rnd)
         self._blinear(tb.h2, W["fc1_w"], tb.f1, R, C, C, bias=Bs["fc1_b"], epilogue=EPI_BIAS_GELU, aux=tb.u,
@@ -503,17 +509,17 @@ class FusionBlockEngine:
         B, P_, p = self._B, self.p, self.dropout_p
         R = B * S
         tb, tk, W = ws["tbi"], self.tk, self.pws
-        gk = lambda kk: [g[tk[X][kk]] for X in range(NM)]  # noqa: E731
+        gk = lambda kk: [g[tk[X][kk]] for X in range(self.nm)]  # noqa: E731
         dq = ws["dqkvi"]
         self._fork()
         with self._side_ctx():
-            self._bwgrad(dq, tb.x3, [g[f"qkv_{m}.weight"] for m in MODALITIES], R, 3 * C, C)
-            self._bcolsum(dq, 3 * C, R, [g[f"qkv_{m}.bias"] for m in MODALITIES], sc)
+            self._bwgrad(dq, tb.x3, [g[f"qkv_{m}.weight"] for m in self.mods], R, 3 * C, C)
+            self._bcolsum(dq, 3 * C, R, [g[f"qkv_{m}.bias"] for m in self.mods], sc)
         self._bdgrad(dq, W["qkvc_w"], tb.din, R, 3 * C, C)                          # d(trans_X)
         # ---- FeedForward branch
         df2 = tb.din
         if p > 0:
-            for X in range(NM):
+            for X in range(self.nm):
                 ops.dropout_colsum(tb.din[X], tb.t0[X], R, C, p, self.seed, self._site(X, SITE_FFN2),
                                    g[tk[X]["fc2_b"]], self.seed_dev)
             df2 = tb.t0
@@ -530,7 +536,7 @@ class FusionBlockEngine:
             self._bcolsum(tb.t1, C, R, gk("fc1_b"), sc)
         self._bdgrad(tb.t1, W["fc1_w"], tb.t2, R, C, C)                            # d(h2)
         self._join()                                     # t0 / t1 are about to be overwritten
-        for X in range(NM):     # t1 = d(x2); with dropout also t0 = d(x2) * keep(proj_drop) * keep(PreNormDrop)
+        for X in range(self.nm):     # t1 = d(x2); with dropout also t0 = d(x2) * keep(proj_drop) * keep(PreNormDrop)
             dd = dict(dx_drop=tb.t0[X], p=p, seed=self.seed, seed_dev=self.seed_dev,
                       site_a=self._site(X, SITE_PROJ), site_b=self._site(X, SITE_PRENORM)) if p > 0 else {}
             ops.layernorm_bwd(tb.t2[X], tb.x2[X], P_[tk[X]["ln2_w"]], tb.mean2[X], tb.rstd2[X], tb.din[X],
@@ -543,14 +549,14 @@ class FusionBlockEngine:
             self._bwgrad(dy, tb.O, gk("proj_w"), R, C, C)
             self._bcolsum(dy, C, R, gk("proj_b"), sc)
         self._bdgrad(dy, W["proj_w"], tb.t2, R, C, C)                              # d(O)
-        ops.attention_bwd(tb.qkv, tb.O, tb.t2, tb.lse, tb.maskbits, tb.delta, tb.dqkv, NM * B, S, HEADS, HD,
+        ops.attention_bwd(tb.qkv, tb.O, tb.t2, tb.lse, tb.maskbits, tb.delta, tb.dqkv, self.nm * B, S, HEADS, HD,
                           HD ** -0.5, p)
         self._fork()
         with self._side_ctx():
             self._bwgrad(tb.dqkv, tb.h, gk("qkv_w"), R, 3 * C, C)
         self._bdgrad(tb.dqkv, W["qkv_w"], tb.t2, R, 3 * C, C)                      # d(h)
         self._join()                                     # t0 (dy) is about to be overwritten
-        for X, m in enumerate(MODALITIES):
+        for X, m in enumerate(self.mods):
             # d(token) = d(x1) + skip-path gradient (:505) in the same pass: dres2.  The pos gradient of modality m
             # is the batch sum of d(x1) here PLUS that of the multimodal token gradient dtokc[X] - i.e. the batch
             # sum of dtok3[X] - so _backward leaves the first three groups to the one batchsum below.
@@ -560,12 +566,12 @@ class FusionBlockEngine:
         # ---- encode convs (weight / bias / pos gradients beside the last dgrad)
         self._fork()
         with self._side_ctx():
-            for X, m in enumerate(MODALITIES):
+            for X, m in enumerate(self.mods):
                 ops.batchsum(ws["dtok3"][X], B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
-            self._bwgrad(ws["dtok3"], ws["x6tok"], [g[f"{m}_encode_conv.weight"] for m in MODALITIES], R, C, ENC)
-            self._bcolsum(ws["dtok3"], C, R, [g[f"{m}_encode_conv.bias"] for m in MODALITIES], sc)
+            self._bwgrad(ws["dtok3"], ws["x6tok"], [g[f"{m}_encode_conv.weight"] for m in self.mods], R, C, ENC)
+            self._bcolsum(ws["dtok3"], C, R, [g[f"{m}_encode_conv.bias"] for m in self.mods], sc)
         self._bdgrad(ws["dtok3"], W["enc_w"], ws["dx6tok3"], R, C, ENC)
-        ops.transpose(ws["dx6tok3"], ws["dx6"], NM * B, S, ENC)
+        ops.transpose(ws["dx6tok3"], ws["dx6"], self.nm * B, S, ENC)
         self._join()
 
     # ------------------------------------------------------------------------------------------
@@ -624,8 +630,8 @@ class FusionBlockEngine:
         st = self._stage.get(B)
         if st is None:
             f = lambda *shape: torch.empty(*shape, device=self.dev, dtype=torch.float32)  # noqa: E731
-            st = self._stage[B] = {"x6": [f(B, ENC, 8, 8, 8) for _ in range(NM)], "fused": f(B, ENC * NM, 8, 8, 8),
-                                   "gout": f(B, ENC * NM, 8, 8, 8)}
+            st = self._stage[B] = {"x6": [f(B, ENC, 8, 8, 8) for _ in range(self.nm)], "fused": f(B, ENC * self.nm, 8, 8, 8),
+                                   "gout": f(B, ENC * self.nm, 8, 8, 8)}
         return st
 
     def forward(self, x6: List[torch.Tensor], fused_x6: torch.Tensor) -> torch.Tensor:
@@ -648,7 +654,7 @@ class FusionBlockEngine:
         If ``grads`` is given the parameter gradients are accumulated into it."""
         if not self.use_graphs or grads is None:
             return self._backward(gout, grads)
-        gkey = tuple(grads[n].data_ptr() for n in param_names()[:4])
+        gkey = tuple(grads[n].data_ptr() for n in param_names(self.mods)[:4])
         key = ("bwd", gout.data_ptr()) + gkey + (self._B,)
         if self._static_mode("bwd", self._B, key):
             st = self._staging(self._B)
@@ -665,31 +671,31 @@ class FusionBlockEngine:
         if self.batched:
             self._intra_fwd_batched(x6, ws)
         else:
-            for X, m in enumerate(MODALITIES):
+            for X, m in enumerate(self.mods):
                 ops.transpose(x6[X], ws["x6tok"][X], B, ENC, S, round_out=self.rnd)            # :459
                 self._linear(ws["x6tok"][X], W[f"{m}_encode_conv.weight"], ws["skip"][X], B * S, C, ENC,
                              bias=P_[f"{m}_encode_conv.bias"], epilogue=EPI_BIAS)              # :458
                 x3 = self._transformer_fwd(X, ws["skip"][X], P_[f"{m}_pos"], S, ws["tb"][X])   # :462
                 self._linear(x3, W[f"qkv_{m}.weight"], ws["qkvi"][X], B * S, 3 * C, C,
                              bias=P_[f"qkv_{m}.bias"], epilogue=EPI_BIAS)                      # :477-479
-        ops.inter_corr_fwd(ws["qkvi"], ws["skip"], ws["tokens"], NM, B, S, C)              # :481-507
-        ops.transpose(fused_x6, ws["fx6tok"], B, ENC * NM, S, round_out=self.rnd)
-        self._gemm(ws["fx6tok"], W["fused6_encode_conv.weight"], (ws["tokens"], NM * S * C),
-                   M=S, N=C, K=ENC * NM, lda=ENC * NM, ldb=ENC * NM, ldd=C,
+        ops.inter_corr_fwd(ws["qkvi"], ws["skip"], ws["tokens"], self.nm, B, S, C)              # :481-507
+        ops.transpose(fused_x6, ws["fx6tok"], B, ENC * self.nm, S, round_out=self.rnd)
+        self._gemm(ws["fx6tok"], W["fused6_encode_conv.weight"], (ws["tokens"], self.nm * S * C),
+                   M=S, N=C, K=ENC * self.nm, lda=ENC * self.nm, ldb=ENC * self.nm, ldd=C,
                    bias=P_["fused6_encode_conv.bias"], epilogue=EPI_BIAS, batch=(B, 1), tag="linear",
-                   a_step=(S * ENC * NM, 0), d_step=((NM + 1) * S * C, 0))                 # :510-513
+                   a_step=(S * ENC * self.nm, 0), d_step=((self.nm + 1) * S * C, 0))                 # :510-513
         if self.rnd:
             posmm = self._posmm                          # filled by refresh_weights()
         else:
             posmm = ws["posmm"]
-            for X, m in enumerate(MODALITIES + ("fused6",)):
+            for X, m in enumerate(self.mods + ("fused6",)):
                 posmm[X * S:(X + 1) * S].copy_(P_[f"{m}_pos"][0])                          # :516,521
-        tbm = ws["tb"][NM]
-        x3 = self._transformer_fwd(NM, ws["tokens"], posmm, (NM + 1) * S, tbm)             # :519-522
-        self._linear(x3, W["multimodal_decode_conv.weight"], ws["ytok"], B * S, ENC * NM,
-                     (NM + 1) * C, bias=P_["multimodal_decode_conv.bias"], epilogue=EPI_BIAS)  # :525
-        ops.transpose(ws["ytok"], ws["out"], B, S, ENC * NM)                               # :527-528
-        return ws["out"].view(B, ENC * NM, 8, 8, 8)
+        tbm = ws["tb"][self.nm]
+        x3 = self._transformer_fwd(self.nm, ws["tokens"], posmm, (self.nm + 1) * S, tbm)             # :519-522
+        self._linear(x3, W["multimodal_decode_conv.weight"], ws["ytok"], B * S, ENC * self.nm,
+                     (self.nm + 1) * C, bias=P_["multimodal_decode_conv.bias"], epilogue=EPI_BIAS)  # :525
+        ops.transpose(ws["ytok"], ws["out"], B, S, ENC * self.nm)                               # :527-528
+        return ws["out"].view(B, ENC * self.nm, 8, 8, 8)
 
     def _backward(self, gout: torch.Tensor, grads: Optional[Dict[str, torch.Tensor]] = None):
         B = self._B
@@ -699,35 +705,35 @@ class FusionBlockEngine:
         g, sc = grads, ws["scratch"]
         R = B * S
         # ---- decode conv
-        ops.transpose(gout, ws["dytok"], B, ENC * NM, S, round_out=self.rnd)
-        tbm = ws["tb"][NM]
+        ops.transpose(gout, ws["dytok"], B, ENC * self.nm, S, round_out=self.rnd)
+        tbm = ws["tb"][self.nm]
         self._fork()
         with self._side_ctx():
-            self._wgrad(ws["dytok"], tbm.x3, g["multimodal_decode_conv.weight"], R, ENC * NM, (NM + 1) * C)
-            ops.colsum(ws["dytok"], ENC * NM, R, ENC * NM, g["multimodal_decode_conv.bias"], sc, accumulate=True)
-        self._dgrad(ws["dytok"], self.pw["multimodal_decode_conv.weight"], tbm.din, R, ENC * NM, (NM + 1) * C)
+            self._wgrad(ws["dytok"], tbm.x3, g["multimodal_decode_conv.weight"], R, ENC * self.nm, (self.nm + 1) * C)
+            ops.colsum(ws["dytok"], ENC * self.nm, R, ENC * self.nm, g["multimodal_decode_conv.bias"], sc, accumulate=True)
+        self._dgrad(ws["dytok"], self.pw["multimodal_decode_conv.weight"], tbm.din, R, ENC * self.nm, (self.nm + 1) * C)
         # ---- multimodal transformer
         # the token gradient [B,2048,512] leaves the last LayerNorm-backward group-major, [4][B*S][512]: per-group
         # contiguous for the fused6 conv, the skip paths and the pos sums (it used to be a 134 MB strided copy)
-        self._transformer_bwd(NM, tbm.din, tbm, g, sc, regroup=(ws["dtokc"], NM + 1, S))
+        self._transformer_bwd(self.nm, tbm.din, tbm, g, sc, regroup=(ws["dtokc"], self.nm + 1, S))
         # ---- fused6 encode conv; pos grads of the concatenated [2048,512] beside it
-        df6 = ws["dtokc"][NM]
+        df6 = ws["dtokc"][self.nm]
         self._fork()
         with self._side_ctx():
-            for X, m in enumerate(MODALITIES + ("fused6",)):
-                if self.batched and X < NM:
+            for X, m in enumerate(self.mods + ("fused6",)):
+                if self.batched and X < self.nm:
                     continue                       # folded into the batch sum of dtok3[X] (_intra_bwd_batched)
                 ops.batchsum(ws["dtokc"][X], B, S * C, S * C, g[f"{m}_pos"], accumulate=True)
-            self._wgrad(df6, ws["fx6tok"], g["fused6_encode_conv.weight"], R, C, ENC * NM)
+            self._wgrad(df6, ws["fx6tok"], g["fused6_encode_conv.weight"], R, C, ENC * self.nm)
             ops.colsum(df6, C, R, C, g["fused6_encode_conv.bias"], sc, accumulate=True)
-        self._dgrad(df6, self.pw["fused6_encode_conv.weight"], ws["dfx6tok"], R, C, ENC * NM)
-        ops.transpose(ws["dfx6tok"], ws["dfused"], B, S, ENC * NM)
+        self._dgrad(df6, self.pw["fused6_encode_conv.weight"], ws["dfx6tok"], R, C, ENC * self.nm)
+        ops.transpose(ws["dfx6tok"], ws["dfused"], B, S, ENC * self.nm)
         # ---- inter-modal correlation
-        ops.inter_corr_bwd(ws["qkvi"], ws["dtokc"], ws["dqkvi"], NM, B, S, C, g_group_major=True)
+        ops.inter_corr_bwd(ws["qkvi"], ws["dtokc"], ws["dqkvi"], self.nm, B, S, C, g_group_major=True)
         if self.batched:
             self._intra_bwd_batched(ws, g, sc)          # joins the side stream at its end
-            return (ws["dx6"].view(NM, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * NM, 8, 8, 8), grads)
-        for X, m in enumerate(MODALITIES):
+            return (ws["dx6"].view(self.nm, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * self.nm, 8, 8, 8), grads)
+        for X, m in enumerate(self.mods):
             tb = ws["tb"][X]
             dq = ws["dqkvi"][X]
             self._wgrad(dq, tb.x3, g[f"qkv_{m}.weight"], R, 3 * C, C)
@@ -741,4 +747,4 @@ class FusionBlockEngine:
             self._dgrad(ws["dtok"], self.pw[f"{m}_encode_conv.weight"], ws["dx6tok"], R, C, ENC)
             ops.transpose(ws["dx6tok"], ws["dx6"][X], B, S, ENC)
         self._join()
-        return (ws["dx6"].view(NM, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * NM, 8, 8, 8), grads)
+        return (ws["dx6"].view(self.nm, B, ENC, 8, 8, 8), ws["dfused"].view(B, ENC * self.nm, 8, 8, 8), grads)

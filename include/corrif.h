@@ -254,7 +254,7 @@ int corrif_add_rows(const float* a, int64_t lda, const float* b, int64_t ldb, fl
  *   tokens[B, (M+1)*S, C] rows X*S+s receive skip_X + sum_i A_X[m,b] * v_i[b'],
  *                          (m,b) = divmod(M*b'+i, B), A_X[:,b] = softmax_m(q_X[b]*k_m[b]/sqrt(M)).
  * Backward: g = dL/dtokens (same layout) -> dqkv [M,B,S,3C] (overwritten).  dskip_X = g_X.
- * M must be 3.
+ * M = 2..6 modalities (the reference hard-wires 3, mmvit4.py:15; BASELINE.json configs[4] runs 6).
  * ------------------------------------------------------------------------------------------ */
 int corrif_inter_corr_fwd(const float* qkv, const float* skip, float* tokens, int32_t M,
                           int32_t B, int32_t S, int32_t C, void* stream);

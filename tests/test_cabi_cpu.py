@@ -56,8 +56,8 @@ def test_argument_errors_are_reported_without_a_gpu(lib):
     assert rc == -1 and b"null descriptor" in lib.corrif_last_error()
     rc = lib.corrif_layernorm_fwd(1, None, 0, 1, 1, None, 1, 1, 1, 8, 256, 0, None)
     assert rc == -1 and b"C must be 512" in lib.corrif_last_error()
-    rc = lib.corrif_inter_corr_fwd(1, 1, 1, 4, 2, 8, 8, None)
-    assert rc == -1 and b"M must be 3" in lib.corrif_last_error()
+    rc = lib.corrif_inter_corr_fwd(1, 1, 1, 7, 2, 8, 8, None)
+    assert rc == -1 and b"M must be 2..6" in lib.corrif_last_error()
     with pytest.raises(_lib.CorrifError):
         _lib.check(rc, "inter_corr")
 
