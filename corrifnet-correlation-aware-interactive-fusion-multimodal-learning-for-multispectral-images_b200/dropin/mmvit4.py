@@ -103,9 +103,9 @@ class Encoder(nn.Module):
         lv = []
         for i, f in enumerate((f1, f2, f3, f4, f5), start=1):
             a = getattr(self, f"adapt{i}")
-            lv.append(_V.conv_block([_V.to_channels_last(f)], a.weight, a.bias, 1, relu=False, norm=False))
+            lv.append(_V.pointwise_conv(f, a.weight, a.bias, channels_first=True))         # tcgen05 GEMM
         pooled = torch.cat([_V.resize_trilinear(t, (8, 8, 8)) for t in lv], dim=-1)       # [B,8,8,8,184]
-        x6 = _V.conv_block([pooled], self.conv6.weight, self.conv6.bias, 1, relu=False, norm=False)
+        x6 = _V.pointwise_conv(pooled, self.conv6.weight, self.conv6.bias)
         # same shapes as the reference's outputs ([B,C,D,H,W]); the memory underneath stays channels-last
         return tuple(_V.to_channels_first(t) for t in (*lv, x6))
 
@@ -181,7 +181,7 @@ class Decoder_fuse(nn.Module):
     def forward(self, x1, x2, x3, x4, x5):
         """x1..x4: early-fusion volumes [B,D,H,W,C]; x5: x6_inter [B,8,8,8,192] -> sigmoid probs [B,3,1,224,224]."""
         y = self.RFM5(x5)
-        y = _V.conv_block([y], self.RFM5_reduce.weight, self.RFM5_reduce.bias, 1, relu=False, norm=False)
+        y = _V.pointwise_conv(y, self.RFM5_reduce.weight, self.RFM5_reduce.bias)           # tcgen05 GEMM
         for (lvl, _, _, _, cube), skip in zip(self._LEVELS, (x4, x3, x2, x1)):
             up = _V.resize_trilinear(y, tuple(2 * d for d in y.shape[1:4]))                 # self.up2 (:269)
             y = getattr(self, f"d{lvl}_c1")(up)

@@ -227,6 +227,76 @@ def conv_block(srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optiona
     return _ConvBlock.apply(weight, bias, ksize, pad_mode, relu, norm, *srcs)
 
 
+class _PointwiseGemm(torch.autograd.Function):
+    """Bias-only 1x1x1 convolution with many channels and few voxels (the encoders' adapt1-5 / conv6,
+    mmvit4.py:157-164, and RFM5_reduce, :231) as ONE tcgen05 TF32 GEMM [voxels x Cin] . [Cout x Cin]^T + bias - the
+    kernel family of the fusion block (corrif_gemm), which at these shapes (K up to 2048, 1.5 k-98 k rows) is the
+    right tool; the window-staging convolution kernel would run a handful of CTAs through 64 channel passes.
+    ``channels_first``: x is a contiguous [B, Cin, D, H, W] tensor (cuDNN's output); the NCDHW -> channels-last
+    transpose then doubles as the TF32 round-to-nearest pass of the A operand.  Returns a volume [B, D, H, W, Cout]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, channels_first):
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        dev = weight.device
+        if channels_first:
+            x = x.contiguous()
+            B, _, D, H, W = x.shape
+            S = D * H * W
+            xt = torch.empty(B * S, Cin, device=dev, dtype=torch.float32)
+            ops.transpose(x, xt, B, Cin, S, round_out=True)
+        else:
+            x = x.contiguous()
+            B, D, H, W, _ = x.shape
+            S = D * H * W
+            xt = torch.empty(B * S, Cin, device=dev, dtype=torch.float32)
+            ops.round_tf32(x, xt, x.numel())
+        wr = torch.empty(Cout, Cin, device=dev, dtype=torch.float32)
+        ops.round_tf32(weight.detach().contiguous(), wr, wr.numel())
+        out = torch.empty(B, D, H, W, Cout, device=dev, dtype=torch.float32)
+        ops.gemm(xt, wr, out, M=B * S, N=Cout, K=Cin, lda=Cin, ldb=Cin, ldd=Cout, bias=bias.detach().contiguous(),
+                 epilogue=ops.EPI_BIAS, tag="pointwise")
+        ctx.save_for_backward(xt, wr)
+        ctx.cfg = (channels_first, (B, D, H, W))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        xt, wr = ctx.saved_tensors
+        channels_first, (B, D, H, W) = ctx.cfg
+        Cout, Cin = wr.shape
+        R = B * D * H * W
+        dev = dy.device
+        dyc = dy.contiguous()
+        dyr = torch.empty(R, Cout, device=dev, dtype=torch.float32)
+        ops.round_tf32(dyc, dyr, dyr.numel())
+        dbias = torch.zeros(Cout, device=dev, dtype=torch.float32)
+        with ops._rec("volume_colsum", 4.0 * R * Cout):
+            L.check(ops.lib().corrif_volume_colsum(dyc.data_ptr(), Cout, dbias.data_ptr(), R, Cout, _stream()), "volume_colsum")
+        ops._count()
+        dW = torch.zeros(Cout, Cin, 1, 1, 1, device=dev, dtype=torch.float32)
+        split = max(1, min(64, R // 2048)) if R % 32 == 0 else 1
+        ops.gemm(dyr, xt, dW, M=Cout, N=Cin, K=R, lda=Cout, ldb=Cin, ldd=Cin, a_mn=True, b_mn=True, split_k=split,
+                 epilogue=ops.EPI_ATOMIC_ADD, tag="pointwise_wgrad")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxt = torch.empty(R, Cin, device=dev, dtype=torch.float32)
+            ops.gemm(dyr, wr, dxt, M=R, N=Cin, K=Cout, lda=Cout, ldb=Cin, ldd=Cin, b_mn=True, tag="pointwise_dgrad")
+            if channels_first:
+                dx = torch.empty(B, Cin, D, H, W, device=dev, dtype=torch.float32)
+                ops.transpose(dxt, dx, B, D * H * W, Cin)
+            else:
+                dx = dxt.view(B, D, H, W, Cin)
+        return dx, dW, dbias, None
+
+
+def pointwise_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, channels_first: bool = False) -> torch.Tensor:
+    """nn.Conv3d(kernel_size=1) with bias, no activation / norm, as a tcgen05 GEMM; see _PointwiseGemm."""
+    if weight.shape[0] % 4 or weight.shape[1] % 4:
+        raise ValueError("pointwise_conv: channel counts must be multiples of 4")
+    return _PointwiseGemm.apply(x, weight, bias, channels_first)
+
+
 class _Resize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, size, mode):

@@ -321,3 +321,36 @@ def test_kernels_against_stock_pytorch_on_the_same_gpu():
             assert rel_l2(grads[k].cpu().numpy(), named[k].grad.cpu().numpy()) < TOL["tf32"]["pgrad"], k
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+
+
+def test_six_modalities_3584_token_block_against_oracle():
+    """BASELINE.json configs[4] groundwork: every 3-band group of the 20-band cube as its own modality - six modalities,
+    a 7 x 512 = 3584-token multimodal transformer.  The reference hard-wires three (mmvit4.py:15, 394-396), so the
+    checker is the parametrised restatement (oracle.fusion_block(modalities=...)), which IS the reference at M = 3
+    (tests/test_oracle_golden.py pins it to the reference fixtures); engine and restatement share nothing."""
+    mods = ("RGB", "NIR", "SWIR", "G4", "G5", "G6")
+    seed, batch = 606, 1
+    params = O.make_params(seed, mods)
+    x6, fused, gout = O.make_inputs(seed, batch, mods)
+    assert fused.shape[1] == 64 * 6 and params["multimodal_decode_conv.weight"].shape[:2] == (384, 3584)
+    torch.set_num_threads(os.cpu_count() or 1)
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    xs = [x.double().requires_grad_(True) for x in x6]
+    fx = fused.double().requires_grad_(True)
+    ref = O.fusion_block(p64, xs, fx, None, mods)
+    ref.backward(gout.double())
+    dev = torch.device("cuda:0")
+    eng = fusion.FusionBlockEngine({k: v.to(dev).contiguous() for k, v in params.items()}, dropout_p=0.0,
+                                   precision="tf32", modalities=mods)
+    out = eng.forward([x.to(dev) for x in x6], fused.to(dev)).clone()
+    dx6, dfused, grads = eng.backward(gout.to(dev))
+    torch.cuda.synchronize()
+    assert out.shape == (batch, 384, 8, 8, 8)
+    tol = TOL["tf32"]
+    assert rel_l2(out.cpu().numpy(), ref.detach().numpy()) < tol["out"]
+    assert rel_l2(dfused.cpu().numpy(), fx.grad.numpy()) < tol["xgrad"]
+    for i in range(6):
+        assert rel_l2(dx6[i].cpu().numpy(), xs[i].grad.numpy()) < tol["xgrad"], i
+    for k in ("G6_pos", "qkv_G5.weight", "G4_transformer.cross_attention_list.0.fn.fn.qkv.weight", "fused6_encode_conv.weight",
+              "multimodal_transformer.cross_attention_list.0.fn.fn.proj.weight", "multimodal_decode_conv.weight", "RGB_encode_conv.bias"):
+        assert rel_l2(grads[k].cpu().numpy(), p64[k].grad.numpy()) < tol["pgrad"], k

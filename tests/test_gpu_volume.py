@@ -268,3 +268,31 @@ def test_decoder_and_early_fusion_against_stock_pytorch_modules():
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
         sys.path.remove(dropin_dir)
         sys.modules.pop("mmvit4", None)
+
+
+@pytest.mark.parametrize("case", [(2, 2048, 64, 3, 8, 8, True), (2, 256, 16, 3, 16, 16, True), (1, 64, 8, 3, 14, 14, True),
+                                  (2, 184, 64, 8, 8, 8, False), (2, 192, 128, 8, 8, 8, False), (1, 1024, 64, 3, 7, 7, True)])
+def test_pointwise_conv_gemm_path(case):
+    """Bias-only 1x1x1 convolutions of the encoder tail / RFM5_reduce on the tcgen05 GEMM (volume.pointwise_conv),
+    from cuDNN-layout ([B,C,D,H,W]) and channels-last inputs, forward and all three gradients, against fp64 PyTorch."""
+    B, cin, cout, D, H, W, cf = case
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(B, cin, D, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, 1, 1, 1, generator=g, dtype=torch.float64) * cin ** -0.5
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    go = torch.randn(B, cout, D, H, W, generator=g, dtype=torch.float64)
+    dev = torch.device("cuda:0")
+    rx, rw, rb = (t.to(dev).requires_grad_(True) for t in (x, w, b))
+    F.conv3d(rx, rw, rb).backward(go.to(dev))
+    xin = x.float().to(dev) if cf else x.float().to(dev).permute(0, 2, 3, 4, 1).contiguous()
+    xin.requires_grad_(True)
+    wt, bt = w.float().to(dev).requires_grad_(True), b.float().to(dev).requires_grad_(True)
+    y = V.pointwise_conv(xin, wt, bt, channels_first=cf)
+    y.backward(go.float().to(dev).permute(0, 2, 3, 4, 1).contiguous())
+    torch.cuda.synchronize()
+    ref_y = F.conv3d(rx, rw, rb).detach()
+    assert rel_l2(y.detach().permute(0, 4, 1, 2, 3).cpu().numpy(), ref_y.cpu().numpy()) < TOL_OUT
+    dx = xin.grad if cf else xin.grad.permute(0, 4, 1, 2, 3)
+    assert rel_l2(dx.cpu().numpy(), rx.grad.cpu().numpy()) < TOL_GRAD
+    assert rel_l2(wt.grad.cpu().numpy(), rw.grad.cpu().numpy()) < TOL_GRAD
+    assert rel_l2(bt.grad.cpu().numpy(), rb.grad.cpu().numpy()) < 1e-5
