@@ -45,19 +45,21 @@ struct Geom {
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(   // not volatile: a pure function of its operands, the scheduler may interleave it with the fragment loads
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// Shared-memory fragment loads as ordinary C++ loads through the shared window (ordered against __syncthreads by
+// the compiler, free to be scheduled ahead of the MMAs that do not depend on them - volatile asm pinned every load
+// and every MMA in program order).
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
+  return *reinterpret_cast<const uint32_t*>(__cvta_shared_to_generic(addr));
 }
 __device__ __forceinline__ void lds64(uint32_t addr, uint32_t& a, uint32_t& b) {
-  asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+  const uint2 v = *reinterpret_cast<const uint2*>(__cvta_shared_to_generic(addr));
+  a = v.x; b = v.y;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
@@ -169,6 +171,59 @@ __device__ __forceinline__ void stage_window(uint32_t smem_in, const Src (&src)[
   }
 }
 
+// ---- asynchronous staging (cp.async): global -> shared without a register round trip, zero-filled when invalid --
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// The 3x3x3 window of stage_window<3>, issued as cp.async copies (same thread -> (x, channel group) mapping).  The
+// data lands un-rounded; consumers add half a TF32 ulp when they load their fragments (see rnd_u32).
+__device__ __forceinline__ void stage_window3_async(uint32_t smem_in, const Src (&src)[MAX_SRC], int nsrc, const Geom& g,
+                                                    int b, int z0, int y0, int x0, int c0, int kc, bool replicate) {
+  const int gshift = kc == 32 ? 3 : (kc == 16 ? 2 : 1);
+  const int groups = 1 << gshift;
+  const int cg = threadIdx.x & (groups - 1);
+  const float* sp = nullptr;
+  long long sld = 0;
+  {
+    int c = c0 + cg * 4;
+#pragma unroll
+    for (int s = 0; s < MAX_SRC; ++s)
+      if (s < nsrc && sp == nullptr) {
+        if (c < src[s].C) { sp = src[s].p + c; sld = src[s].ld; }
+        else c -= src[s].C;
+      }
+  }
+  const int per = HX << gshift;
+  const int lines_per_iter = NTHREADS / per;
+  const int rl = threadIdx.x / per, hx = (threadIdx.x - rl * per) >> gshift;
+  if (rl >= lines_per_iter) return;
+  int x = x0 + hx - 1;
+  const bool xin = x >= 0 && x < g.W;
+  x = min(max(x, 0), g.W - 1);
+  const uint32_t sdst = smem_in + cg * CGS3 + hx * 16;
+  const float* any = src[0].p;                       // a valid address for the zero-fill form
+#pragma unroll 4
+  for (int r = rl; r < HZ * HY; r += lines_per_iter) {
+    const int hz = r / HY, hy = r - hz * HY;
+    int z = z0 + hz - 1, y = y0 + hy - 1;
+    bool inside = xin && z >= 0 && z < g.D && y >= 0 && y < g.H;
+    if (replicate) { z = min(max(z, 0), g.D - 1); y = min(max(y, 0), g.H - 1); inside = true; }
+    inside = inside && sp != nullptr;
+    const float* p = inside ? sp + (long long)(((b * g.D + z) * g.H + y) * g.W + x) * sld : any;
+    cp_async16(sdst + r * (HX * 16), p, inside);
+  }
+}
+__device__ __forceinline__ void stage_linear_async(uint32_t smem_dst, const float4* __restrict__ gsrc, int n16) {
+  for (int i = threadIdx.x; i < n16; i += NTHREADS) cp_async16(smem_dst + i * 16, gsrc + i, true);
+}
+// round-to-nearest TF32 of a raw fp32 bit pattern headed for an MMA operand (the MMA drops the low 13 bits)
+__device__ __forceinline__ uint32_t rnd_u32(uint32_t v) { return v + 0x1000u; }
+
 // batched copy of n16 16-byte words global -> shared (packed weights), loads first, then stores
 __device__ __forceinline__ void stage_linear(uint32_t smem_dst, const float4* __restrict__ gsrc, int n16) {
   constexpr int U = 8;
@@ -188,16 +243,16 @@ __device__ __forceinline__ void stage_linear(uint32_t smem_dst, const float4* __
 }
 
 // Tiling plan shared by the packer and the kernels: NB = 8-channel output blocks per CTA, KC = input channels
-// staged per pass.  Sized for occupancy (the loader's DRAM latency is hidden by the OTHER resident CTAs' math):
-// NB = 1 -> 52 KB of shared memory and 112 registers = 4 CTAs per SM, NB = 2 -> 3, wider blocks -> 2.  KC never
-// exceeds the channel count rounded up to 8 / 16 / 32 (no passes over zero padding).
+// staged per pass.  Sized so that TWO window buffers plus the packed weights of a pass leave room for 2-3 CTAs per
+// SM (3x3x3: 16 channels per pass for one output block, 8 for wider ones).  KC never exceeds the channel count
+// rounded up to 8 / 16 / 32 (no passes over zero padding).
 struct Plan { int NB, KC; };
 inline Plan conv_plan(int Cin, int Cout, int ks) {
   static const int cand[6] = {8, 6, 4, 3, 2, 1};
   Plan p{1, 32};
   for (int i = 0; i < 6; ++i)
     if ((Cout / 8) % cand[i] == 0) { p.NB = cand[i]; break; }
-  if (ks == 3) p.KC = p.NB <= 4 ? 16 : 8;
+  if (ks == 3) p.KC = p.NB == 1 ? 16 : 8;
   else p.KC = 32;
   const int need = Cin <= 8 ? 8 : (Cin <= 16 ? 16 : 32);
   if (p.KC > need) p.KC = need;

@@ -12,6 +12,7 @@
 // The epilogue adds the bias, applies ReLU, stores channels-last and reduces the per-(sample, channel) sum and sum
 // of squares of what it stored (InstanceNorm statistics) through warp shuffles -> shared -> one double atomic per
 // channel and CTA.
+#include <stdlib.h>
 #include "conv3d.cuh"
 
 namespace corrif {
@@ -219,6 +220,180 @@ __global__ void __launch_bounds__(NTHREADS, NB == 1 ? 4 : (NB == 2 ? 3 : 2)) con
   }   // tile loop
 }
 
+// ---- 3x3x3, software-pipelined: cp.async double buffering of the window (and of the weights when they change per
+// stage) -----------------------------------------------------------------------------------------------------
+// The kernel above alternates "stage" and "compute" inside a CTA and relies on the other resident CTAs to cover the
+// staging latency; here a CTA walks its sequence of (tile, channel pass) stages with TWO window buffers: the
+// cp.async copies of stage s+1 are in flight while the warps run the MMAs of stage s.  The packed weights stay
+// resident in shared memory when all passes fit (Cin <= 32 with one output block: the 128^3 / 64^3 layers), else
+// they are double-buffered with the window.  Fragments are rounded to TF32 when loaded (one integer add each).
+template <int NB>
+__global__ void __launch_bounds__(NTHREADS, NB == 1 ? 2 : (NB == 2 ? 3 : 2)) conv3d_fwd3_async_kernel(const FwdArgs a, const int w_resident) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ float s_stat[NB * 8 * 2];
+  const int KC = a.KC, steps = KC / 8, groups = KC / 4;
+  const int w_floats = 27 * steps * NB * 64;
+  const int passes = (a.Cin + KC - 1) / KC;
+  const uint32_t win_bytes = groups * CGS3;
+  const uint32_t s_in0 = smem_addr(smem);
+  const uint32_t s_w0 = s_in0 + 2 * win_bytes;       // resident: [pass][w]; else two buffers
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nt = blockIdx.y;
+  const int per = a.g.tiles_x * a.g.tiles_y * a.g.tiles_z;
+  const int total_tiles = per * a.g.B;
+  const int my_tiles = total_tiles > (int)blockIdx.x ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int nstages = my_tiles * passes;
+  const float4* wbase = reinterpret_cast<const float4*>(a.wpk + (long long)nt * passes * w_floats);
+
+  auto tile_coords = [&](int stage, int& b, int& z0, int& y0, int& x0, int& pass) {
+    const int ti = stage / passes;
+    pass = stage - ti * passes;
+    int tile = blockIdx.x + ti * gridDim.x;
+    b = tile / per; tile -= b * per;
+    x0 = (tile % a.g.tiles_x) * TX; tile /= a.g.tiles_x;
+    y0 = (tile % a.g.tiles_y) * TY;
+    z0 = (tile / a.g.tiles_y) * TZ;
+  };
+  auto issue = [&](int stage) {
+    int b, z0, y0, x0, pass;
+    tile_coords(stage, b, z0, y0, x0, pass);
+    stage_window3_async(s_in0 + (stage & 1) * win_bytes, a.src, a.nsrc, a.g, b, z0, y0, x0, pass * KC, KC, a.replicate != 0);
+    if (!w_resident) stage_linear_async(s_w0 + (stage & 1) * (w_floats * 4), wbase + (long long)pass * (w_floats / 4), w_floats / 4);
+  };
+
+  if (nstages > 0) {
+    if (w_resident) stage_linear_async(s_w0, wbase, passes * (w_floats / 4));
+    issue(0);
+  }
+  cp_async_commit();
+
+  float acc[4][NB][4];
+  for (int stage = 0; stage < nstages; ++stage) {
+    int b, z0, y0, x0, pass;
+    tile_coords(stage, b, z0, y0, x0, pass);
+    if (stage + 1 < nstages) issue(stage + 1);
+    cp_async_commit();
+    cp_async_wait<1>();                               // everything but the newest group: stage `stage` has landed
+    __syncthreads();
+    if (pass == 0) {
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[mb][nb][j] = 0.f;
+    }
+    const uint32_t s_in = s_in0 + (stage & 1) * win_bytes;
+    const uint32_t s_w = w_resident ? s_w0 + pass * (w_floats * 4) : s_w0 + (stage & 1) * (w_floats * 4);
+    for (int step = 0; step < steps; ++step) {
+      const uint32_t in0 = s_in + (2 * step) * CGS3 + t * 4;
+#pragma unroll 1
+      for (int dz = 0; dz < 3; ++dz) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          uint32_t A[10][2];
+#pragma unroll
+          for (int r = 0; r < 10; ++r) {
+            const uint32_t ad = in0 + ((((warp + dz) * HY + r) * HX) + g + dx) * 16;
+            A[r][0] = rnd_u32(lds32(ad));
+            A[r][1] = rnd_u32(lds32(ad + CGS3));
+          }
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const int tap = (dz * 3 + dy) * 3 + dx;
+            uint32_t Bf[NB][2];
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+              lds64(s_w + (((tap * steps + step) * NB + nb) * 64 + lane * 2) * 4, Bf[nb][0], Bf[nb][1]);
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb)
+                mma_tf32(acc[mb][nb], A[2 * mb + dy][0], A[2 * mb + 1 + dy][0], A[2 * mb + dy][1],
+                         A[2 * mb + 1 + dy][1], Bf[nb][0], Bf[nb][1]);
+          }
+        }
+      }
+    }
+    if (pass == passes - 1) {
+      // ---- epilogue of the tile (same as the first kernel) ----
+      if (a.stats != nullptr)
+        for (int i = threadIdx.x; i < NB * 16; i += NTHREADS) s_stat[i] = 0.f;
+      __syncthreads();
+      float cs[NB][2], cq[NB][2];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) { cs[nb][0] = cs[nb][1] = cq[nb][0] = cq[nb][1] = 0.f; }
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int z = z0 + warp, y = y0 + 2 * mb + h, x = x0 + g;
+          const bool ok = z < a.g.D && y < a.g.H && x < a.g.W;
+          const long long vox = ((b * a.g.D + z) * a.g.H + y) * a.g.W + x;
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            const int co = (nt * NB + nb) * 8 + 2 * t;
+            float v0f = acc[mb][nb][2 * h], v1f = acc[mb][nb][2 * h + 1];
+            if (a.bias != nullptr) { v0f += __ldg(a.bias + co); v1f += __ldg(a.bias + co + 1); }
+            if (a.relu) { v0f = fmaxf(v0f, 0.f); v1f = fmaxf(v1f, 0.f); }
+            if (ok) {
+              *reinterpret_cast<float2*>(a.out + vox * a.ldo + co) = make_float2(v0f, v1f);
+              cs[nb][0] += v0f; cs[nb][1] += v1f;
+              cq[nb][0] += v0f * v0f; cq[nb][1] += v1f * v1f;
+            }
+          }
+        }
+      }
+      if (a.stats != nullptr) {
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float s = cs[nb][j], q = cq[nb][j];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              s += __shfl_xor_sync(0xffffffffu, s, o);
+              q += __shfl_xor_sync(0xffffffffu, q, o);
+            }
+            if (g == 0) {
+              atomicAdd(&s_stat[(nb * 8 + 2 * t + j) * 2], s);
+              atomicAdd(&s_stat[(nb * 8 + 2 * t + j) * 2 + 1], q);
+            }
+          }
+        __syncthreads();
+        for (int i = threadIdx.x; i < NB * 16; i += NTHREADS) {
+          const int co = nt * NB * 8 + (i >> 1);
+          atomicAdd(a.stats + ((long long)b * a.Cout + co) * 2 + (i & 1), (double)s_stat[i]);
+        }
+      }
+    }
+    __syncthreads();                                  // buffer (stage & 1) may be refilled by the next iteration's issue
+  }
+  cp_async_wait<0>();
+}
+
+template <int NB>
+static int launch_async(const FwdArgs& a, cudaStream_t stream) {
+  const int steps = a.KC / 8, groups = a.KC / 4;
+  const int w_bytes = 27 * steps * NB * 64 * 4;
+  const int passes = (a.Cin + a.KC - 1) / a.KC;
+  const int w_resident = passes * w_bytes <= 32 * 1024;
+  const int smem = 2 * groups * CGS3 + (w_resident ? passes * w_bytes : 2 * w_bytes);
+  auto kern = conv3d_fwd3_async_kernel<NB>;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_last_error("conv3d_fwd(async): smem attribute (%d B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+    configured = smem;
+  }
+  const long long total = (long long)a.g.tiles_x * a.g.tiles_y * a.g.tiles_z * a.g.B;
+  const int ntiles = a.Cout / (NB * 8);
+  long long gx = (long long)num_sms() * 16 / ntiles;
+  gx = gx < 1 ? 1 : (gx > total ? total : gx);
+  kern<<<dim3((unsigned)gx, (unsigned)ntiles, 1), NTHREADS, smem, stream>>>(a, w_resident);
+  return launch_status("conv3d_fwd(async)");
+}
+
 template <int KS, int NB>
 static int launch(const FwdArgs& a, cudaStream_t stream) {
   constexpr int TAPS = KS == 3 ? 27 : 1;
@@ -339,6 +514,19 @@ extern "C" int corrif_conv3d_fwd(const corrif_conv3d_desc* desc, void* stream) {
   a.Cin = d.Cin; a.Cout = d.Cout; a.KC = p.KC;
   a.replicate = d.pad_mode == CORRIF_PAD_REPLICATE; a.relu = d.relu;
   a.wpk = d.wpk; a.bias = d.bias; a.out = d.out; a.ldo = d.ldo; a.stats = d.stats;
+  // A/B switch.  Measured on B200 (tools/conv_bench.py, batch 8): the double-buffered kernel needs 2 x window of shared
+  // memory, i.e. 2 CTAs per SM instead of 4, and loses: 32 -> 8 channels at 128^3 2.77 ms vs 2.21 ms, 64 -> 16 at 64^3
+  // 0.91 vs 0.76 ms.  With the loader's instruction count fixed the kernel is co-limited by shared-memory fragment
+  // loads (1.9 per MMA) and the MMA pipe, which more resident warps overlap better than a deeper copy pipeline.
+  static const bool use_async = getenv("CORRIF_CONV_ASYNC") != nullptr;
+  if (d.ksize == 3 && p.NB <= 4 && use_async) {
+    switch (p.NB) {
+      case 1: return launch_async<1>(a, (cudaStream_t)stream);
+      case 2: return launch_async<2>(a, (cudaStream_t)stream);
+      case 3: return launch_async<3>(a, (cudaStream_t)stream);
+      default: return launch_async<4>(a, (cudaStream_t)stream);
+    }
+  }
   if (d.ksize == 3) return launch_nb<3>(p.NB, a, (cudaStream_t)stream);
   return launch_nb<1>(p.NB, a, (cudaStream_t)stream);
 }

@@ -164,11 +164,14 @@ __global__ void __launch_bounds__(NTHREADS, NB <= 2 ? 3 : 2) conv3d_wgrad_kernel
 // and keeps their gradient fragments in 16 registers; it walks the 3 x 10 x 3 (dz, window line, dx) A fragments
 // once, and each of them is multiplied with the gradient lines y = line - dy of all three dy taps: 360 + 16 loads
 // feed 216 MMAs (1.7 per MMA).  All 27 taps accumulate in registers (108); 8 output channels per CTA (grid.z).
-__global__ void __launch_bounds__(NTHREADS, 3) conv3d_wgrad3_kernel(const WgradArgs a) {
+// Window and gradient tile are double-buffered with cp.async (the next tile travels while this one is multiplied);
+// fragments are rounded to TF32 as they are loaded.
+__global__ void __launch_bounds__(NTHREADS, 2) conv3d_wgrad3_kernel(const WgradArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int GLD = 12;                            // 8 channels + 4 padding floats per gradient voxel
-  const uint32_t s_in = smem_addr(smem);
-  const uint32_t s_g = s_in + (WKC / 4) * CGS3;
+  constexpr uint32_t WIN = (WKC / 4) * CGS3, GT = TILE_VOX * GLD * 4;
+  const uint32_t s_in0 = smem_addr(smem);            // two window buffers, then two gradient-tile buffers
+  const uint32_t s_g0 = s_in0 + 2 * WIN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int pass = blockIdx.y, nt = blockIdx.z;
   const int per = a.g.tiles_x * a.g.tiles_y * a.g.tiles_z;
@@ -179,38 +182,39 @@ __global__ void __launch_bounds__(NTHREADS, 3) conv3d_wgrad3_kernel(const WgradA
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+  // cp.async double buffering over this CTA's tiles: tile i+1 is in flight while tile i is multiplied
+  auto issue = [&](int tile, int buf) {
     const int b = tile / per;
     int rem = tile - b * per;
     const int x0 = (rem % a.g.tiles_x) * TX; rem /= a.g.tiles_x;
     const int y0 = (rem % a.g.tiles_y) * TY;
     const int z0 = (rem / a.g.tiles_y) * TZ;
-    __syncthreads();
-    stage_window<3>(s_in, a.src, a.nsrc, a.g, b, z0, y0, x0, 0, 0, pass * WKC, WKC, a.replicate != 0);
-    {   // gradient tile: 256 voxels x 8 channels (2 float4 per voxel), zeros outside the volume
-      float4 val[4];
+    stage_window3_async(s_in0 + buf * WIN, a.src, a.nsrc, a.g, b, z0, y0, x0, pass * WKC, WKC, a.replicate != 0);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = threadIdx.x + u * NTHREADS;          // 512 items
-        const int q = i & 1, v = i >> 1;
-        const int x = x0 + (v & 7), y = y0 + ((v >> 3) & 7), z = z0 + (v >> 6);
-        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (z < a.g.D && y < a.g.H && x < a.g.W)
-          val[u] = ld4(a.grad + (long long)(((b * a.g.D + z) * a.g.H + y) * a.g.W + x) * a.ldg + nt * 8 + q * 4);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = threadIdx.x + u * NTHREADS;
-        sts128(s_g + ((i >> 1) * GLD + (i & 1) * 4) * 4, rnd4(val[u]));
-      }
+    for (int u = 0; u < 4; ++u) {                     // gradient tile: 256 voxels x 8 channels, zeros outside the volume
+      const int i = threadIdx.x + u * NTHREADS;
+      const int q = i & 1, v = i >> 1;
+      const int x = x0 + (v & 7), y = y0 + ((v >> 3) & 7), z = z0 + (v >> 6);
+      const bool ok = z < a.g.D && y < a.g.H && x < a.g.W;
+      const float* p = ok ? a.grad + (long long)(((b * a.g.D + z) * a.g.H + y) * a.g.W + x) * a.ldg + nt * 8 + q * 4 : a.grad;
+      cp_async16(s_g0 + buf * GT + (v * GLD + q * 4) * 4, p, ok);
     }
+  };
+  int tile = blockIdx.x, buf = 0;
+  if (tile < a.total_tiles) issue(tile, 0);
+  cp_async_commit();
+  for (; tile < a.total_tiles; tile += gridDim.x, buf ^= 1) {
+    if (tile + (int)gridDim.x < a.total_tiles) issue(tile + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    const uint32_t s_in = s_in0 + buf * WIN, s_g = s_g0 + buf * GT;
     uint32_t Bf[8][2];
 #pragma unroll
     for (int yy = 0; yy < 8; ++yy) {
       const uint32_t gb = s_g + (((warp * 8 + yy) * 8 + 2 * t) * GLD + g) * 4;
-      Bf[yy][0] = lds32(gb);
-      Bf[yy][1] = lds32(gb + GLD * 4);
+      Bf[yy][0] = rnd_u32(lds32(gb));
+      Bf[yy][1] = rnd_u32(lds32(gb + GLD * 4));
     }
     const uint32_t a_lane = s_in + (g >> 2) * CGS3 + (g & 3) * 4 + (2 * t) * 16;
 #pragma unroll
@@ -220,7 +224,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) conv3d_wgrad3_kernel(const WgradA
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const uint32_t ad = a_lane + ((((warp + dz) * HY + hy) * HX) + dx) * 16;
-          const uint32_t a0 = lds32(ad), a1 = lds32(ad + 2 * CGS3), a2 = lds32(ad + 16), a3 = lds32(ad + 2 * CGS3 + 16);
+          const uint32_t a0 = rnd_u32(lds32(ad)), a1 = rnd_u32(lds32(ad + 2 * CGS3)), a2 = rnd_u32(lds32(ad + 16)),
+                         a3 = rnd_u32(lds32(ad + 2 * CGS3 + 16));
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             const int yy = hy - dy;
@@ -229,7 +234,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) conv3d_wgrad3_kernel(const WgradA
         }
       }
     }
+    __syncthreads();                                  // this buffer is refilled by the next iteration's issue
   }
+  cp_async_wait<0>();
 #pragma unroll
   for (int tap = 0; tap < 27; ++tap)
 #pragma unroll
@@ -242,7 +249,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) conv3d_wgrad3_kernel(const WgradA
 
 static int launch_wgrad3(const WgradArgs& a0, cudaStream_t stream) {
   WgradArgs a = a0;
-  const int smem = (WKC / 4) * CGS3 + TILE_VOX * 12 * 4;
+  const int smem = 2 * ((WKC / 4) * CGS3 + TILE_VOX * 12 * 4);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv3d_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -251,7 +258,7 @@ static int launch_wgrad3(const WgradArgs& a0, cudaStream_t stream) {
   }
   a.total_tiles = a.g.tiles_x * a.g.tiles_y * a.g.tiles_z * a.g.B;
   const int passes = (a.Cin + WKC - 1) / WKC, ntiles = a.Cout / 8;
-  int px = (6 * num_sms() + passes * ntiles - 1) / (passes * ntiles);     // two rounds of the 3 resident CTAs per SM
+  int px = (4 * num_sms() + passes * ntiles - 1) / (passes * ntiles);     // two rounds of the 2 resident CTAs per SM
   px = px < 1 ? 1 : (px > a.total_tiles ? a.total_tiles : px);
   dim3 grid((unsigned)px, (unsigned)passes, (unsigned)ntiles);
   conv3d_wgrad3_kernel<<<grid, NTHREADS, smem, stream>>>(a);
