@@ -72,10 +72,18 @@ __global__ void __launch_bounds__(THREADS) instnorm_apply_kernel(float* x, long 
     }
   }
   float* base = x + (long long)b * nvox * ld + 4 * l.q;
-  for (long long v = l.v; v < nvox; v += l.vstep) {
-    float4 r = ld4(base + v * ld);
-    r.x = (r.x - mu[0]) * rs[0]; r.y = (r.y - mu[1]) * rs[1]; r.z = (r.z - mu[2]) * rs[2]; r.w = (r.w - mu[3]) * rs[3];
-    st4(base + v * ld, r);
+  for (long long v = l.v; v < nvox; v += 4 * l.vstep) {        // 4 independent loads in flight per thread
+    float4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u * l.vstep < nvox) r[u] = ld4(base + (v + u * l.vstep) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u * l.vstep < nvox) {
+        r[u].x = (r[u].x - mu[0]) * rs[0]; r[u].y = (r[u].y - mu[1]) * rs[1];
+        r[u].z = (r[u].z - mu[2]) * rs[2]; r[u].w = (r[u].w - mu[3]) * rs[3];
+        st4(base + (v + u * l.vstep) * ld, r[u]);
+      }
   }
 }
 
@@ -91,6 +99,7 @@ __global__ void __launch_bounds__(THREADS) instnorm_bwd_stats_kernel(const float
     const float* py = y + (long long)b * nvox * ldy + 4 * l.q;
     float fs[4] = {0, 0, 0, 0}, ft[4] = {0, 0, 0, 0};
     int n = 0;
+#pragma unroll 4
     for (long long v = l.v; v < nvox; v += l.vstep) {
       const float4 d = ld4_stream(pd + v * lddy), yy = ld4_stream(py + v * ldy);
       fs[0] += d.x; fs[1] += d.y; fs[2] += d.z; fs[3] += d.w;
@@ -129,17 +138,25 @@ __global__ void __launch_bounds__(THREADS) instnorm_relu_bwd_apply_kernel(
     const float* pd = dy + (long long)b * nvox * lddy + 4 * l.q;
     const float* py = y + (long long)b * nvox * ldy + 4 * l.q;
     float* pg = g + (long long)b * nvox * ldg + 4 * l.q;
-    for (long long v = l.v; v < nvox; v += l.vstep) {
-      const float4 d = ld4(pd + v * lddy), yy = ld4_stream(py + v * ldy);
-      float4 o;
-      o.x = rs[0] * (d.x - m1[0] - yy.x * m2[0]); o.y = rs[1] * (d.y - m1[1] - yy.y * m2[1]);
-      o.z = rs[2] * (d.z - m1[2] - yy.z * m2[2]); o.w = rs[3] * (d.w - m1[3] - yy.w * m2[3]);
-      if (relu) {
-        o.x = yy.x > thr[0] ? o.x : 0.f; o.y = yy.y > thr[1] ? o.y : 0.f;
-        o.z = yy.z > thr[2] ? o.z : 0.f; o.w = yy.w > thr[3] ? o.w : 0.f;
+    for (long long v0 = l.v; v0 < nvox; v0 += 2 * l.vstep) {      // two voxels per iteration: 4 loads in flight
+      float4 d[2], yy[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (v0 + u * l.vstep < nvox) { d[u] = ld4(pd + (v0 + u * l.vstep) * lddy); yy[u] = ld4_stream(py + (v0 + u * l.vstep) * ldy); }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const long long v = v0 + u * l.vstep;
+        if (v >= nvox) continue;
+        float4 o;
+        o.x = rs[0] * (d[u].x - m1[0] - yy[u].x * m2[0]); o.y = rs[1] * (d[u].y - m1[1] - yy[u].y * m2[1]);
+        o.z = rs[2] * (d[u].z - m1[2] - yy[u].z * m2[2]); o.w = rs[3] * (d[u].w - m1[3] - yy[u].w * m2[3]);
+        if (relu) {
+          o.x = yy[u].x > thr[0] ? o.x : 0.f; o.y = yy[u].y > thr[1] ? o.y : 0.f;
+          o.z = yy[u].z > thr[2] ? o.z : 0.f; o.w = yy[u].w > thr[3] ? o.w : 0.f;
+        }
+        st4(pg + v * ldg, o);
+        acc[0] += o.x; acc[1] += o.y; acc[2] += o.z; acc[3] += o.w;
       }
-      st4(pg + v * ldg, o);
-      acc[0] += o.x; acc[1] += o.y; acc[2] += o.z; acc[3] += o.w;
     }
   }
   if (dbias != nullptr) {
@@ -343,7 +360,10 @@ __device__ __forceinline__ void nn_range(int i, float scale, int in, int out, in
   while (lo <= hi && nn_src(lo, scale, in) != i) ++lo;
   while (hi >= lo && nn_src(hi, scale, in) != i) --hi;
 }
-// one warp per (input voxel, channel quad group): lanes stride the contributing output voxels, then shuffle-reduce
+// One warp per input voxel.  Lanes are (slot, quad): `slots` contributing output voxels are read side by side, each
+// with its Q = C/4 quads by consecutive lanes, so a warp load covers slots x (C*4 contiguous bytes) - the first version
+// (one warp per quad, lanes over voxels) fetched 16 bytes out of every 32-byte sector.  Partial sums of the slots are
+// folded with shuffles.  C > 128 loops over groups of 32 quads.
 __global__ void __launch_bounds__(THREADS) nearest_bwd_kernel(const float* __restrict__ dy, long long lddy, float* dx,
                                                               long long lddx, int C, int Di, int Hi, int Wi, int Do,
                                                               int Ho, int Wo, long long total_warps) {
@@ -351,8 +371,7 @@ __global__ void __launch_bounds__(THREADS) nearest_bwd_kernel(const float* __res
   const float sz = (float)Di / (float)Do, sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= total_warps) return;
-  const int q = (int)(wid % Q);
-  long long v = wid / Q;
+  long long v = wid;
   const int xi = (int)(v % Wi); v /= Wi;
   const int yi = (int)(v % Hi); v /= Hi;
   const int zi = (int)(v % Di);
@@ -360,15 +379,27 @@ __global__ void __launch_bounds__(THREADS) nearest_bwd_kernel(const float* __res
   int zl, zh, yl, yh, xl, xh;
   nn_range(zi, sz, Di, Do, zl, zh); nn_range(yi, sy, Hi, Ho, yl, yh); nn_range(xi, sx, Wi, Wo, xl, xh);
   const int nz = zh - zl + 1, ny = yh - yl + 1, nx = xh - xl + 1;
-  float4 o = f4(0.f);
-  if (nz > 0 && ny > 0 && nx > 0)
-    for (int j = lane; j < nz * ny * nx; j += 32) {
-      const int xo = xl + j % nx, yo = yl + (j / nx) % ny, zo = zl + j / (nx * ny);
-      const float4 d = ld4_stream(dy + ((((long long)b * Do + zo) * Ho + yo) * Wo + xo) * lddy + 4 * q);
-      o.x += d.x; o.y += d.y; o.z += d.z; o.w += d.w;
+  const int n = (nz > 0 && ny > 0 && nx > 0) ? nz * ny * nx : 0;
+  float* o = dx + ((((long long)b * Di + zi) * Hi + yi) * Wi + xi) * lddx;
+  for (int q0 = 0; q0 < Q; q0 += 32) {
+    const int qn = Q - q0 < 32 ? Q - q0 : 32;            // quads handled in this round
+    const int slots = 32 / qn;                           // output voxels read side by side
+    const int slot = lane / qn, q = q0 + lane - slot * qn;
+    float4 acc = f4(0.f);
+    if (slot < slots)
+      for (int j = slot; j < n; j += slots) {
+        const int xo = xl + j % nx, yo = yl + (j / nx) % ny, zo = zl + j / (nx * ny);
+        const float4 d = ld4_stream(dy + ((((long long)b * Do + zo) * Ho + yo) * Wo + xo) * lddy + 4 * q);
+        acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+      }
+    for (int k = 1; k < slots; ++k) {                    // fold slot k onto slot 0 (lanes 0 .. qn-1)
+      const int srcl = lane + k * qn;
+      const float ax = __shfl_sync(0xffffffffu, acc.x, srcl & 31), ay = __shfl_sync(0xffffffffu, acc.y, srcl & 31),
+                  az = __shfl_sync(0xffffffffu, acc.z, srcl & 31), aw = __shfl_sync(0xffffffffu, acc.w, srcl & 31);
+      if (lane < qn) { acc.x += ax; acc.y += ay; acc.z += az; acc.w += aw; }
     }
-  o.x = warp_sum(o.x); o.y = warp_sum(o.y); o.z = warp_sum(o.z); o.w = warp_sum(o.w);
-  if (lane == 0) st4(dx + ((((long long)b * Di + zi) * Hi + yi) * Wi + xi) * lddx + 4 * q, o);
+    if (lane < qn) st4(o + 4 * q, acc);
+  }
 }
 
 static int grid_for(long long nvox, int Q) {
@@ -478,7 +509,7 @@ extern "C" int corrif_resize_nearest_bwd(const float* dy, int64_t lddy, float* d
                                          void* stream) {
   int rc = resize_check(dx, lddx, dy, lddy, B, C, Di, Hi, Wi, Do, Ho, Wo);
   if (rc) return rc;
-  const long long warps = (long long)B * Di * Hi * Wi * (C / 4);
+  const long long warps = (long long)B * Di * Hi * Wi;
   const long long blocks = (warps * 32 + THREADS - 1) / THREADS;
   nearest_bwd_kernel<<<(unsigned)blocks, THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, lddx, C, Di, Hi, Wi, Do, Ho, Wo, warps);
   return launch_status("resize_nearest_bwd");
