@@ -189,6 +189,36 @@ def _event_ms(fn, steps, sync):
     return e0.elapsed_time(e1) / steps
 
 
+def measure_tf32_peak(dev):
+    """cuBLAS TF32 GEMM 8192^3 on this box (torch.matmul with allow_tf32): the measured counterpart of the
+    "TF32 = bf16 / 2" denominator.  Best of 10 (burst) and the mean of a 1-second loop (sustained)."""
+    import torch
+    saved = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a, b = torch.randn(8192, 8192, device=dev), torch.randn(8192, 8192, device=dev)
+        for _ in range(3):
+            a @ b
+        best = 1e9
+        for _ in range(10):
+            best = min(best, _event_ms(lambda i: a @ b, 1, torch.cuda.synchronize))
+        n, t0 = 0, time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        while time.perf_counter() - t0 < 1.0:
+            for _ in range(10):
+                a @ b
+            n += 10
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        flop = 2.0 * 8192 ** 3
+        return {"burst_tflops": flop / (best * 1e-3) / 1e12, "sustained_tflops": flop * n / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": "torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS), best of 10 / 1 s loop"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = saved
+
+
 def bench_fusion_block(dev, steps, warmup, peaks):
     """BASELINE configs[1]: fusion block fwd+bwd, batch 16, dropout 0.1, inputs resident in HBM, replayed as two CUDA
     graphs; plus the per-kernel-family device times of one extra step (CUDA events around every launch)."""
@@ -340,6 +370,47 @@ def bench_metric_kernels(dev, peaks):
     return res
 
 
+def summarise_volume(details, peaks):
+    """details: [(class, shape string, ms, algorithmic work)] of one micro-batch step.  Roofline of the convolution
+    family (conv3d fwd / dgrad / wgrad: warp-level TF32 MMAs over shared-memory windows) and a per-class table."""
+    agg = {}
+    for cls, det, ms, work in details:
+        a = agg.setdefault(cls, [0, 0.0, 0.0])
+        a[0] += 1; a[1] += ms; a[2] += work
+    conv = {k: v for k, v in agg.items() if k in ("conv3d_fwd", "conv3d_dgrad", "conv3d_wgrad")}
+    n_, ms_, fl_ = (sum(v[i] for v in conv.values()) for i in range(3))
+    # algorithmic bytes of the convolution launches: the forward's shape string carries them; dgrad / wgrad move the
+    # same two tensors (+ the tiny weights)
+    byts = 0.0
+    for cls, det, ms, work in details:
+        if cls == "conv3d_fwd" and "bytes=" in det:
+            byts += 3.0 * float(det.split("bytes=")[1])
+    tc = ("gemm", "attn", "conv3d_fwd", "conv3d_dgrad", "conv3d_wgrad")
+    table = {k: {"launches": v[0], "ms": round(v[1], 3),
+                 ("tflops" if k.startswith(tc) and k != "conv3d_dgrad_border" else "gbs"):
+                 round(v[2] / (v[1] * 1e-3) / (1e12 if k.startswith(tc) and k != "conv3d_dgrad_border" else 1e9), 1) if v[1] > 0 else 0.0}
+             for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]}
+    ach = fl_ / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0
+    gbs = byts / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0
+    peak_tf32 = peaks["bf16_sustained"] / 2.0
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    traffic = None
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("conv3d", {}).get("dram_bytes_per_launch")
+    roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "traffic": traffic,
+            "kernel": "channels-last conv3d family (fwd + data gradient + weight gradient, %d launches of one micro-batch "
+                      "of 8): warp-level TF32 mma.sync over shared-memory windows" % n_,
+            "algorithmic_bytes_per_step": byts, "flops_per_step": fl_, "kernel_ms_per_step": ms_,
+            "tensor_tflops": ach, "frac_of_tf32_tcgen05_peak": ach / peak_tf32,
+            "mma_sync_peak_tflops_measured": 270.0, "frac_of_mma_sync_peak": ach / 270.0,
+            "note": "these layers have 8-64 output channels: ~90 FLOP per HBM byte, so they sit between the HBM roof and "
+                    "the 270 TFLOP/s warp-level MMA rate measured on this GPU (profiles/r02a_mma_sync_probe.txt); "
+                    "DESIGN.md section 4.4 explains why tcgen05 does not apply"}
+    return roof, table
+
+
 def run_ours(args):
     saved_stdout = os.dup(1)                 # keep stdout clean for the single JSON line (NCCL prints a banner)
     os.dup2(2, 1)
@@ -427,6 +498,13 @@ def run_ours(args):
             train.broadcast_module(model)            # the muted steps let the ranks drift: re-synchronise
             exposed = ms - ms_nocomm
 
+        # ---- the library's own kernels inside one micro-batch step (CUDA events per launch, stream launches)
+        vol_prof = None
+        if world == 1:
+            with ops.profile() as rec:
+                stepper([resident[0]], total_micro_batches=1)
+            vol_prof = rec.details()
+
         # ---- end to end: every step's inputs from pinned host memory, loss read back every step
         pipe = PinnedPipeline(dev)
         hloss = torch.zeros(1).pin_memory()
@@ -474,11 +552,18 @@ def run_ours(args):
                            "(what dropin/F4_TRAIN.train_model runs per step); loss read back to pinned host memory"},
             "gpu_launches": launches,
         })
+        if vol_prof is not None:
+            line["roofline_volume"], line["kernel_breakdown_full_step"] = summarise_volume(vol_prof, peaks)
         del stepper, optim, model, resident
         torch.cuda.empty_cache()
     barrier()
     if rank == 0 and args.only in ("all", "block"):
         fb, roof_gemm, roof_attn = bench_fusion_block(dev, args.steps, args.warmup, peaks)
+        tf32 = measure_tf32_peak(dev)
+        for r in (roof_gemm, roof_attn):
+            r["tf32_cublas_measured"] = tf32
+            r["frac_of_measured_tf32_cublas_sustained"] = r["achieved"] / tf32["sustained_tflops"]
+            r["frac_of_measured_tf32_cublas_burst"] = r["achieved"] / tf32["burst_tflops"]
         dominant, other, other_key = ((roof_attn, roof_gemm, "roofline_gemm")
                                       if roof_attn["kernel_ms_per_step"] >= roof_gemm["kernel_ms_per_step"]
                                       else (roof_gemm, roof_attn, "roofline_attention"))
