@@ -107,6 +107,11 @@ PROTOTYPES = {
     "corrif_instnorm_relu_bwd_apply": (C.c_int, [f32p, i64, f32p, i64, f32p, f32p, f64p, f32p, i64, f32p, i32, i64, i32,
                                                  i32, stream_t]),
     "corrif_volume_colsum": (C.c_int, [f32p, i64, f32p, i64, i32, stream_t]),
+    "corrif_batchnorm_fwd": (C.c_int, [f32p, i64, f64p, f32p, f32p, f32p, i64, f32p, i64, f32p, f32p, f32p, i64, i32, f32, i32,
+                                       stream_t]),
+    "corrif_batchnorm_bwd_stats": (C.c_int, [f32p, i64, f32p, i64, f32p, i64, f32p, f32p, f64p, i64, i32, i32, stream_t]),
+    "corrif_batchnorm_bwd_apply": (C.c_int, [f32p, i64, f32p, i64, f32p, i64, f32p, f32p, f32p, f64p, f32p, i64, f32p, i64,
+                                             f32p, f32p, i64, i32, i32, stream_t]),
     "corrif_resize_trilinear_fwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),
     "corrif_resize_trilinear_bwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),
     "corrif_resize_nearest_fwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),

@@ -176,6 +176,127 @@ __global__ void __launch_bounds__(THREADS) instnorm_relu_bwd_apply_kernel(
   }
 }
 
+// ---- train-mode BatchNorm3d (+ residual add) (+ ReLU) on a channels-last volume --------------------------------
+// The encoders' Bottleneck3D (mmvit4.py:196-212): conv -> BN -> ReLU, and conv -> BN -> (+identity) -> ReLU.  Statistics
+// are per channel over ALL samples and voxels (the volume is treated as one sample of B*D*H*W rows).  Forward: the
+// per-channel (sum, sum of squares) come from instnorm_bwd_stats_kernel(x, x); this kernel normalises, scales, adds the
+// residual, clamps, and writes mean / biased variance / rstd.  Backward: g = dy * [y > 0]; sums = (sum g, sum g * xhat)
+// (= d beta, d gamma); dx = gamma * rstd * (g - sum_g / n - xhat * sum_gx / n); d residual = g.
+__global__ void __launch_bounds__(THREADS) bn_apply_kernel(const float* __restrict__ x, long long ldx,
+                                                           const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const float* __restrict__ res,
+                                                           long long ldr, float* __restrict__ y, long long ldy, float* mean_out,
+                                                           float* var_out, float* rstd_out, long long rows, int C, float eps,
+                                                           int relu) {
+  const int Q = C / 4;
+  const Lane l = lane_of(Q, gridDim.x);
+  if (!l.active) return;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = 4 * l.q + e;
+    const double m = stats[c * 2] / (double)rows;
+    double var = stats[c * 2 + 1] / (double)rows - m * m;
+    var = var > 0.0 ? var : 0.0;
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    if (blockIdx.x == 0 && (int)threadIdx.x < Q) { mean_out[c] = (float)m; var_out[c] = (float)var; rstd_out[c] = rs; }
+    sc[e] = rs * gamma[c];
+    sh[e] = beta[c] - (float)m * sc[e];
+  }
+  for (long long v = l.v; v < rows; v += 2 * l.vstep) {
+    float4 a[2], r[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long vv = v + u * l.vstep;
+      if (vv < rows) {
+        a[u] = ld4_stream(x + vv * ldx + 4 * l.q);
+        r[u] = res != nullptr ? ld4_stream(res + vv * ldr + 4 * l.q) : f4(0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long vv = v + u * l.vstep;
+      if (vv >= rows) continue;
+      float4 o;
+      o.x = a[u].x * sc[0] + sh[0] + r[u].x; o.y = a[u].y * sc[1] + sh[1] + r[u].y;
+      o.z = a[u].z * sc[2] + sh[2] + r[u].z; o.w = a[u].w * sc[3] + sh[3] + r[u].w;
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      st4(y + vv * ldy + 4 * l.q, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) bn_bwd_stats_kernel(const float* __restrict__ dy, long long lddy,
+                                                               const float* __restrict__ y, long long ldy,
+                                                               const float* __restrict__ x, long long ldx,
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               double* sums, long long rows, int C, int relu) {
+  const int Q = C / 4;
+  const Lane l = lane_of(Q, gridDim.x);
+  double s[4] = {0, 0, 0, 0}, t[4] = {0, 0, 0, 0};
+  if (l.active) {
+    float mu[4], rs[4], fs[4] = {0, 0, 0, 0}, ft[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { mu[e] = mean[4 * l.q + e]; rs[e] = rstd[4 * l.q + e]; }
+    int n = 0;
+#pragma unroll 2
+    for (long long v = l.v; v < rows; v += l.vstep) {
+      float4 g = ld4_stream(dy + v * lddy + 4 * l.q);
+      const float4 xx = ld4_stream(x + v * ldx + 4 * l.q);
+      if (relu) {
+        const float4 yy = ld4_stream(y + v * ldy + 4 * l.q);
+        g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+      }
+      fs[0] += g.x; fs[1] += g.y; fs[2] += g.z; fs[3] += g.w;
+      ft[0] += g.x * (xx.x - mu[0]) * rs[0]; ft[1] += g.y * (xx.y - mu[1]) * rs[1];
+      ft[2] += g.z * (xx.z - mu[2]) * rs[2]; ft[3] += g.w * (xx.w - mu[3]) * rs[3];
+      if (++n == 64) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s[e] += fs[e]; t[e] += ft[e]; fs[e] = ft[e] = 0.f; }
+        n = 0;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s[e] += fs[e]; t[e] += ft[e]; }
+  }
+  reduce_pairs_to_global(s, t, Q, l.q, l.active, sums, 0, C);
+}
+
+__global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const float* __restrict__ dy, long long lddy,
+                                                               const float* __restrict__ y, long long ldy,
+                                                               const float* __restrict__ x, long long ldx,
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               const float* __restrict__ gamma, const double* __restrict__ sums,
+                                                               float* __restrict__ dx, long long lddx, float* __restrict__ dres,
+                                                               long long lddr, float* dgamma, float* dbeta, long long rows, int C,
+                                                               int relu) {
+  const int Q = C / 4;
+  const Lane l = lane_of(Q, gridDim.x);
+  if (!l.active) return;
+  float mu[4], rs[4], k[4], m1[4], m2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = 4 * l.q + e;
+    mu[e] = mean[c]; rs[e] = rstd[c]; k[e] = gamma[c] * rs[e];
+    m1[e] = (float)(sums[c * 2] / (double)rows);
+    m2[e] = (float)(sums[c * 2 + 1] / (double)rows);
+    if (blockIdx.x == 0 && (int)threadIdx.x < Q) { dbeta[c] = (float)sums[c * 2]; dgamma[c] = (float)sums[c * 2 + 1]; }
+  }
+  for (long long v = l.v; v < rows; v += l.vstep) {
+    float4 g = ld4_stream(dy + v * lddy + 4 * l.q);
+    const float4 xx = ld4_stream(x + v * ldx + 4 * l.q);
+    if (relu) {
+      const float4 yy = ld4_stream(y + v * ldy + 4 * l.q);
+      g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+    }
+    if (dres != nullptr) st4(dres + v * lddr + 4 * l.q, g);
+    float4 o;
+    o.x = k[0] * (g.x - m1[0] - (xx.x - mu[0]) * rs[0] * m2[0]); o.y = k[1] * (g.y - m1[1] - (xx.y - mu[1]) * rs[1] * m2[1]);
+    o.z = k[2] * (g.z - m1[2] - (xx.z - mu[2]) * rs[2] * m2[2]); o.w = k[3] * (g.w - m1[3] - (xx.w - mu[3]) * rs[3] * m2[3]);
+    st4(dx + v * lddx + 4 * l.q, o);
+  }
+}
+
 __global__ void __launch_bounds__(THREADS) colsum_kernel(const float* __restrict__ g, long long ldg, float* dbias,
                                                          long long rows, int C) {
   const int Q = C / 4;
@@ -513,4 +634,43 @@ extern "C" int corrif_resize_nearest_bwd(const float* dy, int64_t lddy, float* d
   const long long blocks = (warps * 32 + THREADS - 1) / THREADS;
   nearest_bwd_kernel<<<(unsigned)blocks, THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, lddx, C, Di, Hi, Wi, Do, Ho, Wo, warps);
   return launch_status("resize_nearest_bwd");
+}
+
+/* ---- train-mode BatchNorm (+ residual) (+ ReLU) on [rows, C] channels-last data (C <= 1024 per call) ---- */
+extern "C" int corrif_batchnorm_fwd(const float* x, int64_t ldx, const double* stats, const float* gamma,
+                                    const float* beta, const float* res, int64_t ldr, float* y, int64_t ldy, float* mean,
+                                    float* var, float* rstd, int64_t rows, int32_t C, float eps, int32_t relu, void* stream) {
+  VOL_CHECK(x, ldx, C, "batchnorm_fwd(x)");
+  VOL_CHECK(y, ldy, C, "batchnorm_fwd(y)");
+  CORRIF_REQUIRE(stats && gamma && beta && mean && var && rstd && rows > 0, "batchnorm_fwd: null pointer / empty");
+  CORRIF_REQUIRE(res == nullptr || (((uintptr_t)res % 16) == 0 && ldr % 4 == 0 && ldr >= C), "batchnorm_fwd: residual unaligned");
+  bn_apply_kernel<<<grid_for(rows, C / 4), THREADS, 0, (cudaStream_t)stream>>>(x, ldx, stats, gamma, beta, res, ldr, y, ldy,
+                                                                              mean, var, rstd, rows, C, eps, relu);
+  return launch_status("batchnorm_fwd");
+}
+
+extern "C" int corrif_batchnorm_bwd_stats(const float* dy, int64_t lddy, const float* y, int64_t ldy, const float* x,
+                                          int64_t ldx, const float* mean, const float* rstd, double* sums, int64_t rows,
+                                          int32_t C, int32_t relu, void* stream) {
+  VOL_CHECK(dy, lddy, C, "batchnorm_bwd_stats(dy)");
+  VOL_CHECK(x, ldx, C, "batchnorm_bwd_stats(x)");
+  CORRIF_REQUIRE(mean && rstd && sums && rows > 0 && (!relu || y != nullptr), "batchnorm_bwd_stats: null pointer / empty");
+  bn_bwd_stats_kernel<<<grid_for(rows, C / 4), THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, sums,
+                                                                                  rows, C, relu);
+  return launch_status("batchnorm_bwd_stats");
+}
+
+extern "C" int corrif_batchnorm_bwd_apply(const float* dy, int64_t lddy, const float* y, int64_t ldy, const float* x,
+                                          int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+                                          const double* sums, float* dx, int64_t lddx, float* dres, int64_t lddr,
+                                          float* dgamma, float* dbeta, int64_t rows, int32_t C, int32_t relu, void* stream) {
+  VOL_CHECK(dy, lddy, C, "batchnorm_bwd_apply(dy)");
+  VOL_CHECK(x, ldx, C, "batchnorm_bwd_apply(x)");
+  VOL_CHECK(dx, lddx, C, "batchnorm_bwd_apply(dx)");
+  CORRIF_REQUIRE(mean && rstd && gamma && sums && dgamma && dbeta && rows > 0 && (!relu || y != nullptr),
+                 "batchnorm_bwd_apply: null pointer / empty");
+  bn_bwd_apply_kernel<<<grid_for(rows, C / 4), THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, y, ldy, x, ldx, mean, rstd, gamma,
+                                                                                  sums, dx, lddx, dres, lddr, dgamma, dbeta,
+                                                                                  rows, C, relu);
+  return launch_status("batchnorm_bwd_apply");
 }

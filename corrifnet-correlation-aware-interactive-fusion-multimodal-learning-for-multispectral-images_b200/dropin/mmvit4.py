@@ -38,6 +38,12 @@ num_modals = 3
 patch_size = 8
 
 _MODS = ("RGB", "NIR", "SWIR")
+# Measured switches.  CORRIF_FUSED_BN=1 runs the encoders' train-mode BatchNorm (+ residual)
+# (+ ReLU) on the fused channels-last kernels: 1.5 ms less GPU time per micro-batch but 636 more Python-level launches,
+# and the step is host-bound there (93.4 vs 97.9 imgs/s) - off until the encoder step is captured in a CUDA graph.
+# CORRIF_ENCODER_NCDHW=1 keeps the encoder trunks in PyTorch's default memory format instead of channels_last_3d.
+_FUSED_BN = os.environ.get("CORRIF_FUSED_BN") == "1"
+_ENC_CL3D = os.environ.get("CORRIF_ENCODER_NCDHW") != "1"
 
 
 # ----------------------------------------------------------------------------------------------
@@ -60,11 +66,21 @@ class Bottleneck3D(nn.Module):
             self.downsample = nn.Sequential(_conv2d_as_3d(cin, 4 * planes, 1, stride, 0),
                                             nn.BatchNorm3d(4 * planes))
 
+    @staticmethod
+    def _bn(bn, x, residual=None, relu=True):
+        """BatchNorm (+ residual) (+ ReLU): in training on the fused channels-last kernels (one normalise pass instead of
+        cuDNN batch-norm + add + ReLU), in eval mode (running statistics) on stock PyTorch."""
+        if not (bn.training and x.is_cuda and _FUSED_BN):
+            y = bn(x) if residual is None else bn(x) + residual
+            return F.relu(y) if relu else y
+        r = None if residual is None else _V.to_channels_last(residual)
+        return _V.to_channels_first(_V.batchnorm_relu(_V.to_channels_last(x), bn, r, relu))
+
     def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.relu(self.bn2(self.conv2(y)))
-        y = self.bn3(self.conv3(y))
-        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+        y = self._bn(self.bn1, self.conv1(x))
+        y = self._bn(self.bn2, self.conv2(y))
+        identity = x if self.downsample is None else self._bn(self.downsample[1], self.downsample[0](x), relu=False)
+        return self._bn(self.bn3, self.conv3(y), residual=identity)
 
 
 def _stage(cin, planes, blocks, stride):
@@ -74,8 +90,10 @@ def _stage(cin, planes, blocks, stride):
 
 
 class Encoder(nn.Module):
-    """One modality encoder.  Returns the five adapted pyramid levels and x6 [B,64,8,8,8].  The ResNet-50 trunk is
-    stock PyTorch / cuDNN; the tail runs on corrif_b200.volume kernels."""
+    """One modality encoder.  Returns the five adapted pyramid levels and x6 [B,64,8,8,8].  The ResNet-50 trunk's
+    convolutions and max-pool are stock PyTorch / cuDNN in channels_last_3d memory format, i.e.
+    directly on the volume layout; its train-mode BatchNorm (+ residual) (+ ReLU) and the tail run on corrif_b200.volume
+    kernels."""
 
     def __init__(self, inflate_time=3):
         super().__init__()
@@ -93,7 +111,7 @@ class Encoder(nn.Module):
             setattr(self, f"adapt{i}", nn.Conv3d(cin, cout, kernel_size=1))
 
     def forward(self, x):
-        f1 = self.e1_mp(self.e1_bn(self.e1_relu(self.e1_c1(x))))      # ReLU before BN, as the reference
+        f1 = self.e1_mp(Bottleneck3D._bn(self.e1_bn, self.e1_relu(self.e1_c1(x)), relu=False))   # ReLU BEFORE BN, as the reference
         f2 = self.e2(f1)
         f3 = self.e3(f2)
         f4 = self.e4(f3)
@@ -201,7 +219,7 @@ class MMVit4(nn.Module):
         self.dropout_rate, self.precision = dropout_rate, precision
         self._step, self.base_seed = 0, _module.default_base_seed()
         for m in _MODS:
-            setattr(self, f"{m}_encoder", Encoder())
+            setattr(self, f"{m}_encoder", Encoder().to(memory_format=torch.channels_last_3d) if _ENC_CL3D else Encoder())
         for m in _MODS:
             setattr(self, f"{m}_encode_conv", nn.Conv3d(E, C, 1))
         self.fused6_encode_conv = nn.Conv3d(E * 3, C, 1)
@@ -237,7 +255,8 @@ class MMVit4(nn.Module):
         return [named[n] for n in self._fusion_names]
 
     def forward(self, x):
-        feats = [getattr(self, f"{m}_encoder")(x[:, i:i + 1]) for i, m in enumerate(_MODS)]
+        fmt = torch.channels_last_3d if _ENC_CL3D else torch.contiguous_format
+        feats = [getattr(self, f"{m}_encoder")(x[:, i:i + 1].contiguous(memory_format=fmt)) for i, m in enumerate(_MODS)]
         fused = [getattr(self, f"fusion{lv + 1}")(*(f[lv] for f in feats)) for lv in (0, 1, 2, 3, 5)]
         fused_x1, fused_x2, fused_x3, fused_x4, fused_x6 = fused          # fusion5's output is unused
         p = self.dropout_rate if self.training else 0.0

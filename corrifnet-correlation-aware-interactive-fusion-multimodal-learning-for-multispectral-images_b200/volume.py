@@ -294,7 +294,89 @@ def pointwise_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, ch
     """nn.Conv3d(kernel_size=1) with bias, no activation / norm, as a tcgen05 GEMM; see _PointwiseGemm."""
     if weight.shape[0] % 4 or weight.shape[1] % 4:
         raise ValueError("pointwise_conv: channel counts must be multiples of 4")
+    if channels_first and x.dim() == 5 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last_3d):
+        x, channels_first = x.permute(0, 2, 3, 4, 1), False          # cuDNN already produced the volume layout
     return _PointwiseGemm.apply(x, weight, bias, channels_first)
+
+
+class _BatchNormReLU(torch.autograd.Function):
+    """Train-mode BatchNorm3d (+ residual add) (+ ReLU) on a channels-last volume: statistics pass + one normalise pass
+    forward, statistics + apply backward (include/corrif.h, corrif_batchnorm_*).  Returns (y, mean, biased var)."""
+    CH = 1024                                            # channels per launch
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, res, relu, eps):
+        x = as_volume(x)
+        res = as_volume(res) if res is not None else None
+        B, D, H, W, Cc = x.shape
+        rows, ldx, dev = B * D * H * W, _ld(x), x.device
+        y = torch.empty(B, D, H, W, Cc, device=dev, dtype=torch.float32)
+        stats = torch.zeros(Cc, 2, device=dev, dtype=torch.float64)
+        mean, var, rstd = (torch.empty(Cc, device=dev, dtype=torch.float32) for _ in range(3))
+        g, bt = gamma.detach().contiguous(), beta.detach().contiguous()
+        lib = ops.lib()
+        for c0 in range(0, Cc, _BatchNormReLU.CH):
+            c = min(_BatchNormReLU.CH, Cc - c0)
+            o = 4 * c0
+            with ops._rec("batchnorm_stats", 4.0 * rows * c):
+                L.check(lib.corrif_instnorm_bwd_stats(x.data_ptr() + o, ldx, x.data_ptr() + o, ldx, stats.data_ptr() + 16 * c0,
+                                                      1, rows, c, _stream()), "batchnorm stats")
+            with ops._rec("batchnorm_fwd", (12.0 if res is not None else 8.0) * rows * c):
+                L.check(lib.corrif_batchnorm_fwd(x.data_ptr() + o, ldx, stats.data_ptr() + 16 * c0, g.data_ptr() + o,
+                                                 bt.data_ptr() + o, (res.data_ptr() + o) if res is not None else None,
+                                                 _ld(res) if res is not None else 0, y.data_ptr() + o, Cc,
+                                                 mean.data_ptr() + o, var.data_ptr() + o, rstd.data_ptr() + o, rows, c,
+                                                 float(eps), int(relu), _stream()), "batchnorm_fwd")
+            ops._count(2)
+        ctx.save_for_backward(x, y if relu else None, mean, rstd, g)
+        ctx.cfg = (bool(relu), res is not None)
+        ctx.mark_non_differentiable(mean, var)
+        return y, mean, var
+
+    @staticmethod
+    def backward(ctx, dy, _dmean, _dvar):
+        x, y, mean, rstd, g = ctx.saved_tensors
+        relu, has_res = ctx.cfg
+        dy = as_volume(dy)
+        B, D, H, W, Cc = x.shape
+        rows, dev = B * D * H * W, x.device
+        sums = torch.zeros(Cc, 2, device=dev, dtype=torch.float64)
+        dx = torch.empty(B, D, H, W, Cc, device=dev, dtype=torch.float32)
+        dres = torch.empty(B, D, H, W, Cc, device=dev, dtype=torch.float32) if has_res else None
+        dgamma, dbeta = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
+        lib = ops.lib()
+        ldx, lddy = _ld(x), _ld(dy)
+        for c0 in range(0, Cc, _BatchNormReLU.CH):
+            c = min(_BatchNormReLU.CH, Cc - c0)
+            o = 4 * c0
+            yp = (y.data_ptr() + o) if relu else None
+            with ops._rec("batchnorm_bwd_stats", (12.0 if relu else 8.0) * rows * c):
+                L.check(lib.corrif_batchnorm_bwd_stats(dy.data_ptr() + o, lddy, yp, Cc, x.data_ptr() + o, ldx, mean.data_ptr() + o,
+                                                       rstd.data_ptr() + o, sums.data_ptr() + 16 * c0, rows, c, int(relu),
+                                                       _stream()), "batchnorm_bwd_stats")
+            with ops._rec("batchnorm_bwd_apply", ((16.0 if relu else 12.0) + (4.0 if has_res else 0.0)) * rows * c):
+                L.check(lib.corrif_batchnorm_bwd_apply(dy.data_ptr() + o, lddy, yp, Cc, x.data_ptr() + o, ldx, mean.data_ptr() + o,
+                                                       rstd.data_ptr() + o, g.data_ptr() + o, sums.data_ptr() + 16 * c0,
+                                                       dx.data_ptr() + o, Cc, (dres.data_ptr() + o) if has_res else None, Cc,
+                                                       dgamma.data_ptr() + o, dbeta.data_ptr() + o, rows, c, int(relu),
+                                                       _stream()), "batchnorm_bwd_apply")
+            ops._count(2)
+        return dx, dgamma, dbeta, dres, None, None
+
+
+def batchnorm_relu(x: torch.Tensor, bn: torch.nn.BatchNorm3d, residual: Optional[torch.Tensor] = None,
+                   relu: bool = True) -> torch.Tensor:
+    """y = relu?(BatchNorm3d(x) (+ residual)) in TRAIN mode on channels-last volumes [B, D, H, W, C], updating the
+    module's running statistics like nn.BatchNorm3d does (momentum, unbiased running variance)."""
+    y, mean, var = _BatchNormReLU.apply(x, bn.weight, bn.bias, residual, relu, bn.eps)
+    if bn.track_running_stats and bn.running_mean is not None:
+        with torch.no_grad():
+            n = x.numel() // x.shape[-1]
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked.item() + 1)
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var, alpha=m * n / max(n - 1, 1))
+            bn.num_batches_tracked += 1
+    return y
 
 
 class _Resize(torch.autograd.Function):

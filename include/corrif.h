@@ -375,6 +375,25 @@ int corrif_instnorm_relu_bwd_apply(const float* dy, int64_t lddy, const float* y
 /* dbias[c] += sum over voxels of g (bias gradient of a convolution without norm) */
 int corrif_volume_colsum(const float* g, int64_t ldg, float* dbias, int64_t rows, int32_t C, void* stream);
 
+/* Train-mode BatchNorm3d (+ residual add) (+ ReLU) on channels-last data [rows, C] (rows = B*D*H*W, C <= 1024 per call,
+ * wider tensors in channel chunks): the encoders' Bottleneck3D (mmvit4.py:196-212: conv -> BN -> ReLU and
+ * conv -> BN -> += identity -> ReLU) as one normalise pass forward and a statistics + apply pair backward, instead of
+ * cuDNN batch-norm + separate add / ReLU / threshold_backward kernels.
+ *   fwd:  stats[c] = (sum x, sum x^2) (from corrif_instnorm_bwd_stats(x, x) with B = 1);
+ *         y = relu?((x - mean) * rstd * gamma + beta (+ res)); mean / var (biased) / rstd [C] are written.
+ *   bwd:  g = dy * [y > 0]; sums[c] = (sum g, sum g * xhat); dx = gamma * rstd * (g - sum_g/n - xhat * sum_gx/n);
+ *         dres = g (optional); dbeta = sum g; dgamma = sum g * xhat. */
+int corrif_batchnorm_fwd(const float* x, int64_t ldx, const double* stats, const float* gamma, const float* beta,
+                         const float* res, int64_t ldr, float* y, int64_t ldy, float* mean, float* var, float* rstd,
+                         int64_t rows, int32_t C, float eps, int32_t relu, void* stream);
+int corrif_batchnorm_bwd_stats(const float* dy, int64_t lddy, const float* y, int64_t ldy, const float* x, int64_t ldx,
+                               const float* mean, const float* rstd, double* sums, int64_t rows, int32_t C, int32_t relu,
+                               void* stream);
+int corrif_batchnorm_bwd_apply(const float* dy, int64_t lddy, const float* y, int64_t ldy, const float* x, int64_t ldx,
+                               const float* mean, const float* rstd, const float* gamma, const double* sums, float* dx,
+                               int64_t lddx, float* dres, int64_t lddr, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                               int32_t relu, void* stream);
+
 /* Trilinear resize with align_corners=True (nn.Upsample / F.interpolate, mmvit4.py:187-191, 260, 269-285) and
  * nearest resize (F.interpolate default, mmvit4.py:271-286) on channels-last volumes, forward and backward
  * (backward in gather form: every input voxel sums its few contributing output voxels - no atomics; `dx` is

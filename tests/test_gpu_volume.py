@@ -296,3 +296,44 @@ def test_pointwise_conv_gemm_path(case):
     assert rel_l2(dx.cpu().numpy(), rx.grad.cpu().numpy()) < TOL_GRAD
     assert rel_l2(wt.grad.cpu().numpy(), rw.grad.cpu().numpy()) < TOL_GRAD
     assert rel_l2(bt.grad.cpu().numpy(), rb.grad.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(2, 3, 16, 16, 64, True, False), (2, 3, 8, 8, 256, True, True), (1, 3, 4, 4, 2048, True, True),
+                                  (2, 3, 9, 7, 128, False, False), (3, 1, 5, 5, 1024, False, True)])
+def test_batchnorm_relu_against_pytorch(case):
+    """Train-mode BatchNorm3d (+ residual) (+ ReLU) of the encoders' Bottleneck3D (mmvit4.py:196-212) on the fused
+    channels-last kernels against fp64 PyTorch: output, dx, d residual, d gamma, d beta and the running statistics."""
+    B, D, H, W, C, relu, with_res = case
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C + D)
+    x = (torch.randn(B, C, D, H, W, generator=g, dtype=torch.float64) * 2 + 0.5).to(dev)
+    res = torch.randn(B, C, D, H, W, generator=g, dtype=torch.float64).to(dev) if with_res else None
+    go = torch.randn(B, C, D, H, W, generator=g, dtype=torch.float64).to(dev)
+    ref_bn = torch.nn.BatchNorm3d(C).double().to(dev).train()
+    with torch.no_grad():
+        ref_bn.weight.copy_(torch.rand(C, generator=g, dtype=torch.float64) + 0.5)
+        ref_bn.bias.copy_(torch.randn(C, generator=g, dtype=torch.float64) * 0.2)
+    rx = x.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if with_res else None
+    ry = ref_bn(rx) if rr is None else ref_bn(rx) + rr
+    ry = torch.relu(ry) if relu else ry
+    ry.backward(go)
+    bn = torch.nn.BatchNorm3d(C).to(dev).train()
+    with torch.no_grad():
+        bn.weight.copy_(ref_bn.weight.float()); bn.bias.copy_(ref_bn.bias.float())
+    mx = x.float().permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True)
+    mr = res.float().permute(0, 2, 3, 4, 1).contiguous().requires_grad_(True) if with_res else None
+    y = V.batchnorm_relu(mx, bn, mr, relu)
+    y.backward(go.float().permute(0, 2, 3, 4, 1).contiguous())
+    torch.cuda.synchronize()
+    cf = lambda t: t.permute(0, 4, 1, 2, 3).double().cpu().numpy()   # noqa: E731
+    assert rel_l2(cf(y.detach()), ry.detach().cpu().numpy()) < 1e-5
+    # the ReLU mask can differ where the fp32 output rounds across zero: compare gradients on a 1e-4 budget
+    assert rel_l2(cf(mx.grad), rx.grad.cpu().numpy()) < 2e-3
+    if with_res:
+        assert rel_l2(cf(mr.grad), rr.grad.cpu().numpy()) < 2e-3
+    assert rel_l2(bn.weight.grad.double().cpu().numpy(), ref_bn.weight.grad.cpu().numpy()) < 2e-3
+    assert rel_l2(bn.bias.grad.double().cpu().numpy(), ref_bn.bias.grad.cpu().numpy()) < 2e-3
+    assert rel_l2(bn.running_mean.double().cpu().numpy(), ref_bn.running_mean.cpu().numpy()) < 1e-5
+    assert rel_l2(bn.running_var.double().cpu().numpy(), ref_bn.running_var.cpu().numpy()) < 1e-5
+    assert int(bn.num_batches_tracked) == 1
