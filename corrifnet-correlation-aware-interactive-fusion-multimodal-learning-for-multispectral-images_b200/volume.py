@@ -85,8 +85,34 @@ def _desc(srcs: Sequence[torch.Tensor], Cout: int, ksize: int, pad_mode: int) ->
     return d
 
 
+# Packed operands are cached per weight tensor and re-used until the weight changes: a step of 8 micro-batches packs
+# each weight twice (forward + mirrored form) instead of 16 times.  "Changed" = another storage address, a bumped
+# autograd version counter (every in-place torch update, load_state_dict), or a bumped epoch (FlatAdam updates the
+# weights through libcorrif_b200 directly, behind autograd's back, and calls bump_weight_epoch()).
+_PACK_CACHE: dict = {}
+_WEIGHT_EPOCH = 0
+
+
+def bump_weight_epoch() -> None:
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+    if len(_PACK_CACHE) > 4096:
+        _PACK_CACHE.clear()
+
+
 def pack_weights(weight: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
     """[Cout, Cin, k, k, k] -> the kernels' fragment-ordered TF32 operand (forward, or data-gradient form)."""
+    key = (weight.data_ptr(), bool(transpose_flip), tuple(weight.shape))
+    stamp = (weight._version, _WEIGHT_EPOCH)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    wpk = _pack_weights(weight, transpose_flip)
+    _PACK_CACHE[key] = (stamp, wpk)
+    return wpk
+
+
+def _pack_weights(weight: torch.Tensor, transpose_flip: bool) -> torch.Tensor:
     Cout, Cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
     n = ops.lib().corrif_conv3d_pack_floats(Cin, Cout, k)
     if n <= 0:
