@@ -236,6 +236,8 @@ def broadcast_module(model: nn.Module, src: int = 0, process_group=None, buffers
     tensors = list(model.buffers()) if buffers_only else list(model.parameters()) + list(model.buffers())
     for t in tensors:
         dist.broadcast(t.data, src=src, group=process_group)
+    from . import volume
+    volume.bump_weight_epoch()               # parameters were written through .data
 
 
 def shard_micro_batches(n_batches: int, group: int, rank: int, world: int):

@@ -19,6 +19,7 @@ No CPU path: CUDA fp32 tensors only.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -87,8 +88,9 @@ def _desc(srcs: Sequence[torch.Tensor], Cout: int, ksize: int, pad_mode: int) ->
 
 # Packed operands are cached per weight tensor and re-used until the weight changes: a step of 8 micro-batches packs
 # each weight twice (forward + mirrored form) instead of 16 times.  "Changed" = another storage address, a bumped
-# autograd version counter (every in-place torch update, load_state_dict), or a bumped epoch (FlatAdam updates the
-# weights through libcorrif_b200 directly, behind autograd's back, and calls bump_weight_epoch()).
+# autograd version counter (every in-place torch update, load_state_dict), or a bumped epoch (FlatAdam and
+# broadcast_module change weights behind autograd's version counters and call bump_weight_epoch(); so must any caller
+# that writes through ``param.data``).  Entries are tied to the tensor OBJECT by a weak reference.
 _PACK_CACHE: dict = {}
 _WEIGHT_EPOCH = 0
 
@@ -102,13 +104,17 @@ def bump_weight_epoch() -> None:
 
 def pack_weights(weight: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
     """[Cout, Cin, k, k, k] -> the kernels' fragment-ordered TF32 operand (forward, or data-gradient form)."""
-    key = (weight.data_ptr(), bool(transpose_flip), tuple(weight.shape))
-    stamp = (weight._version, _WEIGHT_EPOCH)
+    key = (id(weight), bool(transpose_flip))
+    stamp = (weight.data_ptr(), weight._version, _WEIGHT_EPOCH)
     hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == stamp:
-        return hit[1]
+    # the entry must belong to THIS tensor object (ids and addresses are recycled once a tensor dies)
+    if hit is not None and hit[0]() is weight and hit[1] == stamp:
+        return hit[2]
     wpk = _pack_weights(weight, transpose_flip)
-    _PACK_CACHE[key] = (stamp, wpk)
+    try:
+        _PACK_CACHE[key] = (weakref.ref(weight), stamp, wpk)
+    except TypeError:
+        pass
     return wpk
 
 
