@@ -452,7 +452,7 @@ def run_ours(args):
                     p.normal_(0, 0.02)
         train.broadcast_module(model)
         optim = torch.optim.Adam(model.parameters(), 1e-4)
-        stepper = train.TrainStep(model, optim, lim=224)
+        stepper = train.TrainStep(model, optim, lim=224, graphs=not args.no_graphs)
         mine, total = train.shard_micro_batches(MICRO_BATCHES, MICRO_BATCHES, rank, world)[0]
         host = [tuple(t.pin_memory() for t in make_tiles(MICRO_BATCH, 100 + j)) for j in mine]
         resident = [(im.to(dev), ma.to(dev)) for im, ma in host]
@@ -505,9 +505,15 @@ def run_ours(args):
         # ---- the library's own kernels inside one micro-batch step (CUDA events per launch, stream launches)
         vol_prof = None
         if world == 1:
+            saved_graphs = stepper.graphs
+            stepper.graphs = False                       # per-launch events need real launches
+            fwd_graphed = model.forward
+            if stepper._eager_forward is not None:
+                model.forward = stepper._eager_forward
             with ops.profile() as rec:
                 stepper([resident[0]], total_micro_batches=1)
             vol_prof = rec.details()
+            model.forward, stepper.graphs = fwd_graphed, saved_graphs
 
         # ---- end to end: every step's inputs from pinned host memory, loss read back every step
         pipe = PinnedPipeline(dev)
@@ -543,7 +549,9 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": shared_config(args),
             "details": {
-                "local_micro_batches": len(mine), "warmup_steps_run": warm, "fusion_block_ms_per_step": fus_ms, "fusion_block_share": fus_ms / ms,
+                "local_micro_batches": len(mine), "warmup_steps_run": warm,
+                "cuda_graphs": "model forward + backward replayed as two CUDA graphs per micro-batch (TrainStep(graphs=True), "
+                               "captured after the first step)" if stepper._graph_shape is not None else "stream launches", "fusion_block_ms_per_step": fus_ms, "fusion_block_share": fus_ms / ms,
                 "grad_allreduce_bytes": grad_bytes if world > 1 else 0,
                 "exposed_allreduce_ms": exposed, "peak_mem_GiB": peak_mem, "loss_last_step": loss_val,
                 "l2": "activations of one micro-batch ~25 GB >> 126 MB L2 (no explicit flush needed)",
@@ -603,6 +611,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graphs", action="store_true", help="stream launches instead of whole-model CUDA graphs")
     ap.add_argument("--only", default="all", choices=["all", "full", "block"],
                     help="full: the train step only; block: the fusion-block microbench only")
     args = ap.parse_args()

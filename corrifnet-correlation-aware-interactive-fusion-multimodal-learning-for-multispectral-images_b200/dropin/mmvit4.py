@@ -217,7 +217,7 @@ class MMVit4(nn.Module):
         super().__init__()
         C, E = transformer_basic_dims, basic_dims * 8
         self.dropout_rate, self.precision = dropout_rate, precision
-        self._step, self.base_seed = 0, _module.default_base_seed()
+        self._step, self.base_seed, self.device_seed = 0, _module.default_base_seed(), False
         for m in _MODS:
             setattr(self, f"{m}_encoder", Encoder().to(memory_format=torch.channels_last_3d) if _ENC_CL3D else Encoder())
         for m in _MODS:
@@ -261,7 +261,9 @@ class MMVit4(nn.Module):
         fused_x1, fused_x2, fused_x3, fused_x4, fused_x6 = fused          # fusion5's output is unused
         p = self.dropout_rate if self.training else 0.0
         self._step += 1
+        # device_seed (set by TrainStep when it captures the model in CUDA graphs): the dropout seed is a device-resident
+        # counter that advances inside the graph, encoded as -1 - base for the operator
+        seed = (-1 - (self.base_seed & 0x3FFFFFFFFFFF)) if self.device_seed else self.base_seed + self._step
         x6_inter = torch.ops.corrif.fusion_block(feats[0][5], feats[1][5], feats[2][5], _V.to_channels_first(fused_x6),
-                                                 self.fusion_parameters(), p,
-                                                 self.base_seed + self._step, self.precision)
+                                                 self.fusion_parameters(), p, seed, self.precision)
         return self.decoder_fuse(fused_x1, fused_x2, fused_x3, fused_x4, _V.to_channels_last(x6_inter))

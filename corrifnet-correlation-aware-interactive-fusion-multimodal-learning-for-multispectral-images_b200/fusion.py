@@ -576,12 +576,27 @@ class FusionBlockEngine:
 
     # ------------------------------------------------------------------------------------------
     def set_seed(self, seed: int) -> None:
-        """Seed of the next forward/backward pair (dropout masks are a pure function of it)."""
+        """Seed of the next forward/backward pair (dropout masks are a pure function of it).  A NEGATIVE seed selects
+        the device-resident counter (whole-model CUDA graphs: nothing the host computes may change between replays):
+        -1 - base initialises the counter to ``base`` once and is a no-op afterwards; advance_device_seed() steps it."""
+        if seed < 0:
+            if not self.use_graphs:
+                raise ValueError("device-resident dropout seeds need an engine built with use_graphs=True")
+            base = -1 - int(seed)
+            if getattr(self, "_dev_seed_base", None) != base:
+                self._dev_seed_base = base
+                self.seed = 0
+                self.seed_dev.fill_(base)
+            return
         if self.use_graphs:
             self.seed = 0
             self.seed_dev.fill_(int(seed))
         else:
             self.seed = int(seed)
+
+    def advance_device_seed(self) -> None:
+        """seed_dev += 1 as a device operation (captured into an outer graph, it advances on every replay)."""
+        self.seed_dev.add_(1)
 
     def _graphed(self, key: tuple, fn):
         """Run ``fn`` eagerly twice per key, then capture it once and replay."""
@@ -637,7 +652,8 @@ class FusionBlockEngine:
     def forward(self, x6: List[torch.Tensor], fused_x6: torch.Tensor) -> torch.Tensor:
         """x6: three [B,64,8,8,8]; fused_x6 [B,192,8,8,8] -> x6_inter [B,192,8,8,8] (workspace-owned;
         clone it if it must survive the next forward)."""
-        if not self.use_graphs:
+        if not self.use_graphs or torch.cuda.is_current_stream_capturing():
+            # stream launches; under an OUTER capture (TrainStep graphs the whole model) they become that graph's nodes
             return self._forward(x6, fused_x6)
         B = self._B = fused_x6.shape[0]
         key = ("fwd",) + tuple(t.data_ptr() for t in x6) + (fused_x6.data_ptr(), B)
@@ -652,7 +668,7 @@ class FusionBlockEngine:
     def backward(self, gout: torch.Tensor, grads: Optional[Dict[str, torch.Tensor]] = None):
         """gout [B,192,8,8,8] -> (dx6 [3,B,64,8,8,8], dfused_x6 [B,192,8,8,8], {param: grad}).
         If ``grads`` is given the parameter gradients are accumulated into it."""
-        if not self.use_graphs or grads is None:
+        if not self.use_graphs or grads is None or torch.cuda.is_current_stream_capturing():
             return self._backward(gout, grads)
         gkey = tuple(grads[n].data_ptr() for n in param_names(self.mods)[:4])
         key = ("bwd", gout.data_ptr()) + gkey + (self._B,)

@@ -51,6 +51,8 @@ def fusion_block_op(x6_rgb: Tensor, x6_nir: Tensor, x6_swir: Tensor, fused_x6: T
     """x6_inter = CorrIFNet fusion block (mmvit4.py:456-529).  ``params`` in ``param_names()`` order."""
     eng = _engine_for(params, dropout_p, precision)
     eng.set_seed(seed)
+    if seed < 0:
+        eng.advance_device_seed()        # device-resident seed counter: a fresh mask set per call / per graph replay
     eng.generation += 1
     out = eng.forward([x6_rgb.contiguous(), x6_nir.contiguous(), x6_swir.contiguous()],
                       fused_x6.contiguous())

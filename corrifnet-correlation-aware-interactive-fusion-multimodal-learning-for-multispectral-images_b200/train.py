@@ -263,8 +263,13 @@ class TrainStep:
     (sum of Jaccard2 * batchLoad, F4_TRAIN.py:70-71) and ``pixels`` (sum of batchLoad)."""
 
     def __init__(self, model: nn.Module, optim: torch.optim.Optimizer, lim: int = 224,
-                 jaccard_fn=None, process_group=None, bucket_bytes: int = 64 << 20, flat_adam: bool = True):
+                 jaccard_fn=None, process_group=None, bucket_bytes: int = 64 << 20, flat_adam: bool = True,
+                 graphs: bool = False):
         self.model, self.optim, self.lim = model, optim, lim
+        # graphs=True: after the first step (buckets and flat parameters in place) the model's forward and backward are
+        # captured as two CUDA graphs (torch.cuda.make_graphed_callables) and replayed: ~2500 host-side launches per
+        # micro-batch become two.  The step is host-bound without it (DESIGN.md section 5).
+        self.graphs, self._graph_shape, self._eager_forward = bool(graphs), None, None
         self.buckets = GradBuckets(list(model.parameters()), bucket_bytes, process_group)
         # a stock Adam with the reference's settings runs as one kernel per bucket (see FlatAdam)
         self.flat_adam = FlatAdam(optim, self.buckets) if flat_adam and FlatAdam.eligible(optim) else None
@@ -273,6 +278,41 @@ class TrainStep:
         if jaccard_fn is None:
             from .metrics import Jaccard2 as jaccard_fn
         self.jaccard_fn = jaccard_fn
+
+    def _forward(self, images):
+        if not self.graphs or not images.is_cuda:
+            return self.model(images)
+        if self._graph_shape is None and self.buckets._built and (self.flat_adam is None or self.flat_adam.slabs is not None):
+            self._capture(images)
+        if self._graph_shape == tuple(images.shape) and self.model.training:
+            from . import ops
+            ops._count(self._graph_launches)                 # kernels replayed by the two graphs of this micro-batch
+            return self.model(images)                        # the graphed forward
+        return (self._eager_forward or self.model)(images)   # another shape (ragged last batch) or eval mode
+
+    def _capture(self, images):
+        """Capture model forward + backward as CUDA graphs.  Needs static parameter addresses (hence after FlatAdam has
+        re-pointed them) and nothing host-computed that changes per step: the fusion block's dropout seed moves to a
+        device-resident counter (``model.device_seed``)."""
+        import warnings
+        eager = self.model.forward
+        try:
+            if hasattr(self.model, "device_seed"):
+                self.model.device_seed = True
+            torch.cuda.synchronize()
+            from . import ops
+            n0 = ops.launch_count()
+            torch.cuda.make_graphed_callables(self.model, (images.detach().clone(),), allow_unused_input=True)
+            # library kernels inside one forward + backward replay: make_graphed_callables ran 3 warm-up passes and
+            # one capturing pass, each launching the same kernel sequence
+            self._graph_launches = (ops.launch_count() - n0) // 4
+            self._graph_shape, self._eager_forward = tuple(images.shape), eager
+        except Exception as e:                               # stay on stream launches; never lose the step
+            warnings.warn("TrainStep: CUDA-graph capture failed (%r); continuing with stream launches" % (e,))
+            if hasattr(self.model, "device_seed"):
+                self.model.device_seed = False
+            self.model.forward = eager
+            self.graphs, self._graph_shape = False, None
 
     def __call__(self, micro_batches, total_micro_batches: Optional[int] = None) -> Dict[str, torch.Tensor]:
         """``micro_batches``: this rank's (images, masks) pairs for the step (a tuple = one micro-batch; may be
@@ -289,7 +329,7 @@ class TrainStep:
         loss_acc, jac_acc, pixels = None, None, 0
         for k, (images, masks) in enumerate(micro_batches):
             self.buckets.set_sync(k == n - 1)
-            outputs = self.model(images)
+            outputs = self._forward(images)
             if self.fused_tail:
                 # loss (F4_TRAIN.py:58-60), its gradient and the Jaccard sums of :65-71 in one pass
                 loss, dout, jac1, load = loss_and_jaccard(outputs, masks)

@@ -104,6 +104,8 @@ def bump_weight_epoch() -> None:
 
 def pack_weights(weight: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
     """[Cout, Cin, k, k, k] -> the kernels' fragment-ordered TF32 operand (forward, or data-gradient form)."""
+    if torch.cuda.is_current_stream_capturing():
+        return _pack_weights(weight, transpose_flip)          # inside a CUDA graph the packing must replay with the graph
     key = (id(weight), bool(transpose_flip))
     stamp = (weight.data_ptr(), weight._version, _WEIGHT_EPOCH)
     hit = _PACK_CACHE.get(key)

@@ -169,6 +169,36 @@ def test_adam_updated_weights_match_reference_step(dropin):
         assert e < 0.5, (k, e, r)
 
 
+def test_train_step_with_whole_model_cuda_graphs_matches_stream_launches(dropin):
+    """TrainStep(graphs=True) captures the model's forward and backward as CUDA graphs after the first step; the losses
+    of the following steps and the updated weights must agree with the same steps on stream launches (dropout off:
+    the only differences are summation orders), and a batch of another shape must fall back to the eager forward."""
+    import copy
+    from corrif_b200 import train
+    mmvit4 = dropin[0]
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    base = mmvit4.MMVit4(num_cls=1, dropout_rate=0.0).to(dev).train()
+    g = torch.Generator().manual_seed(5)
+    data = [(torch.randn(2, 3, 3, 64, 64, generator=g).to(dev),
+             (torch.rand(2, 1, 1, 224, 224, generator=g) < 0.3).float().repeat(1, 3, 1, 1, 1).to(dev)) for _ in range(4)]
+    losses = {}
+    for graphs in (False, True):
+        model = copy.deepcopy(base)
+        step = train.TrainStep(model, torch.optim.Adam(model.parameters(), 1e-4), lim=224, graphs=graphs)
+        losses[graphs] = [step(d)["loss"].item() for d in data]
+        if graphs:
+            assert step._graph_shape == (2, 3, 3, 64, 64), "the model was not captured"
+            odd = (data[0][0][:1].contiguous(), data[0][1][:1].contiguous())
+            assert torch.isfinite(step(odd)["loss"])                    # other batch size: eager forward
+            model.eval()
+            with torch.no_grad():
+                assert model(data[0][0]).shape == (2, 3, 1, 224, 224)   # eval mode: eager forward
+    print("\n[graphs] losses eager %s graphed %s" % (losses[False], losses[True]))
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) < 2e-3, (losses[False], losses[True])
+
+
 def test_f2_main_drop_in_runs_one_synthetic_epoch(dropin, tmp_path, monkeypatch):
     """dropin/F2_MAIN.py end to end on one GPU: 18-line config -> synthetic tiles -> train_model -> test_model ->
     the reference's text logs in the working directory and the two checkpoints in the result directory."""
