@@ -115,7 +115,10 @@ def train_model(n_epochs, trainloss, validationloss, accuracy, model, scheduler,
     rank, world = ensure_distributed()
     group = int(os.environ.get("CORRIF_MICROBATCHES_PER_STEP", str(world)))
     broadcast_module(model)
-    step = TrainStep(model, optim, lim=lim)
+    # CUDA graphs of the model's forward / backward from the second optimizer step on (CORRIF_TRAIN_GRAPHS=0: stream
+    # launches).  Capturing runs four extra passes over that step's first micro-batch, i.e. four extra momentum
+    # updates of the BatchNorm running statistics early in epoch 0; train-mode results are unaffected.
+    step = TrainStep(model, optim, lim=lim, graphs=os.environ.get("CORRIF_TRAIN_GRAPHS", "1") != "0")
     for epoch in range(n_epochs):
         model.train()
         scheduler.step()                                            # before any optimizer step, as :46
