@@ -172,9 +172,10 @@ __device__ __forceinline__ void stage_window(uint32_t smem_in, const Src (&src)[
 }
 
 // ---- asynchronous staging (cp.async): global -> shared without a register round trip, zero-filled when invalid --
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid, bool via_l1 = false) {
   const int n = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
+  if (via_l1) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
+  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -183,7 +184,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // The 3x3x3 window of stage_window<3>, issued as cp.async copies (same thread -> (x, channel group) mapping).  The
 // data lands un-rounded; consumers add half a TF32 ulp when they load their fragments (see rnd_u32).
 __device__ __forceinline__ void stage_window3_async(uint32_t smem_in, const Src (&src)[MAX_SRC], int nsrc, const Geom& g,
-                                                    int b, int z0, int y0, int x0, int c0, int kc, bool replicate) {
+                                                    int b, int z0, int y0, int x0, int c0, int kc, bool replicate,
+                                                    bool via_l1 = false) {
   const int gshift = kc == 32 ? 3 : (kc == 16 ? 2 : 1);
   const int groups = 1 << gshift;
   const int cg = threadIdx.x & (groups - 1);
@@ -215,7 +217,7 @@ __device__ __forceinline__ void stage_window3_async(uint32_t smem_in, const Src 
     if (replicate) { z = min(max(z, 0), g.D - 1); y = min(max(y, 0), g.H - 1); inside = true; }
     inside = inside && sp != nullptr;
     const float* p = inside ? sp + (long long)(((b * g.D + z) * g.H + y) * g.W + x) * sld : any;
-    cp_async16(sdst + r * (HX * 16), p, inside);
+    cp_async16(sdst + r * (HX * 16), p, inside, via_l1);
   }
 }
 __device__ __forceinline__ void stage_linear_async(uint32_t smem_dst, const float4* __restrict__ gsrc, int n16) {

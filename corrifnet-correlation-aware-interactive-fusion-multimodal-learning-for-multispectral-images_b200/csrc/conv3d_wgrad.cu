@@ -28,6 +28,7 @@ struct WgradArgs {
   long long ldg;
   float* dW;              // torch layout [Cout][Cin][taps]
   int total_tiles;
+  int via_l1;             // cp.async through L1 (.ca) instead of L2 only (.cg): A/B switch CORRIF_WGRAD_CA
 };
 
 template <int KS, int NB>
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv3d_wgrad3_kernel(const WgradA
     const int x0 = (rem % a.g.tiles_x) * TX; rem /= a.g.tiles_x;
     const int y0 = (rem % a.g.tiles_y) * TY;
     const int z0 = (rem / a.g.tiles_y) * TZ;
-    stage_window3_async(s_in0 + buf * WIN, a.src, a.nsrc, a.g, b, z0, y0, x0, pass * WKC, WKC, a.replicate != 0);
+    stage_window3_async(s_in0 + buf * WIN, a.src, a.nsrc, a.g, b, z0, y0, x0, pass * WKC, WKC, a.replicate != 0, a.via_l1 != 0);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {                     // gradient tile: 256 voxels x 8 channels, zeros outside the volume
       const int i = threadIdx.x + u * NTHREADS;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv3d_wgrad3_kernel(const WgradA
       const int x = x0 + (v & 7), y = y0 + ((v >> 3) & 7), z = z0 + (v >> 6);
       const bool ok = z < a.g.D && y < a.g.H && x < a.g.W;
       const float* p = ok ? a.grad + (long long)(((b * a.g.D + z) * a.g.H + y) * a.g.W + x) * a.ldg + nt * 8 + q * 4 : a.grad;
-      cp_async16(s_g0 + buf * GT + (v * GLD + q * 4) * 4, p, ok);
+      cp_async16(s_g0 + buf * GT + (v * GLD + q * 4) * 4, p, ok, a.via_l1 != 0);
     }
   };
   int tile = blockIdx.x, buf = 0;
@@ -422,6 +423,8 @@ extern "C" int corrif_conv3d_wgrad(const corrif_conv3d_desc* desc, const float* 
   a.g = Geom{d.B, d.D, d.H, d.W, (d.W + TX - 1) / TX, (d.H + TY - 1) / TY, (d.D + TZ - 1) / TZ};
   a.Cin = d.Cin; a.Cout = d.Cout; a.replicate = d.pad_mode == CORRIF_PAD_REPLICATE;
   a.grad = g; a.ldg = ldg; a.dW = dW; a.total_tiles = 0;
+  static const int via_l1 = getenv("CORRIF_WGRAD_CA") != nullptr;
+  a.via_l1 = via_l1;
   const int NB = wgrad_nb(d.Cout);
   static const bool old3 = getenv("CORRIF_WGRAD_V1") != nullptr;      // A/B switch: first 3x3x3 kernel
   if (d.ksize == 3 && !old3) return launch_wgrad3(a, (cudaStream_t)stream);
