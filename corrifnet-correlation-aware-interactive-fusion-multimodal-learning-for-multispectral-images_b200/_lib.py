@@ -50,7 +50,7 @@ class Conv3dDesc(C.Structure):
     ]
 
 
-PAD_ZEROS, PAD_REPLICATE = 0, 1
+PAD_ZEROS, PAD_REPLICATE, PAD_REPLICATE_ADJOINT = 0, 1, 2
 EPI_STORE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_MUL_DGELU, EPI_ATOMIC_ADD = range(6)
 GEMM_TF32, GEMM_FP32 = 0, 1
 GEMM_ROUND_TF32 = 1
@@ -101,6 +101,10 @@ PROTOTYPES = {
     "corrif_conv3d_pack_weights": (C.c_int, [f32p, f32p, i32, i32, i32, i32, stream_t]),
     "corrif_conv3d_fwd": (C.c_int, [C.POINTER(Conv3dDesc), stream_t]),
     "corrif_conv3d_wgrad": (C.c_int, [C.POINTER(Conv3dDesc), f32p, i64, f32p, stream_t]),
+    "corrif_conv3d_tc_supported": (C.c_int, [C.POINTER(Conv3dDesc)]),
+    "corrif_conv3d_tc_pack_floats": (i64, [C.POINTER(Conv3dDesc)]),
+    "corrif_conv3d_tc_pack_weights": (C.c_int, [C.POINTER(Conv3dDesc), f32p, f32p, i32, stream_t]),
+    "corrif_conv3d_tc_fwd": (C.c_int, [C.POINTER(Conv3dDesc), stream_t]),
     "corrif_conv3d_dgrad_border": (C.c_int, [f32p, i64, f32p, f32p, i64, i32, i32, i32, i32, i32, i32, stream_t]),
     "corrif_instnorm_apply": (C.c_int, [f32p, i64, f64p, f32p, f32p, i32, i64, i32, f32, stream_t]),
     "corrif_instnorm_bwd_stats": (C.c_int, [f32p, i64, f32p, i64, f64p, i32, i64, i32, stream_t]),

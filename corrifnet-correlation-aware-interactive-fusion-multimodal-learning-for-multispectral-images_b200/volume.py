@@ -26,7 +26,9 @@ import torch
 
 from . import _lib as L
 from . import ops
-from ._lib import PAD_REPLICATE, PAD_ZEROS  # noqa: F401
+import os
+
+from ._lib import PAD_REPLICATE, PAD_REPLICATE_ADJOINT, PAD_ZEROS  # noqa: F401
 
 EPS = 1e-5          # nn.InstanceNorm3d default (mmvit4.py:24)
 
@@ -102,22 +104,55 @@ def bump_weight_epoch() -> None:
         _PACK_CACHE.clear()
 
 
-def pack_weights(weight: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
-    """[Cout, Cin, k, k, k] -> the kernels' fragment-ordered TF32 operand (forward, or data-gradient form)."""
+def _cached_pack(weight: torch.Tensor, key_extra, make) -> torch.Tensor:
     if torch.cuda.is_current_stream_capturing():
-        return _pack_weights(weight, transpose_flip)          # inside a CUDA graph the packing must replay with the graph
-    key = (id(weight), bool(transpose_flip))
+        return make()                                         # inside a CUDA graph the packing must replay with the graph
+    key = (id(weight),) + tuple(key_extra)
     stamp = (weight.data_ptr(), weight._version, _WEIGHT_EPOCH)
     hit = _PACK_CACHE.get(key)
     # the entry must belong to THIS tensor object (ids and addresses are recycled once a tensor dies)
     if hit is not None and hit[0]() is weight and hit[1] == stamp:
         return hit[2]
-    wpk = _pack_weights(weight, transpose_flip)
+    wpk = make()
     try:
         _PACK_CACHE[key] = (weakref.ref(weight), stamp, wpk)
     except TypeError:
         pass
     return wpk
+
+
+def pack_weights(weight: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
+    """[Cout, Cin, k, k, k] -> the warp-level kernels' fragment-ordered TF32 operand (forward, or data-gradient form)."""
+    return _cached_pack(weight, (bool(transpose_flip),), lambda: _pack_weights(weight, transpose_flip))
+
+
+def tc_enabled() -> bool:
+    """The tcgen05 line convolution serves the shapes it supports unless CORRIF_CONV_TC=0 (A/B switch)."""
+    return os.environ.get("CORRIF_CONV_TC", "1") != "0"
+
+
+def tc_supported(d: L.Conv3dDesc) -> bool:
+    return d.ksize == 3 and tc_enabled() and bool(ops.lib().corrif_conv3d_tc_supported(C.byref(d)))
+
+
+def pack_weights_tc(weight: torch.Tensor, d: L.Conv3dDesc, transpose_flip: bool = False) -> torch.Tensor:
+    """Forward weight [Cout, Cin, 3, 3, 3] -> the shared-memory image of the tcgen05 line convolution described by
+    ``d`` (swizzled [3*Cout x Cin] tiles per (dz, dy) tap; depends on how the input channels split into sources)."""
+    chans = tuple(d.src[i].C for i in range(d.nsrc))
+
+    def make():
+        n = ops.lib().corrif_conv3d_tc_pack_floats(C.byref(d))
+        if n <= 0:
+            raise ValueError("conv3d_tc: shape not supported")
+        w = weight.detach().contiguous()
+        wpk = torch.empty(n, device=weight.device, dtype=torch.float32)
+        with ops._rec("conv_pack", 8.0 * w.numel()):
+            L.check(ops.lib().corrif_conv3d_tc_pack_weights(C.byref(d), w.data_ptr(), wpk.data_ptr(), int(transpose_flip),
+                                                            _stream()), "conv3d_tc_pack_weights")
+        ops._count()
+        return wpk
+
+    return _cached_pack(weight, ("tc", bool(transpose_flip), chans, d.Cout), make)
 
 
 def _pack_weights(weight: torch.Tensor, transpose_flip: bool) -> torch.Tensor:
@@ -147,6 +182,21 @@ def conv3d_forward(srcs, wpk, bias, Cout, ksize, pad_mode, relu, out, stats=None
     ops._count()
 
 
+def conv3d_forward_auto(srcs, weight, bias, Cout, ksize, pad_mode, relu, out, stats=None):
+    """The convolution forward on the tcgen05 line kernel where it applies, else on the warp-level kernel."""
+    d = _desc(srcs, Cout, ksize, pad_mode)
+    if not tc_supported(d):
+        return conv3d_forward(srcs, pack_weights(weight), bias, Cout, ksize, pad_mode, relu, out, stats)
+    wpk = pack_weights_tc(weight, d)
+    d.relu, d.wpk, d.bias = int(relu), wpk.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    d.out, d.ldo, d.stats = out.data_ptr(), _ld(out), (stats.data_ptr() if stats is not None else None)
+    nvox = d.B * d.D * d.H * d.W
+    with ops._rec("conv3d_fwd", 2.0 * nvox * 27 * d.Cin * Cout, "k3 %dx%dx%dx%d %d->%d tc bytes=%d" % (
+            d.B, d.D, d.H, d.W, d.Cin, Cout, 4 * nvox * (d.Cin + Cout))):
+        L.check(ops.lib().corrif_conv3d_tc_fwd(C.byref(d), _stream()), "conv3d_tc_fwd")
+    ops._count()
+
+
 def conv3d_wgrad(srcs, g, dW, ksize, pad_mode):
     Cout = g.shape[4]
     d = _desc(srcs, Cout, ksize, pad_mode)
@@ -161,6 +211,18 @@ def conv3d_wgrad(srcs, g, dW, ksize, pad_mode):
 def conv3d_dgrad(g, weight, Cin, ksize, pad_mode, dx):
     """dx [B,D,H,W,Cin] = d(cat of the sources) from g = d(pre-activation)."""
     Cout = g.shape[4]
+    if ksize == 3:
+        # tcgen05 line kernel: the adjoint of replicate padding is part of the same pass (no border kernel)
+        dt = _desc([g], Cin, ksize, PAD_REPLICATE_ADJOINT if pad_mode == PAD_REPLICATE else PAD_ZEROS)
+        if tc_supported(dt):
+            wpk_t = pack_weights_tc(weight, dt, transpose_flip=True)
+            dt.relu, dt.wpk, dt.bias, dt.out, dt.ldo, dt.stats = 0, wpk_t.data_ptr(), None, dx.data_ptr(), _ld(dx), None
+            nvox = dt.B * dt.D * dt.H * dt.W
+            with ops._rec("conv3d_dgrad", 2.0 * nvox * 27 * Cin * Cout, "k3 %dx%dx%dx%d %d->%d tc" % (
+                    dt.B, dt.D, dt.H, dt.W, Cout, Cin)):
+                L.check(ops.lib().corrif_conv3d_tc_fwd(C.byref(dt), _stream()), "conv3d_tc_dgrad")
+            ops._count()
+            return
     wpk_t = pack_weights(weight, transpose_flip=True)
     d = _desc([g], Cin, ksize, PAD_ZEROS)
     d.relu, d.wpk, d.bias, d.out, d.ldo, d.stats = 0, wpk_t.data_ptr(), None, dx.data_ptr(), _ld(dx), None
@@ -189,11 +251,10 @@ class _ConvBlock(torch.autograd.Function):
         Cout = weight.shape[0]
         B, D, H, W = srcs[0].shape[:4]
         dev = weight.device
-        wpk = pack_weights(weight)
         out = torch.empty(B, D, H, W, Cout, device=dev, dtype=torch.float32)
         stats = torch.zeros(B, Cout, 2, device=dev, dtype=torch.float64) if norm else None
         b = bias.detach().contiguous() if bias is not None else None
-        conv3d_forward(srcs, wpk, b, Cout, ksize, pad_mode, relu, out, stats)
+        conv3d_forward_auto(srcs, weight, b, Cout, ksize, pad_mode, relu, out, stats)
         mean = rstd = None
         if norm:
             mean = torch.empty(B, Cout, device=dev, dtype=torch.float32)

@@ -326,7 +326,9 @@ typedef struct corrif_vol_src {
   int64_t ld;
 } corrif_vol_src;
 
-enum { CORRIF_PAD_ZEROS = 0, CORRIF_PAD_REPLICATE = 1 };
+/* CORRIF_PAD_REPLICATE_ADJOINT (corrif_conv3d_tc_fwd only): the adjoint of replicate padding - what the data gradient
+ * of a replicate-padded convolution applies at the volume border (a clamped tap uses the mirrored weight). */
+enum { CORRIF_PAD_ZEROS = 0, CORRIF_PAD_REPLICATE = 1, CORRIF_PAD_REPLICATE_ADJOINT = 2 };
 
 typedef struct corrif_conv3d_desc {
   corrif_vol_src src[3];      /* inputs, concatenated along channels in this order      */
@@ -354,6 +356,21 @@ int corrif_conv3d_fwd(const corrif_conv3d_desc* desc, void* stream);
 /* desc: src / geometry / ksize / pad_mode as in the forward (out, wpk, bias, stats ignored); g = d(pre-activation)
  * [B,D,H,W,Cout] with stride ldg; dW: torch layout, accumulated. */
 int corrif_conv3d_wgrad(const corrif_conv3d_desc* desc, const float* g, int64_t ldg, float* dW, void* stream);
+/* The same 3x3x3 convolution as a tcgen05 "line convolution" (csrc/conv3d_tc.cu): a row of 128 voxels along x is the
+ * M dimension of the MMA, the three x-taps are folded into N (= 3 * Cout), every input line is staged once by TMA and
+ * feeds the TMEM accumulators of the nine output lines it touches; the x-tap sum, bias, ReLU and the InstanceNorm
+ * statistics run in the epilogue.  Replaces, for the shapes it supports, corrif_conv3d_fwd (forward: mmvit4.py:29-45,
+ * 222-292) and corrif_conv3d_fwd + corrif_conv3d_dgrad_border (data gradient: describe the gradient as the source,
+ * Cin / Cout swapped, pad_mode CORRIF_PAD_REPLICATE_ADJOINT for a replicate-padded forward, weights packed with
+ * transpose_flip = 1).  Supported: ksize 3, W in {16, 32, 64, 128} with B a multiple of 128 / W, every source with
+ * 8, 16 or a multiple of 32 channels, Cout 8, 16 or a multiple of 32, packed weights resident in shared memory
+ * (corrif_conv3d_tc_supported returns 1).  desc->wpk must come from corrif_conv3d_tc_pack_weights for a descriptor
+ * with the same channel split; `w` there is always the forward weight [Cout_fwd][Cin_fwd][3][3][3]. */
+int corrif_conv3d_tc_supported(const corrif_conv3d_desc* desc);
+int64_t corrif_conv3d_tc_pack_floats(const corrif_conv3d_desc* desc);
+int corrif_conv3d_tc_pack_weights(const corrif_conv3d_desc* desc, const float* w, float* wpk, int32_t transpose_flip,
+                                  void* stream);
+int corrif_conv3d_tc_fwd(const corrif_conv3d_desc* desc, void* stream);
 /* dx[B,D,H,W,Cin] (stride ldx) += the replicate-padding part of the 3x3x3 data gradient; w_taps_major is the weight
  * transposed to [27][Cout][Cin] (weight.permute(2,3,4,0,1)), so that threads of consecutive ci read consecutive words */
 int corrif_conv3d_dgrad_border(const float* g, int64_t ldg, const float* w_taps_major, float* dx, int64_t ldx, int32_t B,

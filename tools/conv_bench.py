@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 from corrif_b200 import volume as V  # noqa: E402
 
 dev = torch.device("cuda:0")
-SHAPES = [((32,), 8, 3, 128), ((16,), 8, 3, 128), ((64,), 16, 3, 64), ((32,), 16, 3, 64), ((128,), 32, 3, 32),
+SHAPES = [((32,), 8, 3, 128), ((16,), 8, 3, 128), ((64,), 16, 3, 64), ((32,), 16, 3, 64), ((128,), 32, 3, 32), ((64,), 32, 3, 32),
           ((320,), 64, 3, 16), ((8,), 8, 1, 128)]
 if len(sys.argv) > 1:
     SHAPES = SHAPES[:int(sys.argv[1])]
@@ -41,9 +41,8 @@ for chans, cout, k, n in SHAPES:
     dx = torch.empty(B, n, n, n, cin, device=dev)
     dW = torch.zeros_like(w)
     stats = torch.zeros(B, cout, 2, device=dev, dtype=torch.float64)
-    wpk = V.pack_weights(w)
     pad = V.PAD_REPLICATE
-    t_f = timed(lambda: V.conv3d_forward(xs, wpk, bias, cout, k, pad, True, out, stats))
+    t_f = timed(lambda: V.conv3d_forward_auto(xs, w, bias, cout, k, pad, True, out, stats))
     t_d = timed(lambda: V.conv3d_dgrad(g, w, cin, k, pad, dx))
     t_w = timed(lambda: V.conv3d_wgrad(xs, g, dW, k, pad))
     flop = 2.0 * B * n ** 3 * (27 if k == 3 else 1) * cin * cout
