@@ -41,8 +41,11 @@ namespace corrif {
 namespace convtc {
 using namespace tc05;
 
-constexpr int MAXKC = 8;          // A sub-tiles (<= 32 channels of one source) per line
-constexpr int NISSUE = 2;         // MMA-issuing warps (lines are dealt round-robin)
+constexpr int MAXKC = 12;         // A sub-tiles (<= 32 channels of one source) per line
+#ifndef CORRIF_TC_NISSUE
+#define CORRIF_TC_NISSUE 2
+#endif
+constexpr int NISSUE = CORRIF_TC_NISSUE;         // MMA-issuing warps (lines are dealt round-robin)
 constexpr int NTHREADS = 320 + 32 * (NISSUE - 1);   // warp 0: TMA producer, warp 1 and warps 10..: MMA issuers, warps 2..9: two epilogue groups of four
 constexpr int ACC_SLOTS = 4;      // output planes in flight in TMEM
 constexpr int MAX_RING = 12;
@@ -99,18 +102,20 @@ static Plan make_plan(const corrif_conv3d_desc& d, int nsm) {
   if (p.T > 4) p.T = 4;
   if (p.T > d.H) p.T = d.H;
   int nk = 0, cs = 0, a_off = 0, w_off = 0;
-  p.SWB = d.src[0].C >= 32 ? 128 : d.src[0].C * 4;     // every K chunk has the same width (the kernel is templated on it)
+  // K chunks: every chunk has the same width (the kernel is templated on it) - the widest of 32 / 16 / 8 channels
+  // that divides every source, so cat(24, 8) runs as four 8-channel chunks and cat(48, 16) as four 16-channel ones
+  int cw = 32;
+  for (int s = 0; s < d.nsrc; ++s)
+    while (cw >= 8 && d.src[s].C % cw) cw >>= 1;
+  if (cw < 8) return p;
+  p.SWB = cw * 4;
   for (int s = 0; s < d.nsrc; ++s) {
-    const int C = d.src[s].C;
-    if (!(C == 8 || C == 16 || (C > 0 && C % 32 == 0))) return p;
-    if ((C >= 32 ? 128 : C * 4) != p.SWB) return p;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      const int ch = C - c0 < 32 ? C - c0 : 32;
+    for (int c0 = 0; c0 < d.src[s].C; c0 += cw) {
       if (nk == MAXKC) return p;
-      p.kc[nk] = KChunk{s, c0, cs, ch * 4, a_off, w_off};
-      a_off += 128 * ch * 4;
-      w_off += (3 * p.NPAD * ch * 4 + 1023) / 1024 * 1024;
-      cs += ch;
+      p.kc[nk] = KChunk{s, c0, cs, cw * 4, a_off, w_off};
+      a_off += 128 * cw * 4;
+      w_off += (3 * p.NPAD * cw * 4 + 1023) / 1024 * 1024;
+      cs += cw;
       ++nk;
     }
   }
@@ -422,6 +427,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       const int b = it.bg * a.R + rsub;
       const int n0 = it.nc * CC + choff;
       const int nm = it.ylast - it.y0 + 1;
+      float bias[CCG];
+#pragma unroll
+      for (int j = 0; j < CCG; ++j) bias[j] = s_bias[n0 + j];
       // the statistics live in registers for a whole item
       float ssum[STATS ? CCG : 1], ssq[STATS ? CCG : 1];
 #pragma unroll
@@ -454,23 +462,52 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           }
           if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
           else asm volatile("bar.sync 2, 128;" ::: "memory");
-          float o[CCG];
+          // left / right x-neighbours: a shuffle for 30 of 32 lanes; the warp-boundary lanes read the other warp's
+          // row from shared memory and the two lanes at the ends of a line apply the padding rule - both as
+          // branches only the affected lanes take (per-element selects made this loop 31 instructions per value)
+          float l[CCG], r[CCG];
 #pragma unroll
           for (int j = 0; j < CCG; ++j) {
-            float l = __shfl_up_sync(0xffffffffu, __uint_as_float(p0[j]), 1);
-            float r = __shfl_down_sync(0xffffffffu, __uint_as_float(p2[j]), 1);
-            if (lane == 0 && quad > 0) l = xb[quad - 1][0][j];
-            if (lane == 31 && quad < 3) r = xb[quad + 1][1][j];
-            if (xfirst) l = pad == CORRIF_PAD_ZEROS ? 0.f : __uint_as_float(pad == CORRIF_PAD_REPLICATE ? p0[j] : p2[j]);
-            if (xlast) r = pad == CORRIF_PAD_ZEROS ? 0.f : __uint_as_float(pad == CORRIF_PAD_REPLICATE ? p2[j] : p0[j]);
-            float v = __uint_as_float(p1[j]) + l + r + s_bias[n0 + j];
-            if (a.relu) v = fmaxf(v, 0.f);
-            o[j] = v;
-            if constexpr (STATS) { ssum[j] += v; ssq[j] = fmaf(v, v, ssq[j]); }
+            l[j] = __shfl_up_sync(0xffffffffu, __uint_as_float(p0[j]), 1);
+            r[j] = __shfl_down_sync(0xffffffffu, __uint_as_float(p2[j]), 1);
+          }
+          if (xfirst) {
+#pragma unroll
+            for (int j = 0; j < CCG; ++j)
+              l[j] = pad == CORRIF_PAD_ZEROS ? 0.f : __uint_as_float(pad == CORRIF_PAD_REPLICATE ? p0[j] : p2[j]);
+          } else if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < CCG; j += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(&xb[quad - 1][0][j]);
+              l[j] = t.x; l[j + 1] = t.y; l[j + 2] = t.z; l[j + 3] = t.w;
+            }
+          }
+          if (xlast) {
+#pragma unroll
+            for (int j = 0; j < CCG; ++j)
+              r[j] = pad == CORRIF_PAD_ZEROS ? 0.f : __uint_as_float(pad == CORRIF_PAD_REPLICATE ? p2[j] : p0[j]);
+          } else if (lane == 31) {
+#pragma unroll
+            for (int j = 0; j < CCG; j += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(&xb[quad + 1][1][j]);
+              r[j] = t.x; r[j + 1] = t.y; r[j + 2] = t.z; r[j + 3] = t.w;
+            }
+          }
+          float o[CCG];
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < CCG; ++j) o[j] = fmaxf((__uint_as_float(p1[j]) + bias[j]) + (l[j] + r[j]), 0.f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CCG; ++j) o[j] = (__uint_as_float(p1[j]) + bias[j]) + (l[j] + r[j]);
+          }
+          if constexpr (STATS) {
+#pragma unroll
+            for (int j = 0; j < CCG; ++j) { ssum[j] += o[j]; ssq[j] = fmaf(o[j], o[j], ssq[j]); }
           }
           float* op = a.out + ((((long long)b * D + z) * H + (it.y0 + m)) * W + x) * a.ldo + n0;
 #pragma unroll
-          for (int j = 0; j < CCG; j += 4) st4(op + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+          for (int j = 0; j < CCG; j += 4) if (!(a.debug & 8)) st4(op + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
         }
         tmem_st_wait();
         tcgen05_fence_before();
@@ -534,10 +571,9 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, float* __restrict__ 
   wpk[i] = round_tf32(v * TRUNC_COMP);
 }
 
-static int encode_line_map(CUtensorMap* map, const corrif_vol_src& s, int B, int D, int H, int W) {
+static int encode_line_map(CUtensorMap* map, const corrif_vol_src& s, int B, int D, int H, int W, int ch) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not found"); return CORRIF_EDRIVER; }
-  const int ch = s.C < 32 ? s.C : 32;
   cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * D};
   cuuint64_t strides[3] = {(cuuint64_t)s.ld * 4, (cuuint64_t)s.ld * 4 * W, (cuuint64_t)s.ld * 4 * W * H};
   cuuint32_t box[4] = {(cuuint32_t)ch, (cuuint32_t)W, 1, 1};
@@ -654,7 +690,7 @@ extern "C" int corrif_conv3d_tc_fwd(const corrif_conv3d_desc* desc, void* stream
   // the packed image depends on the plan only through quantities make_plan derives from the channel split
   CUtensorMap tm[3];
   for (int i = 0; i < 3; ++i) {
-    rc = encode_line_map(&tm[i], d.src[i < d.nsrc ? i : 0], d.B, d.D, d.H, d.W);
+    rc = encode_line_map(&tm[i], d.src[i < d.nsrc ? i : 0], d.B, d.D, d.H, d.W, p.SWB / 4);
     if (rc) return rc;
   }
   Args a{};

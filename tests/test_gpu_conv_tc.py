@@ -30,6 +30,8 @@ CASES = [
     ((8, 8, 8), 8, 0, 8, 2, 16, 16),         # three sources, eight samples per tile, zero padding
     ((32,), 32, 1, 8, 1, 16, 16),            # a single plane (both z taps clamp onto it)
     ((32,), 8, 1, 1, 40, 4, 128),            # several z ranges per strip
+    ((24, 8), 8, 1, 1, 4, 6, 128),           # d1_c2: cat(skip 24, up 8) as four 8-channel chunks
+    ((48, 16), 16, 1, 2, 3, 8, 64),          # d2_c2: four 16-channel chunks
 ]
 IDS = [f"{'+'.join(map(str, c[0]))}to{c[1]}p{c[2]}_{c[3]}x{c[4]}x{c[5]}x{c[6]}" for c in CASES]
 
