@@ -474,15 +474,61 @@ def batchnorm_relu(x: torch.Tensor, bn: torch.nn.BatchNorm3d, residual: Optional
     return y
 
 
+def _separable(shape_in, size) -> bool:
+    """Trilinear resizes that grow the volume (the decoder's 2x up-sampling, mmvit4.py:269) run as three streaming
+    one-axis passes; the small / strongly down-sampling ones keep the single gather kernel."""
+    B, Di, Hi, Wi, Cc = shape_in
+    Do, Ho, Wo = size
+    if os.environ.get("CORRIF_RESIZE_SEPARABLE", "1") == "0" or B * Do * Ho * Wo * Cc < (1 << 22) or B * Do * Ho * Wo * Cc >= (1 << 33):
+        return False
+    return all(o >= i and (i > 1 and (o - 1) <= 3 * (i - 1) or i == o) for i, o in ((Di, Do), (Hi, Ho), (Wi, Wo)))
+
+
+def _linear_axes(t: torch.Tensor, sizes_in, sizes_out, Cc: int, backward: bool) -> torch.Tensor:
+    """Apply the one-axis passes (forward: x, y, z; adjoint: z, y, x) to a contiguous [B, D, H, W, C] tensor."""
+    B = t.shape[0]
+    dims = list(sizes_out if backward else sizes_in)          # current D, H, W
+    lib = ops.lib()
+    order = (0, 1, 2) if backward else (2, 1, 0)
+    for ax in order:
+        n_from, n_to = (sizes_out[ax], sizes_in[ax]) if backward else (sizes_in[ax], sizes_out[ax])
+        if n_from == n_to:
+            continue
+        outer = B
+        for a in range(ax):
+            outer *= dims[a]
+        inner = Cc
+        for a in range(ax + 1, 3):
+            inner *= dims[a]
+        new_dims = list(dims)
+        new_dims[ax] = n_to
+        out = torch.empty(B, *new_dims, Cc, device=t.device, dtype=torch.float32)
+        tag = "resize_trilinear_" + ("bwd" if backward else "fwd")
+        with ops._rec(tag, 4.0 * (t.numel() + out.numel()), "axis%d %dx%dx%dx%d->%d C%d" % (ax, B, *dims, n_to, Cc)):
+            if backward:
+                L.check(lib.corrif_resize_linear_axis_bwd(t.data_ptr(), out.data_ptr(), outer, n_to, n_from, inner, _stream()),
+                        "resize_linear_axis_bwd")
+            else:
+                L.check(lib.corrif_resize_linear_axis_fwd(t.data_ptr(), out.data_ptr(), outer, n_from, n_to, inner, _stream()),
+                        "resize_linear_axis_fwd")
+        ops._count()
+        t, dims = out, new_dims
+    return t
+
+
 class _Resize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, size, mode):
         x = as_volume(x)
         B, Di, Hi, Wi, Cc = x.shape
         Do, Ho, Wo = size
+        if mode == "trilinear" and _separable(x.shape, size):
+            ctx.cfg = (mode, (Di, Hi, Wi), size)
+            return _linear_axes(x.contiguous(), (Di, Hi, Wi), size, Cc, backward=False)
         y = torch.empty(B, Do, Ho, Wo, Cc, device=x.device, dtype=torch.float32)
         fn = ops.lib().corrif_resize_trilinear_fwd if mode == "trilinear" else ops.lib().corrif_resize_nearest_fwd
-        with ops._rec("resize_" + mode + "_fwd", 4.0 * Cc * B * (Di * Hi * Wi + Do * Ho * Wo)):
+        with ops._rec("resize_" + mode + "_fwd", 4.0 * Cc * B * (Di * Hi * Wi + Do * Ho * Wo),
+                      "%dx%dx%dx%d->%dx%dx%d C%d" % (B, Di, Hi, Wi, Do, Ho, Wo, Cc)):
             L.check(fn(x.data_ptr(), _ld(x), y.data_ptr(), Cc, B, Cc, Di, Hi, Wi, Do, Ho, Wo, _stream()), "resize_fwd")
         ops._count()
         ctx.cfg = (mode, (Di, Hi, Wi), size)
@@ -493,9 +539,12 @@ class _Resize(torch.autograd.Function):
         mode, (Di, Hi, Wi), (Do, Ho, Wo) = ctx.cfg
         dy = as_volume(dy)
         B, Cc = dy.shape[0], dy.shape[4]
+        if mode == "trilinear" and _separable((B, Di, Hi, Wi, Cc), (Do, Ho, Wo)):
+            return _linear_axes(dy.contiguous(), (Di, Hi, Wi), (Do, Ho, Wo), Cc, backward=True), None, None
         dx = torch.empty(B, Di, Hi, Wi, Cc, device=dy.device, dtype=torch.float32)
         fn = ops.lib().corrif_resize_trilinear_bwd if mode == "trilinear" else ops.lib().corrif_resize_nearest_bwd
-        with ops._rec("resize_" + mode + "_bwd", 4.0 * Cc * B * (Di * Hi * Wi + Do * Ho * Wo)):
+        with ops._rec("resize_" + mode + "_bwd", 4.0 * Cc * B * (Di * Hi * Wi + Do * Ho * Wo),
+                      "%dx%dx%dx%d->%dx%dx%d C%d" % (B, Di, Hi, Wi, Do, Ho, Wo, Cc)):
             L.check(fn(dy.data_ptr(), _ld(dy), dx.data_ptr(), Cc, B, Cc, Di, Hi, Wi, Do, Ho, Wo, _stream()), "resize_bwd")
         ops._count()
         return dx, None, None

@@ -180,6 +180,7 @@ def test_channel_slice_views_are_valid_sources_and_gradients():
 
 
 @pytest.mark.parametrize("shape", [((2, 4, 5, 6, 8), (8, 10, 12)), ((1, 16, 16, 16, 16), (32, 32, 32)),
+                                   ((2, 32, 32, 32, 16), (64, 64, 64)), ((2, 24, 40, 32, 24), (48, 80, 33)),   # separable passes
                                    ((2, 3, 14, 14, 24), (8, 8, 8)), ((1, 8, 8, 8, 8), (1, 24, 24)),
                                    ((2, 3, 7, 7, 64), (8, 8, 8))])
 def test_trilinear_resize_matches_f_interpolate(shape):

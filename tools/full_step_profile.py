@@ -14,6 +14,7 @@ from corrif_b200 import train  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 dev = torch.device("cuda:0")
+torch.backends.cudnn.benchmark = os.environ.get("CORRIF_CUDNN_BENCHMARK") == "1"
 torch.manual_seed(0)
 model = mmvit4.MMVit4(num_cls=1).to(dev).train()
 optim = torch.optim.Adam(model.parameters(), 1e-4)
@@ -41,7 +42,7 @@ for cls, detail, ms, work in rows:
 print("\n# libcorrif_b200 launches of one micro-batch step (CUDA events per launch; serialised, so the sum exceeds the step)")
 print("%-22s %-34s %6s %10s %12s" % ("kernel", "shape", "n", "ms", "TFLOP/s|GB/s"))
 tot = 0.0
-for (cls, detail), (n, ms, work) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+for (cls, detail), (n, ms, work) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("CORRIF_PROFILE_ROWS", "60"))]:
     rate = work / (ms * 1e-3) / (1e12 if cls.startswith(("conv3d", "gemm", "attn")) else 1e9) if ms > 0 else 0
     print("%-22s %-34s %6d %10.3f %12.1f" % (cls, detail[:34], n, ms, rate))
     tot += ms
