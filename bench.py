@@ -372,7 +372,8 @@ def bench_metric_kernels(dev, peaks):
 
 def summarise_volume(details, peaks):
     """details: [(class, shape string, ms, algorithmic work)] of one micro-batch step.  Roofline of the convolution
-    family (conv3d fwd / dgrad / wgrad: warp-level TF32 MMAs over shared-memory windows) and a per-class table."""
+    family: the tcgen05 line convolution (forward + data gradient of the 128^3 / 64^3 layers: HBM-bound, judged on its
+    algorithmic bytes) beside the whole family (incl. the warp-level weight-gradient kernel), and a per-class table."""
     agg = {}
     for cls, det, ms, work in details:
         a = agg.setdefault(cls, [0, 0.0, 0.0])
@@ -382,9 +383,12 @@ def summarise_volume(details, peaks):
     # algorithmic bytes of the convolution launches: the forward's shape string carries them; dgrad / wgrad move the
     # same two tensors (+ the tiny weights)
     byts = 0.0
+    tc_n, tc_ms, tc_bytes, tc_flops = 0, 0.0, 0.0, 0.0
     for cls, det, ms, work in details:
         if cls == "conv3d_fwd" and "bytes=" in det:
             byts += 3.0 * float(det.split("bytes=")[1])
+        if cls in ("conv3d_fwd", "conv3d_dgrad") and " tc " in det and "bytes=" in det:
+            tc_n += 1; tc_ms += ms; tc_bytes += float(det.split("bytes=")[1]); tc_flops += work
     tc = ("gemm", "attn", "conv3d_fwd", "conv3d_dgrad", "conv3d_wgrad")
     table = {k: {"launches": v[0], "ms": round(v[1], 3),
                  ("tflops" if k.startswith(tc) and k != "conv3d_dgrad_border" else "gbs"):
@@ -392,22 +396,27 @@ def summarise_volume(details, peaks):
              for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]}
     ach = fl_ / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0
     gbs = byts / (ms_ * 1e-3) / 1e9 if ms_ > 0 else 0.0
+    tc_gbs = tc_bytes / (tc_ms * 1e-3) / 1e9 if tc_ms > 0 else 0.0
     peak_tf32 = peaks["bf16_sustained"] / 2.0
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     traffic = None
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("conv3d", {}).get("dram_bytes_per_launch")
-    roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": traffic,
-            "kernel": "channels-last conv3d family (fwd + data gradient + weight gradient, %d launches of one micro-batch "
-                      "of 8): warp-level TF32 mma.sync over shared-memory windows" % n_,
-            "algorithmic_bytes_per_step": byts, "flops_per_step": fl_, "kernel_ms_per_step": ms_,
-            "tensor_tflops": ach, "frac_of_tf32_tcgen05_peak": ach / peak_tf32,
-            "mma_sync_peak_tflops_measured": 270.0, "frac_of_mma_sync_peak": ach / 270.0,
-            "note": "these layers have 8-64 output channels: ~90 FLOP per HBM byte, so they sit between the HBM roof and "
-                    "the 270 TFLOP/s warp-level MMA rate measured on this GPU (profiles/r02a_mma_sync_probe.txt); "
-                    "DESIGN.md section 4.4 explains why tcgen05 does not apply"}
+            traffic = json.load(f).get("conv3d_tc", {}).get("dram_bytes_per_launch")
+    roof = {"bound": "hbm", "achieved": tc_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": tc_gbs / peaks["hbm_gbs"], "traffic": traffic,
+            "kernel": "conv3d_tc_kernel: tcgen05 line convolution, forward + data gradient of the 3x3x3 layers at 128^3 / "
+                      "64^3 voxels (%d launches of one micro-batch of 8); achieved = algorithmic bytes (sources read once "
+                      "+ result written once) / CUDA-event time" % tc_n,
+            "algorithmic_bytes_per_step": tc_bytes, "flops_per_step": tc_flops, "kernel_ms_per_step": tc_ms,
+            "tensor_tflops": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0,
+            "family": {"what": "every conv3d launch of the step: line convolution, warp-level forward / data gradient of the "
+                               "small layers, warp-level weight gradient (%d launches)" % n_,
+                       "ms": ms_, "tflops": ach, "frac_of_tf32_tcgen05_peak": ach / peak_tf32,
+                       "gbs_algorithmic": gbs, "frac_of_hbm": gbs / peaks["hbm_gbs"],
+                       "mma_sync_peak_tflops_measured": 270.0},
+            "note": "these layers have 8-64 output channels: ~90 FLOP per HBM byte puts them on the HBM side of the "
+                    "tcgen05 ridge; DESIGN.md section 4.4"}
     return roof, table
 
 

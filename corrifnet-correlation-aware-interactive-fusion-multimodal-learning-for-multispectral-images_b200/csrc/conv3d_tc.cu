@@ -316,12 +316,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     }
   } else if (warp == 1 || warp >= 10) {
     // ================= MMA issuers =================
-    // Every MMA accumulates, so MMAs of different lines need no order among themselves: the lines are dealt
+    // Every MMA accumulates, so MMAs of different lines need no order among themselves: the ring slots are dealt
     // round-robin to NISSUE warps (the single issuing thread, not the tensor pipe, was the limit: ~160 mostly
     // uniform-datapath instructions per line at ~8 cycles each).  Each issuer commits its own MMAs to the plane's
     // acc_full barrier (count NISSUE).
     const int iss = warp == 1 ? 0 : warp - 9;
-    int lc = 0;
     // One thread issues every MMA.  An input line feeds, per y-tap, the accumulators of the (up to) three output
     // planes zv-1, zv, zv+1: they sit side by side in TMEM (column = (line * 4 + plane slot) * NPAD) and the weight
     // tile stacks the z-taps +1, 0, -1 in the same order, so ONE MMA with N = 3 * NPAD serves all three (two MMAs
@@ -366,8 +365,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           for (int yv = it.y0 - 1; yv <= it.ylast + 1; ++yv) {
             const bool yoob = yv < 0 || yv >= H;
             if (yoob && zeros) continue;
-            const bool mine = lc == iss;
-            if (++lc == NISSUE) lc = 0;
+            // a ring slot always belongs to the same issuer: a waiter that skipped one use of a barrier would see
+            // the phase parity of two uses ago and fall through before the line has landed
+            const bool mine = (s % NISSUE) == iss;
             if (mine) {
             mbar_wait(&full_bar[s], ph);
             tcgen05_fence_after();

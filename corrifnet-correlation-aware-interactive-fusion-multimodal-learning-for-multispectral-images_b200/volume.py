@@ -218,8 +218,8 @@ def conv3d_dgrad(g, weight, Cin, ksize, pad_mode, dx):
             wpk_t = pack_weights_tc(weight, dt, transpose_flip=True)
             dt.relu, dt.wpk, dt.bias, dt.out, dt.ldo, dt.stats = 0, wpk_t.data_ptr(), None, dx.data_ptr(), _ld(dx), None
             nvox = dt.B * dt.D * dt.H * dt.W
-            with ops._rec("conv3d_dgrad", 2.0 * nvox * 27 * Cin * Cout, "k3 %dx%dx%dx%d %d->%d tc" % (
-                    dt.B, dt.D, dt.H, dt.W, Cout, Cin)):
+            with ops._rec("conv3d_dgrad", 2.0 * nvox * 27 * Cin * Cout, "k3 %dx%dx%dx%d %d->%d tc bytes=%d" % (
+                    dt.B, dt.D, dt.H, dt.W, Cout, Cin, 4 * nvox * (Cin + Cout))):
                 L.check(ops.lib().corrif_conv3d_tc_fwd(C.byref(dt), _stream()), "conv3d_tc_dgrad")
             ops._count()
             return
