@@ -2,18 +2,17 @@
 // shared-memory layout of the staged input window, the multi-source channels-last loader and the warp-level
 // TF32 MMA.
 //
-// Why warp-level mma.sync here and tcgen05 in the GEMM / attention kernels.  The decoder's convolutions
-// (mmvit4.py:29-45, 222-292) have 8..64 output channels over up to 128^3 voxels: as implicit GEMMs they are
-// [16.8 M x 27*Cin] . [27*Cin x 8].  (1) The im2col operand is 27x the activation tensor; streaming it through
-// L2 (TMA im2col boxes) costs 58 GB for one 32 -> 8 channel layer, 10x the HBM floor, so the input window has to
-// be staged ONCE in shared memory and the 27 taps read as shifted views of it.  (2) tcgen05 shared-memory
-// descriptors address 8-row core matrices at fixed strides; a one-voxel shift is expressible only in the
-// un-swizzled K-major layout and not at all for the weight gradient (reduction over voxels with a per-tap shift of
-// one operand).  (3) With C_out = 8 a tcgen05 tile (M = 128, N >= 16) streams a 4 KB A operand from shared memory
-// for 8 cycles of math - it is shared-memory bound exactly like the warp-level path, but cannot reuse A fragments
-// across taps in registers, which the code below does (10 staged rows serve 3 dy-taps x 4 row pairs).
-// Measured mma.sync m16n8k8 TF32 rate on B200: 270 TFLOP/s (profiles/r02a_mma_sync_probe.txt); these layers need
-// ~90 FLOP per HBM byte, i.e. 270 TFLOP/s sits at the HBM ridge of 41 FLOP/B x 6.5 TB/s.
+// Which convolution runs where.  The 3x3x3 layers at 128^3 / 64^3 voxels - forward and data gradient, where most of the
+// time is - run on the tcgen05 "line convolution" of conv3d_tc.cu (a 128-voxel row is the M dimension, the x-taps are
+// folded into N, the y / z taps are a choice of TMEM accumulator).  The kernels in this header keep
+//   * the weight gradient (reduction over voxels: both operands would have to be K(= voxel)-contiguous, which
+//     channels-last lines are not),
+//   * the 1x1x1 convolutions and the 3x3x3 layers whose packed weights do not fit in shared memory (>= 64 channels on
+//     both sides, 32^3 voxels and below) or whose geometry the line kernel does not take (ragged W, channel counts
+//     that are not 8 / 16 / a multiple of 32),
+// as warp-level mma.sync over an input window staged once in shared memory with the 27 taps read as shifted views of
+// it (A fragments reused across taps in registers: 10 staged rows serve 3 dy-taps x 4 row pairs).
+// Measured mma.sync m16n8k8 TF32 rate on B200: 270 TFLOP/s (profiles/r02a_mma_sync_probe.txt).
 #pragma once
 #include "common.cuh"
 

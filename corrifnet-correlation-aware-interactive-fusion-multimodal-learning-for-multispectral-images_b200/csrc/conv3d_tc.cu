@@ -62,7 +62,7 @@ struct KChunk {
 
 struct Plan {
   int ok;
-  int R, T, ZL, CC, NPAD, NKC, NS, SWB;
+  int R, T, ZL, CC, NPAD, NKC, NS, SWB, w_resident;
   int n_nchunks, n_zchunks, n_bgroups, n_strips;
   long long total_items;
   int slot_bytes, tap_bytes, w_bytes;
@@ -73,7 +73,7 @@ struct Plan {
 struct Args {
   int B, D, H, W, R, T, ZL, NKC, NS;
   int n_nchunks, n_zchunks, n_bgroups, n_strips, total_items;
-  int pad_mode, relu, Cout;
+  int pad_mode, relu, Cout, w_resident;
   int debug;    // CORRIF_CONV_TC_DEBUG bit 0: epilogue only hands the accumulators back, 1: no MMAs, 2: no TMA loads (timing experiments)
   int slot_bytes, tap_bytes, w_bytes;
   KChunk kc[MAXKC];
@@ -84,18 +84,12 @@ struct Args {
   double* stats;
 };
 
-static Plan make_plan(const corrif_conv3d_desc& d, int nsm) {
+// plan for one output-channel chunk width CC (32, 16 or 8)
+static Plan make_plan_cc(const corrif_conv3d_desc& d, int nsm, int CC) {
   Plan p{};
   p.ok = 0;
-  if (d.ksize != 3) return p;
-  if (!(d.W == 16 || d.W == 32 || d.W == 64 || d.W == 128)) return p;
   p.R = 128 / d.W;
-  if (d.B % p.R) return p;
-  if (d.Cout > 256) return p;
-  if (d.Cout % 32 == 0) p.CC = 32;
-  else if (d.Cout == 16) p.CC = 16;
-  else if (d.Cout == 8) p.CC = 8;
-  else return p;
+  p.CC = CC;
   p.n_nchunks = d.Cout / p.CC;
   p.NPAD = (3 * p.CC + 15) / 16 * 16;                 // 32, 48, 96
   p.T = 512 / (ACC_SLOTS * p.NPAD);                   // 4, 2, 1
@@ -124,7 +118,11 @@ static Plan make_plan(const corrif_conv3d_desc& d, int nsm) {
   p.tap_bytes = w_off;
   p.w_bytes = 3 * w_off;
   const int budget = 232448 - 4096 - 1024;            // 227 KB per CTA minus static shared memory and the alignment slack
-  const long long wtot = (long long)p.n_nchunks * p.w_bytes;
+  // the weights of every output-channel chunk stay in shared memory if they fit beside a ring of >= 4 line slots;
+  // otherwise one chunk at a time (reloaded when a CTA's items move on to the next chunk)
+  long long wtot = (long long)p.n_nchunks * p.w_bytes;
+  p.w_resident = 1;
+  if (wtot + 4ll * p.slot_bytes > budget) { wtot = p.w_bytes; p.w_resident = 0; }
   if (wtot + 3ll * p.slot_bytes > budget) return p;
   long long ns = (budget - wtot) / p.slot_bytes;
   p.NS = (int)(ns > MAX_RING ? MAX_RING : ns);
@@ -143,6 +141,24 @@ static Plan make_plan(const corrif_conv3d_desc& d, int nsm) {
   if (p.total_items >= (1ll << 31)) return p;
   p.ok = 1;
   return p;
+}
+
+// The widest output-channel chunk (32, 16, 8) that divides Cout and whose weights fit in shared memory: wide chunks
+// read the input fewer times, narrow ones need less shared memory per chunk (64 -> 320 channels at 16^3 runs as 20
+// chunks of 16).
+static Plan make_plan(const corrif_conv3d_desc& d, int nsm) {
+  Plan none{};
+  none.ok = 0;
+  if (d.ksize != 3) return none;
+  if (!(d.W == 16 || d.W == 32 || d.W == 64 || d.W == 128)) return none;
+  if (d.B % (128 / d.W)) return none;
+  if (d.Cout > 512 || d.Cout % 8) return none;
+  for (int cc = 32; cc >= 8; cc >>= 1) {
+    if (d.Cout % cc) continue;
+    const Plan p = make_plan_cc(d, nsm, cc);
+    if (p.ok) return p;
+  }
+  return none;
 }
 
 // ---- device helpers --------------------------------------------------------------------------------------------
@@ -227,11 +243,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   __shared__ uint32_t tmem_base_holder;
   // [group][parity][quadrant][0: last row's dx=-1 part, 1: first row's dx=+1 part][channel]
   __shared__ __align__(16) float xchg[2][2][4][2][CC == 32 ? 16 : CC];
-  __shared__ float s_bias[256];
+  __shared__ float s_bias[512];
 
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t s_w = sbase;
-  const uint32_t s_ring = sbase + (uint32_t)(a.n_nchunks * a.w_bytes);
+  const uint32_t s_ring = sbase + (uint32_t)((a.w_resident ? a.n_nchunks : 1) * a.w_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = a.D, H = a.H, W = a.W, T = a.T, NS = a.NS;
   const int pad = a.pad_mode;
@@ -243,11 +259,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_base_holder, 512);
-  for (int i = threadIdx.x; i < a.Cout && i < 256; i += NTHREADS) s_bias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
-  {
-    // packed weights of every output-channel chunk -> shared memory (the image is already swizzled)
-    const float4* src = reinterpret_cast<const float4*>(a.wpk);
-    const int n16 = a.n_nchunks * a.w_bytes / 16;
+  for (int i = threadIdx.x; i < a.Cout && i < 512; i += NTHREADS) s_bias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+  // packed weights -> shared memory (the image is already swizzled): every chunk once, or chunk `nc` on demand
+  auto stage_weights = [&](int first_chunk, int nchunks) {
+    const float4* src = reinterpret_cast<const float4*>(a.wpk) + (size_t)first_chunk * (a.w_bytes / 16);
+    const int n16 = nchunks * a.w_bytes / 16;
     constexpr int U = 8;
     for (int base = threadIdx.x; base < n16; base += NTHREADS * U) {
       float4 v[U];
@@ -265,7 +281,19 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       }
     }
     fence_proxy_async();
-  }
+  };
+  if (a.w_resident) stage_weights(0, a.n_nchunks);
+  // Non-resident weights: when a CTA's next item belongs to another output-channel chunk, every warp meets at a
+  // CTA barrier (the epilogue warps get there only after the last plane of the previous item, i.e. after every MMA
+  // that reads the old chunk has completed), the chunk is replaced, and a second barrier releases the issuers.
+  int cur_nc = -1;
+  auto switch_chunk = [&](int nc) {
+    if (a.w_resident || nc == cur_nc) return;
+    __syncthreads();
+    stage_weights(nc, 1);
+    __syncthreads();
+    cur_nc = nc;
+  };
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -289,6 +317,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     uint32_t ph = 0;
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       const Item it = decode_item(a, item);
+      switch_chunk(it.nc);
       for (int zv = it.zb - 1; zv <= it.ze; ++zv) {
         const bool zoob = zv < 0 || zv >= D;
         if (zoob && pad == CORRIF_PAD_ZEROS) continue;
@@ -342,7 +371,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     uint32_t ph = 0, pc_base = 0;
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       const Item it = decode_item(a, item);
-      const uint32_t w_item16 = desc_lo_kmajor(s_w + (uint32_t)(it.nc * a.w_bytes));
+      switch_chunk(it.nc);
+      const uint32_t w_item16 = desc_lo_kmajor(s_w + (uint32_t)((a.w_resident ? it.nc : 0) * a.w_bytes));
       for (int zv = it.zb - 1; zv <= it.ze; ++zv) {
         const int zo = zv + 1;                             // the output plane this input plane touches first
         if (zo < it.ze) {
@@ -424,6 +454,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     uint32_t pc_base = 0, tcnt = 0;
     for (int item = blockIdx.x; item < a.total_items; item += gridDim.x) {
       const Item it = decode_item(a, item);
+      switch_chunk(it.nc);
       const int b = it.bg * a.R + rsub;
       const int n0 = it.nc * CC + choff;
       const int nm = it.ylast - it.y0 + 1;
@@ -595,7 +626,7 @@ static void fill_args(Args& a, const corrif_conv3d_desc& d, const Plan& p) {
   a.B = d.B; a.D = d.D; a.H = d.H; a.W = d.W; a.R = p.R; a.T = p.T; a.ZL = p.ZL; a.NKC = p.NKC; a.NS = p.NS;
   a.n_nchunks = p.n_nchunks; a.n_zchunks = p.n_zchunks; a.n_bgroups = p.n_bgroups; a.n_strips = p.n_strips;
   a.total_items = (int)p.total_items;
-  a.pad_mode = d.pad_mode; a.relu = d.relu; a.Cout = d.Cout;
+  a.pad_mode = d.pad_mode; a.relu = d.relu; a.Cout = d.Cout; a.w_resident = p.w_resident;
   static const int debug = getenv("CORRIF_CONV_TC_DEBUG") ? atoi(getenv("CORRIF_CONV_TC_DEBUG")) : 0;
   a.debug = debug;
   a.slot_bytes = p.slot_bytes; a.tap_bytes = p.tap_bytes; a.w_bytes = p.w_bytes;

@@ -362,10 +362,11 @@ int corrif_conv3d_wgrad(const corrif_conv3d_desc* desc, const float* g, int64_t 
  * statistics run in the epilogue.  Replaces, for the shapes it supports, corrif_conv3d_fwd (forward: mmvit4.py:29-45,
  * 222-292) and corrif_conv3d_fwd + corrif_conv3d_dgrad_border (data gradient: describe the gradient as the source,
  * Cin / Cout swapped, pad_mode CORRIF_PAD_REPLICATE_ADJOINT for a replicate-padded forward, weights packed with
- * transpose_flip = 1).  Supported: ksize 3, W in {16, 32, 64, 128} with B a multiple of 128 / W, every source with
- * 8, 16 or a multiple of 32 channels, Cout 8, 16 or a multiple of 32, packed weights resident in shared memory
- * (corrif_conv3d_tc_supported returns 1).  desc->wpk must come from corrif_conv3d_tc_pack_weights for a descriptor
- * with the same channel split; `w` there is always the forward weight [Cout_fwd][Cin_fwd][3][3][3]. */
+ * transpose_flip = 1).  Supported: ksize 3, W in {16, 32, 64, 128} with B a multiple of 128 / W, source channel counts
+ * that are multiples of 8 (a concatenation runs as uniform 8 / 16 / 32-channel pieces), Cout a multiple of 8 (processed
+ * in chunks of 32, 16 or 8 output channels), and the packed weights of one chunk resident in shared memory beside
+ * three line buffers (corrif_conv3d_tc_supported returns 1).  desc->wpk must come from corrif_conv3d_tc_pack_weights
+ * for a descriptor with the same channel split; `w` there is always the forward weight [Cout_fwd][Cin_fwd][3][3][3]. */
 int corrif_conv3d_tc_supported(const corrif_conv3d_desc* desc);
 int64_t corrif_conv3d_tc_pack_floats(const corrif_conv3d_desc* desc);
 int corrif_conv3d_tc_pack_weights(const corrif_conv3d_desc* desc, const float* w, float* wpk, int32_t transpose_flip,

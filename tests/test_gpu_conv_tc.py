@@ -32,6 +32,9 @@ CASES = [
     ((32,), 8, 1, 1, 40, 4, 128),            # several z ranges per strip
     ((24, 8), 8, 1, 1, 4, 6, 128),           # d1_c2: cat(skip 24, up 8) as four 8-channel chunks
     ((48, 16), 16, 1, 2, 3, 8, 64),          # d2_c2: four 16-channel chunks
+    ((32,), 128, 1, 8, 4, 32, 32),           # four output-channel chunks whose weights are staged one chunk at a time
+    ((24,), 24, 0, 2, 3, 64, 64),            # RFM1 3x3x3: three chunks of 8 output channels, zero padding, depth 3
+    ((64,), 320, 1, 8, 5, 16, 16),           # data-gradient shape of d4_c2: 20 chunks of 16 output channels
 ]
 IDS = [f"{'+'.join(map(str, c[0]))}to{c[1]}p{c[2]}_{c[3]}x{c[4]}x{c[5]}x{c[6]}" for c in CASES]
 
@@ -69,7 +72,14 @@ def test_line_convolution_forward_and_statistics(case):
         assert e_s < 2e-3, (case, relu, e_s)       # sums cancel: a looser bound than the element-wise one
 
 
-@pytest.mark.parametrize("case", CASES, ids=IDS)
+# forward shapes the line kernel does not take (weights too large) but whose data gradient it does
+DGRAD_ONLY = [
+    ((128,), 32, 1, 8, 4, 32, 32),           # d3_c2: dX has 128 channels = four chunks, weights staged per chunk
+    ((64,), 32, 1, 4, 6, 32, 32),            # d3_c1
+]
+
+
+@pytest.mark.parametrize("case", CASES + DGRAD_ONLY, ids=IDS + [f"dgrad_only{i}" for i in range(len(DGRAD_ONLY))])
 def test_line_convolution_data_gradient(case):
     """dX of the convolution whose forward is ``case`` (the kernel runs with the channel roles swapped)."""
     chans, cout, pad, B, D, H, W = case
