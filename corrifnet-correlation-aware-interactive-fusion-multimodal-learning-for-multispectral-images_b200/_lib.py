@@ -118,6 +118,8 @@ PROTOTYPES = {
                                              f32p, f32p, i64, i32, i32, stream_t]),
     "corrif_resize_trilinear_fwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),
     "corrif_resize_trilinear_bwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),
+    "corrif_conv1_small_fwd": (C.c_int, [f32p, i64, f32p, f32p, f32p, i64, f64p, i32, i64, i32, i32, i32, stream_t]),
+    "corrif_conv1_small_wgrad": (C.c_int, [f32p, i64, f32p, i64, f32p, i64, i32, stream_t]),
     "corrif_resize_linear_axis_fwd": (C.c_int, [f32p, f32p, i64, i32, i32, i64, stream_t]),
     "corrif_resize_linear_axis_bwd": (C.c_int, [f32p, f32p, i64, i32, i32, i64, stream_t]),
     "corrif_resize_nearest_fwd": (C.c_int, [f32p, i64, f32p, i64, i32, i32, i32, i32, i32, i32, i32, i32, stream_t]),

@@ -622,6 +622,103 @@ __global__ void __launch_bounds__(THREADS) nearest_bwd_kernel(const float* __res
   }
 }
 
+// ---- 1x1x1 convolution with C = 8 or 16 channels on both sides (d1_out / d2_out, mmvit4.py:231-236) -----------------
+// 8 -> 8 channels at 128^3 is 64 FMAs per 64 bytes moved: HBM-bound by a wide margin, and the window-staging tensor-core
+// kernel ran it at a third of the bandwidth (0.45 ms against a 0.17 ms floor).  One thread per voxel: the voxel's C
+// inputs in registers, the C x C weights broadcast from shared memory, exact fp32 FMAs; the InstanceNorm statistics of
+// the stored output are kept per thread and leave through one block reduction.  The data gradient is the same kernel
+// with the transposed weight.
+template <int C>
+__global__ void __launch_bounds__(THREADS) conv1_small_kernel(const float* __restrict__ x, long long ldx,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              float* __restrict__ out, long long ldo, double* stats,
+                                                              long long nvox, int relu, int transpose) {
+  __shared__ __align__(16) float sw[C][C];              // sw[ci][co]
+  __shared__ float sb[C];
+  __shared__ double sred[2][C];
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    const int ci = i / C, co = i - ci * C;
+    sw[ci][co] = transpose ? w[ci * C + co] : w[co * C + ci];     // w is [Cout][Cin]; transposed: out index = ci of w
+  }
+  if (threadIdx.x < C) { sb[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f; sred[0][threadIdx.x] = 0.0; sred[1][threadIdx.x] = 0.0; }
+  __syncthreads();
+  const int b = blockIdx.y;
+  float s1[C], s2[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+    const float* xp = x + ((long long)b * nvox + v) * ldx;
+    float xi[C], o[C];
+#pragma unroll
+    for (int j = 0; j < C; j += 4) { const float4 t = ld4(xp + j); xi[j] = t.x; xi[j + 1] = t.y; xi[j + 2] = t.z; xi[j + 3] = t.w; }
+#pragma unroll
+    for (int j = 0; j < C; ++j) o[j] = sb[j];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+      for (int j = 0; j < C; j += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&sw[ci][j]);
+        o[j] = fmaf(xi[ci], wv.x, o[j]); o[j + 1] = fmaf(xi[ci], wv.y, o[j + 1]);
+        o[j + 2] = fmaf(xi[ci], wv.z, o[j + 2]); o[j + 3] = fmaf(xi[ci], wv.w, o[j + 3]);
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    float* op = out + ((long long)b * nvox + v) * ldo;
+#pragma unroll
+    for (int j = 0; j < C; j += 4) st4(op + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+#pragma unroll
+    for (int j = 0; j < C; ++j) { s1[j] += o[j]; s2[j] = fmaf(o[j], o[j], s2[j]); }
+  }
+  if (stats) {
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float a1 = warp_sum(s1[j]), a2 = warp_sum(s2[j]);
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&sred[0][j], (double)a1); atomicAdd(&sred[1][j], (double)a2); }
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+      atomicAdd(stats + ((long long)b * C + threadIdx.x) * 2, sred[0][threadIdx.x]);
+      atomicAdd(stats + ((long long)b * C + threadIdx.x) * 2 + 1, sred[1][threadIdx.x]);
+    }
+  }
+}
+// dW[co][ci] += sum over rows of g[row][co] * x[row][ci], C = 8: 64 partial sums per thread, folded through shuffles and
+// shared memory into one atomic per element and block
+__global__ void __launch_bounds__(THREADS) conv1_small_wgrad8_kernel(const float* __restrict__ x, long long ldx,
+                                                                     const float* __restrict__ g, long long ldg,
+                                                                     float* __restrict__ dW, long long rows) {
+  constexpr int C = 8;
+  __shared__ float sred[C * C];
+  if (threadIdx.x < C * C) sred[threadIdx.x] = 0.f;
+  __syncthreads();
+  float acc[C][C];
+#pragma unroll
+  for (int a = 0; a < C; ++a)
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[a][c] = 0.f;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const float4 x0 = ld4(x + r * ldx), x1 = ld4(x + r * ldx + 4), g0 = ld4(g + r * ldg), g1 = ld4(g + r * ldg + 4);
+    const float xv[C] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    const float gv[C] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int co = 0; co < C; ++co)
+#pragma unroll
+      for (int ci = 0; ci < C; ++ci) acc[co][ci] = fmaf(gv[co], xv[ci], acc[co][ci]);
+  }
+#pragma unroll
+  for (int co = 0; co < C; ++co)
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) {
+      const float t = warp_sum(acc[co][ci]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&sred[co * C + ci], t);
+    }
+  __syncthreads();
+  if (threadIdx.x < C * C) atomicAdd(dW + threadIdx.x, sred[threadIdx.x]);
+}
+
 static int grid_for(long long nvox, int Q) {
   const int rows = ((THREADS / Q) * Q) / Q;
   long long blocks = (nvox + (long long)rows * 8 - 1) / ((long long)rows * 8);      // ~8 voxels per thread
@@ -715,6 +812,34 @@ extern "C" int corrif_resize_trilinear_bwd(const float* dy, int64_t lddy, float*
   trilinear_bwd_kernel<<<flat_grid(total), THREADS, 0, (cudaStream_t)stream>>>(dy, lddy, dx, lddx, C, Di, Hi, Wi, Do, Ho, Wo, total, small);
   return launch_status("resize_trilinear_bwd");
 }
+extern "C" int corrif_conv1_small_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* out,
+                                      int64_t ldo, double* stats, int32_t B, int64_t nvox, int32_t C, int32_t relu,
+                                      int32_t transpose, void* stream) {
+  CORRIF_REQUIRE(C == 8 || C == 16, "conv1_small_fwd: C must be 8 or 16 (got %d)", C);
+  VOL_CHECK(x, ldx, C, "conv1_small_fwd(in)");
+  VOL_CHECK(out, ldo, C, "conv1_small_fwd(out)");
+  CORRIF_REQUIRE(w != nullptr && B > 0 && nvox > 0 && B <= 65535, "conv1_small_fwd: bad arguments");
+  long long bx = (nvox + THREADS * 4 - 1) / (THREADS * 4);          // ~4 voxels per thread: the statistics amortise
+  const long long cap = ((long long)num_sms() * 8 + B - 1) / B;
+  bx = bx < 1 ? 1 : (bx > cap ? cap : bx);
+  const dim3 grid((unsigned)bx, (unsigned)B);
+  if (C == 8) conv1_small_kernel<8><<<grid, THREADS, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, out, ldo, stats, nvox, relu, transpose);
+  else conv1_small_kernel<16><<<grid, THREADS, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, out, ldo, stats, nvox, relu, transpose);
+  return launch_status("conv1_small_fwd");
+}
+extern "C" int corrif_conv1_small_wgrad(const float* x, int64_t ldx, const float* g, int64_t ldg, float* dW, int64_t rows,
+                                        int32_t C, void* stream) {
+  CORRIF_REQUIRE(C == 8, "conv1_small_wgrad: C must be 8 (got %d)", C);
+  VOL_CHECK(x, ldx, C, "conv1_small_wgrad(x)");
+  VOL_CHECK(g, ldg, C, "conv1_small_wgrad(g)");
+  CORRIF_REQUIRE(dW != nullptr && rows > 0, "conv1_small_wgrad: bad arguments");
+  long long bx = (rows + THREADS * 16 - 1) / (THREADS * 16);
+  const long long cap = (long long)num_sms() * 4;
+  bx = bx < 1 ? 1 : (bx > cap ? cap : bx);
+  conv1_small_wgrad8_kernel<<<(unsigned)bx, THREADS, 0, (cudaStream_t)stream>>>(x, ldx, g, ldg, dW, rows);
+  return launch_status("conv1_small_wgrad");
+}
+
 /* One axis of the trilinear resize on a contiguous tensor [outer][n][inner] (inner a multiple of 4 floats):
  * y[outer][n_out][inner] from x[outer][n_in][inner], and the adjoint (dx from dy; needs (n_out - 1) <= 3 (n_in - 1)). */
 extern "C" int corrif_resize_linear_axis_fwd(const float* x, float* y, int64_t outer, int32_t n_in, int32_t n_out,

@@ -182,8 +182,29 @@ def conv3d_forward(srcs, wpk, bias, Cout, ksize, pad_mode, relu, out, stats=None
     ops._count()
 
 
+def _small_pointwise(srcs, Cout, ksize) -> bool:
+    """1x1x1 with 8 channels on both sides (d1_out at 128^3): the HBM-bound per-voxel kernel (the 16-channel
+    instantiation exists in the library but measured slower than the tensor-core kernel: 0.69 vs 0.14 ms at 64^3)."""
+    return (ksize == 1 and len(srcs) == 1 and srcs[0].shape[4] == Cout and Cout == 8
+            and os.environ.get("CORRIF_CONV1_SMALL", "1") != "0" and srcs[0].shape[0] <= 65535)
+
+
+def conv1_small(x, weight, bias, out, stats, relu, transpose):
+    B, D, H, W, Cc = x.shape
+    nvox = D * H * W
+    w = weight.detach().contiguous()
+    with ops._rec("conv3d_dgrad" if transpose else "conv3d_fwd", 2.0 * B * nvox * Cc * Cc,
+                  "k1 %dx%dx%dx%d %d->%d small bytes=%d" % (B, D, H, W, Cc, Cc, 8 * B * nvox * Cc)):
+        L.check(ops.lib().corrif_conv1_small_fwd(x.data_ptr(), _ld(x), w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                                 out.data_ptr(), _ld(out), stats.data_ptr() if stats is not None else None,
+                                                 B, nvox, Cc, int(relu), int(transpose), _stream()), "conv1_small_fwd")
+    ops._count()
+
+
 def conv3d_forward_auto(srcs, weight, bias, Cout, ksize, pad_mode, relu, out, stats=None):
     """The convolution forward on the tcgen05 line kernel where it applies, else on the warp-level kernel."""
+    if _small_pointwise(srcs, Cout, ksize):
+        return conv1_small(srcs[0], weight, bias, out, stats, relu, transpose=False)
     d = _desc(srcs, Cout, ksize, pad_mode)
     if not tc_supported(d):
         return conv3d_forward(srcs, pack_weights(weight), bias, Cout, ksize, pad_mode, relu, out, stats)
@@ -199,6 +220,14 @@ def conv3d_forward_auto(srcs, weight, bias, Cout, ksize, pad_mode, relu, out, st
 
 def conv3d_wgrad(srcs, g, dW, ksize, pad_mode):
     Cout = g.shape[4]
+    if _small_pointwise(srcs, Cout, ksize) and Cout == 8:
+        x = srcs[0]
+        rows = x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3]
+        with ops._rec("conv3d_wgrad", 2.0 * rows * 64, "k1 %dx%dx%dx%d 8->8 small" % tuple(x.shape[:4])):
+            L.check(ops.lib().corrif_conv1_small_wgrad(x.data_ptr(), _ld(x), g.data_ptr(), _ld(g), dW.data_ptr(), rows, 8,
+                                                       _stream()), "conv1_small_wgrad")
+        ops._count()
+        return
     d = _desc(srcs, Cout, ksize, pad_mode)
     nvox = d.B * d.D * d.H * d.W
     taps = 27 if ksize == 3 else 1
@@ -211,6 +240,8 @@ def conv3d_wgrad(srcs, g, dW, ksize, pad_mode):
 def conv3d_dgrad(g, weight, Cin, ksize, pad_mode, dx):
     """dx [B,D,H,W,Cin] = d(cat of the sources) from g = d(pre-activation)."""
     Cout = g.shape[4]
+    if _small_pointwise([g], Cin, ksize):
+        return conv1_small(g, weight, None, dx, None, relu=False, transpose=True)
     if ksize == 3:
         # tcgen05 line kernel: the adjoint of replicate padding is part of the same pass (no border kernel)
         dt = _desc([g], Cin, ksize, PAD_REPLICATE_ADJOINT if pad_mode == PAD_REPLICATE else PAD_ZEROS)

@@ -420,6 +420,16 @@ int corrif_resize_trilinear_fwd(const float* x, int64_t ldx, float* y, int64_t l
                                 int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo, void* stream);
 int corrif_resize_trilinear_bwd(const float* dy, int64_t lddy, float* dx, int64_t lddx, int32_t B, int32_t C,
                                 int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho, int32_t Wo, void* stream);
+/* 1x1x1 convolution with the same small channel count C (8 or 16) on both sides - the decoder's d1_out / d2_out blocks
+ * (mmvit4.py:231-236, 8 -> 8 channels at 128^3): HBM-bound, so one thread per voxel with exact fp32 FMAs instead of
+ * the window-staging tensor-core kernel.  out = act(W x + bias) with W = w [Cout][Cin] (transpose = 0) or w^T (the
+ * data gradient); `stats` as in corrif_conv3d_fwd.  corrif_conv1_small_wgrad: dW[co][ci] += sum g[row][co] x[row][ci]
+ * (C = 8). */
+int corrif_conv1_small_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* out, int64_t ldo,
+                           double* stats, int32_t B, int64_t nvox, int32_t C, int32_t relu, int32_t transpose,
+                           void* stream);
+int corrif_conv1_small_wgrad(const float* x, int64_t ldx, const float* g, int64_t ldg, float* dW, int64_t rows, int32_t C,
+                             void* stream);
 /* One axis of the trilinear resize (same align_corners arithmetic) on a contiguous tensor [outer][n][inner], inner a
  * multiple of 4 floats: the separable form of nn.Upsample(scale_factor=2, trilinear, align_corners=True)
  * (mmvit4.py:269) - three streaming passes instead of 8 gathered loads per output (forward) / 64 per input (backward).

@@ -112,7 +112,8 @@ CASES = [
     ((128,), 128, 3, 1, 1, 4, 8, 8),           # d4_c1: two output tiles
     ((24,), 24, 3, 0, 2, 3, 14, 14),           # RFM 3x3x3, ZERO padding, depth 3
     ((192,), 192, 3, 0, 1, 3, 7, 7),           # RFM4 at 224^2 tiles
-    ((8,), 8, 1, 1, 2, 6, 8, 9),               # d1_out (1x1x1)
+    ((8,), 8, 1, 1, 2, 6, 8, 9),               # d1_out (1x1x1): per-voxel fp32 kernel
+    ((16,), 16, 1, 1, 2, 4, 8, 8),             # d2_out
     ((64,), 64, 1, 1, 1, 4, 8, 8),             # d4_out
     ((8, 8, 8), 24, 1, 0, 2, 3, 10, 10),       # EarlyFusionBlock(8): three sources
     ((64, 64, 64), 192, 1, 0, 1, 8, 8, 8),     # fusion6
