@@ -105,6 +105,8 @@ PROTOTYPES = {
     "corrif_conv3d_tc_pack_floats": (i64, [C.POINTER(Conv3dDesc)]),
     "corrif_conv3d_tc_pack_weights": (C.c_int, [C.POINTER(Conv3dDesc), f32p, f32p, i32, stream_t]),
     "corrif_conv3d_tc_fwd": (C.c_int, [C.POINTER(Conv3dDesc), stream_t]),
+    "corrif_conv3d_wgrad_tc_supported": (C.c_int, [C.POINTER(Conv3dDesc)]),
+    "corrif_conv3d_wgrad_tc": (C.c_int, [C.POINTER(Conv3dDesc), f32p, i64, f32p, stream_t]),
     "corrif_conv3d_dgrad_border": (C.c_int, [f32p, i64, f32p, f32p, i64, i32, i32, i32, i32, i32, i32, stream_t]),
     "corrif_instnorm_apply": (C.c_int, [f32p, i64, f64p, f32p, f32p, i32, i64, i32, f32, stream_t]),
     "corrif_instnorm_bwd_stats": (C.c_int, [f32p, i64, f32p, i64, f64p, i32, i64, i32, stream_t]),

@@ -231,6 +231,14 @@ def conv3d_wgrad(srcs, g, dW, ksize, pad_mode):
     d = _desc(srcs, Cout, ksize, pad_mode)
     nvox = d.B * d.D * d.H * d.W
     taps = 27 if ksize == 3 else 1
+    if (ksize == 3 and os.environ.get("CORRIF_WGRAD_TC", "1") != "0"
+            and ops.lib().corrif_conv3d_wgrad_tc_supported(C.byref(d))):
+        with ops._rec("conv3d_wgrad", 2.0 * nvox * 27 * d.Cin * Cout, "k3 %dx%dx%dx%d %d->%d tc" % (
+                d.B, d.D, d.H, d.W, d.Cin, Cout)):
+            L.check(ops.lib().corrif_conv3d_wgrad_tc(C.byref(d), g.data_ptr(), _ld(g), dW.data_ptr(), _stream()),
+                    "conv3d_wgrad_tc")
+        ops._count()
+        return
     with ops._rec("conv3d_wgrad", 2.0 * nvox * taps * d.Cin * Cout, "k%d %dx%dx%dx%d %d->%d" % (
             ksize, d.B, d.D, d.H, d.W, d.Cin, Cout)):
         L.check(ops.lib().corrif_conv3d_wgrad(C.byref(d), g.data_ptr(), _ld(g), dW.data_ptr(), _stream()), "conv3d_wgrad")

@@ -372,6 +372,13 @@ int64_t corrif_conv3d_tc_pack_floats(const corrif_conv3d_desc* desc);
 int corrif_conv3d_tc_pack_weights(const corrif_conv3d_desc* desc, const float* w, float* wpk, int32_t transpose_flip,
                                   void* stream);
 int corrif_conv3d_tc_fwd(const corrif_conv3d_desc* desc, void* stream);
+/* The weight gradient of the big 3x3x3 layers on tcgen05 (csrc/conv3d_wgrad_tc.cu): transposer warps rewrite the input
+ * and gradient lines as K(= voxel)-major swizzled tiles, one warp issues M = 128 ((4 input lines) x (32 channels))
+ * x N = 8 * Cout MMAs whose three accumulators (z-taps) stay in TMEM for the whole kernel.  Same contract as
+ * corrif_conv3d_wgrad (dW accumulated, torch layout).  Supported: ksize 3, W a multiple of 64, H even, Cout 8 or 16,
+ * Cin <= 64 (32 channels per pass), pad_mode zeros / replicate. */
+int corrif_conv3d_wgrad_tc_supported(const corrif_conv3d_desc* desc);
+int corrif_conv3d_wgrad_tc(const corrif_conv3d_desc* desc, const float* g, int64_t ldg, float* dW, void* stream);
 /* dx[B,D,H,W,Cin] (stride ldx) += the replicate-padding part of the 3x3x3 data gradient; w_taps_major is the weight
  * transposed to [27][Cout][Cin] (weight.permute(2,3,4,0,1)), so that threads of consecutive ci read consecutive words */
 int corrif_conv3d_dgrad_border(const float* g, int64_t ldg, const float* w_taps_major, float* dx, int64_t ldx, int32_t B,

@@ -140,3 +140,41 @@ def test_conv_block_on_the_line_kernel_matches_the_warp_level_kernel(monkeypatch
         print(f"[conv_block tc vs warp-level] {name} {e:.2e}")
         # two TF32 evaluations of the same block: ReLU mask flips at the 1e-3 level separate the gradients
         assert e < (2e-3 if name == "y" else 8e-2), (name, e)
+
+
+WGRAD_CASES = [
+    # (source channels, Cout, pad_mode, B, D, H, W)
+    ((32,), 8, 1, 1, 5, 8, 128),             # d1_c1-like, two 64-voxel halves per line
+    ((24, 8), 8, 1, 1, 3, 6, 128),           # d1_c2: cat(skip 24, up 8)
+    ((16,), 8, 1, 2, 4, 4, 64),              # 16 input channels: half of the MMA rows are padding
+    ((32,), 16, 1, 2, 6, 8, 64),             # d2_c1: 16 output channels (N = 128)
+    ((48, 16), 16, 1, 1, 4, 6, 64),          # d2_c2: 64 input channels = two passes of 32
+    ((32,), 8, 0, 1, 3, 4, 64),              # zero padding
+    ((32,), 8, 1, 1, 1, 2, 64),              # a single plane, a single line pair
+    ((32,), 8, 1, 2, 37, 32, 64),            # several z ranges, many items per CTA (ring wrap-around across items)
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=[f"{'+'.join(map(str, c[0]))}to{c[1]}p{c[2]}_{c[3]}x{c[4]}x{c[5]}x{c[6]}" for c in WGRAD_CASES])
+def test_tensor_core_weight_gradient(case):
+    """corrif_conv3d_wgrad_tc (transposing producers + tcgen05 MMAs over voxels) against the fp64 weight gradient."""
+    chans, cout, pad, B, D, H, W = case
+    cin = sum(chans)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(cin * 13 + cout + D)
+    xs = [torch.randn(B, D, H, W, c, generator=g).to(dev) for c in chans]
+    gy = torch.randn(B, D, H, W, cout, generator=g).to(dev)
+    d = V._desc(xs, cout, 3, pad)
+    from corrif_b200 import ops
+    assert ops.lib().corrif_conv3d_wgrad_tc_supported(d), "case must run on the tcgen05 kernel"
+    dW = torch.zeros(cout, cin, 3, 3, 3, device=dev)
+    V.conv3d_wgrad(xs, gy, dW, 3, pad)
+    torch.cuda.synchronize()
+    x64 = torch.cat([x.double() for x in xs], dim=4).permute(0, 4, 1, 2, 3)
+    w64 = torch.zeros(cout, cin, 3, 3, 3, device=dev, dtype=torch.float64, requires_grad=True)
+    y = F.conv3d(F.pad(x64, (1,) * 6, mode="replicate" if pad == 1 else "constant"), w64)
+    y.backward(gy.double().permute(0, 4, 1, 2, 3))
+    e = rel_l2(dW.cpu().numpy(), w64.grad.cpu().numpy())
+    print(f"\n[conv_tc wgrad {case}] dW {e:.2e}")
+    assert torch.isfinite(dW).all()
+    assert e < TOL, (case, e)
