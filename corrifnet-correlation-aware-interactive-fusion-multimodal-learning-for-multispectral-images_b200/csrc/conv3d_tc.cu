@@ -1,6 +1,5 @@
 // Channels-last 3x3x3 convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA): forward and data
-// gradient of the decoder's / early-fusion blocks (mmvit4.py:29-45, 222-292) at the resolutions where the time is
-// (128^3 and 64^3 voxels, 8..64 channels).
+// gradient of the decoder's / early-fusion blocks (mmvit4.py:29-45, 47-56, 222-292).
 //
 // "Line convolution".  A row of 128 voxels along x of one (sample, z, y) - a LINE - is the M dimension of the MMA.
 // The three x-taps are moved into N:
@@ -9,31 +8,36 @@
 //     out[x, co]     = P[x - 1, (-1, co)] + P[x, (0, co)] + P[x + 1, (+1, co)]
 //
 // so one input line, staged ONCE in shared memory by TMA exactly as it lies in HBM ([x][channels], K-major with the
-// hardware swizzle), is the A operand of nine MMAs (one per (dz, dy)) that accumulate into the TMEM accumulators of
-// the nine output lines it touches, with B = W[dz, dy] as a [3*Cout x Cin] tile.  No im2col operand and no shifted
-// shared-memory view exists: the y / z shifts are a choice of accumulator, the x shift is two warp shuffles in the
-// epilogue.  Replicate padding (mmvit4.py:225-236) is a clamped line coordinate in y / z and "use your own value"
-// at the two x borders; its adjoint (the data gradient of a replicate-padded convolution, which the mma.sync path
-// computes with a separate border kernel) is the same with the mirrored weight tap on the clamped axis.
-// Per MMA (M = 128, N = 3*Cout rounded to 16, K = 8) the tensor core reads 4 KB of A from shared memory: at N = 32
-// the kernel is bound by that read (~32 cycles per MMA, 4x the math), i.e. 36 MMAs = ~1.3 k cycles per 128 voxels
-// of a 32 -> 8 channel layer, against ~6 k cycles for the warp-level kernel.
+// hardware swizzle), is the A operand of every tap: no im2col operand and no shifted shared-memory view exists - the
+// y / z shifts are a choice of TMEM accumulator, the x shift is two warp shuffles in the epilogue.  An input line of
+// plane zv feeds, per y-tap, the accumulators of the output planes zv-1, zv, zv+1; they sit side by side in TMEM and
+// the weight tile stacks the three z-taps in the same order, so ONE MMA with N = 3 * NPAD (NPAD = 3 * Cout rounded to
+// 16) serves all three.  Every MMA accumulates; the epilogue zeroes an accumulator as soon as it has read it.
+// Replicate padding (mmvit4.py:225-236) is a clamped line coordinate in y / z and "use your own value" at the two x
+// borders; its adjoint (the data gradient of a replicate-padded convolution, for which the warp-level path needs a
+// separate border kernel) is the same with the mirrored weight tap on the clamped axis.
 //
 // Lines narrower than 128 voxels (W = 64, 32, 16) stack the same (z, y) line of R = 128 / W SAMPLES in one tile:
-// taps never cross samples, so a tap shift moves the whole tile.
+// taps never cross samples, so a tap shift moves the whole tile.  A concatenation of sources runs as uniform 8 / 16 /
+// 32-channel K chunks (one TMA box each); wide outputs run as chunks of 32 / 16 / 8 output channels whose weights are
+// resident in shared memory, all at once or one chunk at a time.
 //
-// CTA = 10 warps: TMA producer (ring of line slots), MMA issuer, two groups of four epilogue warps (TMEM quadrant =
-// warp % 4) that take alternate tiles.
-// A work item is (output-channel chunk, z range, sample group, strip of T lines in y); the issuer walks the input
-// planes of the range in order and keeps four output planes x T lines of accumulators in TMEM (512 columns): three
-// being accumulated, one being drained by the epilogue.  The epilogue adds the two x neighbours (shuffles; the three
+// CTA = 11 warps, one CTA per SM: a TMA producer (ring of up to 12 line slots), two MMA-issuing warps (the ring slots
+// are dealt between them; a single issuing thread was the limit), two groups of four epilogue warps (TMEM quadrant =
+// warp % 4).  A work item is (output-channel chunk, z range, sample group, strip of T = 4 / 2 / 1 lines in y); the
+// issuers walk the input planes of the range in order and keep four output planes x T lines of accumulators in TMEM
+// (512 columns): three being accumulated, one being drained.  The epilogue adds the two x neighbours (shuffles; the
 // warp boundaries through shared memory), bias, ReLU, stores channels-last and keeps the InstanceNorm statistics
 // (sum, sum of squares per (sample, channel)) in registers until the item ends.
+//
+// Measured (batch 8, 128^3, profiles/r03_*): 32 -> 8 channels forward 0.67 ms (warp-level kernel: 2.21; HBM floor at
+// the measured 6.55 TB/s: 0.42), 8 -> 32 data gradient 1.15 ms incl. the padding adjoint (1.97), 64^3 64 -> 16
+// forward 0.23 ms (0.76).
 //
 // Operand precision: tcgen05.mma.kind::tf32 truncates fp32 operands to 10 mantissa bits.  Weights are rounded to
 // nearest when packed; activations arrive by TMA untouched, so their truncation (relative bias -2^-11 E[1/mantissa]
 // = -3.52e-4, the same constant the attention kernels use for P) is compensated by scaling the packed weights by
-// 1 + 3.52e-4: zero-mean error with the RMS of round-to-nearest.
+// 1 + 3.52e-4: zero-mean error with the RMS of round-to-nearest (measured 3.0e-4 relative L2 against fp64).
 #include <stdlib.h>
 #include "tc05.cuh"
 
