@@ -161,8 +161,8 @@ class general_conv3d_prenorm(nn.Module):
         self.norm = nn.InstanceNorm3d(out_ch)
         self.k, self.pad_mode = k_size, (_V.PAD_REPLICATE if pad_type == "replicate" else _V.PAD_ZEROS)
 
-    def forward(self, *xs):
-        return _V.conv_block(xs, self.conv.weight, self.conv.bias, self.k, self.pad_mode)
+    def forward(self, *xs, out=None):
+        return _V.conv_block(xs, self.conv.weight, self.conv.bias, self.k, self.pad_mode, out=out)
 
 
 class fusion_prenorm(nn.Module):
@@ -202,6 +202,10 @@ class Decoder_fuse(nn.Module):
         y = _V.pointwise_conv(y, self.RFM5_reduce.weight, self.RFM5_reduce.bias)           # tcgen05 GEMM
         for (lvl, _, _, _, cube), skip in zip(self._LEVELS, (x4, x3, x2, x1)):
             up = _V.resize_trilinear(y, tuple(2 * d for d in y.shape[1:4]))                 # self.up2 (:269)
+            # Measured and not used: letting d*_c1 and the nearest resize write side by side into ONE buffer
+            # (conv_block(out=...), resize_nearest(out=...)) so that d*_c2 reads a single 128-byte-row source makes its
+            # forward 0.4 ms faster (1.11 -> 0.71 ms at 128^3) but the in-place InstanceNorm passes over the 8-of-32
+            # channel slice lose as much (0.92 -> 1.30 ms apply, 1.54 -> 1.78 ms backward statistics).
             y = getattr(self, f"d{lvl}_c1")(up)
             s = _V.resize_nearest(getattr(self, f"RFM{lvl}")(skip), (cube, cube, cube))     # F.interpolate (:271)
             y = getattr(self, f"d{lvl}_out")(getattr(self, f"d{lvl}_c2")(s, y))             # cat((s, y)) (:272)

@@ -74,15 +74,31 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _merge_adjacent(srcs):
+    """[(data_ptr, C, ld)] of the sources, with consecutive channel slices of ONE buffer fused into one entry: when two
+    producers wrote side by side into a wider buffer (conv_block(out=...), resize_nearest(out=...)) the consumer reads
+    cat(24, 8) as 128-byte rows of one source instead of four 32-byte pieces per voxel."""
+    B, D, H, W = srcs[0].shape[:4]
+    out = []
+    for s in srcs:
+        if tuple(s.shape[:4]) != (B, D, H, W):
+            raise ValueError("sources of a convolution must share [B, D, H, W]")
+        ptr, C_, ld = s.data_ptr(), s.shape[4], _ld(s)
+        if out and out[-1][2] == ld and ptr == out[-1][0] + 4 * out[-1][1] and out[-1][1] + C_ <= ld:
+            out[-1] = (out[-1][0], out[-1][1] + C_, ld)
+        else:
+            out.append((ptr, C_, ld))
+    return out
+
+
 def _desc(srcs: Sequence[torch.Tensor], Cout: int, ksize: int, pad_mode: int) -> L.Conv3dDesc:
     d = L.Conv3dDesc()
     B, D, H, W = srcs[0].shape[:4]
     cin = 0
-    for i, s in enumerate(srcs):
-        if tuple(s.shape[:4]) != (B, D, H, W):
-            raise ValueError("sources of a convolution must share [B, D, H, W]")
-        d.src[i].p, d.src[i].C, d.src[i].ld = s.data_ptr(), s.shape[4], _ld(s)
-        cin += s.shape[4]
+    srcs = _merge_adjacent(srcs)
+    for i, (ptr, C_, ld) in enumerate(srcs):
+        d.src[i].p, d.src[i].C, d.src[i].ld = ptr, C_, ld
+        cin += C_
     d.nsrc, d.B, d.D, d.H, d.W, d.Cin, d.Cout = len(srcs), B, D, H, W, cin, Cout
     d.ksize, d.pad_mode = ksize, pad_mode
     return d
@@ -283,14 +299,18 @@ class _ConvBlock(torch.autograd.Function):
     """conv (+bias) [-> ReLU] [-> InstanceNorm3d] over the channel concatenation of 1..3 volumes."""
 
     @staticmethod
-    def forward(ctx, weight, bias, ksize, pad_mode, relu, norm, *srcs):
+    def forward(ctx, weight, bias, ksize, pad_mode, relu, norm, out_holder, *srcs):
         if relu and not norm:
             raise ValueError("conv_block: ReLU without InstanceNorm does not occur in the model and has no backward")
         srcs = [as_volume(s) for s in srcs]
         Cout = weight.shape[0]
         B, D, H, W = srcs[0].shape[:4]
         dev = weight.device
-        out = torch.empty(B, D, H, W, Cout, device=dev, dtype=torch.float32)
+        # out_holder: (tensor,) = write the block's output into this channel slice of a wider buffer (its consumer then
+        # reads the buffer as ONE source: the reference's torch.cat, mmvit4.py:272, without a copy and without narrow rows)
+        out = out_holder[0] if out_holder is not None else torch.empty(B, D, H, W, Cout, device=dev, dtype=torch.float32)
+        if tuple(out.shape) != (B, D, H, W, Cout):
+            raise ValueError("conv_block: out has shape %s, expected %s" % (tuple(out.shape), (B, D, H, W, Cout)))
         stats = torch.zeros(B, Cout, 2, device=dev, dtype=torch.float64) if norm else None
         b = bias.detach().contiguous() if bias is not None else None
         conv3d_forward_auto(srcs, weight, b, Cout, ksize, pad_mode, relu, out, stats)
@@ -300,7 +320,7 @@ class _ConvBlock(torch.autograd.Function):
             rstd = torch.empty(B, Cout, device=dev, dtype=torch.float32)
             nvox = D * H * W
             with ops._rec("instnorm_apply", 8.0 * B * nvox * Cout):
-                L.check(ops.lib().corrif_instnorm_apply(out.data_ptr(), Cout, stats.data_ptr(), mean.data_ptr(),
+                L.check(ops.lib().corrif_instnorm_apply(out.data_ptr(), _ld(out), stats.data_ptr(), mean.data_ptr(),
                                                         rstd.data_ptr(), B, nvox, Cout, EPS, _stream()), "instnorm_apply")
             ops._count()
         ctx.cfg = (ksize, pad_mode, relu, norm, bias is not None, [s.shape[4] for s in srcs])
@@ -340,25 +360,26 @@ class _ConvBlock(torch.autograd.Function):
             dW = torch.zeros_like(weight, memory_format=torch.contiguous_format)
             conv3d_wgrad(srcs, g, dW, ksize, pad_mode)
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
-        if any(ctx.needs_input_grad[6:]):
+        if any(ctx.needs_input_grad[7:]):
             cin = sum(chans)
             dx = torch.empty(B, D, H, W, cin, device=dev, dtype=torch.float32)
             conv3d_dgrad(g, weight, cin, ksize, pad_mode, dx)
             off = 0
             for i, c in enumerate(chans):
-                if ctx.needs_input_grad[6 + i]:
+                if ctx.needs_input_grad[7 + i]:
                     dsrcs[i] = dx[..., off:off + c]
                 off += c
-        return (dW, dbias, None, None, None, None, *dsrcs)
+        return (dW, dbias, None, None, None, None, None, *dsrcs)
 
 
 def conv_block(srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor], ksize: int,
-               pad_mode: int = PAD_ZEROS, relu: bool = True, norm: bool = True) -> torch.Tensor:
+               pad_mode: int = PAD_ZEROS, relu: bool = True, norm: bool = True,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """general_conv3d_prenorm / EarlyFusionBlock (relu=norm=True) or a plain biased convolution (relu=norm=False)
     over cat(srcs, channels).  srcs and the result are channels-last volumes [B, D, H, W, C]."""
     if not 1 <= len(srcs) <= 3:
         raise ValueError("conv_block takes 1..3 sources")
-    return _ConvBlock.apply(weight, bias, ksize, pad_mode, relu, norm, *srcs)
+    return _ConvBlock.apply(weight, bias, ksize, pad_mode, relu, norm, (out,) if out is not None else None, *srcs)
 
 
 class _PointwiseGemm(torch.autograd.Function):
@@ -557,18 +578,20 @@ def _linear_axes(t: torch.Tensor, sizes_in, sizes_out, Cc: int, backward: bool) 
 
 class _Resize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, size, mode):
+    def forward(ctx, x, size, mode, out_holder=None):
         x = as_volume(x)
         B, Di, Hi, Wi, Cc = x.shape
         Do, Ho, Wo = size
-        if mode == "trilinear" and _separable(x.shape, size):
+        if mode == "trilinear" and out_holder is None and _separable(x.shape, size):
             ctx.cfg = (mode, (Di, Hi, Wi), size)
             return _linear_axes(x.contiguous(), (Di, Hi, Wi), size, Cc, backward=False)
-        y = torch.empty(B, Do, Ho, Wo, Cc, device=x.device, dtype=torch.float32)
+        y = out_holder[0] if out_holder is not None else torch.empty(B, Do, Ho, Wo, Cc, device=x.device, dtype=torch.float32)
+        if tuple(y.shape) != (B, Do, Ho, Wo, Cc):
+            raise ValueError("resize: out has shape %s, expected %s" % (tuple(y.shape), (B, Do, Ho, Wo, Cc)))
         fn = ops.lib().corrif_resize_trilinear_fwd if mode == "trilinear" else ops.lib().corrif_resize_nearest_fwd
         with ops._rec("resize_" + mode + "_fwd", 4.0 * Cc * B * (Di * Hi * Wi + Do * Ho * Wo),
                       "%dx%dx%dx%d->%dx%dx%d C%d" % (B, Di, Hi, Wi, Do, Ho, Wo, Cc)):
-            L.check(fn(x.data_ptr(), _ld(x), y.data_ptr(), Cc, B, Cc, Di, Hi, Wi, Do, Ho, Wo, _stream()), "resize_fwd")
+            L.check(fn(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), B, Cc, Di, Hi, Wi, Do, Ho, Wo, _stream()), "resize_fwd")
         ops._count()
         ctx.cfg = (mode, (Di, Hi, Wi), size)
         return y
@@ -579,14 +602,14 @@ class _Resize(torch.autograd.Function):
         dy = as_volume(dy)
         B, Cc = dy.shape[0], dy.shape[4]
         if mode == "trilinear" and _separable((B, Di, Hi, Wi, Cc), (Do, Ho, Wo)):
-            return _linear_axes(dy.contiguous(), (Di, Hi, Wi), (Do, Ho, Wo), Cc, backward=True), None, None
+            return _linear_axes(dy.contiguous(), (Di, Hi, Wi), (Do, Ho, Wo), Cc, backward=True), None, None, None
         dx = torch.empty(B, Di, Hi, Wi, Cc, device=dy.device, dtype=torch.float32)
         fn = ops.lib().corrif_resize_trilinear_bwd if mode == "trilinear" else ops.lib().corrif_resize_nearest_bwd
         with ops._rec("resize_" + mode + "_bwd", 4.0 * Cc * B * (Di * Hi * Wi + Do * Ho * Wo),
                       "%dx%dx%dx%d->%dx%dx%d C%d" % (B, Di, Hi, Wi, Do, Ho, Wo, Cc)):
             L.check(fn(dy.data_ptr(), _ld(dy), dx.data_ptr(), Cc, B, Cc, Di, Hi, Wi, Do, Ho, Wo, _stream()), "resize_bwd")
         ops._count()
-        return dx, None, None
+        return dx, None, None, None
 
 
 def resize_trilinear(x: torch.Tensor, size: Tuple[int, int, int]) -> torch.Tensor:
@@ -594,6 +617,7 @@ def resize_trilinear(x: torch.Tensor, size: Tuple[int, int, int]) -> torch.Tenso
     return _Resize.apply(x, tuple(int(s) for s in size), "trilinear")
 
 
-def resize_nearest(x: torch.Tensor, size: Tuple[int, int, int]) -> torch.Tensor:
-    """F.interpolate(x, size) (default nearest, mmvit4.py:271) on a channels-last volume."""
-    return _Resize.apply(x, tuple(int(s) for s in size), "nearest")
+def resize_nearest(x: torch.Tensor, size: Tuple[int, int, int], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.interpolate(x, size) (default nearest, mmvit4.py:271) on a channels-last volume; ``out``: write into this
+    channel slice of a wider buffer."""
+    return _Resize.apply(x, tuple(int(s) for s in size), "nearest", (out,) if out is not None else None)

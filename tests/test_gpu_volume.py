@@ -339,3 +339,31 @@ def test_batchnorm_relu_against_pytorch(case):
     assert rel_l2(bn.running_mean.double().cpu().numpy(), ref_bn.running_mean.cpu().numpy()) < 1e-5
     assert rel_l2(bn.running_var.double().cpu().numpy(), ref_bn.running_var.cpu().numpy()) < 1e-5
     assert int(bn.num_batches_tracked) == 1
+
+
+def test_two_producers_writing_into_one_buffer_are_one_source():
+    """conv_block(out=slice) / resize_nearest(out=slice): the reference's torch.cat (mmvit4.py:272) as two producers that
+    write side by side into one buffer, which the consumer then reads as a single source - same numbers as separate
+    tensors, forward and backward."""
+    dev = torch.device("cuda:0")
+    gen = lambda s: torch.Generator().manual_seed(s)   # noqa: E731
+    res = {}
+    for shared in (False, True):
+        up = torch.randn(2, 6, 8, 64, 16, generator=gen(1)).to(dev).requires_grad_(True)
+        skip = torch.randn(2, 3, 4, 32, 24, generator=gen(2)).to(dev).requires_grad_(True)
+        w1 = (torch.randn(8, 16, 3, 3, 3, generator=gen(3)) * 0.1).to(dev).requires_grad_(True)
+        w2 = (torch.randn(8, 32, 3, 3, 3, generator=gen(4)) * 0.1).to(dev).requires_grad_(True)
+        b1, b2 = torch.zeros(8, device=dev, requires_grad=True), torch.zeros(8, device=dev, requires_grad=True)
+        buf = torch.empty(2, 6, 8, 64, 32, device=dev)
+        y = V.conv_block([up], w1, b1, 3, V.PAD_REPLICATE, out=buf[..., 24:] if shared else None)
+        s = V.resize_nearest(skip, (6, 8, 64), out=buf[..., :24] if shared else None)
+        if shared:
+            assert V._desc([s, y], 8, 3, 1).nsrc == 1          # the consumer sees one 32-channel source
+        z = V.conv_block([s, y], w2, b2, 3, V.PAD_REPLICATE)
+        z.backward(torch.randn(z.shape, generator=gen(5)).to(dev))
+        torch.cuda.synchronize()
+        res[shared] = [t.detach().cpu().numpy() for t in (z, up.grad, skip.grad, w1.grad, w2.grad)]
+    for a, b_, name in zip(res[True], res[False], ("z", "dup", "dskip", "dw1", "dw2")):
+        e = rel_l2(a, b_)
+        # same kernels on the same values; only the summation order of the statistics' atomics differs
+        assert e < (1e-4 if name == "z" else 5e-2), (name, e)

@@ -17,7 +17,10 @@ for r in rows[hi + 1:]:
         continue
     k = re.sub(r"\(.*", "", r[ix["Kernel Name"]]).replace("void ", "").replace("corrif::", "")
     m, u = r[ix["Metric Name"]], r[ix["Metric Unit"]]
-    v = float(r[ix["Metric Value"]].replace(",", ""))
+    try:
+        v = float(r[ix["Metric Value"]].replace(",", ""))
+    except ValueError:                      # "n/a" (a metric the kernel does not have)
+        continue
     a = agg.setdefault(k, collections.defaultdict(float))
     if m == "gpu__time_duration.sum":
         t = v / 1000 if u in ("ns", "nsecond") else (v if u in ("us", "usecond") else v * 1000)
