@@ -71,7 +71,14 @@ class Bottleneck3D(nn.Module):
         """BatchNorm (+ residual) (+ ReLU): in training on the fused channels-last kernels (one normalise pass instead of
         cuDNN batch-norm + add + ReLU), in eval mode (running statistics) on stock PyTorch."""
         if not (bn.training and x.is_cuda and _FUSED_BN):
-            y = bn(x) if residual is None else bn(x) + residual
+            if bn.training and bn.track_running_stats and bn.momentum is not None and getattr(bn, "_deferred_count", False):
+                # same arithmetic as nn.BatchNorm3d.forward; the num_batches_tracked increment of all the encoder's
+                # BatchNorms is ONE multi-tensor add at the end of Encoder.forward instead of 53 one-element kernels
+                y = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
+            else:
+                y = bn(x)
+            if residual is not None:
+                y = y + residual
             return F.relu(y) if relu else y
         r = None if residual is None else _V.to_channels_last(residual)
         return _V.to_channels_first(_V.batchnorm_relu(_V.to_channels_last(x), bn, r, relu))
@@ -111,6 +118,12 @@ class Encoder(nn.Module):
             setattr(self, f"adapt{i}", nn.Conv3d(cin, cout, kernel_size=1))
 
     def forward(self, x):
+        bns = [m for m in self.modules() if isinstance(m, nn.BatchNorm3d)]
+        defer = self.training and x.is_cuda and not _FUSED_BN
+        for m in bns:
+            m._deferred_count = defer
+        if defer:
+            torch._foreach_add_([m.num_batches_tracked for m in bns if m.track_running_stats and m.momentum is not None], 1)
         f1 = self.e1_mp(Bottleneck3D._bn(self.e1_bn, self.e1_relu(self.e1_c1(x)), relu=False))   # ReLU BEFORE BN, as the reference
         f2 = self.e2(f1)
         f3 = self.e3(f2)
