@@ -28,6 +28,17 @@ import torch.nn.functional as F
 from .metrics import loss_and_jaccard
 
 
+def _view_like(flat: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
+    """A view of ``flat[off : off + p.numel()]`` with p's shape AND strides.  The encoders' convolution weights live in
+    channels_last_3d (cuDNN runs them on the volume layout); a plain ``view_as`` would hand autograd / cuDNN a
+    contiguous-strided parameter and every (1,3,3) convolution would convert its weight on every call (measured: 177
+    copy kernels per micro-batch step)."""
+    seg = flat[off:off + p.numel()]
+    if p.dim() == 5 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last_3d):
+        return seg.as_strided(p.shape, p.stride())
+    return seg.view_as(p) if p.is_contiguous() else seg.view(p.shape)
+
+
 class GradBuckets:
     """Flat gradient storage + overlapped all-reduce.  Works with any backend (gloo on CPU for tests,
     NCCL over NVLink on the GPUs)."""
@@ -71,7 +82,7 @@ class GradBuckets:
             flat = torch.zeros(n, dtype=grp[0].dtype, device=grp[0].device)
             views = []
             for p, off in zip(grp, offs):
-                view = flat[off:off + p.numel()].view_as(p)
+                view = _view_like(flat, off, p)
                 view.copy_(p.grad)
                 p.grad = view
                 views.append(view)
@@ -205,12 +216,11 @@ class FlatAdam:
             flat_p = torch.zeros_like(b["flat"])
             m, v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
             for p, off in zip(b["params"], b["offsets"]):
-                n = p.numel()
-                view = flat_p[off:off + n].view_as(p)
+                view = _view_like(flat_p, off, p)
                 view.copy_(p.data)
+                self.optim.state[p] = {"step": self.step_t, "exp_avg": _view_like(m, off, p),
+                                       "exp_avg_sq": _view_like(v, off, p)}
                 p.data = view
-                self.optim.state[p] = {"step": self.step_t, "exp_avg": m[off:off + n].view_as(p),
-                                       "exp_avg_sq": v[off:off + n].view_as(p)}
             self.slabs.append((flat_p, b["flat"], m, v))
         from . import module
         module._ENGINES.clear()              # engines are keyed by parameter addresses, which just moved
