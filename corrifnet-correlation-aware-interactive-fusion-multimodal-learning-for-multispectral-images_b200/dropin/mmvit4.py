@@ -44,6 +44,7 @@ _MODS = ("RGB", "NIR", "SWIR")
 # CORRIF_ENCODER_NCDHW=1 keeps the encoder trunks in PyTorch's default memory format instead of channels_last_3d.
 _FUSED_BN = os.environ.get("CORRIF_FUSED_BN") == "1"
 _ENC_CL3D = os.environ.get("CORRIF_ENCODER_NCDHW") != "1"
+_ENC_STREAMS = os.environ.get("CORRIF_ENCODER_STREAMS", "1") != "0"      # the three encoders on three streams
 
 
 # ----------------------------------------------------------------------------------------------
@@ -273,7 +274,28 @@ class MMVit4(nn.Module):
 
     def forward(self, x):
         fmt = torch.channels_last_3d if _ENC_CL3D else torch.contiguous_format
-        feats = [getattr(self, f"{m}_encoder")(x[:, i:i + 1].contiguous(memory_format=fmt)) for i, m in enumerate(_MODS)]
+        if _ENC_STREAMS and x.is_cuda:
+            # The three modality encoders are independent: on three streams their small late-stage kernels (8 x 8 and
+            # 16 x 16 maps: a dozen CTAs each) overlap instead of leaving most of the 148 SMs idle.  Autograd runs each
+            # encoder's backward on its forward stream, so the backward overlaps the same way; under TrainStep's CUDA
+            # graphs the fork / join becomes parallel branches of the graph.
+            cur = torch.cuda.current_stream()
+            if getattr(self, "_enc_streams", None) is None or self._enc_streams[0].device != x.device:
+                self._enc_streams = [torch.cuda.Stream(device=x.device) for _ in _MODS[1:]]
+            feats = [None] * len(_MODS)
+            for i, m in enumerate(_MODS):
+                st = cur if i == 0 else self._enc_streams[i - 1]
+                if i:
+                    st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    feats[i] = getattr(self, f"{m}_encoder")(x[:, i:i + 1].contiguous(memory_format=fmt))
+            for st in self._enc_streams:
+                cur.wait_stream(st)
+            for fs in feats[1:]:
+                for t in fs:
+                    t.record_stream(cur)
+        else:
+            feats = [getattr(self, f"{m}_encoder")(x[:, i:i + 1].contiguous(memory_format=fmt)) for i, m in enumerate(_MODS)]
         fused = [getattr(self, f"fusion{lv + 1}")(*(f[lv] for f in feats)) for lv in (0, 1, 2, 3, 5)]
         fused_x1, fused_x2, fused_x3, fused_x4, fused_x6 = fused          # fusion5's output is unused
         p = self.dropout_rate if self.training else 0.0
