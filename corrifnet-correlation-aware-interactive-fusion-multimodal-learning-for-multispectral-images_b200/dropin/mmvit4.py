@@ -212,16 +212,38 @@ class Decoder_fuse(nn.Module):
 
     def forward(self, x1, x2, x3, x4, x5):
         """x1..x4: early-fusion volumes [B,D,H,W,C]; x5: x6_inter [B,8,8,8,192] -> sigmoid probs [B,3,1,224,224]."""
+        # The skip branches (RFM_l -> nearest resize, :271) depend only on the early-fusion maps: they run on a side
+        # stream, level 4 first, beside the serial up-path; an event per level hands each result over.  The 1.6 GB
+        # nearest up-sampling of level 1 (bandwidth-bound) then overlaps the small-grid convolutions of levels 4-2.
+        skips = (x4, x3, x2, x1)
+        side_ok = _ENC_STREAMS and x5.is_cuda
+        ready = [None] * 4
+        s_list = [None] * 4
+        if side_ok:
+            cur = torch.cuda.current_stream()
+            if getattr(self, "_side", None) is None or self._side.device != x5.device:
+                self._side = torch.cuda.Stream(device=x5.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                for i, ((lvl, _, _, _, cube), skip) in enumerate(zip(self._LEVELS, skips)):
+                    s_list[i] = _V.resize_nearest(getattr(self, f"RFM{lvl}")(skip), (cube, cube, cube))
+                    ready[i] = torch.cuda.Event()
+                    ready[i].record(self._side)
         y = self.RFM5(x5)
         y = _V.pointwise_conv(y, self.RFM5_reduce.weight, self.RFM5_reduce.bias)           # tcgen05 GEMM
-        for (lvl, _, _, _, cube), skip in zip(self._LEVELS, (x4, x3, x2, x1)):
+        for i, ((lvl, _, _, _, cube), skip) in enumerate(zip(self._LEVELS, skips)):
             up = _V.resize_trilinear(y, tuple(2 * d for d in y.shape[1:4]))                 # self.up2 (:269)
             # Measured and not used: letting d*_c1 and the nearest resize write side by side into ONE buffer
             # (conv_block(out=...), resize_nearest(out=...)) so that d*_c2 reads a single 128-byte-row source makes its
             # forward 0.4 ms faster (1.11 -> 0.71 ms at 128^3) but the in-place InstanceNorm passes over the 8-of-32
             # channel slice lose as much (0.92 -> 1.30 ms apply, 1.54 -> 1.78 ms backward statistics).
             y = getattr(self, f"d{lvl}_c1")(up)
-            s = _V.resize_nearest(getattr(self, f"RFM{lvl}")(skip), (cube, cube, cube))     # F.interpolate (:271)
+            if side_ok:
+                cur.wait_event(ready[i])
+                s = s_list[i]
+                s.record_stream(cur)
+            else:
+                s = _V.resize_nearest(getattr(self, f"RFM{lvl}")(skip), (cube, cube, cube))     # F.interpolate (:271)
             y = getattr(self, f"d{lvl}_out")(getattr(self, f"d{lvl}_c2")(s, y))             # cat((s, y)) (:272)
         # nn.Upsample(size=(1,224,224), trilinear, align_corners=True) (:263, 288): with ONE output slice along
         # depth the source index is 0 for every output voxel, i.e. only depth slice 0 of the 128^3 volume is read
