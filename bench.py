@@ -519,9 +519,12 @@ def run_ours(args):
             fwd_graphed = model.forward
             if stepper._eager_forward is not None:
                 model.forward = stepper._eager_forward
+            saved_streams = mmvit4._ENC_STREAMS
+            mmvit4._ENC_STREAMS = False                  # one stream: a launch's events must not span its neighbours' work
             with ops.profile() as rec:
                 stepper([resident[0]], total_micro_batches=1)
             vol_prof = rec.details()
+            mmvit4._ENC_STREAMS = saved_streams
             model.forward, stepper.graphs = fwd_graphed, saved_graphs
 
         # ---- end to end: every step's inputs from pinned host memory, loss read back every step

@@ -199,6 +199,45 @@ def test_train_step_with_whole_model_cuda_graphs_matches_stream_launches(dropin)
         assert abs(a - b) < 2e-3, (losses[False], losses[True])
 
 
+def test_parallel_streams_change_nothing_but_the_schedule(dropin):
+    """MMVit4 runs its three encoders on three streams and the decoder's skip branches on a side stream.  Same kernels
+    on the same values: output and gradients must agree with the single-stream schedule (up to the summation order of
+    the statistics' atomics), and repeated multi-stream steps must agree with each other (a cross-stream race would
+    not)."""
+    import copy
+    mmvit4 = dropin[0]
+    dev = torch.device("cuda:0")
+    torch.manual_seed(21)
+    base = mmvit4.MMVit4(num_cls=1, dropout_rate=0.0).to(dev).train()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 3, 3, 64, 64, generator=g).to(dev)
+    go = torch.randn(2, 3, 1, 224, 224, generator=g).to(dev)
+    keys = ["RGB_encoder.e2.0.conv2.weight", "SWIR_encoder.e5.2.conv3.weight", "decoder_fuse.RFM2.fusion_layer.1.conv.weight",
+            "decoder_fuse.d1_c2.conv.weight", "fusion3.conv.weight", "multimodal_decode_conv.weight"]
+    runs = {}
+    saved = mmvit4._ENC_STREAMS
+    try:
+        for tag, flag in (("serial", False), ("serial_again", False), ("streams", True), ("streams_again", True)):
+            mmvit4._ENC_STREAMS = flag
+            model = copy.deepcopy(base)
+            y = model(x)
+            y.backward(go)
+            torch.cuda.synchronize()
+            named = dict(model.named_parameters())
+            runs[tag] = [y.detach().cpu().numpy()] + [named[k].grad.cpu().numpy() for k in keys]
+    finally:
+        mmvit4._ENC_STREAMS = saved
+    # the yardstick is the model's own run-to-run spread on ONE stream: last-bit differences in the InstanceNorm
+    # statistics (atomics) flip a handful of ReLU masks, which the decoder's norm chain amplifies (DESIGN.md section 2)
+    base = [rel_l2(a, b) for a, b in zip(runs["serial_again"], runs["serial"])]
+    print("\n[streams] serial run-to-run: y %.1e, gradients %s" % (base[0], ["%.1e" % e for e in base[1:]]))
+    for tag in ("streams", "streams_again"):
+        errs = [rel_l2(a, b) for a, b in zip(runs[tag], runs["serial"])]
+        print("[streams] %s vs serial: y %.1e, gradients %s" % (tag, errs[0], ["%.1e" % e for e in errs[1:]]))
+        assert errs[0] < max(4 * base[0], 2e-3), (errs, base)          # a race would show as O(1)
+        assert max(errs[1:]) < max(4 * max(base[1:]), 0.15), (errs, base)
+
+
 def test_f2_main_drop_in_runs_one_synthetic_epoch(dropin, tmp_path, monkeypatch):
     """dropin/F2_MAIN.py end to end on one GPU: 18-line config -> synthetic tiles -> train_model -> test_model ->
     the reference's text logs in the working directory and the two checkpoints in the result directory."""
