@@ -308,7 +308,8 @@ class _ConvBlock(torch.autograd.Function):
         dev = weight.device
         # out_holder: (tensor,) = write the block's output into this channel slice of a wider buffer (its consumer then
         # reads the buffer as ONE source: the reference's torch.cat, mmvit4.py:272, without a copy and without narrow rows)
-        out = out_holder[0] if out_holder is not None else torch.empty(B, D, H, W, Cout, device=dev, dtype=torch.float32)
+        out = (out_holder[0] if out_holder is not None and out_holder[0] is not None
+               else torch.empty(B, D, H, W, Cout, device=dev, dtype=torch.float32))
         if tuple(out.shape) != (B, D, H, W, Cout):
             raise ValueError("conv_block: out has shape %s, expected %s" % (tuple(out.shape), (B, D, H, W, Cout)))
         stats = torch.zeros(B, Cout, 2, device=dev, dtype=torch.float64) if norm else None
@@ -324,6 +325,7 @@ class _ConvBlock(torch.autograd.Function):
                                                         rstd.data_ptr(), B, nvox, Cout, EPS, _stream()), "instnorm_apply")
             ops._count()
         ctx.cfg = (ksize, pad_mode, relu, norm, bias is not None, [s.shape[4] for s in srcs])
+        ctx.wgrad_holder = out_holder[1] if out_holder is not None and len(out_holder) > 1 else None
         ctx.save_for_backward(weight, out if norm else None, mean, rstd, *srcs)
         return out
 
@@ -359,6 +361,12 @@ class _ConvBlock(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dW = torch.zeros_like(weight, memory_format=torch.contiguous_format)
             conv3d_wgrad(srcs, g, dW, ksize, pad_mode)
+        elif ctx.wgrad_holder is not None:
+            # the weight gradient runs in its own autograd node on a side stream (_WgradLater): hand it the operands
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            ctx.wgrad_holder.update(srcs=srcs, g=g, ksize=ksize, pad_mode=pad_mode, ready=ev,
+                                    main=torch.cuda.current_stream())
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
         if any(ctx.needs_input_grad[7:]):
             cin = sum(chans)
@@ -372,6 +380,60 @@ class _ConvBlock(torch.autograd.Function):
         return (dW, dbias, None, None, None, None, None, *dsrcs)
 
 
+class _WgradLater(torch.autograd.Function):
+    """The weight gradient of a conv block as an autograd node of its own whose forward "ran" on a side stream, so the
+    engine executes its backward there (and joins that stream at the end of the backward pass, also under graph
+    capture).  The block's own backward (data path) stashes g = d(pre-activation) in ``holder`` and goes on; the
+    HBM-bound passes of the NEXT block's backward then overlap this tensor-bound kernel."""
+
+    @staticmethod
+    def forward(ctx, weight, holder):
+        ctx.holder = holder
+        ctx.save_for_backward(weight)
+        return weight.new_empty(0)
+
+    @staticmethod
+    def backward(ctx, _token_grad):
+        (weight,) = ctx.saved_tensors
+        h = ctx.holder
+        if "g" not in h:                                   # the block's backward did not run (its output was unused)
+            return None, None
+        side = torch.cuda.current_stream()
+        side.wait_event(h["ready"])
+        for t in (h["g"], *h["srcs"]):
+            t.record_stream(side)
+        dW = torch.zeros_like(weight, memory_format=torch.contiguous_format)
+        conv3d_wgrad(h["srcs"], h["g"], dW, h["ksize"], h["pad_mode"])
+        dW.record_stream(h["main"])
+        h.clear()
+        return dW, None
+
+
+class _Tap(torch.autograd.Function):
+    """out -> out, with a second (empty) input whose gradient edge makes the engine run _WgradLater."""
+
+    @staticmethod
+    def forward(ctx, out, token):
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g.new_empty(0)
+
+
+_WGRAD_STREAMS: dict = {}
+
+
+def _wgrad_stream(dev: torch.device):
+    """Side stream of the deferred weight gradients (CORRIF_WGRAD_STREAM=0 keeps them inside the block's backward)."""
+    if os.environ.get("CORRIF_WGRAD_STREAM", "1") == "0":
+        return None
+    key = (dev.type, dev.index)
+    if key not in _WGRAD_STREAMS:
+        _WGRAD_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _WGRAD_STREAMS[key]
+
+
 def conv_block(srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor], ksize: int,
                pad_mode: int = PAD_ZEROS, relu: bool = True, norm: bool = True,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -379,7 +441,17 @@ def conv_block(srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optiona
     over cat(srcs, channels).  srcs and the result are channels-last volumes [B, D, H, W, C]."""
     if not 1 <= len(srcs) <= 3:
         raise ValueError("conv_block takes 1..3 sources")
-    return _ConvBlock.apply(weight, bias, ksize, pad_mode, relu, norm, (out,) if out is not None else None, *srcs)
+    # the block's own backward must run (it produces g): some other input has to carry a gradient
+    chain = (bias is not None and bias.requires_grad) or any(s.requires_grad for s in srcs)
+    side = _wgrad_stream(weight.device) if (ksize == 3 and weight.is_cuda and weight.requires_grad and chain
+                                            and torch.is_grad_enabled()) else None
+    if side is None:
+        return _ConvBlock.apply(weight, bias, ksize, pad_mode, relu, norm, (out,) if out is not None else None, *srcs)
+    holder: dict = {}
+    with torch.cuda.stream(side):                          # created FIRST: the engine then runs it after the block's backward
+        token = _WgradLater.apply(weight, holder)
+    y = _ConvBlock.apply(weight.detach(), bias, ksize, pad_mode, relu, norm, (out, holder), *srcs)
+    return _Tap.apply(y, token)
 
 
 class _PointwiseGemm(torch.autograd.Function):
