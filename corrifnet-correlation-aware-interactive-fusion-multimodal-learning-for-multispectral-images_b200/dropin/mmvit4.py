@@ -318,8 +318,21 @@ class MMVit4(nn.Module):
                     t.record_stream(cur)
         else:
             feats = [getattr(self, f"{m}_encoder")(x[:, i:i + 1].contiguous(memory_format=fmt)) for i, m in enumerate(_MODS)]
-        fused = [getattr(self, f"fusion{lv + 1}")(*(f[lv] for f in feats)) for lv in (0, 1, 2, 3, 5)]
-        fused_x1, fused_x2, fused_x3, fused_x4, fused_x6 = fused          # fusion5's output is unused
+        if _ENC_STREAMS and x.is_cuda:
+            # fusion1-4 feed only the decoder's skip branches: they run on the decoder's side stream (which goes on with
+            # RFM_l -> nearest resize there), beside fusion6 -> transformer fusion block on this one
+            cur = torch.cuda.current_stream()
+            dec = self.decoder_fuse
+            if getattr(dec, "_side", None) is None or dec._side.device != x.device:
+                dec._side = torch.cuda.Stream(device=x.device)
+            dec._side.wait_stream(cur)
+            with torch.cuda.stream(dec._side):
+                fused_x1, fused_x2, fused_x3, fused_x4 = (getattr(self, f"fusion{lv + 1}")(*(f[lv] for f in feats))
+                                                          for lv in (0, 1, 2, 3))
+            fused_x6 = self.fusion6(*(f[5] for f in feats))
+        else:
+            fused = [getattr(self, f"fusion{lv + 1}")(*(f[lv] for f in feats)) for lv in (0, 1, 2, 3, 5)]
+            fused_x1, fused_x2, fused_x3, fused_x4, fused_x6 = fused          # fusion5's output is unused
         p = self.dropout_rate if self.training else 0.0
         self._step += 1
         # device_seed (set by TrainStep when it captures the model in CUDA graphs): the dropout seed is a device-resident
