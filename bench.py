@@ -519,12 +519,17 @@ def run_ours(args):
             fwd_graphed = model.forward
             if stepper._eager_forward is not None:
                 model.forward = stepper._eager_forward
-            saved_streams = mmvit4._ENC_STREAMS
+            saved_streams, saved_ws = mmvit4._ENC_STREAMS, os.environ.get("CORRIF_WGRAD_STREAM")
             mmvit4._ENC_STREAMS = False                  # one stream: a launch's events must not span its neighbours' work
+            os.environ["CORRIF_WGRAD_STREAM"] = "0"
             with ops.profile() as rec:
                 stepper([resident[0]], total_micro_batches=1)
             vol_prof = rec.details()
             mmvit4._ENC_STREAMS = saved_streams
+            if saved_ws is None:
+                os.environ.pop("CORRIF_WGRAD_STREAM", None)
+            else:
+                os.environ["CORRIF_WGRAD_STREAM"] = saved_ws
             model.forward, stepper.graphs = fwd_graphed, saved_graphs
 
         # ---- end to end: every step's inputs from pinned host memory, loss read back every step
