@@ -2,7 +2,10 @@
 N1 / N2): ``conv_block`` = Conv3d (1x1x1 or 3x3x3, replicate / zero padding) -> ReLU -> InstanceNorm3d, i.e. the
 reference's ``general_conv3d_prenorm`` (mmvit4.py:29-45) and ``EarlyFusionBlock`` (:64-81, with three sources), the
 bias-only 1x1x1 convolutions, and the trilinear / nearest resizes of the decoder (:260-288), each with a hand-written
-backward, as torch.autograd Functions over libcorrif_b200 kernels (include/corrif.h, "volume operators").
+backward, as torch.autograd Functions over libcorrif_b200 kernels (include/corrif.h, "volume operators").  Per shape
+the convolution runs on the tcgen05 line-convolution kernels (csrc/conv3d_tc.cu, conv3d_wgrad_tc.cu), the per-voxel
+8-channel kernel or the warp-level kernels; the weight gradient of a 3x3x3 block is an autograd node of its own on a side
+stream (_WgradLater).
 
 A volume is a tensor [B, D, H, W, C] whose channel stride is 1 and whose voxel stride ``ld`` is uniform - a
 contiguous tensor or a channel slice of one.  ``torch.cat`` along channels never happens: a convolution takes up to
