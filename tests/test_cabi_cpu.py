@@ -76,3 +76,45 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle/", "").lower() or f == "README.md", (dirpath, f)
+
+
+def _conv_desc(chans, cout, B, D, H, W, ksize=3, pad=1):
+    from corrif_b200 import _lib
+    d = _lib.Conv3dDesc()
+    for i, c in enumerate(chans):
+        d.src[i].p, d.src[i].C, d.src[i].ld = 0x10000 * (i + 1), c, c      # never dereferenced by the planners
+    d.nsrc, d.B, d.D, d.H, d.W, d.Cin, d.Cout = len(chans), B, D, H, W, sum(chans), cout
+    d.ksize, d.pad_mode = ksize, pad
+    return d
+
+
+def test_line_convolution_planner_accepts_the_decoder_shapes_and_rejects_the_rest(lib):
+    """corrif_conv3d_tc_supported / _pack_floats are host-only: which shapes the tcgen05 line convolution takes
+     can be checked without a GPU."""
+    ok = lambda *a, **k: bool(lib.corrif_conv3d_tc_supported(ctypes.byref(_conv_desc(*a, **k))))   # noqa: E731
+    # the decoder at micro-batch 8: forward shapes ...
+    assert ok((24, 8), 8, 8, 128, 128, 128) and ok((16,), 8, 8, 128, 128, 128)
+    assert ok((48, 16), 16, 8, 64, 64, 64) and ok((32,), 16, 8, 64, 64, 64) and ok((64,), 32, 8, 32, 32, 32)
+    # ... and data-gradient shapes (channel roles swapped), incl. the ones whose weights are staged chunk by chunk
+    assert ok((8,), 32, 8, 128, 128, 128, pad=2) and ok((32,), 128, 8, 32, 32, 32, pad=2) and ok((64,), 320, 8, 16, 16, 16, pad=2)
+    assert ok((24,), 24, 8, 3, 64, 64, pad=0)                           # RFM1 3x3x3, zero padding
+    # weights that do not fit in shared memory, even one output chunk at a time
+    assert not ok((96, 32), 32, 8, 32, 32, 32) and not ok((128,), 128, 8, 16, 16, 16) and not ok((192,), 192, 8, 8, 8, 8)
+    # geometry: line width must be 16 / 32 / 64 / 128 and the batch a multiple of 128 / W
+    assert not ok((32,), 8, 1, 8, 16, 10) and not ok((32,), 8, 2, 8, 16, 16) and ok((32,), 8, 8, 8, 16, 16)
+    assert not ok((32,), 8, 8, 16, 16, 16, ksize=1)
+    assert not ok((12,), 8, 1, 4, 8, 128)                               # source channels must be a multiple of 8
+    # the packed operand: 3 y-taps x [3 * NPAD rows x 128-byte rows] per 32-channel chunk, padded to 1 KB
+    n = lib.corrif_conv3d_tc_pack_floats(ctypes.byref(_conv_desc((32,), 8, 1, 8, 8, 128)))
+    assert n == 3 * (3 * 32 * 128) // 4
+    assert lib.corrif_conv3d_tc_pack_floats(ctypes.byref(_conv_desc((12,), 8, 1, 4, 8, 128))) == 0
+
+
+def test_tensor_core_weight_gradient_planner(lib):
+    ok = lambda *a, **k: bool(lib.corrif_conv3d_wgrad_tc_supported(ctypes.byref(_conv_desc(*a, **k))))   # noqa: E731
+    assert ok((24, 8), 8, 8, 128, 128, 128) and ok((16,), 8, 8, 128, 128, 128)
+    assert ok((48, 16), 16, 8, 64, 64, 64) and ok((32,), 16, 8, 64, 64, 64)
+    assert not ok((64,), 32, 8, 32, 32, 32)                             # lines shorter than 64 voxels, 32 output channels
+    assert not ok((96,), 8, 1, 8, 8, 128) and not ok((32,), 8, 1, 8, 7, 128) and not ok((32,), 8, 1, 8, 8, 128, ksize=1)
+    rc = lib.corrif_conv3d_wgrad_tc(ctypes.byref(_conv_desc((64,), 32, 8, 32, 32, 32)), 0x10000, 32, 0x20000, None)
+    assert rc == -1 and b"not supported" in lib.corrif_last_error()
