@@ -34,6 +34,7 @@ import os
 from ._lib import PAD_REPLICATE, PAD_REPLICATE_ADJOINT, PAD_ZEROS  # noqa: F401
 
 EPS = 1e-5          # nn.InstanceNorm3d default (mmvit4.py:24)
+_TRUNC_COMP = 1.0 + 3.52e-4      # mean of the tensor core's TF32 truncation of an fp32 operand, inverted
 
 
 def _ld(t: torch.Tensor) -> int:
@@ -476,38 +477,48 @@ class _PointwiseGemm(torch.autograd.Function):
             xt = torch.empty(B * S, Cin, device=dev, dtype=torch.float32)
             ops.transpose(x, xt, B, Cin, S, round_out=True)
         else:
+            # channels-last input: the GEMM reads it in place.  The tensor core truncates it to TF32; the mean of that
+            # truncation (-3.52e-4, see csrc/conv3d_tc.cu) is folded into the rounded weight copy instead of spending a
+            # rounding pass (one read + one write of the activation, forward and again for dy backward)
             x = x.contiguous()
             B, D, H, W, _ = x.shape
             S = D * H * W
-            xt = torch.empty(B * S, Cin, device=dev, dtype=torch.float32)
-            ops.round_tf32(x, xt, x.numel())
+            xt = x.view(B * S, Cin)
+        comp = not channels_first
+        wsrc = weight.detach().contiguous()
+        if comp:
+            wsrc = wsrc * _TRUNC_COMP
         wr = torch.empty(Cout, Cin, device=dev, dtype=torch.float32)
-        ops.round_tf32(weight.detach().contiguous(), wr, wr.numel())
+        ops.round_tf32(wsrc, wr, wr.numel())
         out = torch.empty(B, D, H, W, Cout, device=dev, dtype=torch.float32)
         ops.gemm(xt, wr, out, M=B * S, N=Cout, K=Cin, lda=Cin, ldb=Cin, ldd=Cout, bias=bias.detach().contiguous(),
                  epilogue=ops.EPI_BIAS, tag="pointwise")
         ctx.save_for_backward(xt, wr)
-        ctx.cfg = (channels_first, (B, D, H, W))
+        ctx.cfg = (channels_first, (B, D, H, W), comp)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         xt, wr = ctx.saved_tensors
-        channels_first, (B, D, H, W) = ctx.cfg
+        channels_first, (B, D, H, W), comp = ctx.cfg
         Cout, Cin = wr.shape
         R = B * D * H * W
         dev = dy.device
         dyc = dy.contiguous()
-        dyr = torch.empty(R, Cout, device=dev, dtype=torch.float32)
-        ops.round_tf32(dyc, dyr, dyr.numel())
+        if comp:
+            dyr = dyc.view(R, Cout)                       # truncated by the tensor core; compensated below
+        else:
+            dyr = torch.empty(R, Cout, device=dev, dtype=torch.float32)
+            ops.round_tf32(dyc, dyr, dyr.numel())
         dbias = torch.zeros(Cout, device=dev, dtype=torch.float32)
         with ops._rec("volume_colsum", 4.0 * R * Cout):
             L.check(ops.lib().corrif_volume_colsum(dyc.data_ptr(), Cout, dbias.data_ptr(), R, Cout, _stream()), "volume_colsum")
         ops._count()
         dW = torch.zeros(Cout, Cin, 1, 1, 1, device=dev, dtype=torch.float32)
         split = max(1, min(64, R // 2048)) if R % 32 == 0 else 1
+        # both operands truncated (comp): (1 + 3.52e-4)^2 restores the mean; wr already carries one factor for dy below
         ops.gemm(dyr, xt, dW, M=Cout, N=Cin, K=R, lda=Cout, ldb=Cin, ldd=Cin, a_mn=True, b_mn=True, split_k=split,
-                 epilogue=ops.EPI_ATOMIC_ADD, tag="pointwise_wgrad")
+                 epilogue=ops.EPI_ATOMIC_ADD, alpha=_TRUNC_COMP * _TRUNC_COMP if comp else 1.0, tag="pointwise_wgrad")
         dx = None
         if ctx.needs_input_grad[0]:
             dxt = torch.empty(R, Cin, device=dev, dtype=torch.float32)
