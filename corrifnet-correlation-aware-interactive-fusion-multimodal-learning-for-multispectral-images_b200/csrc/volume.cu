@@ -29,6 +29,36 @@ __device__ __forceinline__ Lane lane_of(int Q, long long blocks_x) {
 // block-reduce 4 + 4 doubles held per thread for channel quad q and add them to out[(b*C + 4q + e)*2 + {0,1}]
 __device__ __forceinline__ void reduce_pairs_to_global(double (&s)[4], double (&t)[4], int Q, int q, bool active,
                                                        double* out, int b, int C) {
+  // Few channels (Q a power of two <= 32, every thread active): lanes of a warp that own the same quad differ by
+  // multiples of Q, so a butterfly over the offsets Q .. 16 folds a warp, and Q threads then add the 8 warps' partials.
+  // The general path below lets Q threads walk all 256 partials serially - for the 8-channel volumes at 128^3 (Q = 2,
+  // 16 k blocks) that tail was most of a block's life.
+  if (Q <= 32 && (Q & (Q - 1)) == 0 && THREADS % Q == 0) {
+    __shared__ double shw[THREADS / 32][32][8];
+    double v[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[e] = active ? s[e] : 0.0; v[4 + e] = active ? t[e] : 0.0; }
+    for (int o = Q; o < 32; o <<= 1)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += __shfl_xor_sync(0xffffffffu, v[e], o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < Q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) shw[warp][lane][e] = v[e];
+    __syncthreads();
+    if ((int)threadIdx.x < Q) {
+      double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int w = 0; w < THREADS / 32; ++w)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] += shw[w][threadIdx.x][e];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        atomicAdd(out + ((long long)b * C + 4 * threadIdx.x + e) * 2, a[e]);
+        atomicAdd(out + ((long long)b * C + 4 * threadIdx.x + e) * 2 + 1, a[4 + e]);
+      }
+    }
+    return;
+  }
   __shared__ double sh[THREADS][8];
 #pragma unroll
   for (int e = 0; e < 4; ++e) { sh[threadIdx.x][e] = active ? s[e] : 0.0; sh[threadIdx.x][4 + e] = active ? t[e] : 0.0; }
