@@ -1,6 +1,7 @@
-"""The tcgen05 line convolution (csrc/conv3d_tc.cu, corrif_conv3d_tc_fwd) on the B200: forward (replicate / zero
-padding, 1..3 sources, bias, ReLU, InstanceNorm statistics) and data gradient (incl. the adjoint of replicate padding
-in one pass) against fp64 PyTorch on the same inputs, for every tile geometry the kernel has: line widths 128 / 64 /
+"""The tcgen05 convolution kernels on the B200 - the line convolution (csrc/conv3d_tc.cu, corrif_conv3d_tc_fwd):
+forward (replicate / zero padding, 1..3 sources, bias, ReLU, InstanceNorm statistics) and data gradient (incl. the
+adjoint of replicate padding in one pass), and the weight gradient (csrc/conv3d_wgrad_tc.cu) - against fp64 PyTorch on
+the same inputs, for every tile geometry the kernel has: line widths 128 / 64 /
 32 / 16 (1 / 2 / 4 / 8 samples per MMA tile), 32- / 64- / 128-byte swizzled channel chunks, one to four lines per
 strip, several output-channel chunks, ragged strips and depths down to one plane.
 Tolerance (relative L2): TF32 operands (activations truncated by the tensor core with the mean compensated in the
